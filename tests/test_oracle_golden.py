@@ -1,0 +1,91 @@
+"""CPU: pin the NumPy restatement (oracle/mppi_oracle.py) against outputs of the live reference.
+
+Golden files: tests/golden/ref_*.npz, made by tests/golden/make_golden.py from the unmodified
+control/src/mppi.  The noise is regenerated here from the legacy NumPy stream (np.random.seed(0),
+control/src/mppi:15) exactly as the reference draws it (control/src/mppi:143-146).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import scipy.signal
+
+from oracle import mppi_oracle as orc
+from oracle import ref_loader
+
+CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*_k*_t*.npz")))
+
+
+def test_rng_kat(golden_dir):
+    """SURVEY appendix B RNG known-answer test (legacy MT19937 + polar Gaussian)."""
+    g = np.load(os.path.join(golden_dir, "ref_rng_kat.npz"))
+    np.random.seed(0)
+    assert np.array_equal(np.random.normal(size=4), g["normal4"])
+    assert np.array_equal(np.random.normal(0, .9, size=(2, 5)), g["normal_2x5"])
+    assert g["normal4"][0] == 1.764052345967664
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(c)[4:-4] for c in CASES])
+def test_oracle_matches_reference_golden(path):
+    g = np.load(path)
+    K, T = int(g["K"]), int(g["T"])
+    p = orc.Params(K=K, T=T)
+    np.random.seed(0)
+    s = g["x0"].astype(np.float64)
+    U = np.zeros((2, T))
+    for it in range(g["u0"].shape[0]):
+        eps = orc.draw_reference_noise(p)
+        if it == 0 and "eps0" in g:
+            assert np.array_equal(eps, g["eps0"])
+        out = orc.step(p, s, g["goal"], U, eps)
+        if it == 0 and "V0" in g:
+            np.testing.assert_allclose(out["V"], g["V0"], rtol=1e-13, atol=0)
+        # vectorised summation order differs from the reference's .dot() chain by O(1 ulp) of V (~4e-12);
+        # the softmin amplifies that by 1/lam, hence 1e-8 rather than 1e-15.
+        np.testing.assert_allclose(out["u0"], g["u0"][it], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(out["x_next"], g["x_next"][it], rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(out["U_shift"], g["U_shift"][it], rtol=1e-8, atol=1e-9)
+        s, U = out["x_next"], out["U_shift"]
+
+
+@pytest.mark.parametrize("T", [6, 16, 32, 64, 100, 128])
+def test_savgol_matrix_matches_scipy(T):
+    """oracle.savgol_matrix restates scipy.signal.savgol_filter(U, T-1, 3, axis=1) (control/src/mppi:202)."""
+    rng = np.random.RandomState(T)
+    U = rng.normal(size=(2, T)) * 3
+    want = scipy.signal.savgol_filter(U, T - 1, 3, axis=1)
+    got = U @ orc.savgol_matrix(T).T
+    np.testing.assert_allclose(got, want, rtol=0, atol=5e-13)
+
+
+def test_wrap_range():
+    th = np.array([-10.0, -np.pi, -np.pi + 1e-12, 0.0, np.pi, np.pi + 1e-12, 7.0, 100.0])
+    w = orc._wrap(th)
+    assert np.all(w > -np.pi - 1e-15) and np.all(w <= np.pi + 1e-15)
+    np.testing.assert_allclose(np.sin(w), np.sin(th), atol=1e-12)
+
+
+@pytest.mark.skipif(ref_loader.available() is None, reason="reference not loadable here")
+def test_oracle_matches_live_reference_with_replayed_noise():
+    """Direction (ii) of SURVEY 8c: feed OUR noise tensor into the untouched reference by patching
+    np.random.normal, and compare a full get_path."""
+    ref = ref_loader.load_reference()
+    K, T = 64, 16
+    rng = np.random.RandomState(123)
+    eps = (rng.standard_normal((T, 2, K)).astype(np.float32) * np.float32(0.9)).astype(np.float64)
+    m = ref.MPPI(horizon=T, samples=K)
+    m.latest_uvec = rng.normal(size=(2, T))
+    U0 = m.latest_uvec.copy()
+    feed = iter(eps)
+    orig = np.random.normal
+    np.random.normal = lambda *a, **k: next(feed).copy()
+    try:
+        x1 = m.get_path(np.array([0.1, 0.2, 3.0]), np.array([1.0, -1.0, 0.5]))
+    finally:
+        np.random.normal = orig
+    p = orc.Params(K=K, T=T)
+    out = orc.step(p, np.array([0.1, 0.2, 3.0]), np.array([1.0, -1.0, 0.5]), U0, eps)
+    np.testing.assert_allclose(out["u0"], m.uvec[-1], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(out["x_next"], x1, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(out["U_shift"], m.latest_uvec, rtol=1e-8, atol=1e-9)
