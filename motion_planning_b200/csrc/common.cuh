@@ -1,0 +1,349 @@
+// common.cuh -- shared device/host definitions of the B200 MPPI engine.
+//
+// Hot path restated: MPPI.get_path of the reference (control/src/mppi:85-102), i.e.
+// get_cost2go (:127-178) -> update_action (:186-208) -> perform_action (:210-213) -> shift.
+// Everything here is new code written for sm_100a; reference lines are cited for semantics only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mppi_b200.h"
+
+namespace mppi {
+
+constexpr int kMaxCand = 16;        // SCREEN: candidate slots per (CTA, t)
+constexpr int kMaxRefine = 256;     // SCREEN: fp64 re-evaluations per t after the global filter
+constexpr int kRecordStride = 6;    // doubles per t in an exchange record: m, S, N0, N1, E0, E1
+constexpr double kZFixScale = 1048576.0;   // 2^20: fixed-point scale of the floor-term noise sums
+
+enum RolloutMode { MODE_SOFTMIN = 0, MODE_SCREEN = 1 };
+
+// ---- static (engine-lifetime) parameters: passed by value in the constant bank -----------------
+struct StaticParams {
+  int K;                 // rollouts on this device
+  int T;
+  long long k_offset;    // global id of rollout 0 of this device (Philox counter)
+  long long k_total;     // global K (floor term 1e-8*K, control/src/mppi:193-195)
+  int model;
+  int weighting;
+  int noise_external;    // 0: Philox in registers, 1: replay eps (T,2,K) f64 from HBM
+  int capture;           // 1: write cost-to-go (T,K) to HBM (debug get_cost2go)
+  int has_grid;
+  int grid_in_smem;
+  int gW, gH;
+  int grid_bytes_padded; // multiple of 16 (TMA bulk copy granularity)
+  int world;             // ranks exchanging records
+  double dt;
+  double q[3];
+  double p1[3];
+  double u_max[2];
+  double wheel_r, wheel_L;
+  double eps_floor;
+  double g_inv_res, g_x0, g_y0, w_obs;
+  double margin;         // SCREEN window (cost units)
+  unsigned long long seed;
+};
+
+// ---- dynamic state living in HBM (changes every step; lets the CUDA graph stay static) ---------
+struct DynState {
+  double x0[3];          // start state of this step          (get_path arg, control/src/mppi:86)
+  double goal[3];        // goal                              (get_path arg, :87)
+  double lam;            // :89
+  double sig[4];         // :88
+  double R[4];           // :71
+  double noise_std[2];   // :144-146
+  unsigned int step;     // Philox step counter (advanced by finalize)
+  unsigned int pad0;
+  // outputs of finalize
+  double out_u[2];       // uvec[-1] = U[:,0] before shift    (:96-97)
+  double out_x[3];       // predicted next state              (:94,102)
+  int status;            // mppi_status seen on device (NONFINITE), or kStatusRedoF64
+  int refine_candidates; // accumulators of the running step (reduce_screen_kernel)
+  int refine_overflow;
+  int last_candidates;   // statistics of the last finished step (finalize_kernel)
+  double refine_max_dev;
+  double last_max_dev;
+  int overflow_total;    // steps that hit a candidate-list overflow since creation
+  int pad1;
+};
+constexpr int kStatusRedoF64 = 100;   // MIXED: support list overflowed, host must redo the step in fp64
+
+// ---- small math layer ---------------------------------------------------------------------------
+template <typename R> struct Math;
+
+template <> struct Math<float> {
+  typedef float4 Vec4;
+  static __device__ __forceinline__ float pi() { return 3.14159274101257324f; }
+  static __device__ __forceinline__ float inv_2pi() { return 0.159154943091895336f; }
+  static __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+  static __device__ __forceinline__ float ceil_(float a) { return ceilf(a); }
+  static __device__ __forceinline__ float floor_(float a) { return floorf(a); }
+  static __device__ __forceinline__ float exp_(float a) { return __expf(a); }
+  static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+  static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+  // sin/cos for |x| up to ~1e4: 3-term Cody-Waite to [-pi/4, pi/4] + minimax polynomials.
+  // No MUFU (keeps the SFU pipe for the Box-Muller of the noise), ~1.5 ulp.
+  static __device__ __forceinline__ void sincos_(float x, float& s, float& c) {
+    float j = rintf(x * 0.636619772367581343f);
+    int q = __float2int_rn(j);
+    float r = fmaf(-j, 1.57079601e+00f, x);
+    r = fmaf(-j, 3.13916473e-07f, r);
+    r = fmaf(-j, 5.39030253e-15f, r);
+    float z = r * r;
+    float ps = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), z * r, r);
+    float pc = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f),
+                    z * z, fmaf(-0.5f, z, 1.0f));
+    float ss = (q & 1) ? pc : ps;
+    float cc = (q & 1) ? ps : pc;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+  }
+  // theta - (ceil((theta+pi)/(2pi)) - 1) * 2pi   (control/src/mppi:52-53), 2pi split hi/lo
+  static __device__ __forceinline__ float wrap_(float th) {
+    float n = ceilf((th + pi()) * inv_2pi()) - 1.0f;
+    float r = fmaf(-n, 6.28318548202514648f, th);
+    return fmaf(n, 1.74845553146951715e-07f, r);
+  }
+};
+
+template <> struct Math<double> {
+  typedef double4 Vec4;
+  static __device__ __forceinline__ double pi() { return 3.14159265358979323846; }
+  static __device__ __forceinline__ double inv_2pi() { return 0.15915494309189533577; }
+  static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+  static __device__ __forceinline__ double ceil_(double a) { return ceil(a); }
+  static __device__ __forceinline__ double floor_(double a) { return floor(a); }
+  static __device__ __forceinline__ double exp_(double a) { return exp(a); }
+  static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
+  static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+  static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+  static __device__ __forceinline__ void sincos_(double x, double& s, double& c) { sincos(x, &s, &c); }
+  // same expression as the reference, evaluated in f64 (control/src/mppi:52-53)
+  static __device__ __forceinline__ double wrap_(double th) {
+    double n = ceil((th + pi()) / (2.0 * pi())) - 1.0;
+    return th - n * 2.0 * pi();
+  }
+};
+
+template <typename R>
+__device__ __forceinline__ R clamp_(R v, R lim) {
+  return Math<R>::max_(-lim, Math<R>::min_(v, lim));
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), counter-based: the noise of rollout k at step pair
+// t2 of engine step `step` is a pure function of (seed, k_global, t2, step) -- independent of how
+// K is sharded over GPUs and regenerable anywhere (reduction kernels, noise export).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+// 4 standard normals (fp32) = the z of (t=2*t2: ch0, ch1), (t=2*t2+1: ch0, ch1).  Box-Muller on the
+// SFU pipe (lg2, rsqrt/sqrt, sin, cos).  Bit-identical wherever it is called from (intrinsics only,
+// nothing for the compiler to contract).
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long kglobal,
+                                                 unsigned int t2, unsigned int step) {
+  uint4 ctr = make_uint4((uint32_t)kglobal, (uint32_t)(kglobal >> 32), t2, step);
+  uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  uint4 r = philox4x32_10(ctr, key);
+  const float S = 2.3283064365386963e-10f;   // 2^-32
+  float u0 = __fmaf_rn((float)r.x, S, 1.1641532182693481e-10f);   // (0,1]
+  float u1 = __fmul_rn((float)r.y, S);
+  float u2 = __fmaf_rn((float)r.z, S, 1.1641532182693481e-10f);
+  float u3 = __fmul_rn((float)r.w, S);
+  float ra = __fsqrt_rn(__fmul_rn(-2.0f, __logf(u0)));
+  float rb = __fsqrt_rn(__fmul_rn(-2.0f, __logf(u2)));
+  float sa, ca, sb, cb;
+  __sincosf(__fmul_rn(6.28318530717958648f, u1), &sa, &ca);
+  __sincosf(__fmul_rn(6.28318530717958648f, u3), &sb, &cb);
+  return make_float4(__fmul_rn(ra, ca), __fmul_rn(ra, sa), __fmul_rn(rb, cb), __fmul_rn(rb, sb));
+}
+
+// eps = noise_std * z, rounded once in fp32: THE sample value (what mppi_get_noise exports)
+__device__ __forceinline__ float eps_from_z(float std_, float z) { return __fmul_rn(std_, z); }
+
+// eps of (rollout kglobal, time t, channel pair) regenerated from counters
+__device__ __forceinline__ void philox_eps(unsigned long long seed, unsigned long long kglobal, int t,
+                                           unsigned int step, float std0, float std1, float& e0, float& e1) {
+  float4 z = philox_normal4(seed, kglobal, (unsigned)t >> 1, step);
+  e0 = eps_from_z(std0, (t & 1) ? z.z : z.x);
+  e1 = eps_from_z(std1, (t & 1) ? z.w : z.y);
+}
+
+// ---- vehicle models: every supported model has a state-independent yaw rate, so one step is
+//   s = forward speed(u), w = yaw rate(u);  RK4 on (x, y, theta) with u held (control/src/mppi:39-54)
+template <typename R>
+struct ModelConsts {
+  R dt, half_r, r_over_L, inv_L;
+};
+
+template <typename R, int MODEL>
+__device__ __forceinline__ void speed_yaw(const ModelConsts<R>& mc, R u0, R u1, R& s, R& w) {
+  if (MODEL == MPPI_MODEL_DIFF_DRIVE) {          // dd_dynamics, control/src/mppi:23-30
+    s = mc.half_r * (u0 + u1);
+    w = mc.r_over_L * (u1 - u0);
+  } else if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {   // unicycle_dynamics, control/src/mppi:33-36
+    s = u0;
+    w = u1;
+  } else {                                        // NEW bicycle: thdot = v tan(delta) / L
+    R sd, cd;
+    Math<R>::sincos_(u1, sd, cd);
+    s = u0;
+    w = u0 * (sd / cd) * mc.inv_L;
+  }
+}
+
+// One integrator step in DISPLACEMENT coordinates (dx, dy relative to x0; theta absolute, wrapped).
+// RK4: k1 uses theta, k2 == k3 use theta + k_theta/2, k4 uses theta + k_theta (theta-dot does not
+// depend on the state), so x+ = x + dt*s/6 * (c1 + 4 c2 + c4).
+template <typename R, int MODEL>
+__device__ __forceinline__ void model_step(const ModelConsts<R>& mc, R u0, R u1, R& dx, R& dy, R& th) {
+  R s, w;
+  speed_yaw<R, MODEL>(mc, u0, u1, s, w);
+  if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {       // euler, control/src/mppi:57-58 (no wrap)
+    R sn, cs;
+    Math<R>::sincos_(th, sn, cs);
+    dx = Math<R>::fma_(mc.dt * s, cs, dx);
+    dy = Math<R>::fma_(mc.dt * s, sn, dy);
+    th = Math<R>::fma_(mc.dt, w, th);
+    return;
+  }
+  R kth = mc.dt * w;
+  R s1, c1, s2, c2, s4, c4;
+  Math<R>::sincos_(th, s1, c1);
+  Math<R>::sincos_(Math<R>::fma_(R(0.5), kth, th), s2, c2);
+  R thn = th + kth;
+  Math<R>::sincos_(thn, s4, c4);
+  R g = mc.dt * s * R(1.0 / 6.0);
+  dx = Math<R>::fma_(g, Math<R>::fma_(R(4), c2, c1 + c4), dx);
+  dy = Math<R>::fma_(g, Math<R>::fma_(R(4), s2, s1 + s4), dy);
+  th = Math<R>::wrap_(thn);
+}
+
+// ---- cost in delta form --------------------------------------------------------------------------
+// The reference subtracts min_k V[t,k] per t before exponentiating (control/src/mppi:189), so any
+// k-independent term of the running cost is irrelevant to the weights.  We drop the control cost
+// 1/2 u'Ru (u is the NOMINAL control, :160,183) and the cost of "standing still at x0", i.e. we
+// accumulate  1/2 Q (e^2 - a^2) = 1/2 Q d (d + 2a)  with a = x0 - goal, d = displacement.  This keeps
+// fp32 magnitudes ~1e2 instead of ~3e4.  mppi_get_cost_to_go adds the offset back.
+template <typename R>
+struct CostConsts {
+  R hqx, hqy, hqth;      // Q/2
+  R p1x, p1y, p1th;
+  R ax2, ay2;            // 2*(x0 - goal)
+  R th0, gth2;           // theta0, 2*goal_theta
+  // grid
+  R g_inv_res, g_ox, g_oy, w_obs_100;   // (x0 - origin) folded into g_ox/g_oy
+  int gW, gH;
+};
+
+template <typename R>
+__device__ __forceinline__ R running_cost(const CostConsts<R>& cc, R dx, R dy, R th, R g0, R g1, R e0, R e1) {
+  // get_cost, control/src/mppi:180-184:  1/2 (x-g)'Q(x-g) [+ 1/2 u'Ru dropped] + lam * u.sig.eps
+  R c = cc.hqx * dx * (dx + cc.ax2);
+  c = Math<R>::fma_(cc.hqy * dy, dy + cc.ay2, c);
+  if (cc.hqth != R(0)) c = Math<R>::fma_(cc.hqth * (th - cc.th0), th + cc.th0 - cc.gth2, c);
+  c = Math<R>::fma_(g0, e0, c);
+  c = Math<R>::fma_(g1, e1, c);
+  return c;
+}
+
+template <typename R>
+__device__ __forceinline__ R terminal_cost(const CostConsts<R>& cc, R dx, R dy, R th) {
+  // control/src/mppi:165-171: (x_T - g)' P1 (x_T - g), no 1/2, theta difference NOT wrapped
+  R c = cc.p1x * dx * (dx + cc.ax2);
+  c = Math<R>::fma_(cc.p1y * dy, dy + cc.ay2, c);
+  c = Math<R>::fma_(cc.p1th * (th - cc.th0), th + cc.th0 - cc.gth2, c);
+  return c;
+}
+
+// NEW occupancy-grid term: w_obs * cell/100, outside the map = 100.
+template <typename R>
+__device__ __forceinline__ R grid_cost(const CostConsts<R>& cc, const signed char* __restrict__ cells, R dx, R dy) {
+  R fx = Math<R>::floor_((dx + cc.g_ox) * cc.g_inv_res);
+  R fy = Math<R>::floor_((dy + cc.g_oy) * cc.g_inv_res);
+  int v = 100;
+  if (fx >= R(0) && fy >= R(0) && fx < R(cc.gW) && fy < R(cc.gH)) v = cells[(int)fy * cc.gW + (int)fx];
+  return cc.w_obs_100 * R(v);
+}
+
+template <typename R>
+__device__ __forceinline__ void make_consts(const StaticParams& sp, const DynState* __restrict__ ds,
+                                            ModelConsts<R>& mc, CostConsts<R>& cc) {
+  mc.dt = R(sp.dt);
+  mc.half_r = R(sp.wheel_r * 0.5);
+  mc.r_over_L = R(sp.wheel_r / sp.wheel_L);
+  mc.inv_L = R(1.0 / sp.wheel_L);
+  double x0 = ds->x0[0], y0 = ds->x0[1], th0 = ds->x0[2];
+  double gx = ds->goal[0], gy = ds->goal[1], gth = ds->goal[2];
+  cc.hqx = R(0.5 * sp.q[0]);
+  cc.hqy = R(0.5 * sp.q[1]);
+  cc.hqth = R(0.5 * sp.q[2]);
+  cc.p1x = R(sp.p1[0]);
+  cc.p1y = R(sp.p1[1]);
+  cc.p1th = R(sp.p1[2]);
+  cc.ax2 = R(2.0 * (x0 - gx));
+  cc.ay2 = R(2.0 * (y0 - gy));
+  cc.th0 = R(th0);
+  cc.gth2 = R(2.0 * gth);
+  cc.g_inv_res = R(sp.g_inv_res);
+  cc.g_ox = R(x0 - sp.g_x0);
+  cc.g_oy = R(y0 - sp.g_y0);
+  cc.w_obs_100 = R(sp.w_obs / 100.0);
+  cc.gW = sp.gW;
+  cc.gH = sp.gH;
+}
+
+// ---- warp helpers --------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ R warp_min(R v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = Math<R>::min_(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <typename R>
+__device__ __forceinline__ R warp_sum(R v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- TMA 1-D bulk copy + mbarrier (global -> shared), sm_90+/sm_100a -----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+}  // namespace mppi

@@ -1,0 +1,1153 @@
+// engine.cu -- host side of libmppi_b200.so: the C ABI declared in include/mppi_b200.h.
+//
+// One engine = one CUDA device.  A step (= MPPI.get_path, control/src/mppi:85-102) is three kernels
+//   rollout_kernel -> reduce_{softmin,screen}_kernel -> finalize_kernel
+// captured once into a CUDA graph together with the 48-byte H2D copy of (x0, goal) and the D2H copy
+// of the result block; all controller state (nominal U, Philox step counter) stays resident in HBM.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "kernels_api.h"
+
+using namespace mppi;
+
+static thread_local char g_err[512] = "";
+
+static void set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#define CK(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t _e = (call);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      set_err("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));             \
+      return MPPI_ERR_CUDA;                                                                      \
+    }                                                                                            \
+  } while (0)
+
+#define CKS(call)                       \
+  do {                                  \
+    mppi_status _s = (call);            \
+    if (_s != MPPI_OK) return _s;       \
+  } while (0)
+
+struct KindCfg {
+  int block = 0, grid = 0, ntiles = 0, ctas_per_sm = 0, regs = 0;
+  size_t smem = 0;
+  bool ready = false;
+};
+
+struct mppi_engine {
+  mppi_params p;
+  StaticParams sp;
+  int dev = 0, num_sms = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  // device state
+  DynState* d_dyn = nullptr;
+  double *d_Umaster = nullptr, *d_Ulast = nullptr, *d_nomD = nullptr, *d_Utmp = nullptr;
+  float* d_nomF = nullptr;
+  double* d_sg_rows = nullptr;
+  double sg_a = 0, sg_b = 0;
+  double *d_record = nullptr, *d_gather = nullptr, *d_record_tmp = nullptr;
+  void* d_part = nullptr;
+  double* d_epart = nullptr;
+  int* d_cand_count = nullptr;
+  uint2* d_cand = nullptr;
+  float* d_cand_min = nullptr;
+  size_t part_capacity_ctas = 0;
+  signed char* d_grid = nullptr;
+  double* d_eps_ext = nullptr;
+  void* d_vcap = nullptr;
+  void* d_flush = nullptr;
+  size_t flush_bytes = 0;
+  KindCfg cfg[3];
+  // pinned host staging
+  double* h_in = nullptr;      // x0[3], goal[3]
+  DynState* h_out = nullptr;
+  // graphs
+  cudaGraphExec_t g_step = nullptr, g_loop = nullptr;
+  bool dirty = true;
+  // host mirrors
+  double goal[3] = {0, 0, 0};
+  double last_x0[3] = {0, 0, 0}, last_goal[3] = {0, 0, 0};
+  std::vector<double> U_prev;
+  int last_capture_kind = -1;
+  bool local_pending = false;
+  mppi_timing last{};
+};
+
+static int kind_of(int precision) {
+  return precision == MPPI_PRECISION_F32 ? ROLLOUT_F32_SOFTMIN
+                                         : (precision == MPPI_PRECISION_F64 ? ROLLOUT_F64_SOFTMIN : ROLLOUT_F32_SCREEN);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* mppi_last_error(void) { return g_err; }
+extern "C" const char* mppi_version(void) { return "mppi_b200 0.1 (sm_100a)"; }
+extern "C" int32_t mppi_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" mppi_status mppi_default_params(mppi_params* p) {
+  if (!p) return MPPI_ERR_INVALID;
+  memset(p, 0, sizeof(*p));
+  p->struct_size = sizeof(mppi_params);
+  p->abi_version = MPPI_B200_ABI_VERSION;
+  p->K = 10;                                       // control/src/mppi:62
+  p->T = 100;                                      // control/src/mppi:62
+  p->model = MPPI_MODEL_DIFF_DRIVE;                // model=rk4, control/src/mppi:62
+  p->weighting = MPPI_WEIGHT_COST_TO_GO;
+  p->precision = MPPI_PRECISION_MIXED;
+  p->device = 0;
+  p->dt = 0.0;                                     // -> 1/T, control/src/mppi:67
+  p->q[0] = 1e3; p->q[1] = 1e3; p->q[2] = 0.0;     // control/src/mppi:69
+  p->r[0] = 1.0; p->r[3] = 1.0;                    // control/src/mppi:71
+  p->p1[0] = p->p1[1] = p->p1[2] = 1e3;            // control/src/mppi:73
+  p->sig[0] = 0.9; p->sig[3] = 0.9;                // control/src/mppi:88
+  p->noise_std[0] = p->noise_std[1] = 0.9;         // sig[0,0], control/src/mppi:144-146
+  p->lambda = 1e-3;                                // control/src/mppi:89
+  p->u_max[0] = p->u_max[1] = 6.35492;             // WHEEL_VEL_MAX, control/src/mppi:18
+  p->wheel_radius = 0.033;                         // control/src/mppi:19
+  p->wheel_base = 0.16;                            // control/src/mppi:20
+  p->eps_floor = 1e-8;                             // control/src/mppi:193
+  p->seed = 0;                                     // np.random.seed(0), control/src/mppi:15
+  p->k_offset = 0;
+  p->k_total = 0;
+  p->world_size = 1;
+  p->rank = 0;
+  p->stream = nullptr;
+  p->refine_margin = 0.0;
+  return MPPI_OK;
+}
+
+static double default_margin(const mppi_engine* e, double lam) {
+  if (e->p.refine_margin > 0) return e->p.refine_margin;
+  // e^-40 ~ 4e-18 relative weight is far below the 1e-8 floor; 0.06 covers the fp32 screening error
+  // of the cost-to-go (measured max |V32 - V64|) with > 10x head-room.
+  return 40.0 * lam + 0.06;
+}
+
+static void free_partials(mppi_engine* e) {
+  cudaFree(e->d_part);
+  cudaFree(e->d_epart);
+  cudaFree(e->d_cand_count);
+  cudaFree(e->d_cand);
+  cudaFree(e->d_cand_min);
+  e->d_part = nullptr;
+  e->d_epart = nullptr;
+  e->d_cand_count = nullptr;
+  e->d_cand = nullptr;
+  e->d_cand_min = nullptr;
+  e->part_capacity_ctas = 0;
+}
+
+static mppi_status drop_graphs(mppi_engine* e) {
+  if (e->g_step) cudaGraphExecDestroy(e->g_step);
+  if (e->g_loop) cudaGraphExecDestroy(e->g_loop);
+  e->g_step = e->g_loop = nullptr;
+  e->dirty = true;
+  return MPPI_OK;
+}
+
+// (re)compute launch configurations for the three rollout families and size the partial buffers
+static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
+  StaticParams& sp = e->sp;
+  const bool has_grid = sp.has_grid != 0;
+  const char* envb = getenv("MPPI_B200_BLOCK");
+  *max_ctas = 0;
+  for (int kind = 0; kind < 3; ++kind) {
+    KindCfg best;
+    double best_cost = 1e300;
+    for (int block = 64; block <= 128; block *= 2) {
+      if (envb && atoi(envb) != block) continue;
+      KindCfg c;
+      c.block = block;
+      c.ntiles = (sp.K + block - 1) / block;
+      c.smem = rollout_smem(kind, sp.T, block, gin);
+      if (c.smem > 227 * 1024) continue;
+      cudaError_t ce = rollout_prepare(kind, sp.model, has_grid, block, c.smem, &c.ctas_per_sm, &c.regs);
+      if (ce != cudaSuccess || c.ctas_per_sm < 1) {
+        cudaGetLastError();
+        continue;
+      }
+      const long long resident = (long long)e->num_sms * c.ctas_per_sm;
+      c.grid = (int)((c.ntiles < resident) ? c.ntiles : resident);
+      // busiest-SM thread-work: tiles are dealt round-robin over the SMs
+      const double cost = (double)((c.ntiles + e->num_sms - 1) / e->num_sms) * block;
+      c.ready = true;
+      if (cost < best_cost || (cost == best_cost && block > best.block)) {
+        best = c;
+        best_cost = cost;
+      }
+    }
+    e->cfg[kind] = best;
+    if (best.ready && (size_t)best.grid > *max_ctas) *max_ctas = best.grid;
+  }
+  return e->cfg[kind_of(e->p.precision)].ready && e->cfg[ROLLOUT_F64_SOFTMIN].ready;
+}
+
+static mppi_status configure(mppi_engine* e) {
+  StaticParams& sp = e->sp;
+  size_t max_ctas = 0;
+  int gin = (sp.has_grid && sp.grid_bytes_padded <= 96 * 1024) ? sp.grid_bytes_padded : 0;
+  bool ok = try_configure(e, gin, &max_ctas);
+  if (!ok && gin) {   // the grid does not fit beside the cost tile: read it through L1/L2 instead
+    gin = 0;
+    ok = try_configure(e, 0, &max_ctas);
+  }
+  if (!ok) {
+    set_err("no launch configuration fits (T=%d needs too much shared memory)", sp.T);
+    return MPPI_ERR_UNSUPPORTED;
+  }
+  sp.grid_in_smem = gin > 0 ? 1 : 0;
+  if (max_ctas > e->part_capacity_ctas) {
+    free_partials(e);
+    const size_t n = (size_t)sp.T * max_ctas;
+    CK(cudaMalloc(&e->d_part, n * sizeof(double4)));
+    CK(cudaMalloc(&e->d_epart, n * 2 * sizeof(double)));
+    CK(cudaMalloc(&e->d_cand_count, n * sizeof(int)));
+    CK(cudaMalloc(&e->d_cand, n * kMaxCand * sizeof(uint2)));
+    CK(cudaMalloc(&e->d_cand_min, n * sizeof(float)));
+    e->part_capacity_ctas = max_ctas;
+  }
+  return drop_graphs(e);
+}
+
+static void savgol_rows(int T, std::vector<double>& rows, double& a, double& b) {
+  // Gram (discrete orthogonal) cubic basis on z = -h..h, window w = T-1 (control/src/mppi:202):
+  // p0 = 1, p1 = z, p2 = z^2 - a, p3 = z^3 - b z; rows[i][j] = p_i(z_j) / sum_j p_i(z_j)^2
+  const int W = T - 1, h = W / 2;
+  long double s2 = 0, s4 = 0;
+  for (int j = 0; j < W; ++j) {
+    long double z = j - h;
+    s2 += z * z;
+    s4 += z * z * z * z;
+  }
+  const long double la = s2 / W, lb = s4 / s2;
+  long double n[4] = {0, 0, 0, 0};
+  std::vector<long double> pv((size_t)4 * W);
+  for (int j = 0; j < W; ++j) {
+    long double z = j - h;
+    long double pz[4] = {1.0L, z, z * z - la, z * z * z - lb * z};
+    for (int i = 0; i < 4; ++i) {
+      pv[(size_t)i * W + j] = pz[i];
+      n[i] += pz[i] * pz[i];
+    }
+  }
+  rows.resize((size_t)4 * W);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < W; ++j) rows[(size_t)i * W + j] = (double)(pv[(size_t)i * W + j] / n[i]);
+  a = (double)la;
+  b = (double)lb;
+}
+
+static mppi_status upload_dyn_sampling(mppi_engine* e, const double sig[4], double lam, const double nstd[2]) {
+  DynState tmp;
+  CK(cudaMemcpy(&tmp, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; ++i) tmp.sig[i] = sig[i];
+  tmp.lam = lam;
+  tmp.noise_std[0] = nstd[0];
+  tmp.noise_std[1] = nstd[1];
+  CK(cudaMemcpy(e->d_dyn, &tmp, sizeof(DynState), cudaMemcpyHostToDevice));
+  return MPPI_OK;
+}
+
+static mppi_status prep_nominal(mppi_engine* e) {
+  CK(prep_nominal_launch(e->stream, e->d_dyn, e->sp.T, e->d_Umaster, e->d_nomF, e->d_nomD));
+  CK(cudaStreamSynchronize(e->stream));
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
+  if (!pin || !out) {
+    set_err("null argument");
+    return MPPI_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (pin->struct_size != sizeof(mppi_params) || pin->abi_version != MPPI_B200_ABI_VERSION) {
+    set_err("mppi_params ABI mismatch (size %u vs %zu, version %u vs %d)", pin->struct_size, sizeof(mppi_params),
+            pin->abi_version, MPPI_B200_ABI_VERSION);
+    return MPPI_ERR_INVALID;
+  }
+  mppi_params p = *pin;
+  if (p.K < 1 || p.T < 6 || (p.T & 1) || p.T > 1024) {
+    set_err("need K >= 1 and even 6 <= T <= 1024 (savgol window T-1 must be odd, control/src/mppi:202); got K=%d T=%d", p.K, p.T);
+    return MPPI_ERR_INVALID;
+  }
+  if (p.model < 0 || p.model > 2 || p.weighting < 0 || p.weighting > 1 || p.precision < 0 || p.precision > 2) {
+    set_err("bad model/weighting/precision enum");
+    return MPPI_ERR_INVALID;
+  }
+  if (!(p.lambda > 0) || !(p.wheel_base > 0) || !(p.u_max[0] > 0) || !(p.u_max[1] > 0)) {
+    set_err("lambda, wheel_base and u_max must be positive");
+    return MPPI_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    set_err("no CUDA device: the MPPI engine has no CPU fallback");
+    return MPPI_ERR_NO_DEVICE;
+  }
+  if (p.device < 0 || p.device >= ndev) {
+    set_err("device %d out of range (have %d)", p.device, ndev);
+    return MPPI_ERR_INVALID;
+  }
+  CK(cudaSetDevice(p.device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, p.device));
+  if (prop.major < 10) {
+    set_err("device %d is sm_%d%d; this library is built for sm_100a only", p.device, prop.major, prop.minor);
+    return MPPI_ERR_UNSUPPORTED;
+  }
+  if (p.dt <= 0) p.dt = 1.0 / (double)p.T;
+  if (p.k_total <= 0) p.k_total = p.K;
+  if (p.world_size <= 0) p.world_size = 1;
+
+  mppi_engine* e = new mppi_engine();
+  e->p = p;
+  e->dev = p.device;
+  e->num_sms = prop.multiProcessorCount;
+  if (p.stream) {
+    e->stream = (cudaStream_t)p.stream;
+    e->own_stream = false;
+  } else {
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      set_err("cudaStreamCreate failed");
+      delete e;
+      return MPPI_ERR_CUDA;
+    }
+    e->own_stream = true;
+  }
+  StaticParams& sp = e->sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.K = p.K;
+  sp.T = p.T;
+  sp.k_offset = p.k_offset;
+  sp.k_total = p.k_total;
+  sp.model = p.model;
+  sp.weighting = p.weighting;
+  sp.world = p.world_size;
+  sp.dt = p.dt;
+  for (int i = 0; i < 3; ++i) {
+    sp.q[i] = p.q[i];
+    sp.p1[i] = p.p1[i];
+  }
+  sp.u_max[0] = p.u_max[0];
+  sp.u_max[1] = p.u_max[1];
+  sp.wheel_r = p.wheel_radius;
+  sp.wheel_L = p.wheel_base;
+  sp.eps_floor = p.eps_floor;
+  sp.seed = p.seed;
+  sp.margin = default_margin(e, p.lambda);
+  sp.g_inv_res = 1.0;
+
+  const int T = p.T;
+  auto fail = [&](mppi_status s) {
+    mppi_destroy(e);
+    return s;
+  };
+#define CKF(call)                                                                                \
+  do {                                                                                           \
+    cudaError_t _e = (call);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      set_err("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));             \
+      return fail(MPPI_ERR_CUDA);                                                                \
+    }                                                                                            \
+  } while (0)
+  CKF(cudaMalloc(&e->d_dyn, sizeof(DynState)));
+  CKF(cudaMalloc(&e->d_Umaster, 2 * T * sizeof(double)));
+  CKF(cudaMalloc(&e->d_Ulast, 2 * T * sizeof(double)));
+  CKF(cudaMalloc(&e->d_Utmp, 4 * T * sizeof(double)));
+  CKF(cudaMalloc(&e->d_nomD, 4 * T * sizeof(double)));
+  CKF(cudaMalloc(&e->d_nomF, 4 * T * sizeof(float)));
+  CKF(cudaMalloc(&e->d_record, (size_t)T * kRecordStride * sizeof(double)));
+  CKF(cudaMalloc(&e->d_record_tmp, (size_t)T * kRecordStride * sizeof(double)));
+  CKF(cudaMalloc(&e->d_gather, (size_t)p.world_size * T * kRecordStride * sizeof(double)));
+  CKF(cudaMalloc(&e->d_sg_rows, (size_t)4 * (T - 1) * sizeof(double)));
+  CKF(cudaMallocHost(&e->h_in, 6 * sizeof(double)));
+  CKF(cudaMallocHost(&e->h_out, sizeof(DynState)));
+  CKF(cudaMemset(e->d_Umaster, 0, 2 * T * sizeof(double)));     // uvec_init = zeros, control/src/mppi:65
+  CKF(cudaMemset(e->d_Ulast, 0, 2 * T * sizeof(double)));
+  CKF(cudaMemset(e->d_record, 0, (size_t)T * kRecordStride * sizeof(double)));
+  CKF(cudaMemset(e->d_gather, 0, (size_t)p.world_size * T * kRecordStride * sizeof(double)));
+  {
+    std::vector<double> rows;
+    savgol_rows(T, rows, e->sg_a, e->sg_b);
+    CKF(cudaMemcpy(e->d_sg_rows, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  {
+    DynState d;
+    memset(&d, 0, sizeof(d));
+    d.lam = p.lambda;
+    for (int i = 0; i < 4; ++i) {
+      d.sig[i] = p.sig[i];
+      d.R[i] = p.r[i];
+    }
+    d.noise_std[0] = p.noise_std[0];
+    d.noise_std[1] = p.noise_std[1];
+    CKF(cudaMemcpy(e->d_dyn, &d, sizeof(d), cudaMemcpyHostToDevice));
+  }
+  e->U_prev.assign(2 * T, 0.0);
+  mppi_status s = configure(e);
+  if (s != MPPI_OK) return fail(s);
+  s = prep_nominal(e);
+  if (s != MPPI_OK) return fail(s);
+  *out = e;
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_destroy(mppi_handle e) {
+  if (!e) return MPPI_OK;
+  cudaSetDevice(e->dev);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  drop_graphs(e);
+  free_partials(e);
+  cudaFree(e->d_dyn);
+  cudaFree(e->d_Umaster);
+  cudaFree(e->d_Ulast);
+  cudaFree(e->d_Utmp);
+  cudaFree(e->d_nomD);
+  cudaFree(e->d_nomF);
+  cudaFree(e->d_record);
+  cudaFree(e->d_record_tmp);
+  cudaFree(e->d_gather);
+  cudaFree(e->d_sg_rows);
+  cudaFree(e->d_grid);
+  cudaFree(e->d_eps_ext);
+  cudaFree(e->d_vcap);
+  cudaFree(e->d_flush);
+  if (e->h_in) cudaFreeHost(e->h_in);
+  if (e->h_out) cudaFreeHost(e->h_out);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return MPPI_OK;
+}
+
+#define ENTER(e)                                  \
+  if (!(e)) {                                     \
+    set_err("null handle");                       \
+    return MPPI_ERR_INVALID;                      \
+  }                                               \
+  CK(cudaSetDevice((e)->dev))
+
+extern "C" mppi_status mppi_reset(mppi_handle e) {
+  ENTER(e);
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemsetAsync(e->d_Umaster, 0, 2 * e->sp.T * sizeof(double), e->stream));   // control/src/mppi:81
+  e->local_pending = false;
+  return prep_nominal(e);
+}
+
+extern "C" mppi_status mppi_set_goal(mppi_handle e, const double goal[3]) {
+  ENTER(e);
+  if (!goal) return MPPI_ERR_INVALID;
+  for (int i = 0; i < 3; ++i) e->goal[i] = goal[i];
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_set_sampling(mppi_handle e, const double sig[4], double lambda) {
+  ENTER(e);
+  if (!sig || !(lambda > 0)) {
+    set_err("sig must be non-null and lambda > 0");
+    return MPPI_ERR_INVALID;
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  const double nstd[2] = {sig[0], sig[0]};   // reference: normal(0, sig[0,0]) for both rows, control/src/mppi:144-146
+  CKS(upload_dyn_sampling(e, sig, lambda, nstd));
+  for (int i = 0; i < 4; ++i) e->p.sig[i] = sig[i];
+  e->p.lambda = lambda;
+  e->p.noise_std[0] = e->p.noise_std[1] = sig[0];
+  const double m = default_margin(e, lambda);
+  if (m != e->sp.margin) {
+    e->sp.margin = m;
+    drop_graphs(e);
+  }
+  return prep_nominal(e);
+}
+
+extern "C" mppi_status mppi_set_noise_std(mppi_handle e, const double nstd[2]) {
+  ENTER(e);
+  if (!nstd) return MPPI_ERR_INVALID;
+  CK(cudaStreamSynchronize(e->stream));
+  CKS(upload_dyn_sampling(e, e->p.sig, e->p.lambda, nstd));
+  e->p.noise_std[0] = nstd[0];
+  e->p.noise_std[1] = nstd[1];
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_get_nominal(mppi_handle e, double* U) {
+  ENTER(e);
+  if (!U) return MPPI_ERR_INVALID;
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(U, e->d_Umaster, 2 * e->sp.T * sizeof(double), cudaMemcpyDeviceToHost));
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_set_nominal(mppi_handle e, const double* U) {
+  ENTER(e);
+  if (!U) return MPPI_ERR_INVALID;
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(e->d_Umaster, U, 2 * e->sp.T * sizeof(double), cudaMemcpyHostToDevice));
+  return prep_nominal(e);
+}
+
+extern "C" mppi_status mppi_get_last_update(mppi_handle e, double* U) {
+  ENTER(e);
+  if (!U) return MPPI_ERR_INVALID;
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(U, e->d_Ulast, 2 * e->sp.T * sizeof(double), cudaMemcpyDeviceToHost));
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_set_grid(mppi_handle e, const int8_t* cells, int32_t W, int32_t H, double res, double x_min,
+                                     double y_min, double w_obs) {
+  ENTER(e);
+  if (!cells || W < 1 || H < 1 || !(res > 0) || (long long)W * H > (1LL << 30)) {
+    set_err("bad grid");
+    return MPPI_ERR_INVALID;
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  const size_t n = (size_t)W * H, padded = (n + 15) & ~(size_t)15;
+  cudaFree(e->d_grid);
+  e->d_grid = nullptr;
+  CK(cudaMalloc(&e->d_grid, padded));
+  CK(cudaMemset(e->d_grid, 100, padded));
+  CK(cudaMemcpy(e->d_grid, cells, n, cudaMemcpyHostToDevice));
+  StaticParams& sp = e->sp;
+  sp.has_grid = 1;
+  sp.gW = W;
+  sp.gH = H;
+  sp.grid_bytes_padded = (int)padded;
+  sp.g_inv_res = 1.0 / res;
+  sp.g_x0 = x_min;
+  sp.g_y0 = y_min;
+  sp.w_obs = w_obs;
+  return configure(e);
+}
+
+extern "C" mppi_status mppi_clear_grid(mppi_handle e) {
+  ENTER(e);
+  CK(cudaStreamSynchronize(e->stream));
+  e->sp.has_grid = 0;
+  e->sp.grid_in_smem = 0;
+  e->sp.w_obs = 0;
+  return configure(e);
+}
+
+extern "C" mppi_status mppi_set_noise(mppi_handle e, const double* eps) {
+  ENTER(e);
+  if (!eps) return MPPI_ERR_INVALID;
+  CK(cudaStreamSynchronize(e->stream));
+  const size_t n = (size_t)e->sp.T * 2 * e->sp.K;
+  if (!e->d_eps_ext) CK(cudaMalloc(&e->d_eps_ext, n * sizeof(double)));
+  CK(cudaMemcpy(e->d_eps_ext, eps, n * sizeof(double), cudaMemcpyHostToDevice));
+  if (!e->sp.noise_external) {
+    e->sp.noise_external = 1;
+    drop_graphs(e);
+  }
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_use_philox(mppi_handle e, uint64_t seed) {
+  ENTER(e);
+  CK(cudaStreamSynchronize(e->stream));
+  e->sp.noise_external = 0;
+  e->sp.seed = seed;
+  unsigned int zero = 0;
+  CK(cudaMemcpy(&e->d_dyn->step, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+  return drop_graphs(e);
+}
+
+extern "C" mppi_status mppi_get_noise(mppi_handle e, double* eps) {
+  ENTER(e);
+  if (!eps) return MPPI_ERR_INVALID;
+  CK(cudaStreamSynchronize(e->stream));
+  const size_t n = (size_t)e->sp.T * 2 * e->sp.K;
+  if (e->sp.noise_external) {
+    CK(cudaMemcpy(eps, e->d_eps_ext, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return MPPI_OK;
+  }
+  unsigned int step = 0;
+  CK(cudaMemcpy(&step, &e->d_dyn->step, sizeof(step), cudaMemcpyDeviceToHost));
+  if (step == 0) {
+    set_err("mppi_get_noise: no step has been run since the noise stream was (re)seeded");
+    return MPPI_ERR_STATE;
+  }
+  double* tmp = nullptr;
+  CK(cudaMalloc(&tmp, n * sizeof(double)));
+  cudaError_t ce = noise_export_launch(e->stream, e->sp, e->d_dyn, step - 1, tmp);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpy(eps, tmp, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(tmp);
+  CK(ce);
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_set_capture(mppi_handle e, int32_t on) {
+  ENTER(e);
+  CK(cudaStreamSynchronize(e->stream));
+  if (on && !e->d_vcap) CK(cudaMalloc(&e->d_vcap, (size_t)e->sp.T * e->sp.K * sizeof(double)));
+  if ((on != 0) != (e->sp.capture != 0)) {
+    e->sp.capture = on ? 1 : 0;
+    drop_graphs(e);
+  }
+  return MPPI_OK;
+}
+
+// ---- the three-kernel pipeline ---------------------------------------------------------------------
+struct KernelEvents {
+  cudaEvent_t ev[4];
+  bool on = false;
+};
+
+static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, KernelEvents* kev) {
+  const int kind = kind_of(precision);
+  const KindCfg& c = e->cfg[kind];
+  RolloutArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.sp = e->sp;
+  ra.dyn = e->d_dyn;
+  ra.nom = (kind == ROLLOUT_F64_SOFTMIN) ? (const void*)e->d_nomD : (const void*)e->d_nomF;
+  ra.grid = e->d_grid;
+  ra.eps_ext = e->d_eps_ext;
+  ra.part = e->d_part;
+  ra.epart = e->d_epart;
+  ra.cand_count = e->d_cand_count;
+  ra.cand = e->d_cand;
+  ra.cand_min = e->d_cand_min;
+  ra.vcap = e->d_vcap;
+  ra.ntiles = c.ntiles;
+  if (kev && kev->on) CK(cudaEventRecord(kev->ev[0], st));
+  CK(rollout_launch(kind, e->sp.model, e->sp.has_grid != 0, c.block, c.grid, c.smem, st, ra));
+  if (kev && kev->on) CK(cudaEventRecord(kev->ev[1], st));
+  ReduceArgs rd;
+  memset(&rd, 0, sizeof(rd));
+  rd.sp = e->sp;
+  rd.dyn = e->d_dyn;
+  rd.part = e->d_part;
+  rd.epart = e->d_epart;
+  rd.cand_count = e->d_cand_count;
+  rd.cand = e->d_cand;
+  rd.cand_min = e->d_cand_min;
+  rd.nomD = e->d_nomD;
+  rd.grid = e->d_grid;
+  rd.eps_ext = e->d_eps_ext;
+  rd.record = e->d_record;
+  rd.nCTA = c.grid;
+  if (kind == ROLLOUT_F32_SCREEN)
+    CK(reduce_screen_launch(e->sp.model, e->sp.has_grid != 0, e->sp.T, st, rd));
+  else
+    CK(reduce_softmin_launch(kind == ROLLOUT_F64_SOFTMIN, e->sp.T, st, rd));
+  if (kev && kev->on) CK(cudaEventRecord(kev->ev[2], st));
+  e->last_capture_kind = kind;
+  return MPPI_OK;
+}
+
+static mppi_status launch_finalize(mppi_engine* e, cudaStream_t st, bool closed_loop, KernelEvents* kev) {
+  FinalizeArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.sp = e->sp;
+  fa.dyn = e->d_dyn;
+  fa.gather = (e->sp.world > 1) ? e->d_gather : e->d_record;
+  fa.Umaster = e->d_Umaster;
+  fa.Ulast = e->d_Ulast;
+  fa.nomF = e->d_nomF;
+  fa.nomD = e->d_nomD;
+  fa.sg_rows = e->d_sg_rows;
+  fa.sg_a = e->sg_a;
+  fa.sg_b = e->sg_b;
+  fa.mode = 0;
+  fa.closed_loop = closed_loop ? 1 : 0;
+  CK(finalize_launch(st, fa));
+  if (kev && kev->on) CK(cudaEventRecord(kev->ev[3], st));
+  return MPPI_OK;
+}
+
+static mppi_status build_graphs(mppi_engine* e) {
+  if (!e->dirty) return MPPI_OK;
+  drop_graphs(e);
+  for (int which = 0; which < 2; ++which) {
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    mppi_status s = MPPI_OK;
+    if (which == 0) {
+      cudaError_t ce = cudaMemcpyAsync(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+      if (ce != cudaSuccess) s = MPPI_ERR_CUDA;
+    }
+    if (s == MPPI_OK) s = launch_local(e, e->stream, e->p.precision, nullptr);
+    if (s == MPPI_OK) s = launch_finalize(e, e->stream, which == 1, nullptr);
+    if (s == MPPI_OK && which == 0) {
+      cudaError_t ce = cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream);
+      if (ce != cudaSuccess) s = MPPI_ERR_CUDA;
+    }
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+    if (s != MPPI_OK || ce != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      if (s == MPPI_OK) set_err("cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+      return MPPI_ERR_CUDA;
+    }
+    cudaGraphExec_t ge = nullptr;
+    ce = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) {
+      set_err("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+      return MPPI_ERR_CUDA;
+    }
+    if (which == 0)
+      e->g_step = ge;
+    else
+      e->g_loop = ge;
+  }
+  e->dirty = false;
+  return MPPI_OK;
+}
+
+static mppi_status finish_outputs(mppi_engine* e, double u_out[2], double x_next[3]) {
+  const DynState* o = e->h_out;
+  if (o->status == kStatusRedoF64) {
+    // MIXED: a candidate list overflowed; redo this step entirely in fp64 (same noise: the step
+    // counter was not advanced, U and x0 are untouched).
+    CKS(launch_local(e, e->stream, MPPI_PRECISION_F64, nullptr));
+    if (e->sp.world > 1) {
+      set_err("MIXED overflow in a sharded step: rerun with precision F64");
+      return MPPI_ERR_UNSUPPORTED;
+    }
+    CKS(launch_finalize(e, e->stream, false, nullptr));
+    CK(cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->last.refine_overflow += 1;
+  }
+  e->last.refine_candidates = o->last_candidates;
+  e->last.refine_max_dev = o->last_max_dev;
+  if (u_out) {
+    u_out[0] = o->out_u[0];
+    u_out[1] = o->out_u[1];
+  }
+  if (x_next) {
+    x_next[0] = o->out_x[0];
+    x_next[1] = o->out_x[1];
+    x_next[2] = o->out_x[2];
+  }
+  if (o->status == MPPI_ERR_NONFINITE) {
+    set_err("non-finite control update (NaN/Inf input propagated, as in the reference)");
+    return MPPI_ERR_NONFINITE;
+  }
+  return MPPI_OK;
+}
+
+static mppi_status pre_step(mppi_engine* e, const double x0[3]) {
+  if (!x0) {
+    set_err("x0 is null");
+    return MPPI_ERR_INVALID;
+  }
+  for (int i = 0; i < 3; ++i) {
+    e->h_in[i] = x0[i];
+    e->h_in[3 + i] = e->goal[i];
+    e->last_x0[i] = x0[i];
+    e->last_goal[i] = e->goal[i];
+  }
+  if (e->sp.capture) {   // debug: remember the nominal this step starts from (offset of get_cost_to_go)
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(e->U_prev.data(), e->d_Umaster, 2 * e->sp.T * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_step(mppi_handle e, const double x0[3], double u_out[2], double x_next[3]) {
+  ENTER(e);
+  if (e->local_pending) {
+    set_err("mppi_step called between mppi_step_local and mppi_step_finish");
+    return MPPI_ERR_STATE;
+  }
+  if (e->sp.world > 1) {
+    set_err("world_size > 1: use mppi_step_local / exchange / mppi_step_finish");
+    return MPPI_ERR_STATE;
+  }
+  CKS(pre_step(e, x0));
+  if (e->own_stream) {
+    CKS(build_graphs(e));
+    CK(cudaGraphLaunch(e->g_step, e->stream));
+  } else {
+    CK(cudaMemcpyAsync(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CKS(launch_local(e, e->stream, e->p.precision, nullptr));
+    CKS(launch_finalize(e, e->stream, false, nullptr));
+    CK(cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream));
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return finish_outputs(e, u_out, x_next);
+}
+
+extern "C" mppi_status mppi_step_local(mppi_handle e, const double x0[3]) {
+  ENTER(e);
+  if (e->local_pending) {
+    set_err("mppi_step_local called twice");
+    return MPPI_ERR_STATE;
+  }
+  CKS(pre_step(e, x0));
+  CK(cudaMemcpyAsync(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CKS(launch_local(e, e->stream, e->p.precision, nullptr));
+  e->local_pending = true;
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_exchange_buffers(mppi_handle e, void** record, size_t* record_bytes, void** gather,
+                                             size_t* gather_bytes) {
+  ENTER(e);
+  const size_t rb = (size_t)e->sp.T * kRecordStride * sizeof(double);
+  if (record) *record = e->d_record;
+  if (record_bytes) *record_bytes = rb;
+  if (gather) *gather = e->d_gather;
+  if (gather_bytes) *gather_bytes = rb * e->sp.world;
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_read_record(mppi_handle e, double* record) {
+  ENTER(e);
+  if (!record) return MPPI_ERR_INVALID;
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(record, e->d_record, (size_t)e->sp.T * kRecordStride * sizeof(double), cudaMemcpyDeviceToHost));
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_write_gather(mppi_handle e, const double* all) {
+  ENTER(e);
+  if (!all) return MPPI_ERR_INVALID;
+  CK(cudaMemcpyAsync(e->d_gather, all, (size_t)e->sp.world * e->sp.T * kRecordStride * sizeof(double),
+                     cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_step_finish(mppi_handle e, double u_out[2], double x_next[3]) {
+  ENTER(e);
+  if (!e->local_pending) {
+    set_err("mppi_step_finish without mppi_step_local");
+    return MPPI_ERR_STATE;
+  }
+  e->local_pending = false;
+  CKS(launch_finalize(e, e->stream, false, nullptr));
+  CK(cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return finish_outputs(e, u_out, x_next);
+}
+
+// ---- value-function offset dropped by the delta-cost formulation (see common.cuh) -----------------
+static void cost_offsets(const mppi_engine* e, const double* U, const double x0[3], const double goal[3],
+                         std::vector<double>& off) {
+  const int T = e->sp.T;
+  const double a[3] = {x0[0] - goal[0], x0[1] - goal[1], x0[2] - goal[2]};
+  const double still = 0.5 * (e->sp.q[0] * a[0] * a[0] + e->sp.q[1] * a[1] * a[1] + e->sp.q[2] * a[2] * a[2]);
+  const double term = e->sp.p1[0] * a[0] * a[0] + e->sp.p1[1] * a[1] * a[1] + e->sp.p1[2] * a[2] * a[2];
+  off.assign(T, 0.0);
+  double acc = term;
+  const double* R = e->p.r;
+  for (int t = T - 1; t >= 0; --t) {
+    const double u0 = U[t], u1 = U[T + t];
+    // 1/2 u'Ru, control/src/mppi:183
+    acc += 0.5 * (u0 * (R[0] * u0 + R[1] * u1) + u1 * (R[2] * u0 + R[3] * u1)) + still;
+    off[t] = acc;
+  }
+  if (e->sp.weighting == MPPI_WEIGHT_TOTAL_COST)
+    for (int t = 1; t < T; ++t) off[t] = off[0];
+}
+
+static mppi_status read_vcap(mppi_engine* e, int kind, const std::vector<double>& off, double* V) {
+  const int T = e->sp.T, K = e->sp.K;
+  const size_t n = (size_t)T * K;
+  if (kind == ROLLOUT_F64_SOFTMIN) {
+    CK(cudaMemcpy(V, e->d_vcap, n * sizeof(double), cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<float> tmp(n);
+    CK(cudaMemcpy(tmp.data(), e->d_vcap, n * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) V[i] = (double)tmp[i];
+  }
+  for (int t = 0; t < T; ++t)
+    for (int k = 0; k < K; ++k) V[(size_t)t * K + k] += off[t];
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_get_cost_to_go(mppi_handle e, double* V) {
+  ENTER(e);
+  if (!V) return MPPI_ERR_INVALID;
+  if (!e->sp.capture || e->last_capture_kind < 0) {
+    set_err("mppi_get_cost_to_go: enable mppi_set_capture(h, 1) before the step");
+    return MPPI_ERR_STATE;
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  std::vector<double> off;
+  cost_offsets(e, e->U_prev.data(), e->last_x0, e->last_goal, off);
+  return read_vcap(e, e->last_capture_kind, off, V);
+}
+
+// ---- standalone reference-API ops (always fp64) ---------------------------------------------------
+extern "C" mppi_status mppi_cost_to_go(mppi_handle e, const double x0[3], const double* U, const double goal[3],
+                                       const double* eps, double* V) {
+  ENTER(e);
+  if (!x0 || !U || !goal || !eps || !V) return MPPI_ERR_INVALID;
+  CK(cudaStreamSynchronize(e->stream));
+  const int T = e->sp.T;
+  const size_t ne = (size_t)T * 2 * e->sp.K;
+  // save
+  StaticParams sp_save = e->sp;
+  double* eps_save = e->d_eps_ext;
+  DynState dyn_save;
+  CK(cudaMemcpy(&dyn_save, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(e->d_Utmp, e->d_Umaster, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice));
+  double* eps_tmp = nullptr;
+  CK(cudaMalloc(&eps_tmp, ne * sizeof(double)));
+  mppi_status s = MPPI_OK;
+  do {
+    if (!e->d_vcap && cudaMalloc(&e->d_vcap, (size_t)T * e->sp.K * sizeof(double)) != cudaSuccess) {
+      s = MPPI_ERR_CUDA;
+      break;
+    }
+    cudaMemcpy(eps_tmp, eps, ne * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(e->d_Umaster, U, 2 * T * sizeof(double), cudaMemcpyHostToDevice);
+    DynState d = dyn_save;
+    for (int i = 0; i < 3; ++i) {
+      d.x0[i] = x0[i];
+      d.goal[i] = goal[i];
+    }
+    cudaMemcpy(e->d_dyn, &d, sizeof(d), cudaMemcpyHostToDevice);
+    e->d_eps_ext = eps_tmp;
+    e->sp.noise_external = 1;
+    e->sp.capture = 1;
+    if ((s = prep_nominal(e)) != MPPI_OK) break;
+    if ((s = launch_local(e, e->stream, MPPI_PRECISION_F64, nullptr)) != MPPI_OK) break;
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
+      set_err("cost_to_go kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+      s = MPPI_ERR_CUDA;
+      break;
+    }
+    std::vector<double> off;
+    cost_offsets(e, U, x0, goal, off);
+    s = read_vcap(e, ROLLOUT_F64_SOFTMIN, off, V);
+  } while (0);
+  // restore
+  e->sp = sp_save;
+  e->d_eps_ext = eps_save;
+  e->last_capture_kind = -1;
+  cudaMemcpy(e->d_dyn, &dyn_save, sizeof(DynState), cudaMemcpyHostToDevice);
+  cudaMemcpy(e->d_Umaster, e->d_Utmp, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
+  cudaFree(eps_tmp);
+  mppi_status s2 = prep_nominal(e);
+  return s != MPPI_OK ? s : s2;
+}
+
+extern "C" mppi_status mppi_update_action(mppi_handle e, const double* U_in, const double* eps, const double* V,
+                                          double* U_out) {
+  ENTER(e);
+  if (!U_in || !eps || !V || !U_out) return MPPI_ERR_INVALID;
+  CK(cudaStreamSynchronize(e->stream));
+  const int T = e->sp.T, K = e->sp.K;
+  double *dV = nullptr, *deps = nullptr;
+  CK(cudaMalloc(&dV, (size_t)T * K * sizeof(double)));
+  if (cudaMalloc(&deps, (size_t)T * 2 * K * sizeof(double)) != cudaSuccess) {
+    cudaFree(dV);
+    set_err("cudaMalloc failed");
+    return MPPI_ERR_CUDA;
+  }
+  mppi_status s = MPPI_OK;
+  cudaMemcpy(dV, V, (size_t)T * K * sizeof(double), cudaMemcpyHostToDevice);
+  cudaMemcpy(deps, eps, (size_t)T * 2 * K * sizeof(double), cudaMemcpyHostToDevice);
+  cudaMemcpy(e->d_Utmp, e->d_Umaster, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
+  cudaMemcpy(e->d_Utmp + 2 * T, e->d_Ulast, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
+  cudaMemcpy(e->d_Umaster, U_in, 2 * T * sizeof(double), cudaMemcpyHostToDevice);
+  cudaError_t ce = weights_from_v_launch(e->stream, e->sp, e->d_dyn, dV, deps, e->d_record_tmp);
+  if (ce == cudaSuccess) {
+    FinalizeArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.sp = e->sp;
+    fa.sp.world = 1;
+    fa.sp.k_total = K;
+    fa.dyn = e->d_dyn;
+    fa.gather = e->d_record_tmp;
+    fa.Umaster = e->d_Umaster;
+    fa.Ulast = e->d_Ulast;
+    fa.nomF = e->d_nomF;
+    fa.nomD = e->d_nomD;
+    fa.sg_rows = e->d_sg_rows;
+    fa.sg_a = e->sg_a;
+    fa.sg_b = e->sg_b;
+    fa.mode = 1;
+    ce = finalize_launch(e->stream, fa);
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpy(U_out, e->d_Ulast, 2 * T * sizeof(double), cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) {
+    set_err("mppi_update_action: %s", cudaGetErrorString(ce));
+    s = MPPI_ERR_CUDA;
+  }
+  cudaMemcpy(e->d_Umaster, e->d_Utmp, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
+  cudaMemcpy(e->d_Ulast, e->d_Utmp + 2 * T, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
+  cudaFree(dV);
+  cudaFree(deps);
+  return s;
+}
+
+extern "C" mppi_status mppi_model_step(mppi_handle e, const double* x, const double* u, int32_t n, double* x_out) {
+  ENTER(e);
+  if (!x || !u || !x_out || n < 1) return MPPI_ERR_INVALID;
+  double* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)8 * n * sizeof(double)));
+  cudaError_t ce = cudaMemcpy(d, x, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d + 3 * (size_t)n, u, (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = model_step_launch(e->stream, e->sp, d, d + 3 * (size_t)n, n, d + 5 * (size_t)n);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpy(x_out, d + 5 * (size_t)n, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CK(ce);
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_perform_action(mppi_handle e, const double x0[3], const double* U, double x_out[3]) {
+  if (!e || !x0 || !U || !x_out) return MPPI_ERR_INVALID;
+  const double u[2] = {U[0], U[e->sp.T]};   // uvec[:,0], control/src/mppi:212
+  return mppi_model_step(e, x0, u, 1, x_out);
+}
+
+// ---- measurement -------------------------------------------------------------------------------------
+extern "C" mppi_status mppi_last_stats(mppi_handle e, mppi_timing* out) {
+  ENTER(e);
+  if (!out) return MPPI_ERR_INVALID;
+  *out = e->last;
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t steps, int32_t warmup, int32_t flush_l2,
+                                  int32_t per_kernel, mppi_timing* out) {
+  ENTER(e);
+  if (!x0 || !out || steps < 1 || warmup < 0) return MPPI_ERR_INVALID;
+  if (!e->own_stream || e->sp.world > 1) {
+    set_err("mppi_bench needs an engine-owned stream and world_size 1");
+    return MPPI_ERR_STATE;
+  }
+  CKS(pre_step(e, x0));
+  CKS(build_graphs(e));
+  CK(cudaMemcpy(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice));
+  if (flush_l2 && !e->d_flush) {
+    e->flush_bytes = (size_t)256 << 20;   // > 126 MB L2
+    CK(cudaMalloc(&e->d_flush, e->flush_bytes));
+  }
+  for (int i = 0; i < warmup; ++i) CK(cudaGraphLaunch(e->g_loop, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  std::vector<cudaEvent_t> ev((size_t)2 * steps);
+  for (auto& v : ev) CK(cudaEventCreate(&v));
+  for (int i = 0; i < steps; ++i) {
+    if (flush_l2) CK(cudaMemsetAsync(e->d_flush, i & 0xff, e->flush_bytes, e->stream));
+    CK(cudaEventRecord(ev[2 * i], e->stream));
+    CK(cudaGraphLaunch(e->g_loop, e->stream));
+    CK(cudaEventRecord(ev[2 * i + 1], e->stream));
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  double total = 0;
+  for (int i = 0; i < steps; ++i) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+    total += ms;
+  }
+  for (auto& v : ev) cudaEventDestroy(v);
+  mppi_timing t{};
+  t.step_ms = (float)(total / steps);
+  t.steps = steps;
+  t.launches = 3 * steps;
+  if (per_kernel) {
+    KernelEvents kev;
+    kev.on = true;
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&kev.ev[i]));
+    double acc[3] = {0, 0, 0};
+    for (int i = 0; i < steps; ++i) {
+      if (flush_l2) CK(cudaMemsetAsync(e->d_flush, i & 0xff, e->flush_bytes, e->stream));
+      CKS(launch_local(e, e->stream, e->p.precision, &kev));
+      CKS(launch_finalize(e, e->stream, true, &kev));
+      CK(cudaStreamSynchronize(e->stream));
+      for (int j = 0; j < 3; ++j) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, kev.ev[j], kev.ev[j + 1]));
+        acc[j] += ms;
+      }
+    }
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(kev.ev[i]);
+    t.rollout_ms = (float)(acc[0] / steps);
+    t.reduce_ms = (float)(acc[1] / steps);
+    t.finalize_ms = (float)(acc[2] / steps);
+  }
+  CK(cudaMemcpy(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost));
+  t.refine_candidates = e->h_out->last_candidates;
+  t.refine_overflow = e->h_out->overflow_total;
+  t.refine_max_dev = e->h_out->last_max_dev;
+  e->last = t;
+  *out = t;
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_io_bytes(mppi_handle e, size_t* h2d, size_t* d2h) {
+  ENTER(e);
+  if (h2d) *h2d = 6 * sizeof(double);
+  if (d2h) *d2h = sizeof(DynState);
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_launch_info(mppi_handle e, int32_t info[6]) {
+  ENTER(e);
+  if (!info) return MPPI_ERR_INVALID;
+  const KindCfg& c = e->cfg[kind_of(e->p.precision)];
+  info[0] = c.block;
+  info[1] = c.grid;
+  info[2] = c.ntiles;
+  info[3] = (int32_t)c.smem;
+  info[4] = c.ctas_per_sm;
+  info[5] = c.regs;
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_mhz) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    set_err("no such CUDA device");
+    return MPPI_ERR_NO_DEVICE;
+  }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
+  float* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  double best = 0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(a, 0));
+    CK(fp32_peak_launch(0, blocks, threads, d, iters));
+    CK(cudaEventRecord(b, 0));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    const double fl = (double)blocks * threads * (double)iters * 16 * 8 * 2;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+  if (tflops) *tflops = best;
+  if (sm_clock_mhz) *sm_clock_mhz = khz / 1000.0;
+  return MPPI_OK;
+}

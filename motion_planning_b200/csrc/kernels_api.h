@@ -1,0 +1,27 @@
+// kernels_api.h -- host-side launch interface between engine.cu and the kernel translation units.
+#pragma once
+#include "common.cuh"
+#include "reduce_kernels_args.h"
+
+namespace mppi {
+
+// which instantiation family of rollout_kernel
+enum RolloutKind { ROLLOUT_F32_SOFTMIN = 0, ROLLOUT_F32_SCREEN = 1, ROLLOUT_F64_SOFTMIN = 2 };
+
+// occupancy query + opt-in to large dynamic shared memory for one instantiation
+cudaError_t rollout_prepare(int kind, int model, bool has_grid, int block, size_t smem, int* ctas_per_sm, int* regs);
+cudaError_t rollout_launch(int kind, int model, bool has_grid, int block, int grid, size_t smem, cudaStream_t st,
+                           const RolloutArgs& a);
+size_t rollout_smem(int kind, int T, int block, int grid_bytes_in_smem);
+
+cudaError_t reduce_softmin_launch(bool f64, int T, cudaStream_t st, const ReduceArgs& a);
+cudaError_t reduce_screen_launch(int model, bool has_grid, int T, cudaStream_t st, const ReduceArgs& a);
+cudaError_t finalize_launch(cudaStream_t st, const FinalizeArgs& a);
+cudaError_t prep_nominal_launch(cudaStream_t st, const DynState* dyn, int T, const double* Umaster, float* nomF, double* nomD);
+cudaError_t noise_export_launch(cudaStream_t st, const StaticParams& sp, const DynState* dyn, unsigned step, double* eps);
+cudaError_t weights_from_v_launch(cudaStream_t st, const StaticParams& sp, const DynState* dyn, const double* V,
+                                  const double* eps, double* record);
+cudaError_t model_step_launch(cudaStream_t st, const StaticParams& sp, const double* x, const double* u, int n, double* out);
+cudaError_t fp32_peak_launch(cudaStream_t st, int blocks, int threads, float* out, int iters);
+
+}  // namespace mppi

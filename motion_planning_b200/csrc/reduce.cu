@@ -1,0 +1,102 @@
+// reduce.cu -- instantiations + launch wrappers of the reduce / finalize / auxiliary kernels,
+// and the kind-dispatch for the three rollout translation units.
+#include "kernels_api.h"
+#include "reduce_kernels.cuh"
+#include "rollout_kernel.cuh"
+
+namespace mppi {
+
+#define DECL_TU(name)                                                                                          \
+  cudaError_t rollout_##name##_prepare(int model, bool has_grid, int block, size_t smem, int* ctas, int* regs); \
+  cudaError_t rollout_##name##_launch(int model, bool has_grid, int block, int grid, size_t smem, cudaStream_t st, \
+                                      const RolloutArgs& a);
+DECL_TU(f32_softmin)
+DECL_TU(f32_screen)
+DECL_TU(f64_softmin)
+#undef DECL_TU
+
+cudaError_t rollout_prepare(int kind, int model, bool has_grid, int block, size_t smem, int* ctas, int* regs) {
+  switch (kind) {
+    case ROLLOUT_F32_SOFTMIN: return rollout_f32_softmin_prepare(model, has_grid, block, smem, ctas, regs);
+    case ROLLOUT_F32_SCREEN: return rollout_f32_screen_prepare(model, has_grid, block, smem, ctas, regs);
+    default: return rollout_f64_softmin_prepare(model, has_grid, block, smem, ctas, regs);
+  }
+}
+
+cudaError_t rollout_launch(int kind, int model, bool has_grid, int block, int grid, size_t smem, cudaStream_t st,
+                           const RolloutArgs& a) {
+  switch (kind) {
+    case ROLLOUT_F32_SOFTMIN: return rollout_f32_softmin_launch(model, has_grid, block, grid, smem, st, a);
+    case ROLLOUT_F32_SCREEN: return rollout_f32_screen_launch(model, has_grid, block, grid, smem, st, a);
+    default: return rollout_f64_softmin_launch(model, has_grid, block, grid, smem, st, a);
+  }
+}
+
+size_t rollout_smem(int kind, int T, int block, int grid_bytes_in_smem) {
+  return kind == ROLLOUT_F64_SOFTMIN ? rollout_smem_bytes<double>(T, block, grid_bytes_in_smem)
+                                     : rollout_smem_bytes<float>(T, block, grid_bytes_in_smem);
+}
+
+cudaError_t reduce_softmin_launch(bool f64, int T, cudaStream_t st, const ReduceArgs& a) {
+  if (f64)
+    reduce_softmin_kernel<double><<<T, 128, 0, st>>>(a);
+  else
+    reduce_softmin_kernel<float><<<T, 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+typedef void (*ScreenFn)(const ReduceArgs);
+template <int M, bool G>
+static ScreenFn sfn_() { return reduce_screen_kernel<M, G>; }
+
+cudaError_t reduce_screen_launch(int model, bool has_grid, int T, cudaStream_t st, const ReduceArgs& a) {
+  ScreenFn f;
+  switch (model) {
+    case MPPI_MODEL_DIFF_DRIVE: f = has_grid ? sfn_<MPPI_MODEL_DIFF_DRIVE, true>() : sfn_<MPPI_MODEL_DIFF_DRIVE, false>(); break;
+    case MPPI_MODEL_UNICYCLE_EULER:
+      f = has_grid ? sfn_<MPPI_MODEL_UNICYCLE_EULER, true>() : sfn_<MPPI_MODEL_UNICYCLE_EULER, false>();
+      break;
+    default: f = has_grid ? sfn_<MPPI_MODEL_BICYCLE, true>() : sfn_<MPPI_MODEL_BICYCLE, false>(); break;
+  }
+  const size_t smem = (size_t)4 * 7 * T * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  f<<<T, 128, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t finalize_launch(cudaStream_t st, const FinalizeArgs& a) {
+  const size_t smem = (size_t)4 * a.sp.T * sizeof(double);
+  finalize_kernel<<<1, 256, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t prep_nominal_launch(cudaStream_t st, const DynState* dyn, int T, const double* Umaster, float* nomF, double* nomD) {
+  prep_nominal_kernel<<<1, 128, 0, st>>>(dyn, T, Umaster, nomF, nomD);
+  return cudaGetLastError();
+}
+
+cudaError_t noise_export_launch(cudaStream_t st, const StaticParams& sp, const DynState* dyn, unsigned step, double* eps) {
+  noise_export_kernel<<<(sp.K + 127) / 128, 128, 0, st>>>(sp, dyn, step, eps);
+  return cudaGetLastError();
+}
+
+cudaError_t weights_from_v_launch(cudaStream_t st, const StaticParams& sp, const DynState* dyn, const double* V,
+                                  const double* eps, double* record) {
+  weights_from_v_kernel<<<sp.T, 128, 0, st>>>(sp, dyn, V, eps, record);
+  return cudaGetLastError();
+}
+
+cudaError_t model_step_launch(cudaStream_t st, const StaticParams& sp, const double* x, const double* u, int n, double* out) {
+  model_step_kernel<<<(n + 127) / 128, 128, 0, st>>>(sp, x, u, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t fp32_peak_launch(cudaStream_t st, int blocks, int threads, float* out, int iters) {
+  fp32_peak_kernel<<<blocks, threads, 0, st>>>(out, iters);
+  return cudaGetLastError();
+}
+
+}  // namespace mppi

@@ -1,0 +1,542 @@
+// reduce_kernels.cuh -- kernels 2 and 3 of the MPPI step.
+//
+//   reduce_softmin_kernel : merge per-CTA online-softmin partials -> one record per t
+//   reduce_screen_kernel  : MIXED precision: global fp32 minimum -> select the softmin support ->
+//                           re-evaluate those rollouts in fp64 (parallel in time) -> record per t
+//   finalize_kernel       : merge the records of all ranks, U += dU, clip, Savitzky-Golay, clip,
+//                           perform_action, receding-horizon shift, next step's nominal block
+//
+// Replaces update_action (control/src/mppi:186-208), perform_action (:210-213) and the shift
+// (:100-101) of the reference.  Record layout per t (float64): m, S, N0, N1, E0, E1 with
+//   m = min_k V, S = sum_k e_k, N = sum_k e_k eps_k, E = sum_k eps_k, e_k = exp(-(V_k-m)/lam)
+// so that  dU[t] = (N + floor*E) / (S + floor*K)  ==  eps[t] @ (omega/sum(omega)) of :193-196.
+#pragma once
+#include "common.cuh"
+#include "reduce_kernels_args.h"
+
+namespace mppi {
+
+// ---- block reductions (blockDim multiple of 32, <= 1024) ----------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum<double>(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < nw; ++i) r += scratch[i];
+  return r;
+}
+__device__ __forceinline__ double block_min(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_min<double>(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double r = scratch[0];
+  for (int i = 1; i < nw; ++i) r = fmin(r, scratch[i]);
+  return r;
+}
+
+
+__device__ __forceinline__ void floor_scale(const StaticParams& sp, const DynState* dyn, double& s0, double& s1) {
+  // fixed-point integer sums of z -> sums of eps = std * z  (external noise: already real sums)
+  s0 = sp.noise_external ? 1.0 : (double)(float)dyn->noise_std[0] / kZFixScale;
+  s1 = sp.noise_external ? 1.0 : (double)(float)dyn->noise_std[1] / kZFixScale;
+}
+
+// ---- kernel 2a: SOFTMIN merge.  grid = T blocks ---------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(128) reduce_softmin_kernel(const __grid_constant__ ReduceArgs a) {
+  typedef typename Math<R>::Vec4 Vec4;
+  __shared__ double scratch[8];
+  const int t = blockIdx.x;
+  const Vec4* part = reinterpret_cast<const Vec4*>(a.part) + (size_t)t * a.nCTA;
+  const double* ep = a.epart + (size_t)t * a.nCTA * 2;
+  const double neg_inv_lam = -1.0 / a.dyn->lam;
+  double m = Math<double>::inf();
+  for (int i = threadIdx.x; i < a.nCTA; i += blockDim.x) m = fmin(m, (double)part[i].x);
+  m = block_min(m, scratch);
+  double S = 0, N0 = 0, N1 = 0, E0 = 0, E1 = 0;
+  for (int i = threadIdx.x; i < a.nCTA; i += blockDim.x) {
+    const Vec4 p = part[i];
+    const double sc = exp(((double)p.x - m) * neg_inv_lam);
+    S += (double)p.y * sc;
+    N0 += (double)p.z * sc;
+    N1 += (double)p.w * sc;
+    E0 += ep[2 * i];
+    E1 += ep[2 * i + 1];
+  }
+  S = block_sum(S, scratch);
+  N0 = block_sum(N0, scratch);
+  N1 = block_sum(N1, scratch);
+  E0 = block_sum(E0, scratch);
+  E1 = block_sum(E1, scratch);
+  if (threadIdx.x == 0) {
+    double s0, s1;
+    floor_scale(a.sp, a.dyn, s0, s1);
+    double* r = a.record + (size_t)t * kRecordStride;
+    r[0] = m;
+    r[1] = S;
+    r[2] = N0;
+    r[3] = N1;
+    r[4] = E0 * s0;
+    r[5] = E1 * s1;
+  }
+}
+
+// ---- fp64 re-evaluation of ONE rollout by ONE warp, parallel in time ------------------------------
+// Every supported model has theta-dot independent of the state, so theta_t is a prefix sum of the
+// yaw increments and x_t, y_t are prefix sums of the position increments: three warp scans instead
+// of a T-long dependent chain (~2 us instead of ~50 us per rollout).  Per-step wrap and one final
+// wrap differ only by rounding.  `sm` = 7*T doubles of per-warp scratch.
+template <int MODEL, bool HAS_GRID>
+__device__ double resim_cost_to_go_f64(const StaticParams& sp, const DynState* dyn, const double* __restrict__ nomD,
+                                       const signed char* __restrict__ grid, const double* __restrict__ eps_ext,
+                                       const ModelConsts<double>& mc, const CostConsts<double>& cc, int k_local,
+                                       int t_target, double* sm) {
+  const int T = sp.T, lane = threadIdx.x & 31;
+  double* s_kth = sm;          // yaw increment per step, then exclusive theta
+  double* s_spd = sm + T;      // forward speed
+  double* s_ix = sm + 2 * T;   // x increment -> inclusive dx
+  double* s_iy = sm + 3 * T;
+  double* s_e0 = sm + 4 * T;
+  double* s_e1 = sm + 5 * T;
+  double* s_thn = sm + 6 * T;  // theta after the step (wrapped)
+  const float std0 = (float)dyn->noise_std[0], std1 = (float)dyn->noise_std[1];
+  const unsigned int step = dyn->step;
+  const unsigned long long kglobal = (unsigned long long)(sp.k_offset + k_local);
+  for (int t = lane; t < T; t += 32) {
+    double e0, e1;
+    if (sp.noise_external) {
+      e0 = eps_ext[((size_t)t * 2 + 0) * sp.K + k_local];
+      e1 = eps_ext[((size_t)t * 2 + 1) * sp.K + k_local];
+    } else {
+      float f0, f1;
+      philox_eps(sp.seed, kglobal, t, step, std0, std1, f0, f1);
+      e0 = (double)f0;
+      e1 = (double)f1;
+    }
+    const double u0 = clamp_<double>(nomD[t] + e0, sp.u_max[0]);
+    const double u1 = clamp_<double>(nomD[T + t] + e1, sp.u_max[1]);
+    double s, w;
+    speed_yaw<double, MODEL>(mc, u0, u1, s, w);
+    s_kth[t] = mc.dt * w;
+    s_spd[t] = s;
+    s_e0[t] = e0;
+    s_e1[t] = e1;
+  }
+  __syncwarp();
+  // scan 1: theta before each step
+  double carry = cc.th0;
+  for (int base = 0; base < T; base += 32) {
+    const int t = base + lane;
+    const double v = (t < T) ? s_kth[t] : 0.0;
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    const double th_pre = carry + (inc - v);
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+    if (t < T) {
+      const double spd = s_spd[t];
+      double ix, iy, thn;
+      if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {
+        double sn, cs;
+        sincos(th_pre, &sn, &cs);
+        ix = mc.dt * spd * cs;
+        iy = mc.dt * spd * sn;
+        thn = th_pre + v;
+      } else {
+        const double thw = Math<double>::wrap_(th_pre);
+        double s1, c1, s2, c2, s4, c4;
+        sincos(thw, &s1, &c1);
+        sincos(thw + 0.5 * v, &s2, &c2);
+        sincos(thw + v, &s4, &c4);
+        const double g = mc.dt * spd * (1.0 / 6.0);
+        ix = g * (c1 + 4.0 * c2 + c4);
+        iy = g * (s1 + 4.0 * s2 + s4);
+        thn = Math<double>::wrap_(thw + v);
+      }
+      s_ix[t] = ix;
+      s_iy[t] = iy;
+      s_thn[t] = thn;
+    }
+  }
+  __syncwarp();
+  // scan 2: positions after each step, then the costs
+  double cx = 0.0, cy = 0.0, vsum = 0.0;
+  for (int base = 0; base < T; base += 32) {
+    const int t = base + lane;
+    double ax = (t < T) ? s_ix[t] : 0.0, ay = (t < T) ? s_iy[t] : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double nx = __shfl_up_sync(0xffffffffu, ax, o);
+      const double ny = __shfl_up_sync(0xffffffffu, ay, o);
+      if (lane >= o) {
+        ax += nx;
+        ay += ny;
+      }
+    }
+    const double dx = cx + ax, dy = cy + ay;
+    cx += __shfl_sync(0xffffffffu, ax, 31);
+    cy += __shfl_sync(0xffffffffu, ay, 31);
+    if (t < T && t >= t_target) {
+      const double th = s_thn[t];
+      double c = running_cost<double>(cc, dx, dy, th, nomD[2 * T + t], nomD[3 * T + t], s_e0[t], s_e1[t]);
+      if (HAS_GRID) c += grid_cost<double>(cc, grid, dx, dy);
+      if (t == T - 1) c += terminal_cost<double>(cc, dx, dy, th);
+      vsum += c;
+    }
+  }
+  __syncwarp();
+  return warp_sum<double>(vsum);
+}
+
+// ---- kernel 2b: SCREEN -> fp64 refinement.  grid = T blocks of 128 threads -----------------------
+// dynamic smem: 4 warps * 7 * T doubles
+template <int MODEL, bool HAS_GRID>
+__global__ void __launch_bounds__(128) reduce_screen_kernel(const __grid_constant__ ReduceArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw2[];
+  double* warp_scratch = reinterpret_cast<double*>(smem_raw2);
+  __shared__ double scratch[8];
+  __shared__ int sel_k[kMaxRefine];
+  __shared__ float sel_v32[kMaxRefine];
+  __shared__ double sel_v64[kMaxRefine];
+  __shared__ int nsel, overflow;
+  const StaticParams& sp = a.sp;
+  const int T = sp.T;
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t_eval = (sp.weighting == MPPI_WEIGHT_COST_TO_GO) ? t : 0;
+  if (tid == 0) {
+    nsel = 0;
+    overflow = 0;
+  }
+  // phase A: global fp32 minimum, floor sums, overflow check
+  const int* cnt = a.cand_count + (size_t)t * a.nCTA;
+  const float* cmin = a.cand_min + (size_t)t * a.nCTA;
+  const double* ep = a.epart + (size_t)t * a.nCTA * 2;
+  double m32 = Math<double>::inf(), E0 = 0, E1 = 0;
+  int ovf = 0;
+  for (int i = tid; i < a.nCTA; i += blockDim.x) {
+    m32 = fmin(m32, (double)cmin[i]);
+    E0 += ep[2 * i];
+    E1 += ep[2 * i + 1];
+    ovf |= (cnt[i] > kMaxCand);
+  }
+  m32 = block_min(m32, scratch);
+  E0 = block_sum(E0, scratch);
+  E1 = block_sum(E1, scratch);
+  if (ovf) atomicOr(&overflow, 1);
+  // phase B: compact the candidates inside the window of the GLOBAL minimum
+  const float lim = (float)(m32 + sp.margin);
+  for (int i = tid; i < a.nCTA; i += blockDim.x) {
+    const int c = min(cnt[i], kMaxCand);
+    const uint2* cd = a.cand + ((size_t)t * a.nCTA + i) * kMaxCand;
+    for (int s = 0; s < c; ++s) {
+      const uint2 e = cd[s];
+      const float v = __uint_as_float(e.y);
+      if (v <= lim) {
+        const int pos = atomicAdd(&nsel, 1);
+        if (pos < kMaxRefine) {
+          sel_k[pos] = (int)e.x;
+          sel_v32[pos] = v;
+        } else {
+          atomicOr(&overflow, 1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int n = min(nsel, kMaxRefine);
+  // phase C: fp64 re-evaluation, one warp per candidate
+  ModelConsts<double> mc;
+  CostConsts<double> cc;
+  make_consts<double>(sp, a.dyn, mc, cc);
+  double dev = 0.0;
+  for (int c = warp; c < n; c += 4) {
+    const double v64 = resim_cost_to_go_f64<MODEL, HAS_GRID>(sp, a.dyn, a.nomD, a.grid, a.eps_ext, mc, cc, sel_k[c], t_eval,
+                                                              warp_scratch + (size_t)warp * 7 * T);
+    if (lane == 0) sel_v64[c] = v64;
+    dev = fmax(dev, fabs(v64 - (double)sel_v32[c]));
+  }
+  __syncthreads();
+  // phase D: exact softmin over the support (control/src/mppi:189-196)
+  double m64 = Math<double>::inf();
+  for (int c = 0; c < n; ++c) m64 = fmin(m64, sel_v64[c]);
+  const double neg_inv_lam = -1.0 / a.dyn->lam;
+  const float std0 = (float)a.dyn->noise_std[0], std1 = (float)a.dyn->noise_std[1];
+  double S = 0, N0 = 0, N1 = 0;
+  for (int c = tid; c < n; c += blockDim.x) {
+    const double e = exp((sel_v64[c] - m64) * neg_inv_lam);
+    double e0, e1;
+    if (sp.noise_external) {
+      e0 = a.eps_ext[((size_t)t * 2 + 0) * sp.K + sel_k[c]];
+      e1 = a.eps_ext[((size_t)t * 2 + 1) * sp.K + sel_k[c]];
+    } else {
+      float f0, f1;
+      philox_eps(sp.seed, (unsigned long long)(sp.k_offset + sel_k[c]), t, a.dyn->step, std0, std1, f0, f1);
+      e0 = f0;
+      e1 = f1;
+    }
+    S += e;
+    N0 += e * e0;
+    N1 += e * e1;
+  }
+  S = block_sum(S, scratch);
+  N0 = block_sum(N0, scratch);
+  N1 = block_sum(N1, scratch);
+  dev = -block_min(-dev, scratch);
+  if (tid == 0) {
+    double s0, s1;
+    floor_scale(sp, a.dyn, s0, s1);
+    double* r = a.record + (size_t)t * kRecordStride;
+    r[0] = m64;
+    r[1] = S;
+    r[2] = N0;
+    r[3] = N1;
+    r[4] = E0 * s0;
+    r[5] = E1 * s1;
+    atomicAdd(&a.dyn->refine_candidates, n);
+    if (overflow) atomicOr(&a.dyn->refine_overflow, 1);
+    // max of non-negative doubles == max of their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(&a.dyn->refine_max_dev), (unsigned long long)__double_as_longlong(dev));
+  }
+}
+
+// ---- kernel 3: finalize.  one block of 256 threads ------------------------------------------------
+
+__device__ __forceinline__ void write_nominal_block(const DynState* dyn, int T, int t, double u0, double u1, float* nomF,
+                                                    double* nomD) {
+  // g[t] = lam * (u . sig)   so that   lam * u.dot(sig).dot(eps) = g0 eps0 + g1 eps1   (control/src/mppi:184)
+  const double lam = dyn->lam;
+  const double g0 = lam * (u0 * dyn->sig[0] + u1 * dyn->sig[2]);
+  const double g1 = lam * (u0 * dyn->sig[1] + u1 * dyn->sig[3]);
+  nomD[t] = u0;
+  nomD[T + t] = u1;
+  nomD[2 * T + t] = g0;
+  nomD[3 * T + t] = g1;
+  nomF[t] = (float)u0;
+  nomF[T + t] = (float)u1;
+  nomF[2 * T + t] = (float)g0;
+  nomF[3 * T + t] = (float)g1;
+}
+
+__global__ void prep_nominal_kernel(const DynState* dyn, int T, const double* Umaster, float* nomF, double* nomD) {
+  for (int t = threadIdx.x; t < T; t += blockDim.x) write_nominal_block(dyn, T, t, Umaster[t], Umaster[T + t], nomF, nomD);
+}
+
+template <int MODEL>
+__device__ void model_step_abs_f64(const StaticParams& sp, const double x[3], double u0, double u1, double out[3]) {
+  ModelConsts<double> mc;
+  mc.dt = sp.dt;
+  mc.half_r = sp.wheel_r * 0.5;
+  mc.r_over_L = sp.wheel_r / sp.wheel_L;
+  mc.inv_L = 1.0 / sp.wheel_L;
+  double dx = 0.0, dy = 0.0, th = x[2];
+  model_step<double, MODEL>(mc, u0, u1, dx, dy, th);
+  out[0] = x[0] + dx;
+  out[1] = x[1] + dy;
+  out[2] = th;
+}
+
+__device__ inline void model_step_dispatch_f64(const StaticParams& sp, const double x[3], double u0, double u1, double out[3]) {
+  if (sp.model == MPPI_MODEL_DIFF_DRIVE)
+    model_step_abs_f64<MPPI_MODEL_DIFF_DRIVE>(sp, x, u0, u1, out);
+  else if (sp.model == MPPI_MODEL_UNICYCLE_EULER)
+    model_step_abs_f64<MPPI_MODEL_UNICYCLE_EULER>(sp, x, u0, u1, out);
+  else
+    model_step_abs_f64<MPPI_MODEL_BICYCLE>(sp, x, u0, u1, out);
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw3[];
+  double* Us = reinterpret_cast<double*>(smem_raw3);   // [2][T] clipped update
+  double* Uf = Us + 2 * a.sp.T;                        // [2][T] filtered
+  __shared__ double coef[2][2][4];
+  __shared__ int bad;
+  const StaticParams& sp = a.sp;
+  const int T = sp.T, W = T - 1, h = W / 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  if (tid == 0) bad = 0;
+  __syncthreads();
+  if (a.mode == 0 && a.dyn->refine_overflow) {
+    // MIXED: the fp32 screen overflowed a candidate list -> leave U, the step counter and x0
+    // untouched and ask the host to redo this step with the fp64 pipeline (same noise).
+    __syncthreads();
+    if (tid == 0) {
+      DynState* d = a.dyn;
+      d->status = kStatusRedoF64;
+      d->overflow_total += 1;
+      d->refine_candidates = 0;
+      d->refine_overflow = 0;
+      d->refine_max_dev = 0.0;
+    }
+    return;
+  }
+  // -- merge the records of all ranks and apply the weighted noise (control/src/mppi:189-199) ----
+  const double neg_inv_lam = -1.0 / a.dyn->lam;
+  for (int idx = tid; idx < 2 * T; idx += blockDim.x) {
+    const int c = idx / T, t = idx - c * T;
+    double m = Math<double>::inf();
+    for (int g = 0; g < sp.world; ++g) m = fmin(m, a.gather[((size_t)g * T + t) * kRecordStride]);
+    double S = 0, N = 0, E = 0;
+    for (int g = 0; g < sp.world; ++g) {
+      const double* r = a.gather + ((size_t)g * T + t) * kRecordStride;
+      const double sc = (r[0] == m) ? 1.0 : exp((r[0] - m) * neg_inv_lam);
+      S += r[1] * sc;
+      N += r[2 + c] * sc;
+      E += r[4 + c];
+    }
+    const double dU = (N + sp.eps_floor * E) / (S + sp.eps_floor * (double)sp.k_total);
+    const double u = a.Umaster[c * T + t] + dU;
+    if (!isfinite(u)) atomicOr(&bad, 1);
+    Us[c * T + t] = clamp_<double>(u, sp.u_max[c]);                          // :198-199
+  }
+  __syncthreads();
+  // -- Savitzky-Golay, window T-1, cubic, mode='interp' (control/src/mppi:202).  The filter is two
+  //    least-squares cubics: A on samples [0, T-1), B on [1, T); outputs 0..h evaluate A, h+1..T-1
+  //    evaluate B.  Orthogonal (Gram) basis 1, z, z^2-a, z^3-bz on z=-h..h.
+  for (int d = warp; d < 16; d += nw) {
+    const int c = d >> 3, fit = (d >> 2) & 1, i = d & 3;
+    const double* row = a.sg_rows + (size_t)i * W;
+    const double* u = Us + c * T + fit;
+    double s = 0.0;
+    for (int j = lane; j < W; j += 32) s += row[j] * u[j];
+    s = warp_sum<double>(s);
+    if (lane == 0) coef[c][fit][i] = s;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 2 * T; idx += blockDim.x) {
+    const int c = idx / T, t = idx - c * T;
+    const int fit = (t <= h) ? 0 : 1;
+    const double z = (double)(t - fit - h);
+    const double* k = coef[c][fit];
+    const double v = k[0] + k[1] * z + k[2] * (z * z - a.sg_a) + k[3] * (z * z * z - a.sg_b * z);
+    Uf[c * T + t] = clamp_<double>(v, sp.u_max[c]);                          // :205-206
+  }
+  __syncthreads();
+  // -- outputs, perform_action (:210-213), shift (:100-101), next nominal block -----------------
+  for (int idx = tid; idx < 2 * T; idx += blockDim.x) a.Ulast[idx] = Uf[idx];
+  if (a.mode == 0) {
+    for (int t = tid; t < T; t += blockDim.x) {
+      const double u0 = (t + 1 < T) ? Uf[t + 1] : 0.0;
+      const double u1 = (t + 1 < T) ? Uf[T + t + 1] : 0.0;
+      a.Umaster[t] = u0;
+      a.Umaster[T + t] = u1;
+      write_nominal_block(a.dyn, T, t, u0, u1, a.nomF, a.nomD);
+    }
+    if (tid == 0) {
+      DynState* d = a.dyn;
+      double xn[3];
+      model_step_dispatch_f64(sp, d->x0, Uf[0], Uf[T], xn);
+      d->out_u[0] = Uf[0];
+      d->out_u[1] = Uf[T];
+      d->out_x[0] = xn[0];
+      d->out_x[1] = xn[1];
+      d->out_x[2] = xn[2];
+      d->status = bad ? (int)MPPI_ERR_NONFINITE : (int)MPPI_OK;
+      d->step += 1u;
+      if (a.closed_loop) {
+        d->x0[0] = xn[0];
+        d->x0[1] = xn[1];
+        d->x0[2] = xn[2];
+      }
+      d->last_candidates = d->refine_candidates;
+      d->last_max_dev = d->refine_max_dev;
+      d->refine_candidates = 0;
+      d->refine_overflow = 0;
+      d->refine_max_dev = 0.0;
+    }
+  }
+}
+
+// ---- auxiliary kernels (debug / reference-API surface, not on the hot path) -----------------------
+// eps (T,2,K) f64 of engine step `step`, exactly the values rollout_kernel consumed
+__global__ void noise_export_kernel(StaticParams sp, const DynState* dyn, unsigned int step, double* eps) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= sp.K) return;
+  const float std0 = (float)dyn->noise_std[0], std1 = (float)dyn->noise_std[1];
+  for (int t2 = 0; t2 < (sp.T >> 1); ++t2) {
+    const float4 z = philox_normal4(sp.seed, (unsigned long long)(sp.k_offset + k), (unsigned)t2, step);
+    const size_t b = (size_t)(2 * t2) * 2 * sp.K + k;
+    eps[b] = (double)eps_from_z(std0, z.x);
+    eps[b + sp.K] = (double)eps_from_z(std1, z.y);
+    eps[b + 2 * (size_t)sp.K] = (double)eps_from_z(std0, z.z);
+    eps[b + 3 * (size_t)sp.K] = (double)eps_from_z(std1, z.w);
+  }
+}
+
+// generic weighting from an explicit value function (mppi_update_action): grid = T blocks
+__global__ void __launch_bounds__(128) weights_from_v_kernel(StaticParams sp, const DynState* dyn, const double* V,
+                                                              const double* eps, double* record) {
+  __shared__ double scratch[8];
+  const int t = blockIdx.x, K = sp.K;
+  const double* v = V + (size_t)t * K;
+  const double* e0 = eps + ((size_t)t * 2) * K;
+  const double* e1 = e0 + K;
+  double m = Math<double>::inf();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) m = fmin(m, v[k]);
+  m = block_min(m, scratch);
+  const double neg_inv_lam = -1.0 / dyn->lam;
+  double S = 0, N0 = 0, N1 = 0, E0 = 0, E1 = 0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const double e = exp((v[k] - m) * neg_inv_lam);
+    S += e;
+    N0 += e * e0[k];
+    N1 += e * e1[k];
+    E0 += e0[k];
+    E1 += e1[k];
+  }
+  S = block_sum(S, scratch);
+  N0 = block_sum(N0, scratch);
+  N1 = block_sum(N1, scratch);
+  E0 = block_sum(E0, scratch);
+  E1 = block_sum(E1, scratch);
+  if (threadIdx.x == 0) {
+    double* r = record + (size_t)t * kRecordStride;
+    r[0] = m;
+    r[1] = S;
+    r[2] = N0;
+    r[3] = N1;
+    r[4] = E0;
+    r[5] = E1;
+  }
+}
+
+// the `model` functor on n independent states (control/src/mppi:154): x (3,n), u (2,n) -> (3,n)
+__global__ void model_step_kernel(StaticParams sp, const double* x, const double* u, int n, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double xi[3] = {x[i], x[n + i], x[2 * n + i]};
+  double o[3];
+  model_step_dispatch_f64(sp, xi, u[i], u[n + i], o);
+  out[i] = o[0];
+  out[n + i] = o[1];
+  out[2 * n + i] = o[2];
+}
+
+// register-resident FFMA chain: the measured fp32 roofline denominator
+__global__ void fp32_peak_kernel(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f,
+        a7 = a0 + 7.f;
+  const float b = 0.999f, c = 1e-3f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      a0 = fmaf(a0, b, c);
+      a1 = fmaf(a1, b, c);
+      a2 = fmaf(a2, b, c);
+      a3 = fmaf(a3, b, c);
+      a4 = fmaf(a4, b, c);
+      a5 = fmaf(a5, b, c);
+      a6 = fmaf(a6, b, c);
+      a7 = fmaf(a7, b, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace mppi

@@ -1,0 +1,50 @@
+// reduce_kernels_args.h -- kernel argument blocks (plain structs, shared by host and device TUs)
+#pragma once
+#include "common.cuh"
+namespace mppi {
+
+struct RolloutArgs {
+  StaticParams sp;
+  const DynState* dyn;
+  const void* nom;             // nominal block, Real[4][T]: U0, U1, g0, g1 (g = lam * u.sig, per t)
+  const signed char* grid;     // int8 cells (padded to 16 B)
+  const double* eps_ext;       // (T,2,K) f64 when sp.noise_external
+  void* part;                  // SOFTMIN: Vec4[T][nCTA] (m,S,N0,N1)
+  double* epart;               // [T][nCTA][2] floor sums (fixed-point integer as double, or real if external)
+  int* cand_count;             // SCREEN: [T][nCTA]
+  uint2* cand;                 // SCREEN: [T][nCTA][kMaxCand]  (k_local, float bits of V)
+  float* cand_min;             // SCREEN: [T][nCTA] running minimum of the CTA
+  void* vcap;                  // capture: Real[T][K]
+  int ntiles;
+};
+
+struct ReduceArgs {
+  StaticParams sp;
+  DynState* dyn;
+  const void* part;          // SOFTMIN partials Vec4[T][nCTA]
+  const double* epart;       // [T][nCTA][2]
+  const int* cand_count;     // SCREEN
+  const uint2* cand;
+  const float* cand_min;
+  const double* nomD;        // f64 nominal block [4][T]
+  const signed char* grid;
+  const double* eps_ext;
+  double* record;            // [T][6]
+  int nCTA;
+};
+
+struct FinalizeArgs {
+  StaticParams sp;
+  DynState* dyn;
+  const double* gather;      // [world][T][6]
+  double* Umaster;           // [2][T] latest_uvec
+  double* Ulast;             // [2][T] update_action result before the shift
+  float* nomF;               // [4][T]
+  double* nomD;              // [4][T]
+  const double* sg_rows;     // [4][T-1] orthogonal-polynomial projection rows (already / norm)
+  double sg_a, sg_b;         // p2 = z^2 - a, p3 = z^3 - b z
+  int mode;                  // 0: full step, 1: update only (mppi_update_action)
+  int closed_loop;           // 1: dyn->x0 <- x_next (device-resident loop of mppi_bench)
+};
+
+}  // namespace mppi

@@ -1,0 +1,303 @@
+// rollout_kernel.cuh -- kernel 1 of the MPPI step: fused noise -> rollout -> cost -> per-t partials.
+//
+// Replaces the reference's hot loop 1, MPPI.get_cost2go (control/src/mppi:127-178) including the K*T
+// Python calls of get_cost (:158-161,180-184), and the per-rollout half of update_action (:187-196).
+//
+// One thread integrates one rollout for all T steps (state in registers); a CTA owns tiles of BLOCK
+// rollouts and is persistent over tiles.  The only per-(k,t) data that leaves the registers is the
+// running prefix cost, kept in a shared-memory tile P[T][BLOCK] (conflict-free: consecutive threads,
+// consecutive banks).  After the T steps the tile is consumed TRANSPOSED: warp w reduces rows
+// t = w, w+NW, ... over the BLOCK rollouts, with cost-to-go V[t,k] = Tot[k] - P[t-1,k]
+// (= sum_{t'>=t} c[t',k], control/src/mppi:175).  Nothing of size K*T is written to HBM.
+//
+//   MODE_SOFTMIN: per (CTA, t) online-softmin partial (m, S, N0, N1): m = min V, S = sum e,
+//                 N = sum e*eps[t], e = exp(-(V-m)/lam) (control/src/mppi:189-196).  eps is
+//                 regenerated from the Philox counters only for the handful of rollouts with e > 0.
+//   MODE_SCREEN : per (CTA, t) the rollouts within `margin` of the running minimum (the support of
+//                 the softmin) are listed for fp64 re-evaluation by the reduce kernel.
+//
+// The floor term of the weights (+1e-8 per rollout, :193) needs E[t] = sum_k eps[t,k]; it is
+// accumulated exactly in fixed point (2^-20) with one REDUX (warp integer add) per step.
+#pragma once
+#include "common.cuh"
+#include "reduce_kernels_args.h"
+
+namespace mppi {
+
+
+template <typename R>
+__device__ __forceinline__ R load_eps_ext(const double* __restrict__ eps, int t, int c, int K, int k) {
+  return R(eps[((size_t)t * 2 + c) * (size_t)K + k]);
+}
+
+template <typename R, int MODEL, int MODE, bool HAS_GRID, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ RolloutArgs a) {
+  typedef typename Math<R>::Vec4 Vec4;
+  constexpr int NW = BLOCK / 32;
+  constexpr int J = BLOCK / 32;
+  const StaticParams& sp = a.sp;
+  const int T = sp.T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nCTA = gridDim.x, cta = blockIdx.x;
+
+  // ---- shared memory carve-up ------------------------------------------------------------------
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);                      // 16 B
+  R* nomU0 = reinterpret_cast<R*>(smem_raw + 16);                             // 4*T Reals
+  R* nomU1 = nomU0 + T;
+  R* nomG0 = nomU1 + T;
+  R* nomG1 = nomG0 + T;
+  size_t off = 16 + (size_t)4 * T * sizeof(R);
+  off = (off + 15) & ~(size_t)15;
+  Vec4* run = reinterpret_cast<Vec4*>(smem_raw + off);                        // running (m,S,N0,N1) per t
+  off += (size_t)T * sizeof(Vec4);
+  long long* ez64 = reinterpret_cast<long long*>(smem_raw + off);             // [T][2]
+  off += (size_t)T * 2 * sizeof(long long);
+  double* ed = reinterpret_cast<double*>(smem_raw + off);                     // [T][2] (external noise)
+  off += (size_t)T * 2 * sizeof(double);
+  int* ez32 = reinterpret_cast<int*>(smem_raw + off);                         // [T][2] per-tile
+  off += (size_t)T * 2 * sizeof(int);
+  int* ccount = reinterpret_cast<int*>(smem_raw + off);                       // [T] SCREEN counts
+  off += (size_t)T * sizeof(int);
+  off = (off + 15) & ~(size_t)15;
+  R* P = reinterpret_cast<R*>(smem_raw + off);                                // [T][BLOCK]
+  off += (size_t)T * BLOCK * sizeof(R);
+  off = (off + 15) & ~(size_t)15;
+  signed char* gcells = reinterpret_cast<signed char*>(smem_raw + off);       // grid copy (optional)
+
+  // ---- prologue: TMA bulk copies of the nominal block (+ grid) into shared memory -------------
+  const uint32_t nom_bytes = (uint32_t)(4 * T * sizeof(R));
+  const bool grid_smem = HAS_GRID && sp.grid_in_smem;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, nom_bytes + (grid_smem ? (uint32_t)sp.grid_bytes_padded : 0u));
+    tma_bulk_g2s(nomU0, a.nom, nom_bytes, bar);
+    if (grid_smem) tma_bulk_g2s(gcells, a.grid, (uint32_t)sp.grid_bytes_padded, bar);
+  }
+  for (int t = tid; t < T; t += BLOCK) {
+    Vec4 v;
+    v.x = Math<R>::inf();
+    v.y = R(0);
+    v.z = R(0);
+    v.w = R(0);
+    run[t] = v;
+    ez64[2 * t] = 0;
+    ez64[2 * t + 1] = 0;
+    ed[2 * t] = 0.0;
+    ed[2 * t + 1] = 0.0;
+    ez32[2 * t] = 0;
+    ez32[2 * t + 1] = 0;
+    ccount[t] = 0;
+  }
+  ModelConsts<R> mc;
+  CostConsts<R> cc;
+  make_consts<R>(sp, a.dyn, mc, cc);
+  const R um0 = R(sp.u_max[0]), um1 = R(sp.u_max[1]);
+  const float std0 = (float)a.dyn->noise_std[0], std1 = (float)a.dyn->noise_std[1];
+  const unsigned int step = a.dyn->step;
+  const R neg_inv_lam = R(-1.0 / a.dyn->lam);
+  const R margin = R(sp.margin);
+  const signed char* cells = grid_smem ? gcells : a.grid;
+  mbar_wait(bar, 0);
+  __syncthreads();
+
+  for (int tile = cta; tile < a.ntiles; tile += nCTA) {
+    const int k_local = tile * BLOCK + tid;
+    const bool valid = k_local < sp.K;
+    const unsigned long long kglobal = (unsigned long long)(sp.k_offset + k_local);
+    R dx = R(0), dy = R(0), th = cc.th0, acc = R(0);
+
+    // ---- the T-step rollout (hot loop 1, control/src/mppi:136-163) ----------------------------
+    for (int t2 = 0; t2 < (T >> 1); ++t2) {
+      float zf[4];
+      R ev[4];
+      if (sp.noise_external) {
+        const int kk = valid ? k_local : 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ev[i] = load_eps_ext<R>(a.eps_ext, 2 * t2 + (i >> 1), i & 1, sp.K, kk);
+      } else {
+        float4 z = philox_normal4(sp.seed, kglobal, (unsigned)t2, step);
+        zf[0] = z.x;
+        zf[1] = z.y;
+        zf[2] = z.z;
+        zf[3] = z.w;
+        ev[0] = R(eps_from_z(std0, z.x));
+        ev[1] = R(eps_from_z(std1, z.y));
+        ev[2] = R(eps_from_z(std0, z.z));
+        ev[3] = R(eps_from_z(std1, z.w));
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int t = 2 * t2 + s;
+        const R e0 = ev[2 * s], e1 = ev[2 * s + 1];
+        if (!sp.noise_external) {
+          // floor-term sums: exact fixed-point warp reduction (REDUX), one smem atomic per warp
+          int f0 = valid ? __float2int_rn(zf[2 * s] * (float)kZFixScale) : 0;
+          int f1 = valid ? __float2int_rn(zf[2 * s + 1] * (float)kZFixScale) : 0;
+          f0 = __reduce_add_sync(0xffffffffu, f0);
+          f1 = __reduce_add_sync(0xffffffffu, f1);
+          if (lane == 0) {
+            atomicAdd(&ez32[2 * t], f0);
+            atomicAdd(&ez32[2 * t + 1], f1);
+          }
+        }
+        // u_samp = clip(U[:,t] + eps)   control/src/mppi:147-152 (eps itself stays unclipped)
+        const R u0 = clamp_<R>(nomU0[t] + e0, um0);
+        const R u1 = clamp_<R>(nomU1[t] + e1, um1);
+        model_step<R, MODEL>(mc, u0, u1, dx, dy, th);                        // :154
+        R c = running_cost<R>(cc, dx, dy, th, nomG0[t], nomG1[t], e0, e1);   // :160-161,180-184
+        if (HAS_GRID) c += grid_cost<R>(cc, cells, dx, dy);
+        acc += c;
+        P[t * BLOCK + tid] = acc;
+      }
+    }
+    acc += terminal_cost<R>(cc, dx, dy, th);                                 // :165-171
+    if (!valid) acc = Math<R>::inf();
+    P[(T - 1) * BLOCK + tid] = acc;   // row T-1 holds the rollout total Tot[k]
+    __syncthreads();
+
+    // ---- transposed pass: warp w owns rows t = w, w+NW, ... ------------------------------------
+    for (int t = warp; t < T; t += NW) {
+      R v[J];
+      R mloc = Math<R>::inf();
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int col = lane + 32 * j;
+        const R tot = P[(T - 1) * BLOCK + col];
+        const R pre = (t > 0 && sp.weighting == MPPI_WEIGHT_COST_TO_GO) ? P[(t - 1) * BLOCK + col] : R(0);
+        v[j] = tot - pre;                                                    // cost-to-go, :175
+        mloc = Math<R>::min_(mloc, v[j]);
+      }
+      if (sp.capture) {
+        R* vc = reinterpret_cast<R*>(a.vcap);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const int kk = tile * BLOCK + lane + 32 * j;
+          if (kk < sp.K) vc[(size_t)t * sp.K + kk] = v[j];
+        }
+      }
+      if (sp.noise_external) {   // floor sums straight from the replayed noise
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const int kk = tile * BLOCK + lane + 32 * j;
+          if (kk < sp.K) {
+            s0 += a.eps_ext[((size_t)t * 2 + 0) * sp.K + kk];
+            s1 += a.eps_ext[((size_t)t * 2 + 1) * sp.K + kk];
+          }
+        }
+        s0 = warp_sum<double>(s0);
+        s1 = warp_sum<double>(s1);
+        if (lane == 0) {
+          ed[2 * t] += s0;
+          ed[2 * t + 1] += s1;
+        }
+      }
+      const R mtile = warp_min<R>(mloc);
+      if (MODE == MODE_SOFTMIN) {
+        // online softmin: weights relative to the running minimum of this CTA (:189-196)
+        Vec4 rr = run[t];
+        const R mnew = Math<R>::min_(rr.x, mtile);
+        R S = R(0), N0 = R(0), N1 = R(0);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const R arg = (v[j] - mnew) * neg_inv_lam;           // <= 0
+          if (arg > R(-80)) {                                   // e^-80 ~ 2e-35: below any rounding
+            const R e = Math<R>::exp_(arg);
+            const int kk = tile * BLOCK + lane + 32 * j;
+            R e0, e1;
+            if (sp.noise_external) {
+              e0 = load_eps_ext<R>(a.eps_ext, t, 0, sp.K, kk);
+              e1 = load_eps_ext<R>(a.eps_ext, t, 1, sp.K, kk);
+            } else {
+              float f0, f1;
+              philox_eps(sp.seed, (unsigned long long)(sp.k_offset + kk), t, step, std0, std1, f0, f1);
+              e0 = R(f0);
+              e1 = R(f1);
+            }
+            S += e;
+            N0 = Math<R>::fma_(e, e0, N0);
+            N1 = Math<R>::fma_(e, e1, N1);
+          }
+        }
+        S = warp_sum<R>(S);
+        N0 = warp_sum<R>(N0);
+        N1 = warp_sum<R>(N1);
+        if (lane == 0) {
+          const R sc = (rr.x == mnew) ? R(1) : Math<R>::exp_((rr.x - mnew) * neg_inv_lam);
+          rr.y = Math<R>::fma_(rr.y, sc, S);
+          rr.z = Math<R>::fma_(rr.z, sc, N0);
+          rr.w = Math<R>::fma_(rr.w, sc, N1);
+          rr.x = mnew;
+          run[t] = rr;
+        }
+      } else {
+        // screen: list every rollout within `margin` of the CTA's running minimum
+        Vec4 rr = run[t];
+        const R mnew = Math<R>::min_(rr.x, mtile);
+        int cnt = ccount[t];
+        const size_t slot0 = ((size_t)t * nCTA + cta) * kMaxCand;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const bool hit = v[j] <= mnew + margin;
+          const unsigned ball = __ballot_sync(0xffffffffu, hit);
+          if (hit) {
+            const int pos = cnt + __popc(ball & ((1u << lane) - 1u));
+            if (pos < kMaxCand)
+              a.cand[slot0 + pos] = make_uint2((unsigned)(tile * BLOCK + lane + 32 * j), __float_as_uint((float)v[j]));
+          }
+          cnt += __popc(ball);
+        }
+        if (lane == 0) {
+          rr.x = mnew;
+          run[t] = rr;
+          ccount[t] = cnt;
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // fold the per-tile fixed-point sums into the CTA's 64-bit accumulators
+    for (int i = tid; i < 2 * T; i += BLOCK) {
+      ez64[i] += (long long)ez32[i];
+      ez32[i] = 0;
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: one partial per (t, CTA) ------------------------------------------------------
+  for (int t = tid; t < T; t += BLOCK) {
+    const size_t idx = (size_t)t * nCTA + cta;
+    if (MODE == MODE_SOFTMIN) {
+      reinterpret_cast<Vec4*>(a.part)[idx] = run[t];
+    } else {
+      a.cand_count[idx] = ccount[t];
+      a.cand_min[idx] = (float)run[t].x;
+    }
+    a.epart[2 * idx] = sp.noise_external ? ed[2 * t] : (double)ez64[2 * t];
+    a.epart[2 * idx + 1] = sp.noise_external ? ed[2 * t + 1] : (double)ez64[2 * t + 1];
+  }
+}
+
+// shared memory needed by one CTA of rollout_kernel
+template <typename R>
+inline size_t rollout_smem_bytes(int T, int block, int grid_bytes_padded_in_smem) {
+  size_t off = 16 + (size_t)4 * T * sizeof(R);
+  off = (off + 15) & ~(size_t)15;
+  off += (size_t)T * 4 * sizeof(R);              // run
+  off += (size_t)T * 2 * sizeof(long long);
+  off += (size_t)T * 2 * sizeof(double);
+  off += (size_t)T * 2 * sizeof(int);
+  off += (size_t)T * sizeof(int);
+  off = (off + 15) & ~(size_t)15;
+  off += (size_t)T * block * sizeof(R);
+  off = (off + 15) & ~(size_t)15;
+  off += (size_t)grid_bytes_padded_in_smem;
+  return off + 128;   // slack for the 128 B alignment of the dynamic segment
+}
+
+}  // namespace mppi
