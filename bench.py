@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- MPPI rollouts/s on B200 (BASELINE.json metric) with roofline, e2e and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one complete MPPI.get_path (control/src/mppi:85-102): noise -> K rollouts x T RK4 steps ->
+costs -> per-t soft-min weights -> control update -> clip / Savitzky-Golay / clip -> apply & shift.
+
+Workload (N=1): BASELINE.json configs[1] = diff-drive parallel-park, K=65536, T=64, 1 x B200.  For
+N > 1 the rollouts are sharded over ranks with per-GPU K fixed (weak scaling, K_total = N * 65536)
+and one 3 KB all-gather per step.
+
+value   = rollouts/s with the controller state resident in HBM (closed loop on the model entirely on
+          the device), CUDA events on the launch stream, L2 flushed between timed steps.
+e2e     = the same metric through the public API call MPPI.get_path / mppi_step with HOST x0 in and
+          (u_t, x_next) out every step, copies inside the timed region.
+roofline= the fused rollout+cost kernel against the fp32 FMA peak measured in the same run
+          (this path is fp32-ALU/SFU bound, not HBM bound: SURVEY.md 8d) + the HBM view for contrast.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_PER_GPU, T_HORIZON = 65536, 64
+GOAL = np.array([0.0, -1.0, 0.0])          # parallel park, control/src/mppi:337
+X0 = np.array([0.0, 0.0, 0.0])
+F_ALG = 133.0                              # algorithmic FLOP per (rollout, step), SURVEY.md 8(d)
+METRIC = "MPPI rollouts/sec (K x T states/sec = value * T)"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def cpu_baseline_port(budget_s=12.0):
+    """The oracle port timed on the host cores (checker only, never the product path): the C/OpenMP
+    restatement when it is built (all cores), else the vectorised NumPy restatement (1 core)."""
+    try:
+        from oracle import port_c
+        if port_c.available():
+            return port_c.time_workload(K_PER_GPU, T_HORIZON, budget_s)
+    except ImportError:
+        pass
+    from oracle import mppi_oracle as orc
+    Ks = 16384
+    p = orc.Params(K=Ks, T=T_HORIZON)
+    rng = np.random.RandomState(0)
+    U, s = np.zeros((2, T_HORIZON)), X0.copy()
+    t0, n = time.perf_counter(), 0
+    while True:
+        eps = rng.normal(0, 0.9, size=(T_HORIZON, 2, Ks))
+        out = orc.step(p, s, GOAL, U, eps)
+        s, U = out["x_next"], out["U_shift"]
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 50:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return {"value": Ks / dt, "unit": "rollouts/s", "cores": 1, "kind": "port",
+            "sample": "NumPy f64 restatement (oracle/mppi_oracle.py, noise drawn by NumPy inside the timed region), "
+                      "%d of the %d rollouts x T=%d, %d steps, %.3f s/step" % (Ks, K_PER_GPU, T_HORIZON, n, dt)}
+
+
+def run_reference_arm(args):
+    """--impl reference: the UNMODIFIED reference MPPI class (control/src/mppi, byte-compiled into
+    oracle/_ref/mppi.pyc) on the host CPU.  It is single-threaded Python by construction (1 core).
+    Each step is a bounded sample of the workload: Ks of the K rollouts at the full horizon T."""
+    from oracle import ref_loader
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    kind, cores = "reference", 1
+    # ~0.6 ms per rollout at T=64 (8.7 us per (k,t)): keep the whole run near 60-90 s
+    Ks = int(max(64, min(2048, (75.0 / max(steps + warmup, 1)) / 0.6e-3)))
+    Ks -= Ks % 2
+    if ref_loader.available():
+        ref = ref_loader.load_reference()
+        m = ref.MPPI(horizon=T_HORIZON, samples=Ks)
+        stepper = lambda s: m.get_path(s, GOAL)          # noqa: E731
+        what = "unmodified reference control/src/mppi (%s)" % ref.__ref_kind__
+    else:
+        from oracle import mppi_oracle as orc
+        kind = "port"
+        p = orc.Params(K=Ks, T=T_HORIZON)
+        st = {"U": np.zeros((2, T_HORIZON))}
+
+        def stepper(s):
+            out = orc.step(p, s, GOAL, st["U"], orc.draw_reference_noise(p))
+            st["U"] = out["U_shift"]
+            return out["x_next"]
+        what = "NumPy restatement oracle/mppi_oracle.py (reference not loadable here)"
+    s = X0.copy()
+    for _ in range(warmup):
+        s = stepper(s)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s = stepper(s)
+    dt = (time.perf_counter() - t0) / steps
+    val = Ks / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "rollouts/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "diff-drive parallel-park K=%d T=%d (BASELINE.json configs[1])" % (K_PER_GPU, T_HORIZON),
+                   "sample_K": Ks, "T": T_HORIZON},
+        "cpu_baseline": {"value": val, "unit": "rollouts/s", "cores": cores, "kind": kind,
+                         "sample": "%s; %d of the %d rollouts per step at T=%d, %d timed steps" % (what, Ks, K_PER_GPU, T_HORIZON, steps)},
+        "e2e": {"value": val, "unit": "rollouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ ours
+def run_single(args):
+    import motion_planning_b200 as mp
+    from motion_planning_b200 import _capi
+    import ctypes as C
+    lib = _capi.load()
+    if lib.mppi_device_count() < 1:
+        sys.exit("bench.py: no CUDA device and no CPU fallback (use --impl reference for the CPU arm)")
+    K, T = K_PER_GPU, T_HORIZON
+    tf, mhz = C.c_double(), C.c_double()
+    _capi.check(lib.mppi_measure_fp32_peak(0, C.byref(tf), C.byref(mhz)), "mppi_measure_fp32_peak")
+    results = {}
+    sampler = None
+    for prec in ("f32", "f64", args.precision):          # headline precision last (its clocks are sampled)
+        m = mp.MPPI(horizon=T, samples=K, precision=prec, seed=0)
+        m.goal = GOAL
+        if prec == args.precision:
+            sampler = ClockSampler(0)
+        r = m.bench(X0, steps=args.steps, warmup=args.warmup, flush_l2=True, per_kernel=True)
+        # e2e: the public call with host buffers, copies inside the timed region
+        m.initialize()
+        s = X0.copy()
+        for _ in range(args.warmup):
+            s = m.get_path(s, GOAL)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            s = m.get_path(s, GOAL)
+        e2e_dt = (time.perf_counter() - t0) / args.steps
+        r["e2e_ms"] = e2e_dt * 1e3
+        r["io"] = m.io_bytes()
+        r["launch"] = m.launch_info()
+        r["stats"] = m.stats()
+        results[prec] = r
+        m.close()
+    clocks = sampler.stop() if sampler else {}
+    r = results[args.precision]
+    ms = r["step_ms"]
+    value = K / (ms * 1e-3)
+    achieved = F_ALG * K * T / (r["rollout_ms"] * 1e-3) / 1e12
+    hbm_alg_bytes = 16 * T * r["launch"]["grid"] * 3 + 16 * T     # per-CTA partials (m,S,N0,N1 + E) out, nominal in
+    cpu = cpu_baseline_port() if not args.no_cpu else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": "rollouts/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"mixed": "f32 rollouts + f64 re-evaluation of the softmin support", "f32": "f32", "f64": "f64"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": "diff-drive parallel-park K=%d T=%d (BASELINE.json configs[1])" % (K, T), "K": K, "T": T,
+                   "precision": args.precision, "weighting": "cost_to_go (reference)", "noise": "Philox4x32-10 in registers",
+                   "l2": "flushed between timed steps (256 MiB memset outside the timed intervals)",
+                   "loop": "closed loop on the model, state resident in HBM", "launch": r["launch"]},
+        "state_steps_per_s": value * T,
+        "e2e": {"value": K / (r["e2e_ms"] * 1e-3), "unit": "rollouts/s", "h2d_bytes_per_step": r["io"][0],
+                "d2h_bytes_per_step": r["io"][1], "ms_per_step": r["e2e_ms"]},
+        "gpu_launches": r["launches"],
+        "kernels_ms": {"rollout": r["rollout_ms"], "reduce": r["reduce_ms"], "finalize": r["finalize_ms"]},
+        "roofline": {"bound": "fp32_alu", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
+                     "frac": achieved / tf.value if tf.value else None, "traffic": None,
+                     "kernel": "rollout_kernel", "flop_per_state_step": F_ALG,
+                     "peak_source": "FFMA chain measured in this run (mppi_measure_fp32_peak); MEASURED_PEAKS.json has no fp32 entry",
+                     "hbm_view": {"algorithmic_bytes": hbm_alg_bytes,
+                                  "achieved_GBps": hbm_alg_bytes / (r["rollout_ms"] * 1e-3) / 1e9,
+                                  "peak_GBps": peaks.get("hbm_gbs"), "note": "not HBM bound: nothing of size K*T leaves the SM"}},
+        "refine": {"candidates_last_step": r["refine_candidates"], "overflow_steps": r["refine_overflow"],
+                   "max_abs_dev_fp32_vs_fp64": r["refine_max_dev"]},
+        "other_precisions": {p: {"value": K / (v["step_ms"] * 1e-3), "ms_per_step": v["step_ms"], "rollout_ms": v["rollout_ms"],
+                                 "e2e_ms": v["e2e_ms"]} for p, v in results.items() if p != args.precision},
+        "clocks": clocks,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
+def run_multi(args):
+    import torch
+    import torch.distributed as dist
+    from motion_planning_b200.distributed import ShardedMPPI
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K_total, T = K_PER_GPU * world, T_HORIZON
+    m = ShardedMPPI(T, K_total, precision=args.precision, seed=0, device=local)
+    s = X0.copy()
+    for _ in range(max(args.warmup, 3)):
+        s = m.get_path(s, GOAL)
+    sampler = ClockSampler(local) if rank == 0 else None
+    # e2e and device time coincide here: every step takes host x0 and returns host (u, x_next)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        ev[i][0].record()
+        s = m.get_path(s, GOAL)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    # e2e without the flush in the loop
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        s = m.get_path(s, GOAL)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    clocks = sampler.stop() if sampler else {}
+    if rank == 0:
+        io = m.mppi.io_bytes()
+        line = {
+            "metric": METRIC, "value": K_total / (dev_ms * 1e-3), "unit": "rollouts/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"mixed": "f32 rollouts + f64 re-evaluation of the softmin support", "f32": "f32", "f64": "f64"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": "diff-drive parallel-park K=%d per GPU (K_total=%d) T=%d, rollouts sharded over ranks, "
+                                   "one %d-byte all-gather per step" % (K_PER_GPU, K_total, T, T * 48),
+                       "K_total": K_total, "T": T, "precision": args.precision, "exchange": m.exchange,
+                       "l2": "flushed between timed steps", "timing": "CUDA events on the launch stream, max over ranks",
+                       "launch": m.mppi.launch_info()},
+            "state_steps_per_s": K_total / (dev_ms * 1e-3) * T,
+            "e2e": {"value": K_total / (e2e_ms * 1e-3), "unit": "rollouts/s", "h2d_bytes_per_step": io[0] * world,
+                    "d2h_bytes_per_step": io[1] * world, "ms_per_step": e2e_ms},
+            "gpu_launches": 3 * args.steps, "wall_ms_per_step_with_flush": wall / args.steps * 1e3, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "f32", "f64"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_multi(args)
+    if args.gpus > 1:
+        sys.exit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d --master-addr 127.0.0.1 "
+                 "bench.py --gpus %d ..." % (args.gpus, args.gpus))
+    return run_single(args)
+
+
+if __name__ == "__main__":
+    main()

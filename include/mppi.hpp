@@ -1,0 +1,174 @@
+// mppi.hpp -- header-only C++ facade `mppi::MPPI` over the C ABI (include/mppi_b200.h).
+//
+// BASELINE.json's north_star asks for "the reference's mppi::MPPI C++ API surface (construct with
+// diff-drive/bicycle dynamics functor, cost functor, K samples, T horizon; mppi.step(x0) -> u_t)".
+// The reference has no such class (its MPPI is the Python class control/src/mppi:61-213, SURVEY.md
+// section 0), so this facade is NEW; it follows the reference's C++ conventions instead:
+//   - model objects constructed like control::models::DiffDrive(wheel_radius, wheel_base,
+//     abs_max_wheel_vel)                    (control/include/control/Models.hpp:38-42)
+//   - 0-success return codes + out-parameters available through the C ABI underneath
+//                                           (control/include/control/TrajMPC.hpp:72,110-122)
+//   - no Eigen dependency (std::array), so it builds in a plain catkin C++17 package
+//     (control/CMakeLists.txt:5-9).
+// On the device the dynamics and cost "functors" are compile-time kernel template arguments selected
+// by the tag types below; arbitrary std::function models cannot run inside the rollout kernel.
+#ifndef MPPI_HPP_
+#define MPPI_HPP_
+
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mppi_b200.h"
+
+namespace mppi {
+
+using State = std::array<double, 3>;    // x, y, theta
+using Control = std::array<double, 2>;  // (u_l, u_r) wheel rad/s, or (v, delta) for the bicycle
+
+class Error : public std::runtime_error {
+ public:
+  Error(mppi_status s, const std::string& where)
+      : std::runtime_error(where + ": status " + std::to_string(static_cast<int>(s)) + " (" + mppi_last_error() + ")"), status(s) {}
+  mppi_status status;
+};
+
+// ---- dynamics functors (device-side: template tags) ------------------------------------------------
+struct DiffDrive {   // dd_dynamics + rk4, control/src/mppi:23-30,39-54; ctor order as Models.hpp:38-42
+  double wheel_radius = 0.033, wheel_base = 0.16, abs_max_wheel_vel = 6.35492;
+  DiffDrive() = default;
+  DiffDrive(double r, double L, double umax) : wheel_radius(r), wheel_base(L), abs_max_wheel_vel(umax) {}
+  void apply(mppi_params& p) const {
+    p.model = MPPI_MODEL_DIFF_DRIVE;
+    p.wheel_radius = wheel_radius;
+    p.wheel_base = wheel_base;
+    p.u_max[0] = p.u_max[1] = abs_max_wheel_vel;
+  }
+};
+
+struct Bicycle {     // NEW (BASELINE.json config 3): kinematic bicycle, u = (v, delta)
+  double wheel_base = 0.16, max_speed = 0.22, max_steer = 0.6;
+  double speed_noise_std = 0.08, steer_noise_std = 0.25;
+  void apply(mppi_params& p) const {
+    p.model = MPPI_MODEL_BICYCLE;
+    p.wheel_base = wheel_base;
+    p.u_max[0] = max_speed;
+    p.u_max[1] = max_steer;
+    p.noise_std[0] = speed_noise_std;
+    p.noise_std[1] = steer_noise_std;
+  }
+};
+
+struct UnicycleEuler {   // unicycle_dynamics + euler, control/src/mppi:33-36,57-58
+  double max_speed = 0.22, max_yaw_rate = 2.84;
+  void apply(mppi_params& p) const {
+    p.model = MPPI_MODEL_UNICYCLE_EULER;
+    p.u_max[0] = max_speed;
+    p.u_max[1] = max_yaw_rate;
+  }
+};
+
+// ---- cost functor ------------------------------------------------------------------------------------
+struct OccupancyGrid {   // nav_msgs/OccupancyGrid layout as published by map/src/viz_grid.cpp:109-137
+  std::vector<int8_t> cells;   // row-major, idx = ix + iy * width, values 0 / 50 / 100
+  int width = 0, height = 0;
+  double resolution = 1.0, origin_x = 0.0, origin_y = 0.0;
+  double weight = 0.0;         // running cost += weight * cell / 100
+};
+
+struct QuadraticCost {   // get_cost + terminal cost, control/src/mppi:69-73,165-171,180-184
+  std::array<double, 3> Q{{1e3, 1e3, 0.0}};
+  std::array<double, 4> R{{1.0, 0.0, 0.0, 1.0}};
+  std::array<double, 3> P1{{1e3, 1e3, 1e3}};
+  OccupancyGrid grid;    // optional (weight == 0 -> none)
+  void apply(mppi_params& p) const {
+    for (int i = 0; i < 3; ++i) {
+      p.q[i] = Q[i];
+      p.p1[i] = P1[i];
+    }
+    for (int i = 0; i < 4; ++i) p.r[i] = R[i];
+  }
+};
+
+struct Options {
+  mppi_precision precision = MPPI_PRECISION_MIXED;
+  mppi_weighting weighting = MPPI_WEIGHT_COST_TO_GO;
+  double sigma = 0.9;      // sig = sigma * I, control/src/mppi:88
+  double lambda = 1e-3;    // control/src/mppi:89
+  uint64_t seed = 0;
+  int device = 0;
+};
+
+class MPPI {
+ public:
+  // construct with a dynamics functor, a cost functor, K samples and T horizon
+  template <typename Dynamics, typename Cost = QuadraticCost>
+  MPPI(const Dynamics& dyn, const Cost& cost, int K, int T, const Options& opt = Options()) : T_(T) {
+    mppi_params p;
+    check(mppi_default_params(&p), "mppi_default_params");
+    p.K = K;
+    p.T = T;
+    p.precision = opt.precision;
+    p.weighting = opt.weighting;
+    p.sig[0] = p.sig[3] = opt.sigma;
+    p.noise_std[0] = p.noise_std[1] = opt.sigma;
+    p.lambda = opt.lambda;
+    p.seed = opt.seed;
+    p.device = opt.device;
+    dyn.apply(p);
+    cost.apply(p);
+    check(mppi_create(&p, &h_), "mppi_create");
+    if (cost.grid.weight != 0.0 && !cost.grid.cells.empty())
+      check(mppi_set_grid(h_, cost.grid.cells.data(), cost.grid.width, cost.grid.height, cost.grid.resolution,
+                          cost.grid.origin_x, cost.grid.origin_y, cost.grid.weight),
+            "mppi_set_grid");
+  }
+  MPPI(const MPPI&) = delete;
+  MPPI& operator=(const MPPI&) = delete;
+  MPPI(MPPI&& o) noexcept : h_(o.h_), T_(o.T_), x_next_(o.x_next_) { o.h_ = nullptr; }
+  ~MPPI() {
+    if (h_) mppi_destroy(h_);
+  }
+
+  void setGoal(const State& g) { check(mppi_set_goal(h_, g.data()), "mppi_set_goal"); }
+  void reset() { check(mppi_reset(h_), "mppi_reset"); }   // MPPI.initialize, control/src/mppi:79-83
+
+  // mppi.step(x0) -> u_t   (= MPPI.get_path; u_t = uvec[-1], control/src/mppi:85-102,379)
+  Control step(const State& x0) {
+    Control u;
+    check(mppi_step(h_, x0.data(), u.data(), x_next_.data()), "mppi_step");
+    return u;
+  }
+  const State& predictedNextState() const { return x_next_; }   // what get_path returns, :94,102
+
+  std::vector<double> nominal() const {   // latest_uvec (2,T) row-major
+    std::vector<double> U(2 * T_);
+    check(mppi_get_nominal(h_, U.data()), "mppi_get_nominal");
+    return U;
+  }
+  void setNominal(const std::vector<double>& U) {
+    if (static_cast<int>(U.size()) != 2 * T_) throw std::invalid_argument("nominal must have 2*T entries");
+    check(mppi_set_nominal(h_, U.data()), "mppi_set_nominal");
+  }
+
+  // twist for cmd_vel, Controller.wheelsToTwist (control/src/mppi:319-325)
+  static void wheelsToTwist(const Control& u, double wheel_radius, double wheel_base, double& vx, double& wz) {
+    vx = wheel_radius * (u[0] + u[1]) / 2.0;
+    wz = wheel_radius * (-u[0] + u[1]) / wheel_base;
+  }
+
+  mppi_handle handle() const { return h_; }
+
+ private:
+  static void check(mppi_status s, const char* where) {
+    if (s != MPPI_OK) throw Error(s, where);
+  }
+  mppi_handle h_ = nullptr;
+  int T_ = 0;
+  State x_next_{{0, 0, 0}};
+};
+
+}  // namespace mppi
+#endif  // MPPI_HPP_
