@@ -99,11 +99,26 @@ template <> struct Math<float> {
     s = (q & 2) ? -ss : ss;
     c = ((q + 1) & 2) ? -cc : cc;
   }
-  // theta - (ceil((theta+pi)/(2pi)) - 1) * 2pi   (control/src/mppi:52-53), 2pi split hi/lo
+  // sin/cos of an angle INCREMENT: polynomials only when |a| <= pi/4 (always, for sane dt * yaw rate)
+  static __device__ __forceinline__ void sincos_small_(float a, float& s, float& c) {
+    if (fabsf(a) > 0.78539816f) {
+      sincos_(a, s, c);
+      return;
+    }
+    const float z = a * a;
+    s = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), z * a, a);
+    c = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z * z,
+             fmaf(-0.5f, z, 1.0f));
+  }
+  // theta - (ceil((theta+pi)/(2pi)) - 1) * 2pi   (control/src/mppi:52-53), 2pi split hi/lo.
+  // The expression is the identity on (-pi, pi], so it is only evaluated outside that interval.
   static __device__ __forceinline__ float wrap_(float th) {
-    float n = ceilf((th + pi()) * inv_2pi()) - 1.0f;
-    float r = fmaf(-n, 6.28318548202514648f, th);
-    return fmaf(n, 1.74845553146951715e-07f, r);
+    if (th > pi() || th <= -pi()) {
+      float n = ceilf((th + pi()) * inv_2pi()) - 1.0f;
+      float r = fmaf(-n, 6.28318548202514648f, th);
+      th = fmaf(n, 1.74845553146951715e-07f, r);
+    }
+    return th;
   }
 };
 
@@ -118,11 +133,46 @@ template <> struct Math<double> {
   static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
   static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
   static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
-  static __device__ __forceinline__ void sincos_(double x, double& s, double& c) { sincos(x, &s, &c); }
+  // fdlibm-style kernels on [-pi/4, pi/4] (~1 ulp)
+  static __device__ __forceinline__ void sincos_kernel_(double r, double& s, double& c) {
+    const double z = r * r;
+    const double ps = fma(fma(fma(fma(fma(1.58969099521155010221e-10, z, -2.50507602534068634195e-08), z,
+                                      2.75573137070700676789e-06), z, -1.98412698298579493134e-04), z,
+                              8.33333333332248946124e-03), z, -1.66666666666666324348e-01);
+    const double pc = fma(fma(fma(fma(fma(-1.13596475577881948265e-11, z, 2.08757232129817482790e-09), z,
+                                      -2.75573143513906633035e-07), z, 2.48015872894767294178e-05), z,
+                              -1.38888888888741095749e-03), z, 4.16666666666666019037e-02);
+    s = fma(ps * z, r, r);
+    c = fma(pc * z, z, fma(-0.5, z, 1.0));
+  }
+  // sin/cos for |x| up to ~1e5: two-term FMA Cody-Waite reduction (no Payne-Hanek slow path, which
+  // the CUDA library routine drags in together with a local-memory stack frame)
+  static __device__ __forceinline__ void sincos_(double x, double& s, double& c) {
+    const double j = rint(x * 0.63661977236758138);
+    const int q = __double2int_rn(j);
+    double r = fma(-j, 1.5707963267948966, x);
+    r = fma(-j, 6.123233995736766e-17, r);
+    double ps, pc;
+    sincos_kernel_(r, ps, pc);
+    const double ss = (q & 1) ? pc : ps;
+    const double cc = (q & 1) ? ps : pc;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+  }
+  static __device__ __forceinline__ void sincos_small_(double a, double& s, double& c) {
+    if (fabs(a) > 0.78539816339744828) {
+      sincos_(a, s, c);
+      return;
+    }
+    sincos_kernel_(a, s, c);
+  }
   // same expression as the reference, evaluated in f64 (control/src/mppi:52-53)
   static __device__ __forceinline__ double wrap_(double th) {
-    double n = ceil((th + pi()) / (2.0 * pi())) - 1.0;
-    return th - n * 2.0 * pi();
+    if (th > pi() || th <= -pi()) {   // identity on (-pi, pi]
+      double n = ceil((th + pi()) / (2.0 * pi())) - 1.0;
+      th = th - n * 2.0 * pi();
+    }
+    return th;
   }
 };
 
@@ -147,6 +197,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // 4 standard normals (fp32) = the z of (t=2*t2: ch0, ch1), (t=2*t2+1: ch0, ch1).  Box-Muller on the
 // SFU pipe (lg2, rsqrt/sqrt, sin, cos).  Bit-identical wherever it is called from (intrinsics only,
 // nothing for the compiler to contract).
@@ -160,8 +216,9 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsign
   float u1 = __fmul_rn((float)r.y, S);
   float u2 = __fmaf_rn((float)r.z, S, 1.1641532182693481e-10f);
   float u3 = __fmul_rn((float)r.w, S);
-  float ra = __fsqrt_rn(__fmul_rn(-2.0f, __logf(u0)));
-  float rb = __fsqrt_rn(__fmul_rn(-2.0f, __logf(u2)));
+  // sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u): MUFU.LG2 + FMUL + MUFU.SQRT
+  float ra = sqrt_approx(__fmul_rn(-1.38629436111989062f, __log2f(u0)));
+  float rb = sqrt_approx(__fmul_rn(-1.38629436111989062f, __log2f(u2)));
   float sa, ca, sb, cb;
   __sincosf(__fmul_rn(6.28318530717958648f, u1), &sa, &ca);
   __sincosf(__fmul_rn(6.28318530717958648f, u3), &sb, &cb);
@@ -202,32 +259,41 @@ __device__ __forceinline__ void speed_yaw(const ModelConsts<R>& mc, R u0, R u1, 
   }
 }
 
-// One integrator step in DISPLACEMENT coordinates (dx, dy relative to x0; theta absolute, wrapped).
-// RK4: k1 uses theta, k2 == k3 use theta + k_theta/2, k4 uses theta + k_theta (theta-dot does not
-// depend on the state), so x+ = x + dt*s/6 * (c1 + 4 c2 + c4).
+// One integrator step in DISPLACEMENT coordinates (dx, dy relative to x0; theta absolute, wrapped),
+// carrying (c, s) = (cos theta, sin theta) so that the three RK4 trig evaluations become one
+// small-angle sincos of the half increment plus two plane rotations (angle-addition):
+//   RK4: k1 uses theta, k2 == k3 use theta + k/2, k4 uses theta + k  (theta-dot does not depend on the
+//   state)  =>  x+ = x + dt*s/6 * (c1 + 4 c2 + c4).
+// The caller re-synchronises (c, s) from theta every few steps (resync_trig) to stop rounding drift.
 template <typename R, int MODEL>
-__device__ __forceinline__ void model_step(const ModelConsts<R>& mc, R u0, R u1, R& dx, R& dy, R& th) {
-  R s, w;
-  speed_yaw<R, MODEL>(mc, u0, u1, s, w);
+__device__ __forceinline__ void model_step(const ModelConsts<R>& mc, R u0, R u1, R& dx, R& dy, R& th, R& c, R& s) {
+  R spd, w;
+  speed_yaw<R, MODEL>(mc, u0, u1, spd, w);
+  const R kth = mc.dt * w;
   if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {       // euler, control/src/mppi:57-58 (no wrap)
-    R sn, cs;
-    Math<R>::sincos_(th, sn, cs);
-    dx = Math<R>::fma_(mc.dt * s, cs, dx);
-    dy = Math<R>::fma_(mc.dt * s, sn, dy);
-    th = Math<R>::fma_(mc.dt, w, th);
+    dx = Math<R>::fma_(mc.dt * spd, c, dx);
+    dy = Math<R>::fma_(mc.dt * spd, s, dy);
+    th = th + kth;
+    R sa, ca;
+    Math<R>::sincos_small_(kth, sa, ca);
+    const R cn = c * ca - s * sa;
+    s = Math<R>::fma_(s, ca, c * sa);
+    c = cn;
     return;
   }
-  R kth = mc.dt * w;
-  R s1, c1, s2, c2, s4, c4;
-  Math<R>::sincos_(th, s1, c1);
-  Math<R>::sincos_(Math<R>::fma_(R(0.5), kth, th), s2, c2);
-  R thn = th + kth;
-  Math<R>::sincos_(thn, s4, c4);
-  R g = mc.dt * s * R(1.0 / 6.0);
-  dx = Math<R>::fma_(g, Math<R>::fma_(R(4), c2, c1 + c4), dx);
-  dy = Math<R>::fma_(g, Math<R>::fma_(R(4), s2, s1 + s4), dy);
-  th = Math<R>::wrap_(thn);
+  R sa, ca;
+  Math<R>::sincos_small_(R(0.5) * kth, sa, ca);
+  const R c2 = Math<R>::fma_(c, ca, -(s * sa)), s2 = Math<R>::fma_(s, ca, c * sa);
+  const R c4 = Math<R>::fma_(c2, ca, -(s2 * sa)), s4 = Math<R>::fma_(s2, ca, c2 * sa);
+  const R g = mc.dt * spd * R(1.0 / 6.0);
+  dx = Math<R>::fma_(g, Math<R>::fma_(R(4), c2, c + c4), dx);
+  dy = Math<R>::fma_(g, Math<R>::fma_(R(4), s2, s + s4), dy);
+  th = Math<R>::wrap_(th + kth);
+  c = c4;
+  s = s4;
 }
+
+constexpr int kTrigResyncMask = 7;   // (c, s) <- sincos(theta) after every 8th step
 
 // ---- cost in delta form --------------------------------------------------------------------------
 // The reference subtracts min_k V[t,k] per t before exponentiating (control/src/mppi:189), so any

@@ -65,6 +65,7 @@ struct mppi_engine {
   int* d_cand_count = nullptr;
   uint2* d_cand = nullptr;
   float* d_cand_min = nullptr;
+  float* d_cand_lim = nullptr;
   size_t part_capacity_ctas = 0;
   signed char* d_grid = nullptr;
   double* d_eps_ext = nullptr;
@@ -135,9 +136,9 @@ extern "C" mppi_status mppi_default_params(mppi_params* p) {
 
 static double default_margin(const mppi_engine* e, double lam) {
   if (e->p.refine_margin > 0) return e->p.refine_margin;
-  // e^-40 ~ 4e-18 relative weight is far below the 1e-8 floor; 0.06 covers the fp32 screening error
-  // of the cost-to-go (measured max |V32 - V64|) with > 10x head-room.
-  return 40.0 * lam + 0.06;
+  // e^-40 ~ 4e-18 relative weight is far below the 1e-8 floor; 0.01 covers the fp32 screening error
+  // of the cost-to-go (measured max |V32 - V64| ~ 2e-5 at K=65536,T=64) 500x over.
+  return 40.0 * lam + 0.01;
 }
 
 static void free_partials(mppi_engine* e) {
@@ -146,11 +147,13 @@ static void free_partials(mppi_engine* e) {
   cudaFree(e->d_cand_count);
   cudaFree(e->d_cand);
   cudaFree(e->d_cand_min);
+  cudaFree(e->d_cand_lim);
   e->d_part = nullptr;
   e->d_epart = nullptr;
   e->d_cand_count = nullptr;
   e->d_cand = nullptr;
   e->d_cand_min = nullptr;
+  e->d_cand_lim = nullptr;
   e->part_capacity_ctas = 0;
 }
 
@@ -221,6 +224,7 @@ static mppi_status configure(mppi_engine* e) {
     CK(cudaMalloc(&e->d_cand_count, n * sizeof(int)));
     CK(cudaMalloc(&e->d_cand, n * kMaxCand * sizeof(uint2)));
     CK(cudaMalloc(&e->d_cand_min, n * sizeof(float)));
+    CK(cudaMalloc(&e->d_cand_lim, n * sizeof(float)));
     e->part_capacity_ctas = max_ctas;
   }
   return drop_graphs(e);
@@ -628,6 +632,7 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   ra.cand_count = e->d_cand_count;
   ra.cand = e->d_cand;
   ra.cand_min = e->d_cand_min;
+  ra.cand_lim = e->d_cand_lim;
   ra.vcap = e->d_vcap;
   ra.ntiles = c.ntiles;
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[0], st));
@@ -642,6 +647,7 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   rd.cand_count = e->d_cand_count;
   rd.cand = e->d_cand;
   rd.cand_min = e->d_cand_min;
+  rd.cand_lim = e->d_cand_lim;
   rd.nomD = e->d_nomD;
   rd.grid = e->d_grid;
   rd.eps_ext = e->d_eps_ext;

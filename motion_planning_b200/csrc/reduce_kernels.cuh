@@ -45,44 +45,102 @@ __device__ __forceinline__ void floor_scale(const StaticParams& sp, const DynSta
   s1 = sp.noise_external ? 1.0 : (double)(float)dyn->noise_std[1] / kZFixScale;
 }
 
-// ---- kernel 2a: SOFTMIN merge.  grid = T blocks ---------------------------------------------------
+// (m, S, N0, N1) online-softmin tuples: merge b into a (weights relative to the smaller minimum)
+struct Tup {
+  double m, S, N0, N1;
+};
+__device__ __forceinline__ void tup_merge(Tup& a, const Tup& b, double neg_inv_lam) {
+  const double m = fmin(a.m, b.m);
+  const double sa = (a.m == m) ? 1.0 : exp((a.m - m) * neg_inv_lam);
+  const double sb = (b.m == m) ? 1.0 : exp((b.m - m) * neg_inv_lam);
+  a.S = a.S * sa + b.S * sb;
+  a.N0 = a.N0 * sa + b.N0 * sb;
+  a.N1 = a.N1 * sa + b.N1 * sb;
+  a.m = m;
+}
+__device__ __forceinline__ Tup tup_shfl_xor(const Tup& t, int o) {
+  Tup r;
+  r.m = __shfl_xor_sync(0xffffffffu, t.m, o);
+  r.S = __shfl_xor_sync(0xffffffffu, t.S, o);
+  r.N0 = __shfl_xor_sync(0xffffffffu, t.N0, o);
+  r.N1 = __shfl_xor_sync(0xffffffffu, t.N1, o);
+  return r;
+}
+
+__device__ void finalize_body(const FinalizeArgs& a, double* Us);
+
+// "last block done": the block that finishes the last record runs the finalize phase, saving one
+// kernel boundary on the serial tail of the step (world_size 1 only; sharded steps exchange first)
+__device__ __forceinline__ bool last_block_done(unsigned int* counter, unsigned int nblocks) {
+  __shared__ unsigned int ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(counter, 1u);
+  __syncthreads();
+  const bool last = (ticket == nblocks - 1);
+  if (last) {
+    if (threadIdx.x == 0) *counter = 0u;
+    __threadfence();
+  }
+  return last;
+}
+
+// ---- kernel 2a: SOFTMIN merge (single pass, tuple reduction).  grid = T blocks of 128 --------------
 template <typename R>
 __global__ void __launch_bounds__(128) reduce_softmin_kernel(const __grid_constant__ ReduceArgs a) {
   typedef typename Math<R>::Vec4 Vec4;
-  __shared__ double scratch[8];
-  const int t = blockIdx.x;
+  extern __shared__ __align__(16) unsigned char smem_fin[];
+  __shared__ Tup wt[4];
+  __shared__ double we[4][2];
+  const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Vec4* part = reinterpret_cast<const Vec4*>(a.part) + (size_t)t * a.nCTA;
   const double* ep = a.epart + (size_t)t * a.nCTA * 2;
-  const double neg_inv_lam = -1.0 / a.dyn->lam;
-  double m = Math<double>::inf();
-  for (int i = threadIdx.x; i < a.nCTA; i += blockDim.x) m = fmin(m, (double)part[i].x);
-  m = block_min(m, scratch);
-  double S = 0, N0 = 0, N1 = 0, E0 = 0, E1 = 0;
+  const double neg_inv_lam = -1.0 / a.fin.dyn->lam;
+  Tup acc;
+  acc.m = Math<double>::inf();
+  acc.S = acc.N0 = acc.N1 = 0.0;
+  double E0 = 0, E1 = 0;
   for (int i = threadIdx.x; i < a.nCTA; i += blockDim.x) {
     const Vec4 p = part[i];
-    const double sc = exp(((double)p.x - m) * neg_inv_lam);
-    S += (double)p.y * sc;
-    N0 += (double)p.z * sc;
-    N1 += (double)p.w * sc;
+    Tup b;
+    b.m = (double)p.x;
+    b.S = (double)p.y;
+    b.N0 = (double)p.z;
+    b.N1 = (double)p.w;
+    tup_merge(acc, b, neg_inv_lam);
     E0 += ep[2 * i];
     E1 += ep[2 * i + 1];
   }
-  S = block_sum(S, scratch);
-  N0 = block_sum(N0, scratch);
-  N1 = block_sum(N1, scratch);
-  E0 = block_sum(E0, scratch);
-  E1 = block_sum(E1, scratch);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const Tup b = tup_shfl_xor(acc, o);
+    tup_merge(acc, b, neg_inv_lam);
+  }
+  E0 = warp_sum<double>(E0);
+  E1 = warp_sum<double>(E1);
+  if (lane == 0) {
+    wt[warp] = acc;
+    we[warp][0] = E0;
+    we[warp][1] = E1;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    for (int w = 1; w < 4; ++w) {
+      tup_merge(acc, wt[w], neg_inv_lam);
+      E0 += we[w][0];
+      E1 += we[w][1];
+    }
     double s0, s1;
-    floor_scale(a.sp, a.dyn, s0, s1);
+    floor_scale(a.sp, a.fin.dyn, s0, s1);
     double* r = a.record + (size_t)t * kRecordStride;
-    r[0] = m;
-    r[1] = S;
-    r[2] = N0;
-    r[3] = N1;
+    r[0] = acc.m;
+    r[1] = acc.S;
+    r[2] = acc.N0;
+    r[3] = acc.N1;
     r[4] = E0 * s0;
     r[5] = E1 * s1;
   }
+  if (a.fuse_finalize && last_block_done(a.done_counter, gridDim.x)) finalize_body(a.fin, reinterpret_cast<double*>(smem_fin));
 }
 
 // ---- fp64 re-evaluation of ONE rollout by ONE warp, parallel in time ------------------------------
@@ -145,16 +203,17 @@ __device__ double resim_cost_to_go_f64(const StaticParams& sp, const DynState* d
       double ix, iy, thn;
       if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {
         double sn, cs;
-        sincos(th_pre, &sn, &cs);
+        Math<double>::sincos_(th_pre, sn, cs);
         ix = mc.dt * spd * cs;
         iy = mc.dt * spd * sn;
         thn = th_pre + v;
       } else {
         const double thw = Math<double>::wrap_(th_pre);
-        double s1, c1, s2, c2, s4, c4;
-        sincos(thw, &s1, &c1);
-        sincos(thw + 0.5 * v, &s2, &c2);
-        sincos(thw + v, &s4, &c4);
+        double s1, c1, sa, ca;
+        Math<double>::sincos_(thw, s1, c1);
+        Math<double>::sincos_small_(0.5 * v, sa, ca);
+        const double c2 = c1 * ca - s1 * sa, s2 = s1 * ca + c1 * sa;
+        const double c4 = c2 * ca - s2 * sa, s4 = s2 * ca + c2 * sa;
         const double g = mc.dt * spd * (1.0 / 6.0);
         ix = g * (c1 + 4.0 * c2 + c4);
         iy = g * (s1 + 4.0 * s2 + s4);
@@ -196,9 +255,9 @@ __device__ double resim_cost_to_go_f64(const StaticParams& sp, const DynState* d
 }
 
 // ---- kernel 2b: SCREEN -> fp64 refinement.  grid = T blocks of 128 threads -----------------------
-// dynamic smem: 4 warps * 7 * T doubles
+// dynamic smem: 8 warps * 7 * T doubles (reused by the fused finalize phase)
 template <int MODEL, bool HAS_GRID>
-__global__ void __launch_bounds__(128) reduce_screen_kernel(const __grid_constant__ ReduceArgs a) {
+__global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constant__ ReduceArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw2[];
   double* warp_scratch = reinterpret_cast<double*>(smem_raw2);
   __shared__ double scratch[8];
@@ -217,22 +276,22 @@ __global__ void __launch_bounds__(128) reduce_screen_kernel(const __grid_constan
   // phase A: global fp32 minimum, floor sums, overflow check
   const int* cnt = a.cand_count + (size_t)t * a.nCTA;
   const float* cmin = a.cand_min + (size_t)t * a.nCTA;
+  const float* clim = a.cand_lim + (size_t)t * a.nCTA;
   const double* ep = a.epart + (size_t)t * a.nCTA * 2;
   double m32 = Math<double>::inf(), E0 = 0, E1 = 0;
-  int ovf = 0;
   for (int i = tid; i < a.nCTA; i += blockDim.x) {
     m32 = fmin(m32, (double)cmin[i]);
     E0 += ep[2 * i];
     E1 += ep[2 * i + 1];
-    ovf |= (cnt[i] > kMaxCand);
   }
   m32 = block_min(m32, scratch);
   E0 = block_sum(E0, scratch);
   E1 = block_sum(E1, scratch);
-  if (ovf) atomicOr(&overflow, 1);
-  // phase B: compact the candidates inside the window of the GLOBAL minimum
-  const float lim = (float)(m32 + sp.margin);
+  // phase B: compact the candidates inside the window of the GLOBAL minimum; a CTA whose list does
+  // not cover that window (it had to tighten its own window) is an overflow
+  const float lim = (float)m32 + (float)sp.margin;
   for (int i = tid; i < a.nCTA; i += blockDim.x) {
+    if (clim[i] < lim) atomicOr(&overflow, 1);
     const int c = min(cnt[i], kMaxCand);
     const uint2* cd = a.cand + ((size_t)t * a.nCTA + i) * kMaxCand;
     for (int s = 0; s < c; ++s) {
@@ -254,10 +313,10 @@ __global__ void __launch_bounds__(128) reduce_screen_kernel(const __grid_constan
   // phase C: fp64 re-evaluation, one warp per candidate
   ModelConsts<double> mc;
   CostConsts<double> cc;
-  make_consts<double>(sp, a.dyn, mc, cc);
+  make_consts<double>(sp, a.fin.dyn, mc, cc);
   double dev = 0.0;
-  for (int c = warp; c < n; c += 4) {
-    const double v64 = resim_cost_to_go_f64<MODEL, HAS_GRID>(sp, a.dyn, a.nomD, a.grid, a.eps_ext, mc, cc, sel_k[c], t_eval,
+  for (int c = warp; c < n; c += 8) {
+    const double v64 = resim_cost_to_go_f64<MODEL, HAS_GRID>(sp, a.fin.dyn, a.nomD, a.grid, a.eps_ext, mc, cc, sel_k[c], t_eval,
                                                               warp_scratch + (size_t)warp * 7 * T);
     if (lane == 0) sel_v64[c] = v64;
     dev = fmax(dev, fabs(v64 - (double)sel_v32[c]));
@@ -266,8 +325,8 @@ __global__ void __launch_bounds__(128) reduce_screen_kernel(const __grid_constan
   // phase D: exact softmin over the support (control/src/mppi:189-196)
   double m64 = Math<double>::inf();
   for (int c = 0; c < n; ++c) m64 = fmin(m64, sel_v64[c]);
-  const double neg_inv_lam = -1.0 / a.dyn->lam;
-  const float std0 = (float)a.dyn->noise_std[0], std1 = (float)a.dyn->noise_std[1];
+  const double neg_inv_lam = -1.0 / a.fin.dyn->lam;
+  const float std0 = (float)a.fin.dyn->noise_std[0], std1 = (float)a.fin.dyn->noise_std[1];
   double S = 0, N0 = 0, N1 = 0;
   for (int c = tid; c < n; c += blockDim.x) {
     const double e = exp((sel_v64[c] - m64) * neg_inv_lam);
@@ -277,7 +336,7 @@ __global__ void __launch_bounds__(128) reduce_screen_kernel(const __grid_constan
       e1 = a.eps_ext[((size_t)t * 2 + 1) * sp.K + sel_k[c]];
     } else {
       float f0, f1;
-      philox_eps(sp.seed, (unsigned long long)(sp.k_offset + sel_k[c]), t, a.dyn->step, std0, std1, f0, f1);
+      philox_eps(sp.seed, (unsigned long long)(sp.k_offset + sel_k[c]), t, a.fin.dyn->step, std0, std1, f0, f1);
       e0 = f0;
       e1 = f1;
     }
@@ -291,7 +350,7 @@ __global__ void __launch_bounds__(128) reduce_screen_kernel(const __grid_constan
   dev = -block_min(-dev, scratch);
   if (tid == 0) {
     double s0, s1;
-    floor_scale(sp, a.dyn, s0, s1);
+    floor_scale(sp, a.fin.dyn, s0, s1);
     double* r = a.record + (size_t)t * kRecordStride;
     r[0] = m64;
     r[1] = S;
@@ -299,11 +358,12 @@ __global__ void __launch_bounds__(128) reduce_screen_kernel(const __grid_constan
     r[3] = N1;
     r[4] = E0 * s0;
     r[5] = E1 * s1;
-    atomicAdd(&a.dyn->refine_candidates, n);
-    if (overflow) atomicOr(&a.dyn->refine_overflow, 1);
+    atomicAdd(&a.fin.dyn->refine_candidates, n);
+    if (overflow) atomicOr(&a.fin.dyn->refine_overflow, 1);
     // max of non-negative doubles == max of their bit patterns
-    atomicMax(reinterpret_cast<unsigned long long*>(&a.dyn->refine_max_dev), (unsigned long long)__double_as_longlong(dev));
+    atomicMax(reinterpret_cast<unsigned long long*>(&a.fin.dyn->refine_max_dev), (unsigned long long)__double_as_longlong(dev));
   }
+  if (a.fuse_finalize && last_block_done(a.done_counter, gridDim.x)) finalize_body(a.fin, warp_scratch);
 }
 
 // ---- kernel 3: finalize.  one block of 256 threads ------------------------------------------------
@@ -335,8 +395,9 @@ __device__ void model_step_abs_f64(const StaticParams& sp, const double x[3], do
   mc.half_r = sp.wheel_r * 0.5;
   mc.r_over_L = sp.wheel_r / sp.wheel_L;
   mc.inv_L = 1.0 / sp.wheel_L;
-  double dx = 0.0, dy = 0.0, th = x[2];
-  model_step<double, MODEL>(mc, u0, u1, dx, dy, th);
+  double dx = 0.0, dy = 0.0, th = x[2], c, s;
+  Math<double>::sincos_(th, s, c);
+  model_step<double, MODEL>(mc, u0, u1, dx, dy, th, c, s);
   out[0] = x[0] + dx;
   out[1] = x[1] + dy;
   out[2] = th;
@@ -351,9 +412,8 @@ __device__ inline void model_step_dispatch_f64(const StaticParams& sp, const dou
     model_step_abs_f64<MPPI_MODEL_BICYCLE>(sp, x, u0, u1, out);
 }
 
-__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw3[];
-  double* Us = reinterpret_cast<double*>(smem_raw3);   // [2][T] clipped update
+// needs 4*T doubles of shared scratch `Us`; any blockDim that is a multiple of 32
+__device__ void finalize_body(const FinalizeArgs& a, double* Us) {
   double* Uf = Us + 2 * a.sp.T;                        // [2][T] filtered
   __shared__ double coef[2][2][4];
   __shared__ int bad;
@@ -362,12 +422,12 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   if (tid == 0) bad = 0;
   __syncthreads();
-  if (a.mode == 0 && a.dyn->refine_overflow) {
+  if (a.mode == 0 && a.fin.dyn->refine_overflow) {
     // MIXED: the fp32 screen overflowed a candidate list -> leave U, the step counter and x0
     // untouched and ask the host to redo this step with the fp64 pipeline (same noise).
     __syncthreads();
     if (tid == 0) {
-      DynState* d = a.dyn;
+      DynState* d = a.fin.dyn;
       d->status = kStatusRedoF64;
       d->overflow_total += 1;
       d->refine_candidates = 0;
@@ -377,7 +437,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
     return;
   }
   // -- merge the records of all ranks and apply the weighted noise (control/src/mppi:189-199) ----
-  const double neg_inv_lam = -1.0 / a.dyn->lam;
+  const double neg_inv_lam = -1.0 / a.fin.dyn->lam;
   for (int idx = tid; idx < 2 * T; idx += blockDim.x) {
     const int c = idx / T, t = idx - c * T;
     double m = Math<double>::inf();
@@ -426,10 +486,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
       const double u1 = (t + 1 < T) ? Uf[T + t + 1] : 0.0;
       a.Umaster[t] = u0;
       a.Umaster[T + t] = u1;
-      write_nominal_block(a.dyn, T, t, u0, u1, a.nomF, a.nomD);
+      write_nominal_block(a.fin.dyn, T, t, u0, u1, a.nomF, a.nomD);
     }
     if (tid == 0) {
-      DynState* d = a.dyn;
+      DynState* d = a.fin.dyn;
       double xn[3];
       model_step_dispatch_f64(sp, d->x0, Uf[0], Uf[T], xn);
       d->out_u[0] = Uf[0];
@@ -451,6 +511,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
       d->refine_max_dev = 0.0;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw3[];
+  finalize_body(a, reinterpret_cast<double*>(smem_raw3));
 }
 
 // ---- auxiliary kernels (debug / reference-API surface, not on the hot path) -----------------------

@@ -14,23 +14,9 @@ struct RolloutArgs {
   int* cand_count;             // SCREEN: [T][nCTA]
   uint2* cand;                 // SCREEN: [T][nCTA][kMaxCand]  (k_local, float bits of V)
   float* cand_min;             // SCREEN: [T][nCTA] running minimum of the CTA
+  float* cand_lim;             // SCREEN: [T][nCTA] every rollout of the CTA with V <= cand_lim is listed
   void* vcap;                  // capture: Real[T][K]
   int ntiles;
-};
-
-struct ReduceArgs {
-  StaticParams sp;
-  DynState* dyn;
-  const void* part;          // SOFTMIN partials Vec4[T][nCTA]
-  const double* epart;       // [T][nCTA][2]
-  const int* cand_count;     // SCREEN
-  const uint2* cand;
-  const float* cand_min;
-  const double* nomD;        // f64 nominal block [4][T]
-  const signed char* grid;
-  const double* eps_ext;
-  double* record;            // [T][6]
-  int nCTA;
 };
 
 struct FinalizeArgs {
@@ -46,5 +32,24 @@ struct FinalizeArgs {
   int mode;                  // 0: full step, 1: update only (mppi_update_action)
   int closed_loop;           // 1: dyn->x0 <- x_next (device-resident loop of mppi_bench)
 };
+
+struct ReduceArgs {
+  StaticParams sp;
+  FinalizeArgs fin;          // fin.dyn is THE DynState; the rest is used when fuse_finalize != 0
+  int fuse_finalize;         // 1: the last block to finish also runs the finalize phase (world_size 1)
+  unsigned int* done_counter;
+  const void* part;          // SOFTMIN partials Vec4[T][nCTA]
+  const double* epart;       // [T][nCTA][2]
+  const int* cand_count;     // SCREEN
+  const uint2* cand;
+  const float* cand_min;
+  const float* cand_lim;
+  const double* nomD;        // f64 nominal block [4][T]
+  const signed char* grid;
+  const double* eps_ext;
+  double* record;            // [T][6]
+  int nCTA;
+};
+
 
 }  // namespace mppi

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
   for (int t = tid; t < T; t += BLOCK) {
     Vec4 v;
     v.x = Math<R>::inf();
-    v.y = R(0);
+    v.y = (MODE == MODE_SCREEN) ? Math<R>::inf() : R(0);
     v.z = R(0);
     v.w = R(0);
     run[t] = v;
@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     const bool valid = k_local < sp.K;
     const unsigned long long kglobal = (unsigned long long)(sp.k_offset + k_local);
     R dx = R(0), dy = R(0), th = cc.th0, acc = R(0);
+    R cth, sth;
+    Math<R>::sincos_(th, sth, cth);
 
     // ---- the T-step rollout (hot loop 1, control/src/mppi:136-163) ----------------------------
     for (int t2 = 0; t2 < (T >> 1); ++t2) {
@@ -148,7 +150,8 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
         // u_samp = clip(U[:,t] + eps)   control/src/mppi:147-152 (eps itself stays unclipped)
         const R u0 = clamp_<R>(nomU0[t] + e0, um0);
         const R u1 = clamp_<R>(nomU1[t] + e1, um1);
-        model_step<R, MODEL>(mc, u0, u1, dx, dy, th);                        // :154
+        model_step<R, MODEL>(mc, u0, u1, dx, dy, th, cth, sth);              // :154
+        if (s == 1 && (t2 & (kTrigResyncMask >> 1)) == (kTrigResyncMask >> 1)) Math<R>::sincos_(th, sth, cth);
         R c = running_cost<R>(cc, dx, dy, th, nomG0[t], nomG1[t], e0, e1);   // :160-161,180-184
         if (HAS_GRID) c += grid_cost<R>(cc, cells, dx, dy);
         acc += c;
@@ -236,26 +239,52 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
           run[t] = rr;
         }
       } else {
-        // screen: list every rollout within `margin` of the CTA's running minimum
+        // screen: keep every rollout within the window [m, lim] of the CTA's running minimum m.
+        // run[t] = (m, L): L is the tightest limit ever applied, so the list is guaranteed to hold
+        // EVERY rollout of this CTA with V <= L.  Normally lim = m + margin; if more than kMaxCand
+        // rollouts fall inside, the window is halved until they fit (the reduce kernel checks that L
+        // still covers the window of the GLOBAL minimum, else the step is redone in fp64).
         Vec4 rr = run[t];
         const R mnew = Math<R>::min_(rr.x, mtile);
-        int cnt = ccount[t];
-        const size_t slot0 = ((size_t)t * nCTA + cta) * kMaxCand;
+        const int cnt_old = ccount[t];
+        uint2* list = a.cand + ((size_t)t * nCTA + cta) * kMaxCand;
+        uint2 old = make_uint2(0u, 0x7f800000u);
+        if (lane < cnt_old) old = list[lane];
+        const R oldv = R(__uint_as_float(old.y));
+        R lim = mnew + margin;
+        int total = 0;
+        for (int it = 0;; ++it) {
+          total = __popc(__ballot_sync(0xffffffffu, oldv <= lim));
+#pragma unroll
+          for (int j = 0; j < J; ++j) total += __popc(__ballot_sync(0xffffffffu, v[j] <= lim));
+          if (total <= kMaxCand || it >= 30) break;
+          lim = mnew + (lim - mnew) * R(0.5);
+        }
+        if (total > kMaxCand) lim = -Math<R>::inf();    // > kMaxCand exact ties: force the fp64 redo
+        __syncwarp();
+        int pos = 0;
+        {
+          const bool keep = oldv <= lim;
+          const unsigned ball = __ballot_sync(0xffffffffu, keep);
+          if (keep) list[__popc(ball & ((1u << lane) - 1u))] = old;
+          pos = __popc(ball);
+        }
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-          const bool hit = v[j] <= mnew + margin;
+          const bool hit = v[j] <= lim;
           const unsigned ball = __ballot_sync(0xffffffffu, hit);
           if (hit) {
-            const int pos = cnt + __popc(ball & ((1u << lane) - 1u));
-            if (pos < kMaxCand)
-              a.cand[slot0 + pos] = make_uint2((unsigned)(tile * BLOCK + lane + 32 * j), __float_as_uint((float)v[j]));
+            const int p = pos + __popc(ball & ((1u << lane) - 1u));
+            if (p < kMaxCand)
+              list[p] = make_uint2((unsigned)(tile * BLOCK + lane + 32 * j), __float_as_uint((float)v[j]));
           }
-          cnt += __popc(ball);
+          pos += __popc(ball);
         }
         if (lane == 0) {
           rr.x = mnew;
+          rr.y = Math<R>::min_(rr.y, lim);
           run[t] = rr;
-          ccount[t] = cnt;
+          ccount[t] = pos < kMaxCand ? pos : kMaxCand;
         }
       }
       __syncwarp();
@@ -277,6 +306,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     } else {
       a.cand_count[idx] = ccount[t];
       a.cand_min[idx] = (float)run[t].x;
+      a.cand_lim[idx] = (float)run[t].y;
     }
     a.epart[2 * idx] = sp.noise_external ? ed[2 * t] : (double)ez64[2 * t];
     a.epart[2 * idx + 1] = sp.noise_external ? ed[2 * t + 1] : (double)ez64[2 * t + 1];
