@@ -14,7 +14,7 @@ namespace mppi {
 constexpr int kMaxCand = 16;        // SCREEN: candidate slots per (CTA, t)
 constexpr int kMaxRefine = 256;     // SCREEN: fp64 re-evaluations per t after the global filter
 constexpr int kRecordStride = 6;    // doubles per t in an exchange record: m, S, N0, N1, E0, E1
-constexpr double kZFixScale = 1048576.0;   // 2^20: fixed-point scale of the floor-term noise sums
+constexpr double kZFixScale = 128.0;       // 2^7: fixed-point scale of the floor-term noise sums (two 16-bit fields per REDUX)
 
 enum RolloutMode { MODE_SOFTMIN = 0, MODE_SCREEN = 1 };
 
@@ -112,12 +112,13 @@ template <> struct Math<float> {
   }
   // theta - (ceil((theta+pi)/(2pi)) - 1) * 2pi   (control/src/mppi:52-53), 2pi split hi/lo.
   // The expression is the identity on (-pi, pi], so it is only evaluated outside that interval.
+  static __device__ __noinline__ float wrap_slow_(float th) {
+    float n = ceilf((th + pi()) * inv_2pi()) - 1.0f;
+    float r = fmaf(-n, 6.28318548202514648f, th);
+    return fmaf(n, 1.74845553146951715e-07f, r);
+  }
   static __device__ __forceinline__ float wrap_(float th) {
-    if (th > pi() || th <= -pi()) {
-      float n = ceilf((th + pi()) * inv_2pi()) - 1.0f;
-      float r = fmaf(-n, 6.28318548202514648f, th);
-      th = fmaf(n, 1.74845553146951715e-07f, r);
-    }
+    if (th > pi() || th <= -pi()) th = wrap_slow_(th);
     return th;
   }
 };
@@ -202,6 +203,11 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // 4 standard normals (fp32) = the z of (t=2*t2: ch0, ch1), (t=2*t2+1: ch0, ch1).  Box-Muller on the
 // SFU pipe (lg2, rsqrt/sqrt, sin, cos).  Bit-identical wherever it is called from (intrinsics only,
@@ -213,15 +219,14 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsign
   uint4 r = philox4x32_10(ctr, key);
   const float S = 2.3283064365386963e-10f;   // 2^-32
   float u0 = __fmaf_rn((float)r.x, S, 1.1641532182693481e-10f);   // (0,1]
-  float u1 = __fmul_rn((float)r.y, S);
   float u2 = __fmaf_rn((float)r.z, S, 1.1641532182693481e-10f);
-  float u3 = __fmul_rn((float)r.w, S);
   // sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u): MUFU.LG2 + FMUL + MUFU.SQRT
-  float ra = sqrt_approx(__fmul_rn(-1.38629436111989062f, __log2f(u0)));
-  float rb = sqrt_approx(__fmul_rn(-1.38629436111989062f, __log2f(u2)));
+  float ra = sqrt_approx(__fmul_rn(-1.38629436111989062f, lg2_approx(u0)));
+  float rb = sqrt_approx(__fmul_rn(-1.38629436111989062f, lg2_approx(u2)));
   float sa, ca, sb, cb;
-  __sincosf(__fmul_rn(6.28318530717958648f, u1), &sa, &ca);
-  __sincosf(__fmul_rn(6.28318530717958648f, u3), &sb, &cb);
+  const float TWO_PI_2M32 = 1.46291807926715968e-09f;   // 2 pi * 2^-32
+  __sincosf(__fmul_rn((float)r.y, TWO_PI_2M32), &sa, &ca);
+  __sincosf(__fmul_rn((float)r.w, TWO_PI_2M32), &sb, &cb);
   return make_float4(__fmul_rn(ra, ca), __fmul_rn(ra, sa), __fmul_rn(rb, cb), __fmul_rn(rb, sb));
 }
 

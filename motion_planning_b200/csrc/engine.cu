@@ -60,6 +60,7 @@ struct mppi_engine {
   double* d_sg_rows = nullptr;
   double sg_a = 0, sg_b = 0;
   double *d_record = nullptr, *d_gather = nullptr, *d_record_tmp = nullptr;
+  unsigned int* d_done = nullptr;
   void* d_part = nullptr;
   double* d_epart = nullptr;
   int* d_cand_count = nullptr;
@@ -381,6 +382,8 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
   CKF(cudaMalloc(&e->d_record_tmp, (size_t)T * kRecordStride * sizeof(double)));
   CKF(cudaMalloc(&e->d_gather, (size_t)p.world_size * T * kRecordStride * sizeof(double)));
   CKF(cudaMalloc(&e->d_sg_rows, (size_t)4 * (T - 1) * sizeof(double)));
+  CKF(cudaMalloc(&e->d_done, sizeof(unsigned int)));
+  CKF(cudaMemset(e->d_done, 0, sizeof(unsigned int)));
   CKF(cudaMallocHost(&e->h_in, 6 * sizeof(double)));
   CKF(cudaMallocHost(&e->h_out, sizeof(DynState)));
   CKF(cudaMemset(e->d_Umaster, 0, 2 * T * sizeof(double)));     // uvec_init = zeros, control/src/mppi:65
@@ -429,6 +432,7 @@ extern "C" mppi_status mppi_destroy(mppi_handle e) {
   cudaFree(e->d_record_tmp);
   cudaFree(e->d_gather);
   cudaFree(e->d_sg_rows);
+  cudaFree(e->d_done);
   cudaFree(e->d_grid);
   cudaFree(e->d_eps_ext);
   cudaFree(e->d_vcap);
@@ -617,7 +621,28 @@ struct KernelEvents {
   bool on = false;
 };
 
-static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, KernelEvents* kev) {
+static FinalizeArgs make_fin(mppi_engine* e, bool closed_loop) {
+  FinalizeArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.sp = e->sp;
+  fa.dyn = e->d_dyn;
+  fa.gather = (e->sp.world > 1) ? e->d_gather : e->d_record;
+  fa.Umaster = e->d_Umaster;
+  fa.Ulast = e->d_Ulast;
+  fa.nomF = e->d_nomF;
+  fa.nomD = e->d_nomD;
+  fa.sg_rows = e->d_sg_rows;
+  fa.sg_a = e->sg_a;
+  fa.sg_b = e->sg_b;
+  fa.mode = 0;
+  fa.closed_loop = closed_loop ? 1 : 0;
+  return fa;
+}
+
+enum FuseMode { FUSE_NONE = 0, FUSE_STEP = 1, FUSE_LOOP = 2 };
+
+// rollout + reduce (+ finalize fused into the reduce kernel's last block when fuse != FUSE_NONE)
+static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, int fuse, KernelEvents* kev) {
   const int kind = kind_of(precision);
   const KindCfg& c = e->cfg[kind];
   RolloutArgs ra;
@@ -641,7 +666,9 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   ReduceArgs rd;
   memset(&rd, 0, sizeof(rd));
   rd.sp = e->sp;
-  rd.dyn = e->d_dyn;
+  rd.fin = make_fin(e, fuse == FUSE_LOOP);
+  rd.fuse_finalize = (fuse != FUSE_NONE && e->sp.world == 1) ? 1 : 0;
+  rd.done_counter = e->d_done;
   rd.part = e->d_part;
   rd.epart = e->d_epart;
   rd.cand_count = e->d_cand_count;
@@ -662,22 +689,9 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   return MPPI_OK;
 }
 
+// stand-alone finalize (sharded steps: after the exchange)
 static mppi_status launch_finalize(mppi_engine* e, cudaStream_t st, bool closed_loop, KernelEvents* kev) {
-  FinalizeArgs fa;
-  memset(&fa, 0, sizeof(fa));
-  fa.sp = e->sp;
-  fa.dyn = e->d_dyn;
-  fa.gather = (e->sp.world > 1) ? e->d_gather : e->d_record;
-  fa.Umaster = e->d_Umaster;
-  fa.Ulast = e->d_Ulast;
-  fa.nomF = e->d_nomF;
-  fa.nomD = e->d_nomD;
-  fa.sg_rows = e->d_sg_rows;
-  fa.sg_a = e->sg_a;
-  fa.sg_b = e->sg_b;
-  fa.mode = 0;
-  fa.closed_loop = closed_loop ? 1 : 0;
-  CK(finalize_launch(st, fa));
+  CK(finalize_launch(st, make_fin(e, closed_loop)));
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[3], st));
   return MPPI_OK;
 }
@@ -693,8 +707,7 @@ static mppi_status build_graphs(mppi_engine* e) {
       cudaError_t ce = cudaMemcpyAsync(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream);
       if (ce != cudaSuccess) s = MPPI_ERR_CUDA;
     }
-    if (s == MPPI_OK) s = launch_local(e, e->stream, e->p.precision, nullptr);
-    if (s == MPPI_OK) s = launch_finalize(e, e->stream, which == 1, nullptr);
+    if (s == MPPI_OK) s = launch_local(e, e->stream, e->p.precision, which == 1 ? FUSE_LOOP : FUSE_STEP, nullptr);
     if (s == MPPI_OK && which == 0) {
       cudaError_t ce = cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream);
       if (ce != cudaSuccess) s = MPPI_ERR_CUDA;
@@ -726,12 +739,11 @@ static mppi_status finish_outputs(mppi_engine* e, double u_out[2], double x_next
   if (o->status == kStatusRedoF64) {
     // MIXED: a candidate list overflowed; redo this step entirely in fp64 (same noise: the step
     // counter was not advanced, U and x0 are untouched).
-    CKS(launch_local(e, e->stream, MPPI_PRECISION_F64, nullptr));
     if (e->sp.world > 1) {
       set_err("MIXED overflow in a sharded step: rerun with precision F64");
       return MPPI_ERR_UNSUPPORTED;
     }
-    CKS(launch_finalize(e, e->stream, false, nullptr));
+    CKS(launch_local(e, e->stream, MPPI_PRECISION_F64, FUSE_STEP, nullptr));
     CK(cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->last.refine_overflow += 1;
@@ -788,8 +800,7 @@ extern "C" mppi_status mppi_step(mppi_handle e, const double x0[3], double u_out
     CK(cudaGraphLaunch(e->g_step, e->stream));
   } else {
     CK(cudaMemcpyAsync(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    CKS(launch_local(e, e->stream, e->p.precision, nullptr));
-    CKS(launch_finalize(e, e->stream, false, nullptr));
+    CKS(launch_local(e, e->stream, e->p.precision, FUSE_STEP, nullptr));
     CK(cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream));
   }
   CK(cudaStreamSynchronize(e->stream));
@@ -804,7 +815,7 @@ extern "C" mppi_status mppi_step_local(mppi_handle e, const double x0[3]) {
   }
   CKS(pre_step(e, x0));
   CK(cudaMemcpyAsync(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-  CKS(launch_local(e, e->stream, e->p.precision, nullptr));
+  CKS(launch_local(e, e->stream, e->p.precision, FUSE_NONE, nullptr));
   e->local_pending = true;
   return MPPI_OK;
 }
@@ -932,7 +943,7 @@ extern "C" mppi_status mppi_cost_to_go(mppi_handle e, const double x0[3], const 
     e->sp.noise_external = 1;
     e->sp.capture = 1;
     if ((s = prep_nominal(e)) != MPPI_OK) break;
-    if ((s = launch_local(e, e->stream, MPPI_PRECISION_F64, nullptr)) != MPPI_OK) break;
+    if ((s = launch_local(e, e->stream, MPPI_PRECISION_F64, FUSE_NONE, nullptr)) != MPPI_OK) break;
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
       set_err("cost_to_go kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
       s = MPPI_ERR_CUDA;
@@ -1069,7 +1080,7 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
   mppi_timing t{};
   t.step_ms = (float)(total / steps);
   t.steps = steps;
-  t.launches = 3 * steps;
+  t.launches = 2 * steps;   // rollout + reduce (finalize is fused into the reduce kernel's last block)
   if (per_kernel) {
     KernelEvents kev;
     kev.on = true;
@@ -1077,8 +1088,8 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
     double acc[3] = {0, 0, 0};
     for (int i = 0; i < steps; ++i) {
       if (flush_l2) CK(cudaMemsetAsync(e->d_flush, i & 0xff, e->flush_bytes, e->stream));
-      CKS(launch_local(e, e->stream, e->p.precision, &kev));
-      CKS(launch_finalize(e, e->stream, true, &kev));
+      CKS(launch_local(e, e->stream, e->p.precision, FUSE_LOOP, &kev));
+      CK(cudaEventRecord(kev.ev[3], e->stream));
       CK(cudaStreamSynchronize(e->stream));
       for (int j = 0; j < 3; ++j) {
         float ms = 0;

@@ -38,10 +38,11 @@ size_t rollout_smem(int kind, int T, int block, int grid_bytes_in_smem) {
 }
 
 cudaError_t reduce_softmin_launch(bool f64, int T, cudaStream_t st, const ReduceArgs& a) {
+  const size_t smem = (size_t)4 * T * sizeof(double);
   if (f64)
-    reduce_softmin_kernel<double><<<T, 128, 0, st>>>(a);
+    reduce_softmin_kernel<double><<<T, 128, smem, st>>>(a);
   else
-    reduce_softmin_kernel<float><<<T, 128, 0, st>>>(a);
+    reduce_softmin_kernel<float><<<T, 128, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -58,12 +59,12 @@ cudaError_t reduce_screen_launch(int model, bool has_grid, int T, cudaStream_t s
       break;
     default: f = has_grid ? sfn_<MPPI_MODEL_BICYCLE, true>() : sfn_<MPPI_MODEL_BICYCLE, false>(); break;
   }
-  const size_t smem = (size_t)4 * 7 * T * sizeof(double);
+  const size_t smem = (size_t)8 * 7 * T * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  f<<<T, 128, smem, st>>>(a);
+  f<<<T, 256, smem, st>>>(a);
   return cudaGetLastError();
 }
 

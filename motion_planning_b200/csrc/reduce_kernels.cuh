@@ -422,12 +422,12 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   if (tid == 0) bad = 0;
   __syncthreads();
-  if (a.mode == 0 && a.fin.dyn->refine_overflow) {
+  if (a.mode == 0 && a.dyn->refine_overflow) {
     // MIXED: the fp32 screen overflowed a candidate list -> leave U, the step counter and x0
     // untouched and ask the host to redo this step with the fp64 pipeline (same noise).
     __syncthreads();
     if (tid == 0) {
-      DynState* d = a.fin.dyn;
+      DynState* d = a.dyn;
       d->status = kStatusRedoF64;
       d->overflow_total += 1;
       d->refine_candidates = 0;
@@ -437,22 +437,25 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
     return;
   }
   // -- merge the records of all ranks and apply the weighted noise (control/src/mppi:189-199) ----
-  const double neg_inv_lam = -1.0 / a.fin.dyn->lam;
+  const double neg_inv_lam = -1.0 / a.dyn->lam;
   for (int idx = tid; idx < 2 * T; idx += blockDim.x) {
     const int c = idx / T, t = idx - c * T;
     double m = Math<double>::inf();
-    for (int g = 0; g < sp.world; ++g) m = fmin(m, a.gather[((size_t)g * T + t) * kRecordStride]);
+    for (int g = 0; g < sp.world; ++g) m = fmin(m, __ldcg(&a.gather[((size_t)g * T + t) * kRecordStride]));
     double S = 0, N = 0, E = 0;
     for (int g = 0; g < sp.world; ++g) {
       const double* r = a.gather + ((size_t)g * T + t) * kRecordStride;
-      const double sc = (r[0] == m) ? 1.0 : exp((r[0] - m) * neg_inv_lam);
-      S += r[1] * sc;
-      N += r[2 + c] * sc;
-      E += r[4 + c];
+      const double rm = __ldcg(r);
+      const double sc = (rm == m) ? 1.0 : exp((rm - m) * neg_inv_lam);
+      S += __ldcg(r + 1) * sc;
+      N += __ldcg(r + 2 + c) * sc;
+      E += __ldcg(r + 4 + c);
     }
     const double dU = (N + sp.eps_floor * E) / (S + sp.eps_floor * (double)sp.k_total);
     const double u = a.Umaster[c * T + t] + dU;
-    if (!isfinite(u)) atomicOr(&bad, 1);
+    // the reference lets NaN propagate silently; here a non-finite input or an empty
+    // softmin support (S == 0 can only come from NaN costs) is reported as MPPI_ERR_NONFINITE
+    if (!isfinite(u) || !(S > 0.0)) atomicOr(&bad, 1);
     Us[c * T + t] = clamp_<double>(u, sp.u_max[c]);                          // :198-199
   }
   __syncthreads();
@@ -486,10 +489,10 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       const double u1 = (t + 1 < T) ? Uf[T + t + 1] : 0.0;
       a.Umaster[t] = u0;
       a.Umaster[T + t] = u1;
-      write_nominal_block(a.fin.dyn, T, t, u0, u1, a.nomF, a.nomD);
+      write_nominal_block(a.dyn, T, t, u0, u1, a.nomF, a.nomD);
     }
     if (tid == 0) {
-      DynState* d = a.fin.dyn;
+      DynState* d = a.dyn;
       double xn[3];
       model_step_dispatch_f64(sp, d->x0, Uf[0], Uf[T], xn);
       d->out_u[0] = Uf[0];
@@ -504,8 +507,8 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
         d->x0[1] = xn[1];
         d->x0[2] = xn[2];
       }
-      d->last_candidates = d->refine_candidates;
-      d->last_max_dev = d->refine_max_dev;
+      d->last_candidates = __ldcg(&d->refine_candidates);
+      d->last_max_dev = __ldcg(&d->refine_max_dev);
       d->refine_candidates = 0;
       d->refine_overflow = 0;
       d->refine_max_dev = 0.0;

@@ -5,10 +5,12 @@
 //
 // One thread integrates one rollout for all T steps (state in registers); a CTA owns tiles of BLOCK
 // rollouts and is persistent over tiles.  The only per-(k,t) data that leaves the registers is the
-// running prefix cost, kept in a shared-memory tile P[T][BLOCK] (conflict-free: consecutive threads,
-// consecutive banks).  After the T steps the tile is consumed TRANSPOSED: warp w reduces rows
-// t = w, w+NW, ... over the BLOCK rollouts, with cost-to-go V[t,k] = Tot[k] - P[t-1,k]
-// (= sum_{t'>=t} c[t',k], control/src/mppi:175).  Nothing of size K*T is written to HBM.
+// running prefix cost, kept in a shared-memory tile P[T][BLOCK+1] (row stride BLOCK+1 makes both the
+// column-wise writes of the rollout loop and the row-wise reads below bank-conflict free).  After the
+// T steps the tile is consumed TRANSPOSED: LANE l of a warp owns row t = 32*chunk + l and walks the
+// BLOCK rollouts serially, with cost-to-go V[t,k] = Tot[k] - P[t-1,k] (= sum_{t'>=t} c[t',k],
+// control/src/mppi:175) -- 32 time steps are reduced at once with no shuffles.  Nothing of size K*T
+// is written to HBM.
 //
 //   MODE_SOFTMIN: per (CTA, t) online-softmin partial (m, S, N0, N1): m = min V, S = sum e,
 //                 N = sum e*eps[t], e = exp(-(V-m)/lam) (control/src/mppi:189-196).  eps is
@@ -17,7 +19,8 @@
 //                 the softmin) are listed for fp64 re-evaluation by the reduce kernel.
 //
 // The floor term of the weights (+1e-8 per rollout, :193) needs E[t] = sum_k eps[t,k]; it is
-// accumulated exactly in fixed point (2^-20) with one REDUX (warp integer add) per step.
+// accumulated in fixed point (2^-7, both channels packed into one int) with ONE REDUX (warp integer
+// add) per step; integer sums make the term independent of the summation order / sharding.
 #pragma once
 #include "common.cuh"
 #include "reduce_kernels_args.h"
@@ -30,11 +33,37 @@ __device__ __forceinline__ R load_eps_ext(const double* __restrict__ eps, int t,
   return R(eps[((size_t)t * 2 + c) * (size_t)K + k]);
 }
 
+// SCREEN slow path (rare): more than kMaxCand rollouts inside the window -> halve the window until the
+// old list entries plus this tile's rollouts fit, then rebuild the list.  One lane, sequential.
+template <typename R>
+__device__ __noinline__ int screen_tighten(uint2* list, int cnt_old, const R* tot, const R* pre, int block, int tile_base,
+                                           R mnew, R& lim) {
+  int total = 0;
+  for (int it = 0; it < 31; ++it) {
+    lim = mnew + (lim - mnew) * R(0.5);
+    total = 0;
+    for (int i = 0; i < cnt_old; ++i) total += (R(__uint_as_float(list[i].y)) <= lim) ? 1 : 0;
+    for (int k = 0; k < block; ++k) total += ((tot[k] - (pre ? pre[k] : R(0))) <= lim) ? 1 : 0;
+    if (total <= kMaxCand) break;
+  }
+  if (total > kMaxCand) lim = -Math<R>::inf();   // > kMaxCand exact ties: force the fp64 redo
+  int n = 0;
+  for (int i = 0; i < cnt_old; ++i) {
+    const uint2 e = list[i];
+    if (R(__uint_as_float(e.y)) <= lim) list[n++] = e;
+  }
+  for (int k = 0; k < block; ++k) {
+    const R v = tot[k] - (pre ? pre[k] : R(0));
+    if (v <= lim && n < kMaxCand) list[n++] = make_uint2((unsigned)(tile_base + k), __float_as_uint((float)v));
+  }
+  return n;
+}
+
 template <typename R, int MODEL, int MODE, bool HAS_GRID, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ RolloutArgs a) {
   typedef typename Math<R>::Vec4 Vec4;
   constexpr int NW = BLOCK / 32;
-  constexpr int J = BLOCK / 32;
+  constexpr int PS = BLOCK + 1;   // padded row stride of the cost tile
   const StaticParams& sp = a.sp;
   const int T = sp.T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -60,8 +89,8 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
   int* ccount = reinterpret_cast<int*>(smem_raw + off);                       // [T] SCREEN counts
   off += (size_t)T * sizeof(int);
   off = (off + 15) & ~(size_t)15;
-  R* P = reinterpret_cast<R*>(smem_raw + off);                                // [T][BLOCK]
-  off += (size_t)T * BLOCK * sizeof(R);
+  R* P = reinterpret_cast<R*>(smem_raw + off);                                // [T][BLOCK+1]
+  off += (size_t)T * PS * sizeof(R);
   off = (off + 15) & ~(size_t)15;
   signed char* gcells = reinterpret_cast<signed char*>(smem_raw + off);       // grid copy (optional)
 
@@ -102,6 +131,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
   const R neg_inv_lam = R(-1.0 / a.dyn->lam);
   const R margin = R(sp.margin);
   const signed char* cells = grid_smem ? gcells : a.grid;
+  const bool cost_to_go = sp.weighting == MPPI_WEIGHT_COST_TO_GO;
   mbar_wait(bar, 0);
   __syncthreads();
 
@@ -112,6 +142,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     R dx = R(0), dy = R(0), th = cc.th0, acc = R(0);
     R cth, sth;
     Math<R>::sincos_(th, sth, cth);
+    int eown = 0;   // packed fixed-point floor sums of the step this lane owns in the current 32-step chunk
 
     // ---- the T-step rollout (hot loop 1, control/src/mppi:136-163) ----------------------------
     for (int t2 = 0; t2 < (T >> 1); ++t2) {
@@ -137,15 +168,11 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
         const int t = 2 * t2 + s;
         const R e0 = ev[2 * s], e1 = ev[2 * s + 1];
         if (!sp.noise_external) {
-          // floor-term sums: exact fixed-point warp reduction (REDUX), one smem atomic per warp
-          int f0 = valid ? __float2int_rn(zf[2 * s] * (float)kZFixScale) : 0;
-          int f1 = valid ? __float2int_rn(zf[2 * s + 1] * (float)kZFixScale) : 0;
-          f0 = __reduce_add_sync(0xffffffffu, f0);
-          f1 = __reduce_add_sync(0xffffffffu, f1);
-          if (lane == 0) {
-            atomicAdd(&ez32[2 * t], f0);
-            atomicAdd(&ez32[2 * t + 1], f1);
-          }
+          // floor-term sums: both channels packed as q0 * 65536 + q1 (|q| <= 866, 32 lanes fit 16 bits),
+          // ONE warp integer add (REDUX); the lane with lane == t mod 32 keeps the warp sum of step t
+          int q = __float2int_rn(zf[2 * s] * (float)kZFixScale) * 65536 + __float2int_rn(zf[2 * s + 1] * (float)kZFixScale);
+          q = __reduce_add_sync(0xffffffffu, valid ? q : 0);
+          if (lane == (t & 31)) eown = q;
         }
         // u_samp = clip(U[:,t] + eps)   control/src/mppi:147-152 (eps itself stays unclipped)
         const R u0 = clamp_<R>(nomU0[t] + e0, um0);
@@ -155,139 +182,109 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
         R c = running_cost<R>(cc, dx, dy, th, nomG0[t], nomG1[t], e0, e1);   // :160-161,180-184
         if (HAS_GRID) c += grid_cost<R>(cc, cells, dx, dy);
         acc += c;
-        P[t * BLOCK + tid] = acc;
+        P[t * PS + tid] = acc;
+      }
+      if (!sp.noise_external && ((t2 & 15) == 15 || t2 == (T >> 1) - 1)) {
+        // end of a 32-step chunk: every lane flushes the step it owns
+        const int town = ((2 * t2 + 1) & ~31) + lane;
+        if (town < T) {
+          const int q1 = (int)(short)(eown & 0xffff);
+          const int q0 = (eown - q1) >> 16;
+          atomicAdd(&ez32[2 * town], q0);
+          atomicAdd(&ez32[2 * town + 1], q1);
+        }
       }
     }
     acc += terminal_cost<R>(cc, dx, dy, th);                                 // :165-171
     if (!valid) acc = Math<R>::inf();
-    P[(T - 1) * BLOCK + tid] = acc;   // row T-1 holds the rollout total Tot[k]
+    P[(T - 1) * PS + tid] = acc;   // row T-1 holds the rollout total Tot[k]
     __syncthreads();
 
-    // ---- transposed pass: warp w owns rows t = w, w+NW, ... ------------------------------------
-    for (int t = warp; t < T; t += NW) {
-      R v[J];
-      R mloc = Math<R>::inf();
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const int col = lane + 32 * j;
-        const R tot = P[(T - 1) * BLOCK + col];
-        const R pre = (t > 0 && sp.weighting == MPPI_WEIGHT_COST_TO_GO) ? P[(t - 1) * BLOCK + col] : R(0);
-        v[j] = tot - pre;                                                    // cost-to-go, :175
-        mloc = Math<R>::min_(mloc, v[j]);
-      }
-      if (sp.capture) {
-        R* vc = reinterpret_cast<R*>(a.vcap);
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const int kk = tile * BLOCK + lane + 32 * j;
-          if (kk < sp.K) vc[(size_t)t * sp.K + kk] = v[j];
+    // ---- transposed pass: lane l of warp w owns row t = 32*(w + NW*i) + l ----------------------
+    for (int tb = warp * 32; tb < T; tb += NW * 32) {
+      const int t = tb + lane;
+      if (t < T) {
+        const R* tot = P + (size_t)(T - 1) * PS;
+        const R* pre = (t > 0 && cost_to_go) ? P + (size_t)(t - 1) * PS : nullptr;
+        const int tile_base = tile * BLOCK;
+        const int nk = min(BLOCK, sp.K - tile_base);
+        R m = Math<R>::inf();
+        if (pre) {
+#pragma unroll 8
+          for (int k = 0; k < BLOCK; ++k) m = Math<R>::min_(m, tot[k] - pre[k]);   // cost-to-go, :175
+        } else {
+#pragma unroll 8
+          for (int k = 0; k < BLOCK; ++k) m = Math<R>::min_(m, tot[k]);
         }
-      }
-      if (sp.noise_external) {   // floor sums straight from the replayed noise
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const int kk = tile * BLOCK + lane + 32 * j;
-          if (kk < sp.K) {
-            s0 += a.eps_ext[((size_t)t * 2 + 0) * sp.K + kk];
-            s1 += a.eps_ext[((size_t)t * 2 + 1) * sp.K + kk];
+        if (sp.capture) {
+          R* vc = reinterpret_cast<R*>(a.vcap) + (size_t)t * sp.K + tile_base;
+          for (int k = 0; k < nk; ++k) vc[k] = tot[k] - (pre ? pre[k] : R(0));
+        }
+        if (sp.noise_external) {   // floor sums straight from the replayed noise
+          const double* e0p = a.eps_ext + ((size_t)t * 2 + 0) * sp.K + tile_base;
+          const double* e1p = a.eps_ext + ((size_t)t * 2 + 1) * sp.K + tile_base;
+          double s0 = 0.0, s1 = 0.0;
+          for (int k = 0; k < nk; ++k) {
+            s0 += e0p[k];
+            s1 += e1p[k];
           }
-        }
-        s0 = warp_sum<double>(s0);
-        s1 = warp_sum<double>(s1);
-        if (lane == 0) {
           ed[2 * t] += s0;
           ed[2 * t + 1] += s1;
         }
-      }
-      const R mtile = warp_min<R>(mloc);
-      if (MODE == MODE_SOFTMIN) {
-        // online softmin: weights relative to the running minimum of this CTA (:189-196)
         Vec4 rr = run[t];
-        const R mnew = Math<R>::min_(rr.x, mtile);
-        R S = R(0), N0 = R(0), N1 = R(0);
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const R arg = (v[j] - mnew) * neg_inv_lam;           // <= 0
-          if (arg > R(-80)) {                                   // e^-80 ~ 2e-35: below any rounding
-            const R e = Math<R>::exp_(arg);
-            const int kk = tile * BLOCK + lane + 32 * j;
-            R e0, e1;
-            if (sp.noise_external) {
-              e0 = load_eps_ext<R>(a.eps_ext, t, 0, sp.K, kk);
-              e1 = load_eps_ext<R>(a.eps_ext, t, 1, sp.K, kk);
-            } else {
-              float f0, f1;
-              philox_eps(sp.seed, (unsigned long long)(sp.k_offset + kk), t, step, std0, std1, f0, f1);
-              e0 = R(f0);
-              e1 = R(f1);
+        const R mnew = Math<R>::min_(rr.x, m);
+        if (MODE == MODE_SOFTMIN) {
+          // online softmin: weights relative to the running minimum of this CTA (:189-196)
+          R S = R(0), N0 = R(0), N1 = R(0);
+          for (int k = 0; k < BLOCK; ++k) {
+            const R arg = ((tot[k] - (pre ? pre[k] : R(0))) - mnew) * neg_inv_lam;   // <= 0
+            if (arg > R(-80)) {                                   // e^-80 ~ 2e-35: below any rounding
+              const R e = Math<R>::exp_(arg);
+              R e0, e1;
+              if (sp.noise_external) {
+                e0 = load_eps_ext<R>(a.eps_ext, t, 0, sp.K, tile_base + k);
+                e1 = load_eps_ext<R>(a.eps_ext, t, 1, sp.K, tile_base + k);
+              } else {
+                float f0, f1;
+                philox_eps(sp.seed, (unsigned long long)(sp.k_offset + tile_base + k), t, step, std0, std1, f0, f1);
+                e0 = R(f0);
+                e1 = R(f1);
+              }
+              S += e;
+              N0 = Math<R>::fma_(e, e0, N0);
+              N1 = Math<R>::fma_(e, e1, N1);
             }
-            S += e;
-            N0 = Math<R>::fma_(e, e0, N0);
-            N1 = Math<R>::fma_(e, e1, N1);
           }
-        }
-        S = warp_sum<R>(S);
-        N0 = warp_sum<R>(N0);
-        N1 = warp_sum<R>(N1);
-        if (lane == 0) {
           const R sc = (rr.x == mnew) ? R(1) : Math<R>::exp_((rr.x - mnew) * neg_inv_lam);
           rr.y = Math<R>::fma_(rr.y, sc, S);
           rr.z = Math<R>::fma_(rr.z, sc, N0);
           rr.w = Math<R>::fma_(rr.w, sc, N1);
           rr.x = mnew;
           run[t] = rr;
-        }
-      } else {
-        // screen: keep every rollout within the window [m, lim] of the CTA's running minimum m.
-        // run[t] = (m, L): L is the tightest limit ever applied, so the list is guaranteed to hold
-        // EVERY rollout of this CTA with V <= L.  Normally lim = m + margin; if more than kMaxCand
-        // rollouts fall inside, the window is halved until they fit (the reduce kernel checks that L
-        // still covers the window of the GLOBAL minimum, else the step is redone in fp64).
-        Vec4 rr = run[t];
-        const R mnew = Math<R>::min_(rr.x, mtile);
-        const int cnt_old = ccount[t];
-        uint2* list = a.cand + ((size_t)t * nCTA + cta) * kMaxCand;
-        uint2 old = make_uint2(0u, 0x7f800000u);
-        if (lane < cnt_old) old = list[lane];
-        const R oldv = R(__uint_as_float(old.y));
-        R lim = mnew + margin;
-        int total = 0;
-        for (int it = 0;; ++it) {
-          total = __popc(__ballot_sync(0xffffffffu, oldv <= lim));
-#pragma unroll
-          for (int j = 0; j < J; ++j) total += __popc(__ballot_sync(0xffffffffu, v[j] <= lim));
-          if (total <= kMaxCand || it >= 30) break;
-          lim = mnew + (lim - mnew) * R(0.5);
-        }
-        if (total > kMaxCand) lim = -Math<R>::inf();    // > kMaxCand exact ties: force the fp64 redo
-        __syncwarp();
-        int pos = 0;
-        {
-          const bool keep = oldv <= lim;
-          const unsigned ball = __ballot_sync(0xffffffffu, keep);
-          if (keep) list[__popc(ball & ((1u << lane) - 1u))] = old;
-          pos = __popc(ball);
-        }
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const bool hit = v[j] <= lim;
-          const unsigned ball = __ballot_sync(0xffffffffu, hit);
-          if (hit) {
-            const int p = pos + __popc(ball & ((1u << lane) - 1u));
-            if (p < kMaxCand)
-              list[p] = make_uint2((unsigned)(tile * BLOCK + lane + 32 * j), __float_as_uint((float)v[j]));
+        } else {
+          // screen: keep every rollout within the window [m, lim] of the CTA's running minimum m.
+          // run[t] = (m, L): L is the tightest limit ever applied, so the list is guaranteed to hold
+          // EVERY rollout of this CTA with V <= L.  Normally lim = m + margin; if more than kMaxCand
+          // rollouts fall inside, the window is halved until they fit (the reduce kernel checks that L
+          // still covers the window of the GLOBAL minimum, else the step is redone in fp64).
+          R lim = mnew + margin;
+          uint2* list = a.cand + ((size_t)t * nCTA + cta) * kMaxCand;
+          const int cnt_old = ccount[t];
+          int cnt = cnt_old;
+          for (int k = 0; k < BLOCK; ++k) {
+            const R v = tot[k] - (pre ? pre[k] : R(0));
+            if (v <= lim) {
+              if (cnt < kMaxCand) list[cnt] = make_uint2((unsigned)(tile_base + k), __float_as_uint((float)v));
+              ++cnt;
+            }
           }
-          pos += __popc(ball);
-        }
-        if (lane == 0) {
+          if (cnt > kMaxCand) cnt = screen_tighten<R>(list, cnt_old, tot, pre, BLOCK, tile_base, mnew, lim);
           rr.x = mnew;
           rr.y = Math<R>::min_(rr.y, lim);
           run[t] = rr;
-          ccount[t] = pos < kMaxCand ? pos : kMaxCand;
+          ccount[t] = cnt;
         }
       }
-      __syncwarp();
     }
     __syncthreads();
     // fold the per-tile fixed-point sums into the CTA's 64-bit accumulators
@@ -324,7 +321,7 @@ inline size_t rollout_smem_bytes(int T, int block, int grid_bytes_padded_in_smem
   off += (size_t)T * 2 * sizeof(int);
   off += (size_t)T * sizeof(int);
   off = (off + 15) & ~(size_t)15;
-  off += (size_t)T * block * sizeof(R);
+  off += (size_t)T * (block + 1) * sizeof(R);
   off = (off + 15) & ~(size_t)15;
   off += (size_t)grid_bytes_padded_in_smem;
   return off + 128;   // slack for the 128 B alignment of the dynamic segment

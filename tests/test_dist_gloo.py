@@ -66,12 +66,13 @@ def _worker(rank, world, port, K, T, q):
 
 
 @pytest.mark.parametrize("K,T", [(1000, 16), (257, 8)])
+@pytest.mark.timeout(300)
 def test_two_rank_shard_exchange_merge(K, T):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    ctx = tmp.get_context("spawn")
+    ctx = tmp.get_context("fork")       # fork: the children inherit the already-imported torch (fast)
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, K, T, q)) for r in range(2)]
     for pr in procs:
