@@ -14,7 +14,7 @@ namespace mppi {
 constexpr int kMaxCand = 16;        // SCREEN: candidate slots per (CTA, t)
 constexpr int kMaxRefine = 256;     // SCREEN: fp64 re-evaluations per t after the global filter
 constexpr int kRecordStride = 6;    // doubles per t in an exchange record: m, S, N0, N1, E0, E1
-constexpr double kZFixScale = 128.0;       // 2^7: fixed-point scale of the floor-term noise sums (two 16-bit fields per REDUX)
+constexpr double kZFixScale = 1048576.0;   // 2^20: fixed-point scale of the floor-term noise sums
 
 enum RolloutMode { MODE_SOFTMIN = 0, MODE_SCREEN = 1 };
 

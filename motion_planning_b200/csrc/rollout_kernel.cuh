@@ -19,8 +19,8 @@
 //                 the softmin) are listed for fp64 re-evaluation by the reduce kernel.
 //
 // The floor term of the weights (+1e-8 per rollout, :193) needs E[t] = sum_k eps[t,k]; it is
-// accumulated in fixed point (2^-7, both channels packed into one int) with ONE REDUX (warp integer
-// add) per step; integer sums make the term independent of the summation order / sharding.
+// accumulated exactly in fixed point (2^-20) with one REDUX (warp integer add) per channel and step;
+// integer sums make the term independent of the summation order / sharding.
 #pragma once
 #include "common.cuh"
 #include "reduce_kernels_args.h"
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     R dx = R(0), dy = R(0), th = cc.th0, acc = R(0);
     R cth, sth;
     Math<R>::sincos_(th, sth, cth);
-    int eown = 0;   // packed fixed-point floor sums of the step this lane owns in the current 32-step chunk
+    int eown0 = 0, eown1 = 0;   // fixed-point floor sums of the step this lane owns in the current 32-step chunk
 
     // ---- the T-step rollout (hot loop 1, control/src/mppi:136-163) ----------------------------
     for (int t2 = 0; t2 < (T >> 1); ++t2) {
@@ -168,11 +168,16 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
         const int t = 2 * t2 + s;
         const R e0 = ev[2 * s], e1 = ev[2 * s + 1];
         if (!sp.noise_external) {
-          // floor-term sums: both channels packed as q0 * 65536 + q1 (|q| <= 866, 32 lanes fit 16 bits),
-          // ONE warp integer add (REDUX); the lane with lane == t mod 32 keeps the warp sum of step t
-          int q = __float2int_rn(zf[2 * s] * (float)kZFixScale) * 65536 + __float2int_rn(zf[2 * s + 1] * (float)kZFixScale);
-          q = __reduce_add_sync(0xffffffffu, valid ? q : 0);
-          if (lane == (t & 31)) eown = q;
+          // floor-term sums: exact fixed point (2^-20, |z| < 8 so 32 lanes fit an int), one warp integer
+          // add (REDUX) per channel; the lane with lane == t mod 32 keeps the warp sums of step t
+          int q0 = valid ? __float2int_rn(zf[2 * s] * (float)kZFixScale) : 0;
+          int q1 = valid ? __float2int_rn(zf[2 * s + 1] * (float)kZFixScale) : 0;
+          q0 = __reduce_add_sync(0xffffffffu, q0);
+          q1 = __reduce_add_sync(0xffffffffu, q1);
+          if (lane == (t & 31)) {
+            eown0 = q0;
+            eown1 = q1;
+          }
         }
         // u_samp = clip(U[:,t] + eps)   control/src/mppi:147-152 (eps itself stays unclipped)
         const R u0 = clamp_<R>(nomU0[t] + e0, um0);
@@ -188,10 +193,8 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
         // end of a 32-step chunk: every lane flushes the step it owns
         const int town = ((2 * t2 + 1) & ~31) + lane;
         if (town < T) {
-          const int q1 = (int)(short)(eown & 0xffff);
-          const int q0 = (eown - q1) >> 16;
-          atomicAdd(&ez32[2 * town], q0);
-          atomicAdd(&ez32[2 * town + 1], q1);
+          atomicAdd(&ez32[2 * town], eown0);
+          atomicAdd(&ez32[2 * town + 1], eown1);
         }
       }
     }
