@@ -100,9 +100,10 @@ template <> struct Math<float> {
     c = ((q + 1) & 2) ? -cc : cc;
   }
   // sin/cos of an angle INCREMENT: polynomials only when |a| <= pi/4 (always, for sane dt * yaw rate)
+  static __device__ __noinline__ void sincos_cold_(float x, float& s, float& c) { sincos_(x, s, c); }
   static __device__ __forceinline__ void sincos_small_(float a, float& s, float& c) {
     if (fabsf(a) > 0.78539816f) {
-      sincos_(a, s, c);
+      sincos_cold_(a, s, c);
       return;
     }
     const float z = a * a;

@@ -63,10 +63,8 @@ struct mppi_engine {
   unsigned int* d_done = nullptr;
   void* d_part = nullptr;
   double* d_epart = nullptr;
-  int* d_cand_count = nullptr;
+  float4* d_cand_meta = nullptr;
   uint2* d_cand = nullptr;
-  float* d_cand_min = nullptr;
-  float* d_cand_lim = nullptr;
   size_t part_capacity_ctas = 0;
   signed char* d_grid = nullptr;
   double* d_eps_ext = nullptr;
@@ -145,16 +143,12 @@ static double default_margin(const mppi_engine* e, double lam) {
 static void free_partials(mppi_engine* e) {
   cudaFree(e->d_part);
   cudaFree(e->d_epart);
-  cudaFree(e->d_cand_count);
+  cudaFree(e->d_cand_meta);
   cudaFree(e->d_cand);
-  cudaFree(e->d_cand_min);
-  cudaFree(e->d_cand_lim);
   e->d_part = nullptr;
   e->d_epart = nullptr;
-  e->d_cand_count = nullptr;
+  e->d_cand_meta = nullptr;
   e->d_cand = nullptr;
-  e->d_cand_min = nullptr;
-  e->d_cand_lim = nullptr;
   e->part_capacity_ctas = 0;
 }
 
@@ -222,10 +216,8 @@ static mppi_status configure(mppi_engine* e) {
     const size_t n = (size_t)sp.T * max_ctas;
     CK(cudaMalloc(&e->d_part, n * sizeof(double4)));
     CK(cudaMalloc(&e->d_epart, n * 2 * sizeof(double)));
-    CK(cudaMalloc(&e->d_cand_count, n * sizeof(int)));
+    CK(cudaMalloc(&e->d_cand_meta, n * sizeof(float4)));
     CK(cudaMalloc(&e->d_cand, n * kMaxCand * sizeof(uint2)));
-    CK(cudaMalloc(&e->d_cand_min, n * sizeof(float)));
-    CK(cudaMalloc(&e->d_cand_lim, n * sizeof(float)));
     e->part_capacity_ctas = max_ctas;
   }
   return drop_graphs(e);
@@ -654,10 +646,8 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   ra.eps_ext = e->d_eps_ext;
   ra.part = e->d_part;
   ra.epart = e->d_epart;
-  ra.cand_count = e->d_cand_count;
+  ra.cand_meta = e->d_cand_meta;
   ra.cand = e->d_cand;
-  ra.cand_min = e->d_cand_min;
-  ra.cand_lim = e->d_cand_lim;
   ra.vcap = e->d_vcap;
   ra.ntiles = c.ntiles;
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[0], st));
@@ -671,10 +661,8 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   rd.done_counter = e->d_done;
   rd.part = e->d_part;
   rd.epart = e->d_epart;
-  rd.cand_count = e->d_cand_count;
+  rd.cand_meta = e->d_cand_meta;
   rd.cand = e->d_cand;
-  rd.cand_min = e->d_cand_min;
-  rd.cand_lim = e->d_cand_lim;
   rd.nomD = e->d_nomD;
   rd.grid = e->d_grid;
   rd.eps_ext = e->d_eps_ext;

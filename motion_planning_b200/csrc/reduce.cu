@@ -40,9 +40,9 @@ size_t rollout_smem(int kind, int T, int block, int grid_bytes_in_smem) {
 cudaError_t reduce_softmin_launch(bool f64, int T, cudaStream_t st, const ReduceArgs& a) {
   const size_t smem = (size_t)4 * T * sizeof(double);
   if (f64)
-    reduce_softmin_kernel<double><<<T, 128, smem, st>>>(a);
+    reduce_softmin_kernel<double><<<T, 256, smem, st>>>(a);
   else
-    reduce_softmin_kernel<float><<<T, 128, smem, st>>>(a);
+    reduce_softmin_kernel<float><<<T, 256, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -85,58 +85,69 @@ __device__ __forceinline__ bool last_block_done(unsigned int* counter, unsigned 
   return last;
 }
 
-// ---- kernel 2a: SOFTMIN merge (single pass, tuple reduction).  grid = T blocks of 128 --------------
+// ---- kernel 2a: SOFTMIN merge.  grid = T blocks of 256 threads --------------------------------------
+// Two streaming passes over the nCTA partials of this t (second one L1/L2-hot), loads batched 4 deep;
+// pass 1: global minimum, pass 2: rescale by exp(-(m_cta - m)/lam) and sum (one exp per partial).
 template <typename R>
-__global__ void __launch_bounds__(128) reduce_softmin_kernel(const __grid_constant__ ReduceArgs a) {
+__global__ void __launch_bounds__(256) reduce_softmin_kernel(const __grid_constant__ ReduceArgs a) {
   typedef typename Math<R>::Vec4 Vec4;
   extern __shared__ __align__(16) unsigned char smem_fin[];
-  __shared__ Tup wt[4];
-  __shared__ double we[4][2];
-  const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ double scratch[8];
+  const int t = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const Vec4* part = reinterpret_cast<const Vec4*>(a.part) + (size_t)t * a.nCTA;
-  const double* ep = a.epart + (size_t)t * a.nCTA * 2;
+  const double2* ep = reinterpret_cast<const double2*>(a.epart) + (size_t)t * a.nCTA;
   const double neg_inv_lam = -1.0 / a.fin.dyn->lam;
-  Tup acc;
-  acc.m = Math<double>::inf();
-  acc.S = acc.N0 = acc.N1 = 0.0;
-  double E0 = 0, E1 = 0;
-  for (int i = threadIdx.x; i < a.nCTA; i += blockDim.x) {
-    const Vec4 p = part[i];
-    Tup b;
-    b.m = (double)p.x;
-    b.S = (double)p.y;
-    b.N0 = (double)p.z;
-    b.N1 = (double)p.w;
-    tup_merge(acc, b, neg_inv_lam);
-    E0 += ep[2 * i];
-    E1 += ep[2 * i + 1];
-  }
+  double m = Math<double>::inf();
+  for (int base = 0; base < a.nCTA; base += 4 * nth) {
+    R mx[4];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const Tup b = tup_shfl_xor(acc, o);
-    tup_merge(acc, b, neg_inv_lam);
-  }
-  E0 = warp_sum<double>(E0);
-  E1 = warp_sum<double>(E1);
-  if (lane == 0) {
-    wt[warp] = acc;
-    we[warp][0] = E0;
-    we[warp][1] = E1;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 4; ++w) {
-      tup_merge(acc, wt[w], neg_inv_lam);
-      E0 += we[w][0];
-      E1 += we[w][1];
+    for (int j = 0; j < 4; ++j) {
+      const int i = base + j * nth + tid;
+      mx[j] = (i < a.nCTA) ? part[i].x : Math<R>::inf();
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m = fmin(m, (double)mx[j]);
+  }
+  m = block_min(m, scratch);
+  double S = 0, N0 = 0, N1 = 0, E0 = 0, E1 = 0;
+  for (int base = 0; base < a.nCTA; base += 4 * nth) {
+    Vec4 p[4];
+    double2 e[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = base + j * nth + tid;
+      if (i < a.nCTA) {
+        p[j] = part[i];
+        e[j] = ep[i];
+      } else {
+        p[j].x = Math<R>::inf();
+        p[j].y = p[j].z = p[j].w = R(0);
+        e[j] = make_double2(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double sc = exp(((double)p[j].x - m) * neg_inv_lam);   // exp(-inf) = 0 for the padding
+      S += (double)p[j].y * sc;
+      N0 += (double)p[j].z * sc;
+      N1 += (double)p[j].w * sc;
+      E0 += e[j].x;
+      E1 += e[j].y;
+    }
+  }
+  S = block_sum(S, scratch);
+  N0 = block_sum(N0, scratch);
+  N1 = block_sum(N1, scratch);
+  E0 = block_sum(E0, scratch);
+  E1 = block_sum(E1, scratch);
+  if (tid == 0) {
     double s0, s1;
     floor_scale(a.sp, a.fin.dyn, s0, s1);
     double* r = a.record + (size_t)t * kRecordStride;
-    r[0] = acc.m;
-    r[1] = acc.S;
-    r[2] = acc.N0;
-    r[3] = acc.N1;
+    r[0] = m;
+    r[1] = S;
+    r[2] = N0;
+    r[3] = N1;
     r[4] = E0 * s0;
     r[5] = E1 * s1;
   }
@@ -273,16 +284,27 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     nsel = 0;
     overflow = 0;
   }
-  // phase A: global fp32 minimum, floor sums, overflow check
-  const int* cnt = a.cand_count + (size_t)t * a.nCTA;
-  const float* cmin = a.cand_min + (size_t)t * a.nCTA;
-  const float* clim = a.cand_lim + (size_t)t * a.nCTA;
-  const double* ep = a.epart + (size_t)t * a.nCTA * 2;
+  // phase A: global fp32 minimum + floor sums.  meta[t][cta] = (min, limit, count, -) is ONE 16-byte
+  // load per CTA, batched 4 deep; nothing else is touched for CTAs outside the global window.
+  const float4* meta = a.cand_meta + (size_t)t * a.nCTA;
+  const double2* ep = reinterpret_cast<const double2*>(a.epart) + (size_t)t * a.nCTA;
+  const int nth = blockDim.x;
   double m32 = Math<double>::inf(), E0 = 0, E1 = 0;
-  for (int i = tid; i < a.nCTA; i += blockDim.x) {
-    m32 = fmin(m32, (double)cmin[i]);
-    E0 += ep[2 * i];
-    E1 += ep[2 * i + 1];
+  for (int base = 0; base < a.nCTA; base += 4 * nth) {
+    float mx[4];
+    double2 e[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = base + j * nth + tid;
+      mx[j] = (i < a.nCTA) ? meta[i].x : __int_as_float(0x7f800000);
+      e[j] = (i < a.nCTA) ? ep[i] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      m32 = fmin(m32, (double)mx[j]);
+      E0 += e[j].x;
+      E1 += e[j].y;
+    }
   }
   m32 = block_min(m32, scratch);
   E0 = block_sum(E0, scratch);
@@ -290,20 +312,31 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   // phase B: compact the candidates inside the window of the GLOBAL minimum; a CTA whose list does
   // not cover that window (it had to tighten its own window) is an overflow
   const float lim = (float)m32 + (float)sp.margin;
-  for (int i = tid; i < a.nCTA; i += blockDim.x) {
-    if (clim[i] < lim) atomicOr(&overflow, 1);
-    const int c = min(cnt[i], kMaxCand);
-    const uint2* cd = a.cand + ((size_t)t * a.nCTA + i) * kMaxCand;
-    for (int s = 0; s < c; ++s) {
-      const uint2 e = cd[s];
-      const float v = __uint_as_float(e.y);
-      if (v <= lim) {
-        const int pos = atomicAdd(&nsel, 1);
-        if (pos < kMaxRefine) {
-          sel_k[pos] = (int)e.x;
-          sel_v32[pos] = v;
-        } else {
-          atomicOr(&overflow, 1);
+  for (int base = 0; base < a.nCTA; base += 4 * nth) {
+    float4 md[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = base + j * nth + tid;
+      md[j] = (i < a.nCTA) ? meta[i] : make_float4(__int_as_float(0x7f800000), __int_as_float(0x7f800000), 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!(md[j].x <= lim)) continue;                 // this CTA's best rollout is outside the window
+      const int i = base + j * nth + tid;
+      if (md[j].y < lim) atomicOr(&overflow, 1);
+      const int c = min(__float_as_int(md[j].z), kMaxCand);
+      const uint2* cd = a.cand + ((size_t)t * a.nCTA + i) * kMaxCand;
+      for (int s = 0; s < c; ++s) {
+        const uint2 e = cd[s];
+        const float v = __uint_as_float(e.y);
+        if (v <= lim) {
+          const int pos = atomicAdd(&nsel, 1);
+          if (pos < kMaxRefine) {
+            sel_k[pos] = (int)e.x;
+            sel_v32[pos] = v;
+          } else {
+            atomicOr(&overflow, 1);
+          }
         }
       }
     }

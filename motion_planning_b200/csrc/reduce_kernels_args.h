@@ -11,10 +11,8 @@ struct RolloutArgs {
   const double* eps_ext;       // (T,2,K) f64 when sp.noise_external
   void* part;                  // SOFTMIN: Vec4[T][nCTA] (m,S,N0,N1)
   double* epart;               // [T][nCTA][2] floor sums (fixed-point integer as double, or real if external)
-  int* cand_count;             // SCREEN: [T][nCTA]
+  float4* cand_meta;           // SCREEN: [T][nCTA] (running min, applied limit, count as int bits, -)
   uint2* cand;                 // SCREEN: [T][nCTA][kMaxCand]  (k_local, float bits of V)
-  float* cand_min;             // SCREEN: [T][nCTA] running minimum of the CTA
-  float* cand_lim;             // SCREEN: [T][nCTA] every rollout of the CTA with V <= cand_lim is listed
   void* vcap;                  // capture: Real[T][K]
   int ntiles;
 };
@@ -40,10 +38,8 @@ struct ReduceArgs {
   unsigned int* done_counter;
   const void* part;          // SOFTMIN partials Vec4[T][nCTA]
   const double* epart;       // [T][nCTA][2]
-  const int* cand_count;     // SCREEN
+  const float4* cand_meta;   // SCREEN
   const uint2* cand;
-  const float* cand_min;
-  const float* cand_lim;
   const double* nomD;        // f64 nominal block [4][T]
   const signed char* grid;
   const double* eps_ext;

@@ -145,6 +145,10 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     int eown0 = 0, eown1 = 0;   // fixed-point floor sums of the step this lane owns in the current 32-step chunk
 
     // ---- the T-step rollout (hot loop 1, control/src/mppi:136-163) ----------------------------
+    // Software-pipelined noise: the Philox + Box-Muller chain of step pair t2+1 is issued in the same
+    // basic block as the two model steps of pair t2, so the integer/SFU chain overlaps the FP chain.
+    float4 znext = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!sp.noise_external) znext = philox_normal4(sp.seed, kglobal, 0u, step);
     for (int t2 = 0; t2 < (T >> 1); ++t2) {
       float zf[4];
       R ev[4];
@@ -153,7 +157,8 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 4; ++i) ev[i] = load_eps_ext<R>(a.eps_ext, 2 * t2 + (i >> 1), i & 1, sp.K, kk);
       } else {
-        float4 z = philox_normal4(sp.seed, kglobal, (unsigned)t2, step);
+        const float4 z = znext;
+        znext = philox_normal4(sp.seed, kglobal, (unsigned)(t2 + 1), step);   // one pair ahead (last one unused)
         zf[0] = z.x;
         zf[1] = z.y;
         zf[2] = z.z;
@@ -304,9 +309,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     if (MODE == MODE_SOFTMIN) {
       reinterpret_cast<Vec4*>(a.part)[idx] = run[t];
     } else {
-      a.cand_count[idx] = ccount[t];
-      a.cand_min[idx] = (float)run[t].x;
-      a.cand_lim[idx] = (float)run[t].y;
+      a.cand_meta[idx] = make_float4((float)run[t].x, (float)run[t].y, __int_as_float(ccount[t]), 0.f);
     }
     a.epart[2 * idx] = sp.noise_external ? ed[2 * t] : (double)ez64[2 * t];
     a.epart[2 * idx + 1] = sp.noise_external ? ed[2 * t + 1] : (double)ez64[2 * t + 1];
