@@ -183,7 +183,8 @@ def run_single(args):
         if prec == args.precision:
             sampler = ClockSampler(0)
         r = m.bench(X0, steps=args.steps, warmup=args.warmup, flush_l2=True, per_kernel=True)
-        # e2e: the public call with host buffers, copies inside the timed region
+        # e2e: the public call with HOST buffers, copies inside the timed region.
+        # (1) through the Python mirror of the reference class (MPPI.get_path, what Controller calls)
         m.initialize()
         s = X0.copy()
         for _ in range(args.warmup):
@@ -191,8 +192,23 @@ def run_single(args):
         t0 = time.perf_counter()
         for _ in range(args.steps):
             s = m.get_path(s, GOAL)
-        e2e_dt = (time.perf_counter() - t0) / args.steps
-        r["e2e_ms"] = e2e_dt * 1e3
+        r["e2e_shim_ms"] = (time.perf_counter() - t0) / args.steps * 1e3
+        # (2) through the C ABI directly (mppi_step with host double[3] in, double[2]+double[3] out): what a
+        #     C/C++ host pays; same copies, no interpreter overhead around the call
+        m.initialize()
+        x, u, xn = X0.copy(), np.empty(2), np.empty(3)
+        px, pu, pn = _capi.dptr(x), _capi.dptr(u), _capi.dptr(xn)
+        step, h = lib.mppi_step, m._h
+        _capi.check(lib.mppi_set_goal(h, _capi.dptr(GOAL)), "mppi_set_goal")
+        for _ in range(args.warmup):
+            step(h, px, pu, pn)
+            x[:] = xn
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            if step(h, px, pu, pn) != 0:
+                raise RuntimeError("mppi_step failed")
+            x[:] = xn
+        r["e2e_ms"] = (time.perf_counter() - t0) / args.steps * 1e3
         r["io"] = m.io_bytes()
         r["launch"] = m.launch_info()
         r["stats"] = m.stats()
@@ -221,7 +237,9 @@ def run_single(args):
                    "loop": "closed loop on the model, state resident in HBM", "launch": r["launch"]},
         "state_steps_per_s": value * T,
         "e2e": {"value": K / (r["e2e_ms"] * 1e-3), "unit": "rollouts/s", "h2d_bytes_per_step": r["io"][0],
-                "d2h_bytes_per_step": r["io"][1], "ms_per_step": r["e2e_ms"]},
+                "d2h_bytes_per_step": r["io"][1], "ms_per_step": r["e2e_ms"],
+                "call": "mppi_step (C ABI) with host x0 in / (u, x_next) out, closed loop on the host",
+                "python_shim_ms_per_step": r["e2e_shim_ms"], "python_shim_value": K / (r["e2e_shim_ms"] * 1e-3)},
         "gpu_launches": r["launches"],
         "kernels_ms": {"rollout": r["rollout_ms"], "reduce": r["reduce_ms"], "finalize": r["finalize_ms"]},
         "roofline": {"bound": "fp32_alu", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",

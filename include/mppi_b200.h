@@ -200,6 +200,10 @@ MPPI_API mppi_status mppi_io_bytes(mppi_handle h, size_t* h2d, size_t* d2h);
 /* launch configuration of the rollout kernel (diagnostics): block, grid, tiles, dynamic smem, CTAs/SM, regs */
 MPPI_API mppi_status mppi_launch_info(mppi_handle h, int32_t info[6]);
 
+/* profiling aid: globaltimer stamps (ns) of the reduce-kernel phases of the last step, [T][8];
+ * the first call arms the stamps. */
+MPPI_API mppi_status mppi_debug_reduce_timestamps(mppi_handle h, unsigned long long* out);
+
 MPPI_API const char* mppi_last_error(void);
 MPPI_API const char* mppi_version(void);
 MPPI_API int32_t mppi_device_count(void);

@@ -57,10 +57,10 @@ struct mppi_engine {
   DynState* d_dyn = nullptr;
   double *d_Umaster = nullptr, *d_Ulast = nullptr, *d_nomD = nullptr, *d_Utmp = nullptr;
   float* d_nomF = nullptr;
-  double* d_sg_rows = nullptr;
-  double sg_a = 0, sg_b = 0;
+  double sg_a = 0, sg_b = 0, sg_inv_norm[4] = {0, 0, 0, 0};
   double *d_record = nullptr, *d_gather = nullptr, *d_record_tmp = nullptr;
   unsigned int* d_done = nullptr;
+  unsigned long long* d_debug_ts = nullptr;
   void* d_part = nullptr;
   double* d_epart = nullptr;
   float4* d_cand_meta = nullptr;
@@ -223,9 +223,9 @@ static mppi_status configure(mppi_engine* e) {
   return drop_graphs(e);
 }
 
-static void savgol_rows(int T, std::vector<double>& rows, double& a, double& b) {
+static void savgol_basis(int T, double& a, double& b, double inv_norm[4]) {
   // Gram (discrete orthogonal) cubic basis on z = -h..h, window w = T-1 (control/src/mppi:202):
-  // p0 = 1, p1 = z, p2 = z^2 - a, p3 = z^3 - b z; rows[i][j] = p_i(z_j) / sum_j p_i(z_j)^2
+  // p0 = 1, p1 = z, p2 = z^2 - a, p3 = z^3 - b z;  projection coefficient i = sum_j p_i(z_j) u_j / sum_j p_i(z_j)^2
   const int W = T - 1, h = W / 2;
   long double s2 = 0, s4 = 0;
   for (int j = 0; j < W; ++j) {
@@ -235,18 +235,12 @@ static void savgol_rows(int T, std::vector<double>& rows, double& a, double& b) 
   }
   const long double la = s2 / W, lb = s4 / s2;
   long double n[4] = {0, 0, 0, 0};
-  std::vector<long double> pv((size_t)4 * W);
   for (int j = 0; j < W; ++j) {
     long double z = j - h;
     long double pz[4] = {1.0L, z, z * z - la, z * z * z - lb * z};
-    for (int i = 0; i < 4; ++i) {
-      pv[(size_t)i * W + j] = pz[i];
-      n[i] += pz[i] * pz[i];
-    }
+    for (int i = 0; i < 4; ++i) n[i] += pz[i] * pz[i];
   }
-  rows.resize((size_t)4 * W);
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < W; ++j) rows[(size_t)i * W + j] = (double)(pv[(size_t)i * W + j] / n[i]);
+  for (int i = 0; i < 4; ++i) inv_norm[i] = (double)(1.0L / n[i]);
   a = (double)la;
   b = (double)lb;
 }
@@ -373,7 +367,6 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
   CKF(cudaMalloc(&e->d_record, (size_t)T * kRecordStride * sizeof(double)));
   CKF(cudaMalloc(&e->d_record_tmp, (size_t)T * kRecordStride * sizeof(double)));
   CKF(cudaMalloc(&e->d_gather, (size_t)p.world_size * T * kRecordStride * sizeof(double)));
-  CKF(cudaMalloc(&e->d_sg_rows, (size_t)4 * (T - 1) * sizeof(double)));
   CKF(cudaMalloc(&e->d_done, sizeof(unsigned int)));
   CKF(cudaMemset(e->d_done, 0, sizeof(unsigned int)));
   CKF(cudaMallocHost(&e->h_in, 6 * sizeof(double)));
@@ -382,11 +375,7 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
   CKF(cudaMemset(e->d_Ulast, 0, 2 * T * sizeof(double)));
   CKF(cudaMemset(e->d_record, 0, (size_t)T * kRecordStride * sizeof(double)));
   CKF(cudaMemset(e->d_gather, 0, (size_t)p.world_size * T * kRecordStride * sizeof(double)));
-  {
-    std::vector<double> rows;
-    savgol_rows(T, rows, e->sg_a, e->sg_b);
-    CKF(cudaMemcpy(e->d_sg_rows, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
-  }
+  savgol_basis(T, e->sg_a, e->sg_b, e->sg_inv_norm);
   {
     DynState d;
     memset(&d, 0, sizeof(d));
@@ -423,8 +412,8 @@ extern "C" mppi_status mppi_destroy(mppi_handle e) {
   cudaFree(e->d_record);
   cudaFree(e->d_record_tmp);
   cudaFree(e->d_gather);
-  cudaFree(e->d_sg_rows);
   cudaFree(e->d_done);
+  cudaFree(e->d_debug_ts);
   cudaFree(e->d_grid);
   cudaFree(e->d_eps_ext);
   cudaFree(e->d_vcap);
@@ -623,9 +612,9 @@ static FinalizeArgs make_fin(mppi_engine* e, bool closed_loop) {
   fa.Ulast = e->d_Ulast;
   fa.nomF = e->d_nomF;
   fa.nomD = e->d_nomD;
-  fa.sg_rows = e->d_sg_rows;
   fa.sg_a = e->sg_a;
   fa.sg_b = e->sg_b;
+  for (int i = 0; i < 4; ++i) fa.sg_inv_norm[i] = e->sg_inv_norm[i];
   fa.mode = 0;
   fa.closed_loop = closed_loop ? 1 : 0;
   return fa;
@@ -659,6 +648,7 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   rd.fin = make_fin(e, fuse == FUSE_LOOP);
   rd.fuse_finalize = (fuse != FUSE_NONE && e->sp.world == 1) ? 1 : 0;
   rd.done_counter = e->d_done;
+  rd.debug_ts = e->d_debug_ts;
   rd.part = e->d_part;
   rd.epart = e->d_epart;
   rd.cand_meta = e->d_cand_meta;
@@ -984,9 +974,9 @@ extern "C" mppi_status mppi_update_action(mppi_handle e, const double* U_in, con
     fa.Ulast = e->d_Ulast;
     fa.nomF = e->d_nomF;
     fa.nomD = e->d_nomD;
-    fa.sg_rows = e->d_sg_rows;
     fa.sg_a = e->sg_a;
     fa.sg_b = e->sg_b;
+    for (int i = 0; i < 4; ++i) fa.sg_inv_norm[i] = e->sg_inv_norm[i];
     fa.mode = 1;
     ce = finalize_launch(e->stream, fa);
   }
@@ -1096,6 +1086,21 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
   t.refine_max_dev = e->h_out->last_max_dev;
   e->last = t;
   *out = t;
+  return MPPI_OK;
+}
+
+// profiling aid: globaltimer stamps (ns) of the reduce kernel phases of the LAST step, [T][8];
+// the first call only arms the stamps (and invalidates the CUDA graph)
+extern "C" mppi_status mppi_debug_reduce_timestamps(mppi_handle e, unsigned long long* out) {
+  ENTER(e);
+  CK(cudaStreamSynchronize(e->stream));
+  const size_t n = (size_t)e->sp.T * 8;
+  if (!e->d_debug_ts) {
+    CK(cudaMalloc(&e->d_debug_ts, n * sizeof(unsigned long long)));
+    CK(cudaMemset(e->d_debug_ts, 0, n * sizeof(unsigned long long)));
+    drop_graphs(e);
+  }
+  if (out) CK(cudaMemcpy(out, e->d_debug_ts, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return MPPI_OK;
 }
 

@@ -1,10 +1,30 @@
 // reduce.cu -- instantiations + launch wrappers of the reduce / finalize / auxiliary kernels,
 // and the kind-dispatch for the three rollout translation units.
+#include <cstring>
+
 #include "kernels_api.h"
 #include "reduce_kernels.cuh"
 #include "rollout_kernel.cuh"
 
 namespace mppi {
+
+// launch with programmatic stream serialization: the kernel may start while its predecessor in the
+// stream is still draining; it synchronises on-device with griddepcontrol.wait
+template <typename Fn>
+static cudaError_t launch_pdl(Fn f, int grid, int block, size_t smem, cudaStream_t st, const ReduceArgs& a) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, f, a);
+}
 
 #define DECL_TU(name)                                                                                          \
   cudaError_t rollout_##name##_prepare(int model, bool has_grid, int block, size_t smem, int* ctas, int* regs); \
@@ -39,11 +59,8 @@ size_t rollout_smem(int kind, int T, int block, int grid_bytes_in_smem) {
 
 cudaError_t reduce_softmin_launch(bool f64, int T, cudaStream_t st, const ReduceArgs& a) {
   const size_t smem = (size_t)4 * T * sizeof(double);
-  if (f64)
-    reduce_softmin_kernel<double><<<T, 256, smem, st>>>(a);
-  else
-    reduce_softmin_kernel<float><<<T, 256, smem, st>>>(a);
-  return cudaGetLastError();
+  if (f64) return launch_pdl(reduce_softmin_kernel<double>, T, 256, smem, st, a);
+  return launch_pdl(reduce_softmin_kernel<float>, T, 256, smem, st, a);
 }
 
 typedef void (*ScreenFn)(const ReduceArgs);
@@ -64,8 +81,7 @@ cudaError_t reduce_screen_launch(int model, bool has_grid, int T, cudaStream_t s
     cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  f<<<T, 256, smem, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(f, T, 256, smem, st, a);
 }
 
 cudaError_t finalize_launch(cudaStream_t st, const FinalizeArgs& a) {

@@ -46,6 +46,37 @@ __device__ __forceinline__ void floor_scale(const StaticParams& sp, const DynSta
 }
 
 // (m, S, N0, N1) online-softmin tuples: merge b into a (weights relative to the smaller minimum)
+// Programmatic dependent launch (PDL): the reduce kernel is launched while the rollout kernel is still
+// running and blocks here until that grid has completed and flushed its memory.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TS(slot) do { if (a.debug_ts && threadIdx.x == 0) a.debug_ts[(size_t)blockIdx.x * 8 + (slot)] = gtime(); } while (0)
+
+// sum N values over the block with one shared-memory exchange (blockDim <= 256); result in every thread
+template <int N>
+__device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch /* [8*N] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = warp_sum<double>(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) scratch[warp * N + i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += scratch[w * N + i];
+    v[i] = s;
+  }
+}
+
 struct Tup {
   double m, S, N0, N1;
 };
@@ -93,6 +124,8 @@ __global__ void __launch_bounds__(256) reduce_softmin_kernel(const __grid_consta
   typedef typename Math<R>::Vec4 Vec4;
   extern __shared__ __align__(16) unsigned char smem_fin[];
   __shared__ double scratch[8];
+  __shared__ double scratch5[40];
+  griddep_wait();   // PDL: everything above overlapped the rollout kernel's tail
   const int t = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const Vec4* part = reinterpret_cast<const Vec4*>(a.part) + (size_t)t * a.nCTA;
   const double2* ep = reinterpret_cast<const double2*>(a.epart) + (size_t)t * a.nCTA;
@@ -135,21 +168,18 @@ __global__ void __launch_bounds__(256) reduce_softmin_kernel(const __grid_consta
       E1 += e[j].y;
     }
   }
-  S = block_sum(S, scratch);
-  N0 = block_sum(N0, scratch);
-  N1 = block_sum(N1, scratch);
-  E0 = block_sum(E0, scratch);
-  E1 = block_sum(E1, scratch);
+  double v5[5] = {S, N0, N1, E0, E1};
+  block_sum_n<5>(v5, scratch5);
   if (tid == 0) {
     double s0, s1;
     floor_scale(a.sp, a.fin.dyn, s0, s1);
     double* r = a.record + (size_t)t * kRecordStride;
     r[0] = m;
-    r[1] = S;
-    r[2] = N0;
-    r[3] = N1;
-    r[4] = E0 * s0;
-    r[5] = E1 * s1;
+    r[1] = v5[0];
+    r[2] = v5[1];
+    r[3] = v5[2];
+    r[4] = v5[3] * s0;
+    r[5] = v5[4] * s1;
   }
   if (a.fuse_finalize && last_block_done(a.done_counter, gridDim.x)) finalize_body(a.fin, reinterpret_cast<double*>(smem_fin));
 }
@@ -272,6 +302,7 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   extern __shared__ __align__(16) unsigned char smem_raw2[];
   double* warp_scratch = reinterpret_cast<double*>(smem_raw2);
   __shared__ double scratch[8];
+  __shared__ double scratch5[40];
   __shared__ int sel_k[kMaxRefine];
   __shared__ float sel_v32[kMaxRefine];
   __shared__ double sel_v64[kMaxRefine];
@@ -284,6 +315,8 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     nsel = 0;
     overflow = 0;
   }
+  griddep_wait();   // PDL: the block is resident before the rollout kernel has drained
+  TS(0);
   // phase A: global fp32 minimum + floor sums.  meta[t][cta] = (min, limit, count, -) is ONE 16-byte
   // load per CTA, batched 4 deep; nothing else is touched for CTAs outside the global window.
   const float4* meta = a.cand_meta + (size_t)t * a.nCTA;
@@ -307,8 +340,7 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     }
   }
   m32 = block_min(m32, scratch);
-  E0 = block_sum(E0, scratch);
-  E1 = block_sum(E1, scratch);
+  TS(1);
   // phase B: compact the candidates inside the window of the GLOBAL minimum; a CTA whose list does
   // not cover that window (it had to tighten its own window) is an overflow
   const float lim = (float)m32 + (float)sp.margin;
@@ -342,6 +374,7 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     }
   }
   __syncthreads();
+  TS(2);
   const int n = min(nsel, kMaxRefine);
   // phase C: fp64 re-evaluation, one warp per candidate
   ModelConsts<double> mc;
@@ -355,6 +388,7 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     dev = fmax(dev, fabs(v64 - (double)sel_v32[c]));
   }
   __syncthreads();
+  TS(3);
   // phase D: exact softmin over the support (control/src/mppi:189-196)
   double m64 = Math<double>::inf();
   for (int c = 0; c < n; ++c) m64 = fmin(m64, sel_v64[c]);
@@ -377,26 +411,30 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     N0 += e * e0;
     N1 += e * e1;
   }
-  S = block_sum(S, scratch);
-  N0 = block_sum(N0, scratch);
-  N1 = block_sum(N1, scratch);
+  double v5[5] = {S, N0, N1, E0, E1};
+  block_sum_n<5>(v5, scratch5);
   dev = -block_min(-dev, scratch);
   if (tid == 0) {
     double s0, s1;
     floor_scale(sp, a.fin.dyn, s0, s1);
     double* r = a.record + (size_t)t * kRecordStride;
     r[0] = m64;
-    r[1] = S;
-    r[2] = N0;
-    r[3] = N1;
-    r[4] = E0 * s0;
-    r[5] = E1 * s1;
+    r[1] = v5[0];
+    r[2] = v5[1];
+    r[3] = v5[2];
+    r[4] = v5[3] * s0;
+    r[5] = v5[4] * s1;
     atomicAdd(&a.fin.dyn->refine_candidates, n);
     if (overflow) atomicOr(&a.fin.dyn->refine_overflow, 1);
     // max of non-negative doubles == max of their bit patterns
     atomicMax(reinterpret_cast<unsigned long long*>(&a.fin.dyn->refine_max_dev), (unsigned long long)__double_as_longlong(dev));
   }
-  if (a.fuse_finalize && last_block_done(a.done_counter, gridDim.x)) finalize_body(a.fin, warp_scratch);
+  TS(4);
+  if (a.fuse_finalize && last_block_done(a.done_counter, gridDim.x)) {
+    TS(5);
+    finalize_body(a.fin, warp_scratch);
+    TS(6);
+  }
 }
 
 // ---- kernel 3: finalize.  one block of 256 threads ------------------------------------------------
@@ -495,14 +533,28 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
   // -- Savitzky-Golay, window T-1, cubic, mode='interp' (control/src/mppi:202).  The filter is two
   //    least-squares cubics: A on samples [0, T-1), B on [1, T); outputs 0..h evaluate A, h+1..T-1
   //    evaluate B.  Orthogonal (Gram) basis 1, z, z^2-a, z^3-bz on z=-h..h.
-  for (int d = warp; d < 16; d += nw) {
-    const int c = d >> 3, fit = (d >> 2) & 1, i = d & 3;
-    const double* row = a.sg_rows + (size_t)i * W;
+  // projection rows p_i(z_j)/||p_i||^2 are evaluated analytically (no global loads on the serial tail)
+  for (int d = warp; d < 4; d += nw) {
+    const int c = d >> 1, fit = d & 1;
     const double* u = Us + c * T + fit;
-    double s = 0.0;
-    for (int j = lane; j < W; j += 32) s += row[j] * u[j];
-    s = warp_sum<double>(s);
-    if (lane == 0) coef[c][fit][i] = s;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int j = lane; j < W; j += 32) {
+      const double z = (double)(j - h), uj = u[j];
+      s0 += uj;
+      s1 += z * uj;
+      s2 += (z * z - a.sg_a) * uj;
+      s3 += (z * z * z - a.sg_b * z) * uj;
+    }
+    s0 = warp_sum<double>(s0);
+    s1 = warp_sum<double>(s1);
+    s2 = warp_sum<double>(s2);
+    s3 = warp_sum<double>(s3);
+    if (lane == 0) {
+      coef[c][fit][0] = s0 * a.sg_inv_norm[0];
+      coef[c][fit][1] = s1 * a.sg_inv_norm[1];
+      coef[c][fit][2] = s2 * a.sg_inv_norm[2];
+      coef[c][fit][3] = s3 * a.sg_inv_norm[3];
+    }
   }
   __syncthreads();
   for (int idx = tid; idx < 2 * T; idx += blockDim.x) {

@@ -25,8 +25,8 @@ struct FinalizeArgs {
   double* Ulast;             // [2][T] update_action result before the shift
   float* nomF;               // [4][T]
   double* nomD;              // [4][T]
-  const double* sg_rows;     // [4][T-1] orthogonal-polynomial projection rows (already / norm)
-  double sg_a, sg_b;         // p2 = z^2 - a, p3 = z^3 - b z
+  double sg_a, sg_b;         // Gram basis on z=-h..h: p2 = z^2 - a, p3 = z^3 - b z
+  double sg_inv_norm[4];     // 1 / sum_j p_i(z_j)^2
   int mode;                  // 0: full step, 1: update only (mppi_update_action)
   int closed_loop;           // 1: dyn->x0 <- x_next (device-resident loop of mppi_bench)
 };
@@ -36,6 +36,7 @@ struct ReduceArgs {
   FinalizeArgs fin;          // fin.dyn is THE DynState; the rest is used when fuse_finalize != 0
   int fuse_finalize;         // 1: the last block to finish also runs the finalize phase (world_size 1)
   unsigned int* done_counter;
+  unsigned long long* debug_ts;   // optional [T][8] globaltimer stamps of the reduce phases (profiling aid)
   const void* part;          // SOFTMIN partials Vec4[T][nCTA]
   const double* epart;       // [T][nCTA][2]
   const float4* cand_meta;   // SCREEN

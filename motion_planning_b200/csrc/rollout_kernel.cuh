@@ -304,6 +304,8 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
   }
 
   // ---- epilogue: one partial per (t, CTA) ------------------------------------------------------
+  // PDL: let the dependent reduce kernel start launching while the stragglers finish
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int t = tid; t < T; t += BLOCK) {
     const size_t idx = (size_t)t * nCTA + cta;
     if (MODE == MODE_SOFTMIN) {
