@@ -282,6 +282,10 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
     set_err("bad model/weighting/precision enum");
     return MPPI_ERR_INVALID;
   }
+  if (p.precision == MPPI_PRECISION_MIXED && p.T > 400) {
+    set_err("precision MIXED supports T <= 400 (fp64 refinement scratch is 56*T bytes per warp); use F64 or F32");
+    return MPPI_ERR_UNSUPPORTED;
+  }
   if (!(p.lambda > 0) || !(p.wheel_base > 0) || !(p.u_max[0] > 0) || !(p.u_max[1] > 0)) {
     set_err("lambda, wheel_base and u_max must be positive");
     return MPPI_ERR_INVALID;

@@ -1,0 +1,50 @@
+"""Worker for the multi-GPU test / demo (launched by torchrun, one rank per GPU, NCCL):
+K rollouts sharded over ranks must reproduce the single-GPU result (same Philox counters)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+import motion_planning_b200 as mp  # noqa: E402
+from motion_planning_b200.distributed import ShardedMPPI  # noqa: E402
+
+
+def main():
+    K, T = int(sys.argv[1]), int(sys.argv[2])
+    precision = sys.argv[3] if len(sys.argv) > 3 else "mixed"
+    exchange = sys.argv[4] if len(sys.argv) > 4 else "nccl"
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    goal = np.array([0.0, -1.0, 0.0])
+    sh = ShardedMPPI(T, K, precision=precision, seed=0, device=local, exchange=exchange)
+    one = mp.MPPI(horizon=T, samples=K, precision=precision, seed=0, device=local) if rank == 0 else None
+    s = np.zeros(3)
+    worst = 0.0
+    for it in range(4):
+        s1 = sh.get_path(s, goal)
+        if one is not None:
+            s2 = one.get_path(s, goal)
+            err = float(np.max(np.abs(sh.latest_uvec - one.latest_uvec)) / np.max(np.abs(one.latest_uvec)))
+            worst = max(worst, err, float(np.max(np.abs(s1 - s2))))
+        s = s1
+    # every rank must hold the identical nominal sequence (no broadcast is ever done)
+    U = torch.from_numpy(sh.latest_uvec).cuda()
+    lo, hi = U.clone(), U.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    spread = float((hi - lo).abs().max())
+    if rank == 0:
+        ok = worst < 1e-9 and spread == 0.0
+        print("DIST %s world=%d K=%d T=%d %s/%s: max rel err vs 1 GPU %.3e, rank spread %.1e" % (
+            "OK" if ok else "FAIL", world, K, T, precision, exchange, worst, spread))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,32 @@
+"""GPU, >= 2 devices: K sharded over NCCL ranks reproduces the single-GPU controller."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _ngpu():
+    from motion_planning_b200 import _capi
+    return _capi.load().mppi_device_count()
+
+
+@pytest.mark.parametrize("precision,exchange", [("mixed", "nccl"), ("f64", "nccl"), ("mixed", "host")])
+def test_sharded_equals_single_gpu(precision, exchange):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
+           "32768", "32", precision, exchange]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "DIST OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
