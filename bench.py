@@ -280,11 +280,13 @@ def run_multi(args):
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    st = m.stream if m.stream is not None else torch.cuda.current_stream()
     for i in range(args.steps):
-        flush.fill_(i & 0xff)
-        ev[i][0].record()
+        with torch.cuda.stream(st):
+            flush.fill_(i & 0xff)
+            ev[i][0].record(st)
         s = m.get_path(s, GOAL)
-        ev[i][1].record()
+        ev[i][1].record(st)
     torch.cuda.synchronize()
     dist.barrier()
     wall = time.perf_counter() - t0

@@ -62,8 +62,14 @@ class ShardedMPPI(object):
         k_local, k_offset = shard_plan(samples_total, self.world, self.rank)
         backend = dist.get_backend(group)
         self.exchange = exchange or ("nccl" if backend == "nccl" else "host")
+        self.stream = None
         if self.exchange == "nccl":
-            engine.setdefault("stream", torch.cuda.current_stream().cuda_stream)
+            # a dedicated non-default stream: the engine launches its kernels on it and the NCCL collective
+            # is enqueued under the same stream context, so kernels and all-gather are stream-ordered
+            # (handle 0 = the legacy default stream cannot be passed through the C ABI: NULL means
+            # "engine-owned stream")
+            self.stream = torch.cuda.Stream()
+            engine.setdefault("stream", self.stream.cuda_stream)
         self.mppi = MPPI(horizon=horizon, samples=k_local, k_offset=k_offset, k_total=samples_total,
                          world_size=self.world, rank=self.rank, **engine)
         self.horizon = horizon
@@ -83,7 +89,8 @@ class ShardedMPPI(object):
         _capi.check(lib.mppi_set_goal(h, _capi.dptr(_capi.f64(goal, (3,)))), "mppi_set_goal")
         _capi.check(lib.mppi_step_local(h, _capi.dptr(_capi.f64(state, (3,)))), "mppi_step_local")
         if self.exchange == "nccl":
-            self._dist.all_gather_into_tensor(self._gat_t, self._rec_t, group=self.group)
+            with self._torch.cuda.stream(self.stream):
+                self._dist.all_gather_into_tensor(self._gat_t, self._rec_t, group=self.group)
         else:
             rec = np.empty(self._n_rec)
             _capi.check(lib.mppi_read_record(h, _capi.dptr(rec)), "mppi_read_record")
