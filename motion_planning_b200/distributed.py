@@ -118,6 +118,8 @@ class ShardedMPPI(object):
 def exchange_host(torch, dist, rec, world, group=None):
     """all-gather of one host record per rank -> (world * n) float64, rank-major."""
     t = torch.from_numpy(np.ascontiguousarray(rec, dtype=np.float64))
+    if dist.get_backend(group) == "nccl":          # NCCL moves device tensors only
+        t = t.cuda()
     out = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(out, t, group=group)
-    return np.concatenate([o.numpy() for o in out])
+    return np.concatenate([o.cpu().numpy() for o in out])
