@@ -171,6 +171,17 @@ MPPI_API mppi_status mppi_write_gather(mppi_handle h, const double* all_records)
  * merge world_size records, update, filter, shift -- every rank ends with identical U. */
 MPPI_API mppi_status mppi_step_finish(mppi_handle h, double u_out[2], double x_next[3]);
 
+/* ---- fused peer-to-peer exchange over NVLink (ranks of one node) --------------------------------------
+ * Instead of a collective call between mppi_step_local and mppi_step_finish, the ranks map each other's
+ * exchange buffers (CUDA IPC): the reduce kernel of rank r stores its record straight into every peer's
+ * buffer and raises an arrival flag, the finalize kernel spins on its own flags.  After connecting,
+ * mppi_step / mppi_bench work for world_size > 1 and the whole sharded step is ONE CUDA graph per rank.
+ *   1. every rank: mppi_p2p_export(h, handle)      -- 64-byte cudaIpcMemHandle_t of its buffer
+ *   2. all-gather the handles by any means (rank-major, world_size x 64 bytes)
+ *   3. every rank: mppi_p2p_connect(h, all_handles)                                                  */
+MPPI_API mppi_status mppi_p2p_export(mppi_handle h, void* handle64);
+MPPI_API mppi_status mppi_p2p_connect(mppi_handle h, const void* all_handles);
+
 /* ---- measurement ----------------------------------------------------------------------------- */
 typedef struct {
   float step_ms;        /* mean device time of one whole step (all kernels), CUDA events on the launch stream */

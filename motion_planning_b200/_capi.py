@@ -83,6 +83,8 @@ _SIGNATURES = {
     "mppi_step_finish": [_H, _dp, _dp],
     "mppi_read_record": [_H, _dp],
     "mppi_write_gather": [_H, _dp],
+    "mppi_p2p_export": [_H, C.c_void_p],
+    "mppi_p2p_connect": [_H, C.c_void_p],
     "mppi_bench": [_H, _dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(MppiTiming)],
     "mppi_last_stats": [_H, C.POINTER(MppiTiming)],
     "mppi_measure_fp32_peak": [C.c_int32, _dp, _dp],

@@ -64,7 +64,7 @@ struct DynState {
   double refine_max_dev;
   double last_max_dev;
   int overflow_total;    // steps that hit a candidate-list overflow since creation
-  int pad1;
+  unsigned int xchg;     // p2p exchange epoch: +1 per step, never rewound (arrival flags carry xchg+1)
 };
 constexpr int kStatusRedoF64 = 100;   // MIXED: support list overflowed, host must redo the step in fp64
 
@@ -299,7 +299,7 @@ __device__ __forceinline__ void model_step(const ModelConsts<R>& mc, R u0, R u1,
   s = s4;
 }
 
-constexpr int kTrigResyncMask = 7;   // (c, s) <- sincos(theta) after every 8th step
+constexpr int kTrigResyncMask = 3;   // (c, s) <- sincos(theta) after every 4th step
 
 // ---- cost in delta form --------------------------------------------------------------------------
 // The reference subtracts min_k V[t,k] per t before exponentiating (control/src/mppi:189), so any

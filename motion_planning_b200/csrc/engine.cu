@@ -61,6 +61,12 @@ struct mppi_engine {
   double *d_record = nullptr, *d_gather = nullptr, *d_record_tmp = nullptr;
   unsigned int* d_done = nullptr;
   unsigned long long* d_debug_ts = nullptr;
+  // peer-to-peer exchange
+  double* d_p2p = nullptr;          // local buffer (exported through CUDA IPC)
+  size_t p2p_bytes = 0;
+  double** d_p2p_peers = nullptr;   // device array of peer base pointers
+  std::vector<void*> p2p_opened;    // IPC mappings to close
+  bool p2p_on = false;
   void* d_part = nullptr;
   double* d_epart = nullptr;
   float4* d_cand_meta = nullptr;
@@ -135,9 +141,9 @@ extern "C" mppi_status mppi_default_params(mppi_params* p) {
 
 static double default_margin(const mppi_engine* e, double lam) {
   if (e->p.refine_margin > 0) return e->p.refine_margin;
-  // e^-40 ~ 4e-18 relative weight is far below the 1e-8 floor; 0.01 covers the fp32 screening error
-  // of the cost-to-go (measured max |V32 - V64| ~ 2e-5 at K=65536,T=64) 500x over.
-  return 40.0 * lam + 0.01;
+  // e^-40 ~ 4e-18 relative weight is far below the 1e-8 floor; 0.02 covers the fp32 screening error
+  // of the cost-to-go (measured max |V32 - V64| <= 1.3e-3 over all BASELINE configs, see profiles/) 15x over.
+  return 40.0 * lam + 0.02;
 }
 
 static void free_partials(mppi_engine* e) {
@@ -418,6 +424,9 @@ extern "C" mppi_status mppi_destroy(mppi_handle e) {
   cudaFree(e->d_gather);
   cudaFree(e->d_done);
   cudaFree(e->d_debug_ts);
+  for (void* q : e->p2p_opened) cudaIpcCloseMemHandle(q);
+  cudaFree(e->d_p2p_peers);
+  cudaFree(e->d_p2p);
   cudaFree(e->d_grid);
   cudaFree(e->d_eps_ext);
   cudaFree(e->d_vcap);
@@ -612,6 +621,8 @@ static FinalizeArgs make_fin(mppi_engine* e, bool closed_loop) {
   fa.sp = e->sp;
   fa.dyn = e->d_dyn;
   fa.gather = (e->sp.world > 1) ? e->d_gather : e->d_record;
+  fa.p2p = 0;
+  fa.p2p_local = e->d_p2p;
   fa.Umaster = e->d_Umaster;
   fa.Ulast = e->d_Ulast;
   fa.nomF = e->d_nomF;
@@ -652,6 +663,9 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   rd.fin = make_fin(e, fuse == FUSE_LOOP);
   rd.fuse_finalize = (fuse != FUSE_NONE && e->sp.world == 1) ? 1 : 0;
   rd.done_counter = e->d_done;
+  rd.rank = e->p.rank;
+  rd.p2p_push = (fuse != FUSE_NONE && e->p2p_on) ? 1 : 0;
+  rd.p2p_peers = e->d_p2p_peers;
   rd.debug_ts = e->d_debug_ts;
   rd.part = e->d_part;
   rd.epart = e->d_epart;
@@ -672,8 +686,13 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
 }
 
 // stand-alone finalize (sharded steps: after the exchange)
-static mppi_status launch_finalize(mppi_engine* e, cudaStream_t st, bool closed_loop, KernelEvents* kev) {
-  CK(finalize_launch(st, make_fin(e, closed_loop)));
+static mppi_status launch_finalize(mppi_engine* e, cudaStream_t st, bool closed_loop, KernelEvents* kev, bool p2p = false) {
+  FinalizeArgs fa = make_fin(e, closed_loop);
+  if (p2p) {   // records arrive in the local IPC buffer; parity is resolved on the device from dyn->xchg
+    fa.p2p = 1;
+    fa.gather = nullptr;
+  }
+  CK(finalize_launch(st, fa));
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[3], st));
   return MPPI_OK;
 }
@@ -690,6 +709,7 @@ static mppi_status build_graphs(mppi_engine* e) {
       if (ce != cudaSuccess) s = MPPI_ERR_CUDA;
     }
     if (s == MPPI_OK) s = launch_local(e, e->stream, e->p.precision, which == 1 ? FUSE_LOOP : FUSE_STEP, nullptr);
+    if (s == MPPI_OK && e->sp.world > 1) s = launch_finalize(e, e->stream, which == 1, nullptr, true);
     if (s == MPPI_OK && which == 0) {
       cudaError_t ce = cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream);
       if (ce != cudaSuccess) s = MPPI_ERR_CUDA;
@@ -721,11 +741,12 @@ static mppi_status finish_outputs(mppi_engine* e, double u_out[2], double x_next
   if (o->status == kStatusRedoF64) {
     // MIXED: a candidate list overflowed; redo this step entirely in fp64 (same noise: the step
     // counter was not advanced, U and x0 are untouched).
-    if (e->sp.world > 1) {
-      set_err("MIXED overflow in a sharded step: rerun with precision F64");
+    if (e->sp.world > 1 && !e->p2p_on) {
+      set_err("MIXED overflow in a sharded step with an external exchange: rerun with precision F64");
       return MPPI_ERR_UNSUPPORTED;
     }
     CKS(launch_local(e, e->stream, MPPI_PRECISION_F64, FUSE_STEP, nullptr));
+    if (e->sp.world > 1) CKS(launch_finalize(e, e->stream, false, nullptr, true));   // every rank redoes (same record)
     CK(cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->last.refine_overflow += 1;
@@ -772,8 +793,8 @@ extern "C" mppi_status mppi_step(mppi_handle e, const double x0[3], double u_out
     set_err("mppi_step called between mppi_step_local and mppi_step_finish");
     return MPPI_ERR_STATE;
   }
-  if (e->sp.world > 1) {
-    set_err("world_size > 1: use mppi_step_local / exchange / mppi_step_finish");
+  if (e->sp.world > 1 && !e->p2p_on) {
+    set_err("world_size > 1: connect the peer-to-peer exchange (mppi_p2p_connect) or use mppi_step_local / mppi_step_finish");
     return MPPI_ERR_STATE;
   }
   CKS(pre_step(e, x0));
@@ -783,6 +804,7 @@ extern "C" mppi_status mppi_step(mppi_handle e, const double x0[3], double u_out
   } else {
     CK(cudaMemcpyAsync(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CKS(launch_local(e, e->stream, e->p.precision, FUSE_STEP, nullptr));
+    if (e->sp.world > 1) CKS(launch_finalize(e, e->stream, false, nullptr, true));
     CK(cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream));
   }
   CK(cudaStreamSynchronize(e->stream));
@@ -828,6 +850,48 @@ extern "C" mppi_status mppi_write_gather(mppi_handle e, const double* all) {
                      cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_p2p_export(mppi_handle e, void* handle64) {
+  ENTER(e);
+  if (!handle64) return MPPI_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!e->d_p2p) {
+    const size_t nrec = (size_t)2 * e->sp.world * e->sp.T * kRecordStride * sizeof(double);
+    e->p2p_bytes = nrec + (size_t)2 * e->sp.world * sizeof(unsigned int) + 64;
+    CK(cudaMalloc(&e->d_p2p, e->p2p_bytes));
+    CK(cudaMemset(e->d_p2p, 0, e->p2p_bytes));
+  }
+  cudaIpcMemHandle_t hnd;
+  CK(cudaIpcGetMemHandle(&hnd, e->d_p2p));
+  memcpy(handle64, &hnd, 64);
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_p2p_connect(mppi_handle e, const void* handles) {
+  ENTER(e);
+  if (!handles || !e->d_p2p) {
+    set_err("mppi_p2p_connect: call mppi_p2p_export on every rank first and pass all world_size handles");
+    return MPPI_ERR_STATE;
+  }
+  const int world = e->sp.world;
+  std::vector<double*> peers(world, nullptr);
+  for (int g = 0; g < world; ++g) {
+    if (g == e->p.rank) {
+      peers[g] = e->d_p2p;
+      continue;
+    }
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, (const char*)handles + (size_t)g * 64, 64);
+    void* ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+    e->p2p_opened.push_back(ptr);
+    peers[g] = (double*)ptr;
+  }
+  if (!e->d_p2p_peers) CK(cudaMalloc(&e->d_p2p_peers, world * sizeof(double*)));
+  CK(cudaMemcpy(e->d_p2p_peers, peers.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
+  e->p2p_on = true;
+  return drop_graphs(e);
 }
 
 extern "C" mppi_status mppi_step_finish(mppi_handle e, double u_out[2], double x_next[3]) {
@@ -1030,8 +1094,8 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
                                   int32_t per_kernel, mppi_timing* out) {
   ENTER(e);
   if (!x0 || !out || steps < 1 || warmup < 0) return MPPI_ERR_INVALID;
-  if (!e->own_stream || e->sp.world > 1) {
-    set_err("mppi_bench needs an engine-owned stream and world_size 1");
+  if (!e->own_stream || (e->sp.world > 1 && !e->p2p_on)) {
+    set_err("mppi_bench needs an engine-owned stream and world_size 1 (or a connected p2p exchange)");
     return MPPI_ERR_STATE;
   }
   CKS(pre_step(e, x0));
@@ -1062,7 +1126,7 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
   mppi_timing t{};
   t.step_ms = (float)(total / steps);
   t.steps = steps;
-  t.launches = 2 * steps;   // rollout + reduce (finalize is fused into the reduce kernel's last block)
+  t.launches = (e->sp.world > 1 ? 3 : 2) * steps;   // rollout + reduce (+ finalize: fused into the reduce kernel when world == 1)
   if (per_kernel) {
     KernelEvents kev;
     kev.on = true;
@@ -1071,6 +1135,7 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
     for (int i = 0; i < steps; ++i) {
       if (flush_l2) CK(cudaMemsetAsync(e->d_flush, i & 0xff, e->flush_bytes, e->stream));
       CKS(launch_local(e, e->stream, e->p.precision, FUSE_LOOP, &kev));
+      if (e->sp.world > 1) CKS(launch_finalize(e, e->stream, true, nullptr, true));
       CK(cudaEventRecord(kev.ev[3], e->stream));
       CK(cudaStreamSynchronize(e->stream));
       for (int j = 0; j < 3; ++j) {

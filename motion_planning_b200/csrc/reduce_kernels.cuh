@@ -116,6 +116,53 @@ __device__ __forceinline__ bool last_block_done(unsigned int* counter, unsigned 
   return last;
 }
 
+// ---- peer-to-peer exchange over NVLink (world > 1) ------------------------------------------------------
+// Buffer of every rank: doubles [2 parity][world][T*6], then uint32 flags [2][world].  Rank r stores its
+// record into slot r of EVERY rank's buffer (plain stores to CUDA-IPC-mapped peer memory), fences at
+// system scope and raises flag[parity][r] = epoch+1 there; the finalize kernel of each rank spins on its
+// own flags.  Two parities suffice: a rank can be at most one step ahead of its slowest peer.
+__device__ __forceinline__ unsigned int* p2p_flags(double* base, int world, int T) {
+  return reinterpret_cast<unsigned int*>(base + (size_t)2 * world * T * kRecordStride);
+}
+__device__ inline void p2p_push_record(const ReduceArgs& a) {
+  const int T = a.sp.T, world = a.sp.world, rank = a.rank;
+  const unsigned int epoch = a.fin.dyn->xchg;
+  const int par = (int)(epoch & 1u);
+  const int n = T * kRecordStride;
+  for (int g = 0; g < world; ++g) {
+    double* dst = a.p2p_peers[g] + ((size_t)par * world + rank) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcg(a.record + i);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    unsigned int* f = p2p_flags(a.p2p_peers[threadIdx.x], world, T) + (size_t)par * world + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch + 1u) : "memory");
+  }
+}
+__device__ inline bool p2p_wait_all(const FinalizeArgs& a) {
+  __shared__ int timed_out;
+  const int T = a.sp.T, world = a.sp.world;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  const unsigned int epoch = a.dyn->xchg;
+  const int par = (int)(epoch & 1u);
+  if ((int)threadIdx.x < world) {
+    const unsigned int* f = p2p_flags(a.p2p_local, world, T) + (size_t)par * world + threadIdx.x;
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (clock64() - t0 > (1LL << 33)) {   // ~4 s: a peer died
+        timed_out = 1;
+        break;
+      }
+    } while (v != epoch + 1u);
+  }
+  __syncthreads();
+  return timed_out == 0;
+}
+
 // ---- kernel 2a: SOFTMIN merge.  grid = T blocks of 256 threads --------------------------------------
 // Two streaming passes over the nCTA partials of this t (second one L1/L2-hot), loads batched 4 deep;
 // pass 1: global minimum, pass 2: rescale by exp(-(m_cta - m)/lam) and sum (one exp per partial).
@@ -181,7 +228,14 @@ __global__ void __launch_bounds__(256) reduce_softmin_kernel(const __grid_consta
     r[4] = v5[3] * s0;
     r[5] = v5[4] * s1;
   }
-  if (a.fuse_finalize && last_block_done(a.done_counter, gridDim.x)) finalize_body(a.fin, reinterpret_cast<double*>(smem_fin));
+  if (a.fuse_finalize || a.p2p_push) {
+    if (last_block_done(a.done_counter, gridDim.x)) {
+      if (a.p2p_push)
+        p2p_push_record(a);
+      else
+        finalize_body(a.fin, reinterpret_cast<double*>(smem_fin));
+    }
+  }
 }
 
 // ---- fp64 re-evaluation of ONE rollout by ONE warp, parallel in time ------------------------------
@@ -419,7 +473,7 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     floor_scale(sp, a.fin.dyn, s0, s1);
     double* r = a.record + (size_t)t * kRecordStride;
     r[0] = m64;
-    r[1] = v5[0];
+    r[1] = overflow ? -1.0 : v5[0];   // S < 0 marks a candidate-list overflow for every rank that merges this record
     r[2] = v5[1];
     r[3] = v5[2];
     r[4] = v5[3] * s0;
@@ -430,10 +484,15 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     atomicMax(reinterpret_cast<unsigned long long*>(&a.fin.dyn->refine_max_dev), (unsigned long long)__double_as_longlong(dev));
   }
   TS(4);
-  if (a.fuse_finalize && last_block_done(a.done_counter, gridDim.x)) {
-    TS(5);
-    finalize_body(a.fin, warp_scratch);
-    TS(6);
+  if (a.fuse_finalize || a.p2p_push) {
+    if (last_block_done(a.done_counter, gridDim.x)) {
+      TS(5);
+      if (a.p2p_push)
+        p2p_push_record(a);
+      else
+        finalize_body(a.fin, warp_scratch);
+      TS(6);
+    }
   }
 }
 
@@ -491,31 +550,45 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
   const StaticParams& sp = a.sp;
   const int T = sp.T, W = T - 1, h = W / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  if (tid == 0) bad = 0;
-  __syncthreads();
-  if (a.mode == 0 && a.dyn->refine_overflow) {
-    // MIXED: the fp32 screen overflowed a candidate list -> leave U, the step counter and x0
-    // untouched and ask the host to redo this step with the fp64 pipeline (same noise).
+  if (tid == 0) {
+    bad = 0;
+    for (int i = 0; i < 3; ++i)
+      if (a.mode == 0 && (!isfinite(a.dyn->x0[i]) || !isfinite(a.dyn->goal[i]))) bad = 1;
+  }
+  const double* gather = a.p2p ? a.p2p_local + (size_t)(a.dyn->xchg & 1u) * sp.world * T * kRecordStride : a.gather;
+  {
+    // MIXED: a record with S < 0 means some rank's fp32 screen overflowed a candidate list -> every rank
+    // leaves U, the step counter and x0 untouched and asks its host to redo this step with the fp64
+    // pipeline (same noise: the Philox step counter is not advanced; the exchange epoch is).
+    __shared__ int any_ovf;
+    if (tid == 0) any_ovf = 0;
     __syncthreads();
-    if (tid == 0) {
-      DynState* d = a.dyn;
-      d->status = kStatusRedoF64;
-      d->overflow_total += 1;
-      d->refine_candidates = 0;
-      d->refine_overflow = 0;
-      d->refine_max_dev = 0.0;
+    if (a.mode == 0)
+      for (int i = tid; i < sp.world * T; i += blockDim.x)
+        if (__ldcg(&gather[(size_t)i * kRecordStride + 1]) < 0.0) any_ovf = 1;
+    __syncthreads();
+    if (any_ovf) {
+      if (tid == 0) {
+        DynState* d = a.dyn;
+        d->status = kStatusRedoF64;
+        d->overflow_total += 1;
+        d->xchg += 1u;
+        d->refine_candidates = 0;
+        d->refine_overflow = 0;
+        d->refine_max_dev = 0.0;
+      }
+      return;
     }
-    return;
   }
   // -- merge the records of all ranks and apply the weighted noise (control/src/mppi:189-199) ----
   const double neg_inv_lam = -1.0 / a.dyn->lam;
   for (int idx = tid; idx < 2 * T; idx += blockDim.x) {
     const int c = idx / T, t = idx - c * T;
     double m = Math<double>::inf();
-    for (int g = 0; g < sp.world; ++g) m = fmin(m, __ldcg(&a.gather[((size_t)g * T + t) * kRecordStride]));
+    for (int g = 0; g < sp.world; ++g) m = fmin(m, __ldcg(&gather[((size_t)g * T + t) * kRecordStride]));
     double S = 0, N = 0, E = 0;
     for (int g = 0; g < sp.world; ++g) {
-      const double* r = a.gather + ((size_t)g * T + t) * kRecordStride;
+      const double* r = gather + ((size_t)g * T + t) * kRecordStride;
       const double rm = __ldcg(r);
       const double sc = (rm == m) ? 1.0 : exp((rm - m) * neg_inv_lam);
       S += __ldcg(r + 1) * sc;
@@ -587,6 +660,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       d->out_x[2] = xn[2];
       d->status = bad ? (int)MPPI_ERR_NONFINITE : (int)MPPI_OK;
       d->step += 1u;
+      d->xchg += 1u;
       if (a.closed_loop) {
         d->x0[0] = xn[0];
         d->x0[1] = xn[1];
@@ -603,6 +677,10 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
 
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw3[];
+  if (a.p2p && !p2p_wait_all(a)) {
+    if (threadIdx.x == 0) a.dyn->status = (int)MPPI_ERR_STATE;   // exchange timed out
+    return;
+  }
   finalize_body(a, reinterpret_cast<double*>(smem_raw3));
 }
 

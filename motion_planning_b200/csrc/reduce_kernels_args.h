@@ -29,6 +29,9 @@ struct FinalizeArgs {
   double sg_inv_norm[4];     // 1 / sum_j p_i(z_j)^2
   int mode;                  // 0: full step, 1: update only (mppi_update_action)
   int closed_loop;           // 1: dyn->x0 <- x_next (device-resident loop of mppi_bench)
+  // peer-to-peer exchange (world > 1, NVLink): wait for every rank's record to land in p2p_local
+  int p2p;
+  double* p2p_local;         // this rank's buffer: [2 parity][world][T*6] doubles, then flags [2][world] uint32
 };
 
 struct ReduceArgs {
@@ -36,6 +39,9 @@ struct ReduceArgs {
   FinalizeArgs fin;          // fin.dyn is THE DynState; the rest is used when fuse_finalize != 0
   int fuse_finalize;         // 1: the last block to finish also runs the finalize phase (world_size 1)
   unsigned int* done_counter;
+  int rank;
+  int p2p_push;              // 1: the last block stores this rank's record into every peer's buffer
+  double* const* p2p_peers;  // device array [world] of peer buffer base pointers (CUDA IPC mappings)
   unsigned long long* debug_ts;   // optional [T][8] globaltimer stamps of the reduce phases (profiling aid)
   const void* part;          // SOFTMIN partials Vec4[T][nCTA]
   const double* epart;       // [T][nCTA][2]

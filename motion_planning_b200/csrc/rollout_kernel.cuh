@@ -33,14 +33,17 @@ __device__ __forceinline__ R load_eps_ext(const double* __restrict__ eps, int t,
   return R(eps[((size_t)t * 2 + c) * (size_t)K + k]);
 }
 
-// SCREEN slow path (rare): more than kMaxCand rollouts inside the window -> halve the window until the
-// old list entries plus this tile's rollouts fit, then rebuild the list.  One lane, sequential.
+// SCREEN slow path (rare): the list is full -> evict stale entries (listed against an older, higher
+// running minimum), and if more than kMaxCand rollouts really are inside the window halve it until the
+// old entries plus this tile's rollouts fit; then rebuild the list.  One lane, sequential.
 template <typename R>
 __device__ __noinline__ int screen_tighten(uint2* list, int cnt_old, const R* tot, const R* pre, int block, int tile_base,
                                            R mnew, R& lim) {
   int total = 0;
-  for (int it = 0; it < 31; ++it) {
-    lim = mnew + (lim - mnew) * R(0.5);
+  for (int it = 0; it < 32; ++it) {
+    // first pass keeps the full window: entries listed against an older (higher) running minimum of a
+    // persistent CTA are simply stale and get evicted; only if that is not enough the window is halved
+    if (it > 0) lim = mnew + (lim - mnew) * R(0.5);
     total = 0;
     for (int i = 0; i < cnt_old; ++i) total += (R(__uint_as_float(list[i].y)) <= lim) ? 1 : 0;
     for (int k = 0; k < block; ++k) total += ((tot[k] - (pre ? pre[k] : R(0))) <= lim) ? 1 : 0;

@@ -46,8 +46,12 @@ class _DevBuf(object):
 class ShardedMPPI(object):
     """`MPPI` whose `samples` are sharded over the ranks of a torch.distributed process group.
 
-    exchange='nccl' all-gathers the device-resident records in place over NVLink (the engine launches on
-    torch's current stream so kernels and collective are stream-ordered, no host sync in between);
+    exchange='p2p'  (default with the nccl backend): the ranks map each other's exchange buffers through
+                    CUDA IPC once; afterwards the reduce kernel stores the record straight into every
+                    peer's memory over NVLink and the finalize kernel spins on arrival flags -- the whole
+                    sharded step is one CUDA graph per rank and no collective is called per step.
+    exchange='nccl' all-gathers the device-resident records in place with NCCL (engine kernels and the
+                    collective share one stream, no host sync in between).
     exchange='host' stages the 3 KB record through host memory (works with any backend, e.g. gloo).
     """
 
@@ -61,7 +65,7 @@ class ShardedMPPI(object):
         self.samples_total = int(samples_total)
         k_local, k_offset = shard_plan(samples_total, self.world, self.rank)
         backend = dist.get_backend(group)
-        self.exchange = exchange or ("nccl" if backend == "nccl" else "host")
+        self.exchange = exchange or ("p2p" if backend == "nccl" and self.world > 1 else "host")
         self.stream = None
         if self.exchange == "nccl":
             # a dedicated non-default stream: the engine launches its kernels on it and the NCCL collective
@@ -78,6 +82,18 @@ class ShardedMPPI(object):
         rb, gb = C.c_size_t(), C.c_size_t()
         _capi.check(lib.mppi_exchange_buffers(h, C.byref(rec), C.byref(rb), C.byref(gat), C.byref(gb)), "mppi_exchange_buffers")
         self._n_rec = rb.value // 8
+        if self.exchange == "p2p":
+            mine = (C.c_ubyte * 64)()
+            _capi.check(lib.mppi_p2p_export(h, C.cast(mine, C.c_void_p)), "mppi_p2p_export")
+            t = torch.tensor(list(bytes(mine)), dtype=torch.uint8)
+            if backend == "nccl":
+                t = t.cuda()
+            out = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(out, t, group=group)
+            allh = bytes(torch.cat([o.cpu() for o in out]).tolist())
+            buf = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
+            _capi.check(lib.mppi_p2p_connect(h, C.cast(buf, C.c_void_p)), "mppi_p2p_connect")
+            dist.barrier(group=group)
         if self.exchange == "nccl":
             self._rec_t = torch.as_tensor(_DevBuf(rec.value, self._n_rec), device="cuda")
             self._gat_t = torch.as_tensor(_DevBuf(gat.value, self._n_rec * self.world), device="cuda")
@@ -86,6 +102,8 @@ class ShardedMPPI(object):
         """MPPI.get_path (control/src/mppi:85-102) with K sharded over the group."""
         m, lib, h = self.mppi, self.mppi._lib, self.mppi._h
         m._sync_sampling(sig, lam)
+        if self.exchange == "p2p":
+            return m.get_path(state, goal, sig, lam)      # plain mppi_step: the exchange is inside the graph
         _capi.check(lib.mppi_set_goal(h, _capi.dptr(_capi.f64(goal, (3,)))), "mppi_set_goal")
         _capi.check(lib.mppi_step_local(h, _capi.dptr(_capi.f64(state, (3,)))), "mppi_step_local")
         if self.exchange == "nccl":

@@ -15,7 +15,7 @@ def _ngpu():
     return _capi.load().mppi_device_count()
 
 
-@pytest.mark.parametrize("precision,exchange", [("mixed", "nccl"), ("f64", "nccl"), ("mixed", "host")])
+@pytest.mark.parametrize("precision,exchange", [("mixed", "p2p"), ("f32", "p2p"), ("mixed", "nccl"), ("f64", "nccl"), ("mixed", "host")])
 def test_sharded_equals_single_gpu(precision, exchange):
     n = _ngpu()
     if n < 2:
