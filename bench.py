@@ -261,42 +261,67 @@ def run_single(args):
 
 
 def run_multi(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
+    from motion_planning_b200 import _capi
     from motion_planning_b200.distributed import ShardedMPPI
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K_total, T = K_PER_GPU * world, T_HORIZON
-    m = ShardedMPPI(T, K_total, precision=args.precision, seed=0, device=local)
-    s = X0.copy()
-    for _ in range(max(args.warmup, 3)):
-        s = m.get_path(s, GOAL)
+    m = ShardedMPPI(T, K_total, precision=args.precision, seed=0, device=local, exchange=args.exchange)
+    lib, h = m.mppi._lib, m.mppi._h
     sampler = ClockSampler(local) if rank == 0 else None
-    # e2e and device time coincide here: every step takes host x0 and returns host (u, x_next)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if m.exchange == "p2p":
+        # the exchange lives inside the per-rank CUDA graph: time the device-resident closed loop with CUDA
+        # events on the engine's launch stream (ranks run in lockstep through the arrival flags)
+        m.mppi.goal = GOAL
+        dist.barrier()
+        torch.cuda.synchronize()
+        r = m.mppi.bench(X0, steps=args.steps, warmup=args.warmup, flush_l2=True, per_kernel=False)
+        dev_ms, launches = r["step_ms"], r["launches"]
+        timing = "CUDA events on the engine's launch stream around each graph launch, max over ranks"
+    else:
+        s = X0.copy()
+        for _ in range(args.warmup):
+            s = m.get_path(s, GOAL)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        st = m.stream if m.stream is not None else torch.cuda.current_stream()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        dist.barrier()
+        torch.cuda.synchronize()
+        for i in range(args.steps):
+            with torch.cuda.stream(st):
+                flush.fill_(i & 0xff)
+                ev[i][0].record(st)
+            s = m.get_path(s, GOAL)
+            ev[i][1].record(st)
+        torch.cuda.synchronize()
+        dev_ms, launches = sum(a.elapsed_time(b) for a, b in ev) / args.steps, 3 * args.steps
+        timing = "CUDA events on the stream shared by the engine kernels and the NCCL all-gather, max over ranks"
+    # e2e: host x0 in, (u, x_next) out every step through the C ABI, closed loop on the host
+    m.initialize()
+    x, u, xn = X0.copy(), np.empty(2), np.empty(3)
+    if m.exchange == "p2p":
+        px, pu, pn = _capi.dptr(x), _capi.dptr(u), _capi.dptr(xn)
+        _capi.check(lib.mppi_set_goal(h, _capi.dptr(GOAL)), "mppi_set_goal")
+
+        def one():
+            if lib.mppi_step(h, px, pu, pn) != 0:
+                raise RuntimeError("mppi_step failed")
+            x[:] = xn
+    else:
+        def one():
+            x[:] = m.get_path(x.copy(), GOAL)
+    for _ in range(args.warmup):
+        one()
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    st = m.stream if m.stream is not None else torch.cuda.current_stream()
-    for i in range(args.steps):
-        with torch.cuda.stream(st):
-            flush.fill_(i & 0xff)
-            ev[i][0].record(st)
-        s = m.get_path(s, GOAL)
-        ev[i][1].record(st)
-    torch.cuda.synchronize()
-    dist.barrier()
-    wall = time.perf_counter() - t0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    # e2e without the flush in the loop
-    dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        s = m.get_path(s, GOAL)
+    for _ in range(args.steps):
+        one()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
@@ -305,20 +330,24 @@ def run_multi(args):
     clocks = sampler.stop() if sampler else {}
     if rank == 0:
         io = m.mppi.io_bytes()
+        xbytes = T * 48
         line = {
             "metric": METRIC, "value": K_total / (dev_ms * 1e-3), "unit": "rollouts/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"mixed": "f32 rollouts + f64 re-evaluation of the softmin support", "f32": "f32", "f64": "f64"}[args.precision],
             "data": "synthetic",
             "config": {"workload": "diff-drive parallel-park K=%d per GPU (K_total=%d) T=%d, rollouts sharded over ranks, "
-                                   "one %d-byte all-gather per step" % (K_PER_GPU, K_total, T, T * 48),
-                       "K_total": K_total, "T": T, "precision": args.precision, "exchange": m.exchange,
-                       "l2": "flushed between timed steps", "timing": "CUDA events on the launch stream, max over ranks",
-                       "launch": m.mppi.launch_info()},
+                                   "one %d-byte record exchanged all-to-all per step" % (K_PER_GPU, K_total, T, xbytes),
+                       "K_total": K_total, "T": T, "precision": args.precision,
+                       "exchange": {"p2p": "fused: reduce kernel stores its record into every peer's memory over NVLink "
+                                           "(CUDA IPC), finalize kernel spins on arrival flags; one CUDA graph per rank",
+                                    "nccl": "ncclAllGather of the device-resident records (torch.distributed)",
+                                    "host": "host-staged all-gather"}[m.exchange],
+                       "l2": "flushed between timed steps", "timing": timing, "launch": m.mppi.launch_info()},
             "state_steps_per_s": K_total / (dev_ms * 1e-3) * T,
             "e2e": {"value": K_total / (e2e_ms * 1e-3), "unit": "rollouts/s", "h2d_bytes_per_step": io[0] * world,
                     "d2h_bytes_per_step": io[1] * world, "ms_per_step": e2e_ms},
-            "gpu_launches": 3 * args.steps, "wall_ms_per_step_with_flush": wall / args.steps * 1e3, "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line))
     dist.barrier()
@@ -333,6 +362,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="mixed", choices=["mixed", "f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default=None, choices=["p2p", "nccl", "host"], help="multi-GPU record exchange (default p2p)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
