@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmppi_b200.so")
+LIB_PATH = os.environ.get("MPPI_B200_LIB") or os.path.join(_HERE, "lib", "libmppi_b200.so")   # env: experimental variants
 
 MPPI_OK = 0
 STATUS_NAMES = {0: "MPPI_OK", 1: "MPPI_ERR_INVALID", 2: "MPPI_ERR_CUDA", 3: "MPPI_ERR_NO_DEVICE",

@@ -34,8 +34,19 @@ def _stale(out, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), tag=None):
+    """tag/defines: build an experimental variant into lib/libmppi_b200_<tag>.so (select it at run time with
+    the environment variable MPPI_B200_LIB); the default build is the product."""
+    global OBJ, LIB
     nvcc = _nvcc()
+    obj_dir, lib_path = OBJ, LIB
+    if tag:
+        obj_dir = os.path.join(HERE, "build_" + tag)
+        lib_path = os.path.join(HERE, "lib", "libmppi_b200_%s.so" % tag)
+    return _build(nvcc, obj_dir, lib_path, force, verbose, list(defines))
+
+
+def _build(nvcc, OBJ, LIB, force, verbose, defines):
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
@@ -45,7 +56,7 @@ def build(force=False, verbose=False):
         src = os.path.join(CSRC, u)
         obj = os.path.join(OBJ, u[:-3] + ".o")
         if force or _stale(obj, [src] + hdrs):
-            jobs.append([nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+            jobs.append([nvcc] + FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -68,4 +79,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    tags = [a[6:] for a in sys.argv[1:] if a.startswith("--tag=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, tag=tags[0] if tags else None))

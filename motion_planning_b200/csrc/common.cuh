@@ -9,8 +9,16 @@
 
 #include "../../include/mppi_b200.h"
 
+#ifndef MPPI_PHILOX_ROUNDS
+#define MPPI_PHILOX_ROUNDS 10   // Philox4x32-10 (the cuRAND default); 7 is the smallest Crush-resistant count
+#endif
+#ifndef MPPI_UNROLL_T2
+#define MPPI_UNROLL_T2 1
+#endif
+
 namespace mppi {
 
+constexpr int kUnrollT2 = MPPI_UNROLL_T2;   // step pairs per iteration of the rollout loop
 constexpr int kMaxCand = 16;        // SCREEN: candidate slots per (CTA, t)
 constexpr int kMaxRefine = 256;     // SCREEN: fp64 re-evaluations per t after the global filter
 constexpr int kRecordStride = 6;    // doubles per t in an exchange record: m, S, N0, N1, E0, E1
@@ -189,7 +197,7 @@ __device__ __forceinline__ R clamp_(R v, R lim) {
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < MPPI_PHILOX_ROUNDS; ++i) {
     uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
     uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
     c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);

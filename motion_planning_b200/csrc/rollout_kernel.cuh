@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     // basic block as the two model steps of pair t2, so the integer/SFU chain overlaps the FP chain.
     float4 znext = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!sp.noise_external) znext = philox_normal4(sp.seed, kglobal, 0u, step);
+#pragma unroll kUnrollT2
     for (int t2 = 0; t2 < (T >> 1); ++t2) {
       float zf[4];
       R ev[4];
