@@ -221,6 +221,16 @@ def run_single(args):
     achieved = F_ALG * K * T / (r["rollout_ms"] * 1e-3) / 1e12
     hbm_alg_bytes = 16 * T * r["launch"]["grid"] * 3 + 16 * T     # per-CTA partials (m,S,N0,N1 + E) out, nominal in
     cpu = cpu_baseline_port() if not args.no_cpu else None
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
+        key = [k for k in ncu if k.startswith("rollout_kernel") and ("precision %s" % args.precision) in k]
+        if key:
+            m_ = ncu[key[0]]
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            traffic = sum(m_[n]["value"] * mult.get(m_[n]["unit"], 1) for n in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        traffic = None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -243,7 +253,8 @@ def run_single(args):
         "gpu_launches": r["launches"],
         "kernels_ms": {"rollout": r["rollout_ms"], "reduce": r["reduce_ms"], "finalize": r["finalize_ms"]},
         "roofline": {"bound": "fp32_alu", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
-                     "frac": achieved / tf.value if tf.value else None, "traffic": None,
+                     "frac": achieved / tf.value if tf.value else None, "traffic": traffic,
+                     "traffic_note": "DRAM bytes per launch from profiles/r01_ncu_summary.json (ncu --set full); the ~2 MB of per-CTA partials stay in L2",
                      "kernel": "rollout_kernel", "flop_per_state_step": F_ALG,
                      "peak_source": "FFMA chain measured in this run (mppi_measure_fp32_peak); MEASURED_PEAKS.json has no fp32 entry",
                      "hbm_view": {"algorithmic_bytes": hbm_alg_bytes,

@@ -1,26 +1,29 @@
 #!/bin/bash
-# One GPU visit: tests, bench, C++ facade demo, ncu launch list + full capture of the rollout kernel.
-# usage (here): gpurun --timeout 1500 -- 'bash scripts/gpu_round.sh [tag]'
+# One full GPU visit: tests, bench (both arms), C++ facade demo, ncu launch lists + full captures.
+# usage (here): gpurun --timeout 1800 -- 'bash scripts/gpu_round.sh [tag]'
 TAG=${1:-r01}
 O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/gpu_${TAG}.txt 2>&1
 nproc >> $O/gpu_${TAG}.txt; grep -m1 "model name" /proc/cpuinfo >> $O/gpu_${TAG}.txt
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -60 > $O/pytest_gpu_${TAG}.log
-tail -5 $O/pytest_gpu_${TAG}.log
-timeout 600 python bench.py --steps 50 --warmup 5 > $O/bench_${TAG}.json 2> $O/bench_${TAG}.err
-tail -c 3000 $O/bench_${TAG}.json; tail -5 $O/bench_${TAG}.err
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -30 > $O/pytest_gpu_${TAG}.log
+tail -3 $O/pytest_gpu_${TAG}.log
+timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > $O/bench_reference_${TAG}.json 2> $O/bench_reference_${TAG}.err
+timeout 600 python bench.py --steps 100 --warmup 10 > $O/bench_${TAG}.json 2> $O/bench_${TAG}.err
+tail -c 1500 $O/bench_${TAG}.json; tail -3 $O/bench_${TAG}.err
 g++ -std=c++17 -Iinclude examples/ros_control_node.cpp -Lmotion_planning_b200/lib -lmppi_b200 \
   -Wl,-rpath,$PWD/motion_planning_b200/lib -o /tmp/ros_node 2>&1 | grep -v Wcomment | head -5
-timeout 300 /tmp/ros_node 4096 64 1500 > $O/cpp_node_${TAG}.log 2>&1; tail -4 $O/cpp_node_${TAG}.log
+timeout 300 /tmp/ros_node 4096 64 3000 > $O/cpp_node_${TAG}.log 2>&1; tail -2 $O/cpp_node_${TAG}.log
 for P in mixed f32 f64; do
-  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
+  timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -c 40 --csv \
     --log-file $O/launches_${P}_${TAG}.csv python profiles/profile_step.py $P 65536 64 5 > $O/ncu_${P}_${TAG}.log 2>&1
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 4 -c 2 \
-  -o $O/prof_rollout_mixed_${TAG} -f python profiles/profile_step.py mixed 65536 64 4 >> $O/ncu_full_${TAG}.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 4 -c 1 \
+  -o $O/prof_rollout_mixed_${TAG} -f python profiles/profile_step.py mixed 65536 64 4 > $O/ncu_full_${TAG}.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:reduce_screen -s 4 -c 1 \
   -o $O/prof_reduce_mixed_${TAG} -f python profiles/profile_step.py mixed 65536 64 4 >> $O/ncu_full_${TAG}.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 4 -c 1 \
   -o $O/prof_rollout_f32_${TAG} -f python profiles/profile_step.py f32 65536 64 4 >> $O/ncu_full_${TAG}.log 2>&1
-ls -la $O | tail -20
+python profiles/reduce_timeline.py mixed > $O/reduce_timeline_${TAG}.txt 2>&1
+python profiles/sweep_configs.py 30 > $O/sweep_${TAG}.jsonl 2>&1
+ls $O | wc -l
