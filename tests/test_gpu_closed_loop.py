@@ -1,0 +1,80 @@
+"""GPU: behaviour-level checks of the whole controller path (properties that hold at any size)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+PARK = np.array([0.0, -1.0, 0.0])
+
+
+def mp():
+    import motion_planning_b200 as m
+    return m
+
+
+def test_solve_path_reaches_the_goal_like_the_reference_loop():
+    """MPPI.solve_path (control/src/mppi:104-125): closed loop on the model until within `thresh`."""
+    m = mp().MPPI(horizon=32, samples=4096, seed=1)
+    start, goal = np.array([0.0, 0.0, np.pi / 2.0]), np.array([0.3, 0.4, np.pi / 2.0])
+    m.solve_path(start, goal, max_iters=2000)
+    assert np.linalg.norm(m.path[-1][:2] - goal[:2]) <= m.thresh
+    assert np.all(np.abs(m.uvec) <= 6.35492 + 1e-12)
+    assert m.path.shape[0] == m.uvec.shape[0] == len(m.fin_time)
+    m.close()
+
+
+def test_steps_are_deterministic_and_restartable():
+    """Same seed -> bit-identical runs; get/set of latest_uvec + use_philox(seed) restarts a run exactly."""
+    K, T = 8192, 32
+
+    def run(n, m=None):
+        m = m or mp().MPPI(horizon=T, samples=K, seed=5)
+        s = np.array([0.1, 0.0, 0.3])
+        outs = []
+        for _ in range(n):
+            s = m.get_path(s, PARK)
+            outs.append((m.uvec[-1].copy(), s.copy(), m.latest_uvec))
+        return m, outs
+
+    a, oa = run(4)
+    b, ob = run(4)
+    for (u1, s1, U1), (u2, s2, U2) in zip(oa, ob):
+        assert np.array_equal(u1, u2) and np.array_equal(s1, s2) and np.array_equal(U1, U2)
+    a.close()
+    b.close()
+
+
+def test_full_size_properties_c2():
+    """BASELINE config 2 size: controls stay inside the clip, the last column is the shifted-in zero,
+    the applied control equals column 0 of the pre-shift sequence, noise moments are right."""
+    K, T = 65536, 64
+    m = mp().MPPI(horizon=T, samples=K, seed=0)
+    s = np.zeros(3)
+    for it in range(3):
+        s = m.get_path(s, PARK)
+        U, Upre = m.latest_uvec, m.get_last_update()
+        assert np.all(np.abs(U) <= 6.35492) and np.all(np.isfinite(U))
+        assert np.all(U[:, -1] == 0.0) and np.array_equal(U[:, :-1], Upre[:, 1:])      # control/src/mppi:100-101
+        assert np.array_equal(m.uvec[-1], Upre[:, 0])                                   # control/src/mppi:96-97
+    eps = m.get_noise()
+    assert eps.shape == (T, 2, K)
+    assert abs(eps.mean()) < 1e-3 and abs(eps.std() - 0.9) < 1e-3
+    st = m.stats()
+    assert st["refine_overflow"] == 0 and 0 < st["refine_candidates"] < 64 * 32
+    assert st["refine_max_dev"] < 0.01       # fp32 screen vs fp64 re-evaluation, head-room is 0.04
+    m.close()
+
+
+def test_cpp_facade_closed_loop():
+    """include/mppi.hpp: compile examples/ros_control_node.cpp against the built library and run it."""
+    exe = "/tmp/mppi_ros_node_test"
+    lib = os.path.join(ROOT, "motion_planning_b200", "lib")
+    r = subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "ros_control_node.cpp"),
+                        "-L" + lib, "-lmppi_b200", "-Wl,-rpath," + lib, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "2048", "32", "1500"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "WAYPOINT REACHED" in r.stdout
