@@ -661,6 +661,10 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   memset(&rd, 0, sizeof(rd));
   rd.sp = e->sp;
   rd.fin = make_fin(e, fuse == FUSE_LOOP);
+  if (fuse != FUSE_NONE && e->p2p_on) {   // sharded + p2p: the last block also exchanges and finalizes
+    rd.fin.p2p = 1;
+    rd.fin.gather = nullptr;
+  }
   rd.fuse_finalize = (fuse != FUSE_NONE && e->sp.world == 1) ? 1 : 0;
   rd.done_counter = e->d_done;
   rd.rank = e->p.rank;
@@ -709,7 +713,6 @@ static mppi_status build_graphs(mppi_engine* e) {
       if (ce != cudaSuccess) s = MPPI_ERR_CUDA;
     }
     if (s == MPPI_OK) s = launch_local(e, e->stream, e->p.precision, which == 1 ? FUSE_LOOP : FUSE_STEP, nullptr);
-    if (s == MPPI_OK && e->sp.world > 1) s = launch_finalize(e, e->stream, which == 1, nullptr, true);
     if (s == MPPI_OK && which == 0) {
       cudaError_t ce = cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream);
       if (ce != cudaSuccess) s = MPPI_ERR_CUDA;
@@ -746,7 +749,6 @@ static mppi_status finish_outputs(mppi_engine* e, double u_out[2], double x_next
       return MPPI_ERR_UNSUPPORTED;
     }
     CKS(launch_local(e, e->stream, MPPI_PRECISION_F64, FUSE_STEP, nullptr));
-    if (e->sp.world > 1) CKS(launch_finalize(e, e->stream, false, nullptr, true));   // every rank redoes (same record)
     CK(cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->last.refine_overflow += 1;
@@ -804,7 +806,6 @@ extern "C" mppi_status mppi_step(mppi_handle e, const double x0[3], double u_out
   } else {
     CK(cudaMemcpyAsync(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CKS(launch_local(e, e->stream, e->p.precision, FUSE_STEP, nullptr));
-    if (e->sp.world > 1) CKS(launch_finalize(e, e->stream, false, nullptr, true));
     CK(cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream));
   }
   CK(cudaStreamSynchronize(e->stream));
@@ -1126,7 +1127,7 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
   mppi_timing t{};
   t.step_ms = (float)(total / steps);
   t.steps = steps;
-  t.launches = (e->sp.world > 1 ? 3 : 2) * steps;   // rollout + reduce (+ finalize: fused into the reduce kernel when world == 1)
+  t.launches = 2 * steps;   // rollout + reduce (exchange and finalize run in the reduce kernel's last block)
   if (per_kernel) {
     KernelEvents kev;
     kev.on = true;
@@ -1135,7 +1136,6 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
     for (int i = 0; i < steps; ++i) {
       if (flush_l2) CK(cudaMemsetAsync(e->d_flush, i & 0xff, e->flush_bytes, e->stream));
       CKS(launch_local(e, e->stream, e->p.precision, FUSE_LOOP, &kev));
-      if (e->sp.world > 1) CKS(launch_finalize(e, e->stream, true, nullptr, true));
       CK(cudaEventRecord(kev.ev[3], e->stream));
       CK(cudaStreamSynchronize(e->stream));
       for (int j = 0; j < 3; ++j) {

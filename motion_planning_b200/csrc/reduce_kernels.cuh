@@ -163,6 +163,21 @@ __device__ inline bool p2p_wait_all(const FinalizeArgs& a) {
   return timed_out == 0;
 }
 
+// What the last block of a reduce kernel does once every record of this rank is complete:
+//   world == 1 : finalize in place;
+//   world  > 1 : store the record into every peer (NVLink), wait for all peers' records, finalize --
+//                the whole sharded step stays at TWO kernels per rank.
+__device__ inline void last_block_epilogue(const ReduceArgs& a, double* scratch4T) {
+  if (a.p2p_push) {
+    p2p_push_record(a);
+    if (!p2p_wait_all(a.fin)) {
+      if (threadIdx.x == 0) a.fin.dyn->status = (int)MPPI_ERR_STATE;   // exchange timed out (a peer died)
+      return;
+    }
+  }
+  finalize_body(a.fin, scratch4T);
+}
+
 // ---- kernel 2a: SOFTMIN merge.  grid = T blocks of 256 threads --------------------------------------
 // Two streaming passes over the nCTA partials of this t (second one L1/L2-hot), loads batched 4 deep;
 // pass 1: global minimum, pass 2: rescale by exp(-(m_cta - m)/lam) and sum (one exp per partial).
@@ -228,14 +243,8 @@ __global__ void __launch_bounds__(256) reduce_softmin_kernel(const __grid_consta
     r[4] = v5[3] * s0;
     r[5] = v5[4] * s1;
   }
-  if (a.fuse_finalize || a.p2p_push) {
-    if (last_block_done(a.done_counter, gridDim.x)) {
-      if (a.p2p_push)
-        p2p_push_record(a);
-      else
-        finalize_body(a.fin, reinterpret_cast<double*>(smem_fin));
-    }
-  }
+  if ((a.fuse_finalize || a.p2p_push) && last_block_done(a.done_counter, gridDim.x))
+    last_block_epilogue(a, reinterpret_cast<double*>(smem_fin));
 }
 
 // ---- fp64 re-evaluation of ONE rollout by ONE warp, parallel in time ------------------------------
@@ -484,15 +493,10 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     atomicMax(reinterpret_cast<unsigned long long*>(&a.fin.dyn->refine_max_dev), (unsigned long long)__double_as_longlong(dev));
   }
   TS(4);
-  if (a.fuse_finalize || a.p2p_push) {
-    if (last_block_done(a.done_counter, gridDim.x)) {
-      TS(5);
-      if (a.p2p_push)
-        p2p_push_record(a);
-      else
-        finalize_body(a.fin, warp_scratch);
-      TS(6);
-    }
+  if ((a.fuse_finalize || a.p2p_push) && last_block_done(a.done_counter, gridDim.x)) {
+    TS(5);
+    last_block_epilogue(a, warp_scratch);
+    TS(6);
   }
 }
 
