@@ -119,6 +119,20 @@ template <> struct Math<float> {
     c = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z * z,
              fmaf(-0.5f, z, 1.0f));
   }
+  // polynomial sin/cos, |a| <= pi/4 guaranteed by the caller (FAST path: no branch at all)
+  static __device__ __forceinline__ void sincos_poly_(float a, float& s, float& c) {
+    const float z = a * a;
+    s = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), z * a, a);
+    c = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z * z,
+             fmaf(-0.5f, z, 1.0f));
+  }
+  // the reference's wrap for |theta| < 3 pi (one turn at most), branch-free: n = +1 above pi, -1 at or
+  // below -pi, else 0  ==  ceil((theta+pi)/(2pi)) - 1 on that range (control/src/mppi:52-53)
+  static __device__ __forceinline__ float wrap_once_(float th) {
+    const float n = (th > pi()) ? 1.0f : ((th <= -pi()) ? -1.0f : 0.0f);
+    const float r = fmaf(-n, 6.28318548202514648f, th);
+    return fmaf(n, 1.74845553146951715e-07f, r);
+  }
   // theta - (ceil((theta+pi)/(2pi)) - 1) * 2pi   (control/src/mppi:52-53), 2pi split hi/lo.
   // The expression is the identity on (-pi, pi], so it is only evaluated outside that interval.
   static __device__ __noinline__ float wrap_slow_(float th) {
@@ -168,6 +182,11 @@ template <> struct Math<double> {
     const double cc = (q & 1) ? ps : pc;
     s = (q & 2) ? -ss : ss;
     c = ((q + 1) & 2) ? -cc : cc;
+  }
+  static __device__ __forceinline__ void sincos_poly_(double a, double& s, double& c) { sincos_kernel_(a, s, c); }
+  static __device__ __forceinline__ double wrap_once_(double th) {
+    const double n = (th > pi()) ? 1.0 : ((th <= -pi()) ? -1.0 : 0.0);
+    return th - n * 2.0 * pi();
   }
   static __device__ __forceinline__ void sincos_small_(double a, double& s, double& c) {
     if (fabs(a) > 0.78539816339744828) {
@@ -279,7 +298,9 @@ __device__ __forceinline__ void speed_yaw(const ModelConsts<R>& mc, R u0, R u1, 
 //   RK4: k1 uses theta, k2 == k3 use theta + k/2, k4 uses theta + k  (theta-dot does not depend on the
 //   state)  =>  x+ = x + dt*s/6 * (c1 + 4 c2 + c4).
 // The caller re-synchronises (c, s) from theta every few steps (resync_trig) to stop rounding drift.
-template <typename R, int MODEL>
+// FAST = the engine has checked on the host that |dt * yaw rate| <= pi/4 for every admissible control, so
+// the increment's sin/cos are plain polynomials and one wrap turn suffices: no branch in the step.
+template <typename R, int MODEL, bool FAST = false>
 __device__ __forceinline__ void model_step(const ModelConsts<R>& mc, R u0, R u1, R& dx, R& dy, R& th, R& c, R& s) {
   R spd, w;
   speed_yaw<R, MODEL>(mc, u0, u1, spd, w);
@@ -289,20 +310,26 @@ __device__ __forceinline__ void model_step(const ModelConsts<R>& mc, R u0, R u1,
     dy = Math<R>::fma_(mc.dt * spd, s, dy);
     th = th + kth;
     R sa, ca;
-    Math<R>::sincos_small_(kth, sa, ca);
+    if (FAST)
+      Math<R>::sincos_poly_(kth, sa, ca);
+    else
+      Math<R>::sincos_small_(kth, sa, ca);
     const R cn = c * ca - s * sa;
     s = Math<R>::fma_(s, ca, c * sa);
     c = cn;
     return;
   }
   R sa, ca;
-  Math<R>::sincos_small_(R(0.5) * kth, sa, ca);
+  if (FAST)
+    Math<R>::sincos_poly_(R(0.5) * kth, sa, ca);
+  else
+    Math<R>::sincos_small_(R(0.5) * kth, sa, ca);
   const R c2 = Math<R>::fma_(c, ca, -(s * sa)), s2 = Math<R>::fma_(s, ca, c * sa);
   const R c4 = Math<R>::fma_(c2, ca, -(s2 * sa)), s4 = Math<R>::fma_(s2, ca, c2 * sa);
   const R g = mc.dt * spd * R(1.0 / 6.0);
   dx = Math<R>::fma_(g, Math<R>::fma_(R(4), c2, c + c4), dx);
   dy = Math<R>::fma_(g, Math<R>::fma_(R(4), s2, s + s4), dy);
-  th = Math<R>::wrap_(th + kth);
+  th = FAST ? Math<R>::wrap_once_(th + kth) : Math<R>::wrap_(th + kth);
   c = c4;
   s = s4;
 }

@@ -42,6 +42,7 @@ static void set_err(const char* fmt, ...) {
   } while (0)
 
 struct KindCfg {
+  bool fast = false;
   int block = 0, grid = 0, ntiles = 0, ctas_per_sm = 0, regs = 0;
   size_t smem = 0;
   bool ready = false;
@@ -167,22 +168,37 @@ static mppi_status drop_graphs(mppi_engine* e) {
 }
 
 // (re)compute launch configurations for the three rollout families and size the partial buffers
+// largest |dt * yaw rate| any admissible (clipped) control can produce
+static double max_yaw_increment(const StaticParams& sp) {
+  double w;
+  if (sp.model == MPPI_MODEL_DIFF_DRIVE)
+    w = sp.wheel_r / sp.wheel_L * (sp.u_max[0] + sp.u_max[1]);
+  else if (sp.model == MPPI_MODEL_UNICYCLE_EULER)
+    w = sp.u_max[1];
+  else
+    w = sp.u_max[0] * std::tan(std::fmin(sp.u_max[1], 1.55)) / sp.wheel_L;
+  return sp.dt * w;
+}
+
 static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
   StaticParams& sp = e->sp;
   const bool has_grid = sp.has_grid != 0;
+  // FAST kernels: in-register Philox noise and yaw increments small enough for the branch-free step
+  const bool fast = !sp.noise_external && max_yaw_increment(sp) <= 0.78;
   const char* envb = getenv("MPPI_B200_BLOCK");
   *max_ctas = 0;
   for (int kind = 0; kind < 3; ++kind) {
     KindCfg best;
     double best_cost = 1e300;
-    for (int block = 64; block <= 128; block *= 2) {
-      if (envb && atoi(envb) != block) continue;
+    for (int block = 64; block <= (fast ? 128 : 64); block *= 2) {
+      if (envb && atoi(envb) != block && fast) continue;
       KindCfg c;
+      c.fast = fast;
       c.block = block;
       c.ntiles = (sp.K + block - 1) / block;
       c.smem = rollout_smem(kind, sp.T, block, gin);
       if (c.smem > 227 * 1024) continue;
-      cudaError_t ce = rollout_prepare(kind, sp.model, has_grid, block, c.smem, &c.ctas_per_sm, &c.regs);
+      cudaError_t ce = rollout_prepare(kind, sp.model, has_grid, block, fast, c.smem, &c.ctas_per_sm, &c.regs);
       if (ce != cudaSuccess || c.ctas_per_sm < 1) {
         cudaGetLastError();
         continue;
@@ -558,7 +574,7 @@ extern "C" mppi_status mppi_set_noise(mppi_handle e, const double* eps) {
   CK(cudaMemcpy(e->d_eps_ext, eps, n * sizeof(double), cudaMemcpyHostToDevice));
   if (!e->sp.noise_external) {
     e->sp.noise_external = 1;
-    drop_graphs(e);
+    return configure(e);     // replayed noise runs on the GENERAL kernels
   }
   return MPPI_OK;
 }
@@ -570,7 +586,7 @@ extern "C" mppi_status mppi_use_philox(mppi_handle e, uint64_t seed) {
   e->sp.seed = seed;
   unsigned int zero = 0;
   CK(cudaMemcpy(&e->d_dyn->step, &zero, sizeof(zero), cudaMemcpyHostToDevice));
-  return drop_graphs(e);
+  return configure(e);
 }
 
 extern "C" mppi_status mppi_get_noise(mppi_handle e, double* eps) {
@@ -655,7 +671,7 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   ra.vcap = e->d_vcap;
   ra.ntiles = c.ntiles;
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[0], st));
-  CK(rollout_launch(kind, e->sp.model, e->sp.has_grid != 0, c.block, c.grid, c.smem, st, ra));
+  CK(rollout_launch(kind, e->sp.model, e->sp.has_grid != 0, c.block, c.fast, c.grid, c.smem, st, ra));
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[1], st));
   ReduceArgs rd;
   memset(&rd, 0, sizeof(rd));
@@ -989,6 +1005,7 @@ extern "C" mppi_status mppi_cost_to_go(mppi_handle e, const double x0[3], const 
     e->d_eps_ext = eps_tmp;
     e->sp.noise_external = 1;
     e->sp.capture = 1;
+    if ((s = configure(e)) != MPPI_OK) break;
     if ((s = prep_nominal(e)) != MPPI_OK) break;
     if ((s = launch_local(e, e->stream, MPPI_PRECISION_F64, FUSE_NONE, nullptr)) != MPPI_OK) break;
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
@@ -1004,6 +1021,7 @@ extern "C" mppi_status mppi_cost_to_go(mppi_handle e, const double x0[3], const 
   e->sp = sp_save;
   e->d_eps_ext = eps_save;
   e->last_capture_kind = -1;
+  configure(e);
   cudaMemcpy(e->d_dyn, &dyn_save, sizeof(DynState), cudaMemcpyHostToDevice);
   cudaMemcpy(e->d_Umaster, e->d_Utmp, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
   cudaFree(eps_tmp);

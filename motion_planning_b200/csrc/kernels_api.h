@@ -9,8 +9,8 @@ namespace mppi {
 enum RolloutKind { ROLLOUT_F32_SOFTMIN = 0, ROLLOUT_F32_SCREEN = 1, ROLLOUT_F64_SOFTMIN = 2 };
 
 // occupancy query + opt-in to large dynamic shared memory for one instantiation
-cudaError_t rollout_prepare(int kind, int model, bool has_grid, int block, size_t smem, int* ctas_per_sm, int* regs);
-cudaError_t rollout_launch(int kind, int model, bool has_grid, int block, int grid, size_t smem, cudaStream_t st,
+cudaError_t rollout_prepare(int kind, int model, bool has_grid, int block, bool fast, size_t smem, int* ctas_per_sm, int* regs);
+cudaError_t rollout_launch(int kind, int model, bool has_grid, int block, bool fast, int grid, size_t smem, cudaStream_t st,
                            const RolloutArgs& a);
 size_t rollout_smem(int kind, int T, int block, int grid_bytes_in_smem);
 

@@ -27,28 +27,28 @@ static cudaError_t launch_pdl(Fn f, int grid, int block, size_t smem, cudaStream
 }
 
 #define DECL_TU(name)                                                                                          \
-  cudaError_t rollout_##name##_prepare(int model, bool has_grid, int block, size_t smem, int* ctas, int* regs); \
-  cudaError_t rollout_##name##_launch(int model, bool has_grid, int block, int grid, size_t smem, cudaStream_t st, \
+  cudaError_t rollout_##name##_prepare(int model, bool has_grid, int block, bool fast, size_t smem, int* ctas, int* regs); \
+  cudaError_t rollout_##name##_launch(int model, bool has_grid, int block, bool fast, int grid, size_t smem, cudaStream_t st, \
                                       const RolloutArgs& a);
 DECL_TU(f32_softmin)
 DECL_TU(f32_screen)
 DECL_TU(f64_softmin)
 #undef DECL_TU
 
-cudaError_t rollout_prepare(int kind, int model, bool has_grid, int block, size_t smem, int* ctas, int* regs) {
+cudaError_t rollout_prepare(int kind, int model, bool has_grid, int block, bool fast, size_t smem, int* ctas, int* regs) {
   switch (kind) {
-    case ROLLOUT_F32_SOFTMIN: return rollout_f32_softmin_prepare(model, has_grid, block, smem, ctas, regs);
-    case ROLLOUT_F32_SCREEN: return rollout_f32_screen_prepare(model, has_grid, block, smem, ctas, regs);
-    default: return rollout_f64_softmin_prepare(model, has_grid, block, smem, ctas, regs);
+    case ROLLOUT_F32_SOFTMIN: return rollout_f32_softmin_prepare(model, has_grid, block, fast, smem, ctas, regs);
+    case ROLLOUT_F32_SCREEN: return rollout_f32_screen_prepare(model, has_grid, block, fast, smem, ctas, regs);
+    default: return rollout_f64_softmin_prepare(model, has_grid, block, fast, smem, ctas, regs);
   }
 }
 
-cudaError_t rollout_launch(int kind, int model, bool has_grid, int block, int grid, size_t smem, cudaStream_t st,
+cudaError_t rollout_launch(int kind, int model, bool has_grid, int block, bool fast, int grid, size_t smem, cudaStream_t st,
                            const RolloutArgs& a) {
   switch (kind) {
-    case ROLLOUT_F32_SOFTMIN: return rollout_f32_softmin_launch(model, has_grid, block, grid, smem, st, a);
-    case ROLLOUT_F32_SCREEN: return rollout_f32_screen_launch(model, has_grid, block, grid, smem, st, a);
-    default: return rollout_f64_softmin_launch(model, has_grid, block, grid, smem, st, a);
+    case ROLLOUT_F32_SOFTMIN: return rollout_f32_softmin_launch(model, has_grid, block, fast, grid, smem, st, a);
+    case ROLLOUT_F32_SCREEN: return rollout_f32_screen_launch(model, has_grid, block, fast, grid, smem, st, a);
+    default: return rollout_f64_softmin_launch(model, has_grid, block, fast, grid, smem, st, a);
   }
 }
 

@@ -62,7 +62,7 @@ __device__ __noinline__ int screen_tighten(uint2* list, int cnt_old, const R* to
   return n;
 }
 
-template <typename R, int MODEL, int MODE, bool HAS_GRID, int BLOCK>
+template <typename R, int MODEL, int MODE, bool HAS_GRID, int BLOCK, bool FAST>
 __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ RolloutArgs a) {
   typedef typename Math<R>::Vec4 Vec4;
   constexpr int NW = BLOCK / 32;
@@ -148,63 +148,84 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     int eown0 = 0, eown1 = 0;   // fixed-point floor sums of the step this lane owns in the current 32-step chunk
 
     // ---- the T-step rollout (hot loop 1, control/src/mppi:136-163) ----------------------------
-    // Software-pipelined noise: the Philox + Box-Muller chain of step pair t2+1 is issued in the same
-    // basic block as the two model steps of pair t2, so the integer/SFU chain overlaps the FP chain.
-    float4 znext = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!sp.noise_external) znext = philox_normal4(sp.seed, kglobal, 0u, step);
-#pragma unroll kUnrollT2
-    for (int t2 = 0; t2 < (T >> 1); ++t2) {
-      float zf[4];
-      R ev[4];
-      if (sp.noise_external) {
-        const int kk = valid ? k_local : 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ev[i] = load_eps_ext<R>(a.eps_ext, 2 * t2 + (i >> 1), i & 1, sp.K, kk);
-      } else {
-        const float4 z = znext;
-        znext = philox_normal4(sp.seed, kglobal, (unsigned)(t2 + 1), step);   // one pair ahead (last one unused)
-        zf[0] = z.x;
-        zf[1] = z.y;
-        zf[2] = z.z;
-        zf[3] = z.w;
-        ev[0] = R(eps_from_z(std0, z.x));
-        ev[1] = R(eps_from_z(std1, z.y));
-        ev[2] = R(eps_from_z(std0, z.z));
-        ev[3] = R(eps_from_z(std1, z.w));
-      }
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int t = 2 * t2 + s;
-        const R e0 = ev[2 * s], e1 = ev[2 * s + 1];
-        if (!sp.noise_external) {
-          // floor-term sums: exact fixed point (2^-20, |z| < 8 so 32 lanes fit an int), one warp integer
-          // add (REDUX) per channel; the lane with lane == t mod 32 keeps the warp sums of step t
-          int q0 = valid ? __float2int_rn(zf[2 * s] * (float)kZFixScale) : 0;
-          int q1 = valid ? __float2int_rn(zf[2 * s + 1] * (float)kZFixScale) : 0;
-          q0 = __reduce_add_sync(0xffffffffu, q0);
-          q1 = __reduce_add_sync(0xffffffffu, q1);
-          if (lane == (t & 31)) {
-            eown0 = q0;
-            eown1 = q1;
-          }
+    // one model step + running cost + prefix store; `zq` = the two standard normals of the step (FAST)
+    auto one_step = [&](int t, R e0, R e1, float z0, float z1) {
+      if (FAST || !sp.noise_external) {
+        // floor-term sums: exact fixed point (2^-20, |z| < 8 so 32 lanes fit an int), one warp integer
+        // add (REDUX) per channel; the lane with lane == t mod 32 keeps the warp sums of step t
+        int q0 = valid ? __float2int_rn(z0 * (float)kZFixScale) : 0;
+        int q1 = valid ? __float2int_rn(z1 * (float)kZFixScale) : 0;
+        q0 = __reduce_add_sync(0xffffffffu, q0);
+        q1 = __reduce_add_sync(0xffffffffu, q1);
+        if (lane == (t & 31)) {
+          eown0 = q0;
+          eown1 = q1;
         }
-        // u_samp = clip(U[:,t] + eps)   control/src/mppi:147-152 (eps itself stays unclipped)
-        const R u0 = clamp_<R>(nomU0[t] + e0, um0);
-        const R u1 = clamp_<R>(nomU1[t] + e1, um1);
-        model_step<R, MODEL>(mc, u0, u1, dx, dy, th, cth, sth);              // :154
-        if (s == 1 && (t2 & (kTrigResyncMask >> 1)) == (kTrigResyncMask >> 1)) Math<R>::sincos_(th, sth, cth);
-        R c = running_cost<R>(cc, dx, dy, th, nomG0[t], nomG1[t], e0, e1);   // :160-161,180-184
-        if (HAS_GRID) c += grid_cost<R>(cc, cells, dx, dy);
-        acc += c;
-        P[t * PS + tid] = acc;
       }
-      if (!sp.noise_external && ((t2 & 15) == 15 || t2 == (T >> 1) - 1)) {
-        // end of a 32-step chunk: every lane flushes the step it owns
-        const int town = ((2 * t2 + 1) & ~31) + lane;
-        if (town < T) {
-          atomicAdd(&ez32[2 * town], eown0);
-          atomicAdd(&ez32[2 * town + 1], eown1);
+      // u_samp = clip(U[:,t] + eps)   control/src/mppi:147-152 (eps itself stays unclipped)
+      const R u0 = clamp_<R>(nomU0[t] + e0, um0);
+      const R u1 = clamp_<R>(nomU1[t] + e1, um1);
+      model_step<R, MODEL, FAST>(mc, u0, u1, dx, dy, th, cth, sth);          // :154
+      R c = running_cost<R>(cc, dx, dy, th, nomG0[t], nomG1[t], e0, e1);     // :160-161,180-184
+      if (HAS_GRID) c += grid_cost<R>(cc, cells, dx, dy);
+      acc += c;
+      P[t * PS + tid] = acc;
+    };
+    // every lane flushes the step it owns in the 32-step chunk starting at `base`
+    auto flush_chunk = [&](int base) {
+      const int town = base + lane;
+      if (town < T) {
+        atomicAdd(&ez32[2 * town], eown0);
+        atomicAdd(&ez32[2 * town + 1], eown1);
+      }
+    };
+    if (FAST) {
+      // FAST path: Philox noise, four steps per iteration in ONE basic block (no branch inside a step), the
+      // Philox + Box-Muller chains of the NEXT four steps issued alongside so that the integer/SFU work
+      // overlaps the FP chain; (cos, sin) re-synchronised from theta at the end of every iteration.
+      float4 za = philox_normal4(sp.seed, kglobal, 0u, step);
+      float4 zb = philox_normal4(sp.seed, kglobal, 1u, step);
+      int t4 = 0;
+      for (; t4 + 4 <= T; t4 += 4) {
+        const float4 z0 = za, z1 = zb;
+        za = philox_normal4(sp.seed, kglobal, (unsigned)(t4 >> 1) + 2u, step);   // one iteration ahead
+        zb = philox_normal4(sp.seed, kglobal, (unsigned)(t4 >> 1) + 3u, step);
+        one_step(t4 + 0, R(eps_from_z(std0, z0.x)), R(eps_from_z(std1, z0.y)), z0.x, z0.y);
+        one_step(t4 + 1, R(eps_from_z(std0, z0.z)), R(eps_from_z(std1, z0.w)), z0.z, z0.w);
+        one_step(t4 + 2, R(eps_from_z(std0, z1.x)), R(eps_from_z(std1, z1.y)), z1.x, z1.y);
+        one_step(t4 + 3, R(eps_from_z(std0, z1.z)), R(eps_from_z(std1, z1.w)), z1.z, z1.w);
+        Math<R>::sincos_(th, sth, cth);
+        if ((t4 & 31) == 28) flush_chunk(t4 & ~31);
+      }
+      if (t4 < T) {   // T = 4n + 2: one more pair
+        one_step(t4 + 0, R(eps_from_z(std0, za.x)), R(eps_from_z(std1, za.y)), za.x, za.y);
+        one_step(t4 + 1, R(eps_from_z(std0, za.z)), R(eps_from_z(std1, za.w)), za.z, za.w);
+      }
+      if (T & 31) flush_chunk(T & ~31);
+    } else {
+      // GENERAL path: replayed noise from HBM and/or large yaw increments (full-range trig, multi-turn wrap)
+      for (int t2 = 0; t2 < (T >> 1); ++t2) {
+        float zf[4] = {0.f, 0.f, 0.f, 0.f};
+        R ev[4];
+        if (sp.noise_external) {
+          const int kk = valid ? k_local : 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ev[i] = load_eps_ext<R>(a.eps_ext, 2 * t2 + (i >> 1), i & 1, sp.K, kk);
+        } else {
+          const float4 z = philox_normal4(sp.seed, kglobal, (unsigned)t2, step);
+          zf[0] = z.x;
+          zf[1] = z.y;
+          zf[2] = z.z;
+          zf[3] = z.w;
+          ev[0] = R(eps_from_z(std0, z.x));
+          ev[1] = R(eps_from_z(std1, z.y));
+          ev[2] = R(eps_from_z(std0, z.z));
+          ev[3] = R(eps_from_z(std1, z.w));
         }
+        one_step(2 * t2, ev[0], ev[1], zf[0], zf[1]);
+        one_step(2 * t2 + 1, ev[2], ev[3], zf[2], zf[3]);
+        if ((t2 & 1) == 1) Math<R>::sincos_(th, sth, cth);
+        if (!sp.noise_external && ((t2 & 15) == 15 || t2 == (T >> 1) - 1)) flush_chunk((2 * t2 + 1) & ~31);
       }
     }
     acc += terminal_cost<R>(cc, dx, dy, th);                                 // :165-171
