@@ -190,7 +190,7 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
   for (int kind = 0; kind < 3; ++kind) {
     KindCfg best;
     double best_cost = 1e300;
-    for (int block = 64; block <= (fast ? 128 : 64); block *= 2) {
+    for (int block = (fast ? 32 : 64); block <= (fast ? 128 : 64); block *= 2) {
       if (envb && atoi(envb) != block && fast) continue;
       KindCfg c;
       c.fast = fast;

@@ -476,7 +476,11 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   }
   double v5[5] = {S, N0, N1, E0, E1};
   block_sum_n<5>(v5, scratch5);
-  dev = -block_min(-dev, scratch);
+  dev = warp_min<double>(-dev);   // dev is warp-uniform already; negate for the max
+  if (lane == 0) scratch[warp] = dev;
+  __syncthreads();
+  dev = 0.0;
+  for (int w = 0; w < 8; ++w) dev = fmax(dev, -scratch[w]);
   if (tid == 0) {
     double s0, s1;
     floor_scale(sp, a.fin.dyn, s0, s1);
@@ -554,51 +558,56 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
   const StaticParams& sp = a.sp;
   const int T = sp.T, W = T - 1, h = W / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  __shared__ int any_ovf;
+  // the serial tail of the step: issue every global load it needs up front
+  const double lam = a.dyn->lam;
+  double x0r[3] = {0.0, 0.0, 0.0};
   if (tid == 0) {
     bad = 0;
-    for (int i = 0; i < 3; ++i)
-      if (a.mode == 0 && (!isfinite(a.dyn->x0[i]) || !isfinite(a.dyn->goal[i]))) bad = 1;
+    any_ovf = 0;
+    for (int i = 0; i < 3; ++i) {
+      x0r[i] = a.dyn->x0[i];
+      if (a.mode == 0 && (!isfinite(x0r[i]) || !isfinite(a.dyn->goal[i]))) bad = 1;
+    }
   }
   const double* gather = a.p2p ? a.p2p_local + (size_t)(a.dyn->xchg & 1u) * sp.world * T * kRecordStride : a.gather;
-  {
-    // MIXED: a record with S < 0 means some rank's fp32 screen overflowed a candidate list -> every rank
-    // leaves U, the step counter and x0 untouched and asks its host to redo this step with the fp64
-    // pipeline (same noise: the Philox step counter is not advanced; the exchange epoch is).
-    __shared__ int any_ovf;
-    if (tid == 0) any_ovf = 0;
-    __syncthreads();
-    if (a.mode == 0)
-      for (int i = tid; i < sp.world * T; i += blockDim.x)
-        if (__ldcg(&gather[(size_t)i * kRecordStride + 1]) < 0.0) any_ovf = 1;
-    __syncthreads();
-    if (any_ovf) {
-      if (tid == 0) {
-        DynState* d = a.dyn;
-        d->status = kStatusRedoF64;
-        d->overflow_total += 1;
-        d->xchg += 1u;
-        d->refine_candidates = 0;
-        d->refine_overflow = 0;
-        d->refine_max_dev = 0.0;
-      }
-      return;
-    }
-  }
+  __syncthreads();
   // -- merge the records of all ranks and apply the weighted noise (control/src/mppi:189-199) ----
-  const double neg_inv_lam = -1.0 / a.dyn->lam;
+  const double neg_inv_lam = -1.0 / lam;
   for (int idx = tid; idx < 2 * T; idx += blockDim.x) {
     const int c = idx / T, t = idx - c * T;
+    double rec[4];   // world == 1 fast path keeps the record in registers (one batch of loads)
     double m = Math<double>::inf();
-    for (int g = 0; g < sp.world; ++g) m = fmin(m, __ldcg(&gather[((size_t)g * T + t) * kRecordStride]));
-    double S = 0, N = 0, E = 0;
-    for (int g = 0; g < sp.world; ++g) {
-      const double* r = gather + ((size_t)g * T + t) * kRecordStride;
-      const double rm = __ldcg(r);
-      const double sc = (rm == m) ? 1.0 : exp((rm - m) * neg_inv_lam);
-      S += __ldcg(r + 1) * sc;
-      N += __ldcg(r + 2 + c) * sc;
-      E += __ldcg(r + 4 + c);
+    if (sp.world == 1) {
+      const double* r = gather + (size_t)t * kRecordStride;
+      rec[0] = __ldcg(r);
+      rec[1] = __ldcg(r + 1);
+      rec[2] = __ldcg(r + 2 + c);
+      rec[3] = __ldcg(r + 4 + c);
+      m = rec[0];
+    } else {
+      for (int g = 0; g < sp.world; ++g) m = fmin(m, __ldcg(&gather[((size_t)g * T + t) * kRecordStride]));
     }
+    double S = 0, N = 0, E = 0;
+    bool ovf = false;
+    if (sp.world == 1) {
+      S = rec[1];
+      N = rec[2];
+      E = rec[3];
+      ovf = rec[1] < 0.0;
+    } else {
+      for (int g = 0; g < sp.world; ++g) {
+        const double* r = gather + ((size_t)g * T + t) * kRecordStride;
+        const double rm = __ldcg(r), rs = __ldcg(r + 1);
+        const double sc = (rm == m) ? 1.0 : exp((rm - m) * neg_inv_lam);
+        ovf |= rs < 0.0;
+        S += rs * sc;
+        N += __ldcg(r + 2 + c) * sc;
+        E += __ldcg(r + 4 + c);
+      }
+    }
+    // MIXED: a record with S < 0 means some rank's fp32 screen overflowed a candidate list (see below)
+    if (ovf) any_ovf = 1;
     const double dU = (N + sp.eps_floor * E) / (S + sp.eps_floor * (double)sp.k_total);
     const double u = a.Umaster[c * T + t] + dU;
     // the reference lets NaN propagate silently; here a non-finite input or an empty
@@ -607,6 +616,21 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
     Us[c * T + t] = clamp_<double>(u, sp.u_max[c]);                          // :198-199
   }
   __syncthreads();
+  if (a.mode == 0 && any_ovf) {
+    // every rank sees the same records, so every rank leaves U, the step counter and x0 untouched and
+    // asks its host to redo this step with the fp64 pipeline (same noise: the Philox step counter is
+    // not advanced; the exchange epoch is).
+    if (tid == 0) {
+      DynState* d = a.dyn;
+      d->status = kStatusRedoF64;
+      d->overflow_total += 1;
+      d->xchg += 1u;
+      d->refine_candidates = 0;
+      d->refine_overflow = 0;
+      d->refine_max_dev = 0.0;
+    }
+    return;
+  }
   // -- Savitzky-Golay, window T-1, cubic, mode='interp' (control/src/mppi:202).  The filter is two
   //    least-squares cubics: A on samples [0, T-1), B on [1, T); outputs 0..h evaluate A, h+1..T-1
   //    evaluate B.  Orthogonal (Gram) basis 1, z, z^2-a, z^3-bz on z=-h..h.
@@ -656,7 +680,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
     if (tid == 0) {
       DynState* d = a.dyn;
       double xn[3];
-      model_step_dispatch_f64(sp, d->x0, Uf[0], Uf[T], xn);
+      model_step_dispatch_f64(sp, x0r, Uf[0], Uf[T], xn);
       d->out_u[0] = Uf[0];
       d->out_u[1] = Uf[T];
       d->out_x[0] = xn[0];
