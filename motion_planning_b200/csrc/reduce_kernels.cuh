@@ -45,7 +45,6 @@ __device__ __forceinline__ void floor_scale(const StaticParams& sp, const DynSta
   s1 = sp.noise_external ? 1.0 : (double)(float)dyn->noise_std[1] / kZFixScale;
 }
 
-// (m, S, N0, N1) online-softmin tuples: merge b into a (weights relative to the smaller minimum)
 // Programmatic dependent launch (PDL): the reduce kernel is launched while the rollout kernel is still
 // running and blocks here until that grid has completed and flushed its memory.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -75,27 +74,6 @@ __device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch /* [
     for (int w = 0; w < nw; ++w) s += scratch[w * N + i];
     v[i] = s;
   }
-}
-
-struct Tup {
-  double m, S, N0, N1;
-};
-__device__ __forceinline__ void tup_merge(Tup& a, const Tup& b, double neg_inv_lam) {
-  const double m = fmin(a.m, b.m);
-  const double sa = (a.m == m) ? 1.0 : exp((a.m - m) * neg_inv_lam);
-  const double sb = (b.m == m) ? 1.0 : exp((b.m - m) * neg_inv_lam);
-  a.S = a.S * sa + b.S * sb;
-  a.N0 = a.N0 * sa + b.N0 * sb;
-  a.N1 = a.N1 * sa + b.N1 * sb;
-  a.m = m;
-}
-__device__ __forceinline__ Tup tup_shfl_xor(const Tup& t, int o) {
-  Tup r;
-  r.m = __shfl_xor_sync(0xffffffffu, t.m, o);
-  r.S = __shfl_xor_sync(0xffffffffu, t.S, o);
-  r.N0 = __shfl_xor_sync(0xffffffffu, t.N0, o);
-  r.N1 = __shfl_xor_sync(0xffffffffu, t.N1, o);
-  return r;
 }
 
 __device__ void finalize_body(const FinalizeArgs& a, double* Us);
@@ -506,12 +484,11 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
 
 // ---- kernel 3: finalize.  one block of 256 threads ------------------------------------------------
 
-__device__ __forceinline__ void write_nominal_block(const DynState* dyn, int T, int t, double u0, double u1, float* nomF,
-                                                    double* nomD) {
+__device__ __forceinline__ void write_nominal_block(double lam, const double sig[4], int T, int t, double u0, double u1,
+                                                    float* nomF, double* nomD) {
   // g[t] = lam * (u . sig)   so that   lam * u.dot(sig).dot(eps) = g0 eps0 + g1 eps1   (control/src/mppi:184)
-  const double lam = dyn->lam;
-  const double g0 = lam * (u0 * dyn->sig[0] + u1 * dyn->sig[2]);
-  const double g1 = lam * (u0 * dyn->sig[1] + u1 * dyn->sig[3]);
+  const double g0 = lam * (u0 * sig[0] + u1 * sig[2]);
+  const double g1 = lam * (u0 * sig[1] + u1 * sig[3]);
   nomD[t] = u0;
   nomD[T + t] = u1;
   nomD[2 * T + t] = g0;
@@ -523,7 +500,8 @@ __device__ __forceinline__ void write_nominal_block(const DynState* dyn, int T, 
 }
 
 __global__ void prep_nominal_kernel(const DynState* dyn, int T, const double* Umaster, float* nomF, double* nomD) {
-  for (int t = threadIdx.x; t < T; t += blockDim.x) write_nominal_block(dyn, T, t, Umaster[t], Umaster[T + t], nomF, nomD);
+  const double sig[4] = {dyn->sig[0], dyn->sig[1], dyn->sig[2], dyn->sig[3]};
+  for (int t = threadIdx.x; t < T; t += blockDim.x) write_nominal_block(dyn->lam, sig, T, t, Umaster[t], Umaster[T + t], nomF, nomD);
 }
 
 template <int MODEL>
@@ -561,10 +539,18 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
   __shared__ int any_ovf;
   // the serial tail of the step: issue every global load it needs up front
   const double lam = a.dyn->lam;
+  const double sigr[4] = {a.dyn->sig[0], a.dyn->sig[1], a.dyn->sig[2], a.dyn->sig[3]};
   double x0r[3] = {0.0, 0.0, 0.0};
+  unsigned int step_r = 0, xchg_r = 0;
+  int cand_r = 0;
+  double dev_r = 0.0;
   if (tid == 0) {
     bad = 0;
     any_ovf = 0;
+    step_r = a.dyn->step;
+    xchg_r = a.dyn->xchg;
+    cand_r = __ldcg(&a.dyn->refine_candidates);
+    dev_r = __ldcg(&a.dyn->refine_max_dev);
     for (int i = 0; i < 3; ++i) {
       x0r[i] = a.dyn->x0[i];
       if (a.mode == 0 && (!isfinite(x0r[i]) || !isfinite(a.dyn->goal[i]))) bad = 1;
@@ -624,7 +610,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       DynState* d = a.dyn;
       d->status = kStatusRedoF64;
       d->overflow_total += 1;
-      d->xchg += 1u;
+      d->xchg = xchg_r + 1u;
       d->refine_candidates = 0;
       d->refine_overflow = 0;
       d->refine_max_dev = 0.0;
@@ -675,7 +661,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       const double u1 = (t + 1 < T) ? Uf[T + t + 1] : 0.0;
       a.Umaster[t] = u0;
       a.Umaster[T + t] = u1;
-      write_nominal_block(a.dyn, T, t, u0, u1, a.nomF, a.nomD);
+      write_nominal_block(lam, sigr, T, t, u0, u1, a.nomF, a.nomD);
     }
     if (tid == 0) {
       DynState* d = a.dyn;
@@ -687,15 +673,15 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       d->out_x[1] = xn[1];
       d->out_x[2] = xn[2];
       d->status = bad ? (int)MPPI_ERR_NONFINITE : (int)MPPI_OK;
-      d->step += 1u;
-      d->xchg += 1u;
+      d->step = step_r + 1u;
+      d->xchg = xchg_r + 1u;
       if (a.closed_loop) {
         d->x0[0] = xn[0];
         d->x0[1] = xn[1];
         d->x0[2] = xn[2];
       }
-      d->last_candidates = __ldcg(&d->refine_candidates);
-      d->last_max_dev = __ldcg(&d->refine_max_dev);
+      d->last_candidates = cand_r;
+      d->last_max_dev = dev_r;
       d->refine_candidates = 0;
       d->refine_overflow = 0;
       d->refine_max_dev = 0.0;
