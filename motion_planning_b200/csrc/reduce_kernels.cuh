@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(256) reduce_softmin_kernel(const __grid_consta
 template <int MODEL, bool HAS_GRID>
 __device__ double resim_cost_to_go_f64(const StaticParams& sp, const DynState* dyn, const double* __restrict__ nomD,
                                        const signed char* __restrict__ grid, const double* __restrict__ eps_ext,
-                                       const ModelConsts<double>& mc, const CostConsts<double>& cc, int k_local,
-                                       int t_target, double* sm) {
+                                       const ModelConsts<double>& mc, const CostConsts<double>& cc, float std0, float std1,
+                                       unsigned int step, int k_local, int t_target, double* sm) {
   const int T = sp.T, lane = threadIdx.x & 31;
   double* s_kth = sm;          // yaw increment per step, then exclusive theta
   double* s_spd = sm + T;      // forward speed
@@ -243,8 +243,6 @@ __device__ double resim_cost_to_go_f64(const StaticParams& sp, const DynState* d
   double* s_e0 = sm + 4 * T;
   double* s_e1 = sm + 5 * T;
   double* s_thn = sm + 6 * T;  // theta after the step (wrapped)
-  const float std0 = (float)dyn->noise_std[0], std1 = (float)dyn->noise_std[1];
-  const unsigned int step = dyn->step;
   const unsigned long long kglobal = (unsigned long long)(sp.k_offset + k_local);
   for (int t = lane; t < T; t += 32) {
     double e0, e1;
@@ -356,6 +354,14 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     nsel = 0;
     overflow = 0;
   }
+  // everything the block needs from DynState is loaded BEFORE the dependency wait: the rollout kernel does
+  // not write DynState, so these L2 round trips overlap its tail
+  ModelConsts<double> mc;
+  CostConsts<double> cc;
+  make_consts<double>(sp, a.fin.dyn, mc, cc);
+  const double neg_inv_lam = -1.0 / a.fin.dyn->lam;
+  const float std0 = (float)a.fin.dyn->noise_std[0], std1 = (float)a.fin.dyn->noise_std[1];
+  const unsigned int philox_step = a.fin.dyn->step;
   griddep_wait();   // PDL: the block is resident before the rollout kernel has drained
   TS(0);
   // phase A: global fp32 minimum + floor sums.  meta[t][cta] = (min, limit, count, -) is ONE 16-byte
@@ -418,12 +424,10 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   TS(2);
   const int n = min(nsel, kMaxRefine);
   // phase C: fp64 re-evaluation, one warp per candidate
-  ModelConsts<double> mc;
-  CostConsts<double> cc;
-  make_consts<double>(sp, a.fin.dyn, mc, cc);
   double dev = 0.0;
   for (int c = warp; c < n; c += 8) {
-    const double v64 = resim_cost_to_go_f64<MODEL, HAS_GRID>(sp, a.fin.dyn, a.nomD, a.grid, a.eps_ext, mc, cc, sel_k[c], t_eval,
+    const double v64 = resim_cost_to_go_f64<MODEL, HAS_GRID>(sp, a.fin.dyn, a.nomD, a.grid, a.eps_ext, mc, cc, std0, std1, philox_step,
+                                                              sel_k[c], t_eval,
                                                               warp_scratch + (size_t)warp * 7 * T);
     if (lane == 0) sel_v64[c] = v64;
     dev = fmax(dev, fabs(v64 - (double)sel_v32[c]));
@@ -433,8 +437,6 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   // phase D: exact softmin over the support (control/src/mppi:189-196)
   double m64 = Math<double>::inf();
   for (int c = 0; c < n; ++c) m64 = fmin(m64, sel_v64[c]);
-  const double neg_inv_lam = -1.0 / a.fin.dyn->lam;
-  const float std0 = (float)a.fin.dyn->noise_std[0], std1 = (float)a.fin.dyn->noise_std[1];
   double S = 0, N0 = 0, N1 = 0;
   for (int c = tid; c < n; c += blockDim.x) {
     const double e = exp((sel_v64[c] - m64) * neg_inv_lam);
@@ -444,7 +446,7 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
       e1 = a.eps_ext[((size_t)t * 2 + 1) * sp.K + sel_k[c]];
     } else {
       float f0, f1;
-      philox_eps(sp.seed, (unsigned long long)(sp.k_offset + sel_k[c]), t, a.fin.dyn->step, std0, std1, f0, f1);
+      philox_eps(sp.seed, (unsigned long long)(sp.k_offset + sel_k[c]), t, philox_step, std0, std1, f0, f1);
       e0 = f0;
       e1 = f1;
     }
