@@ -176,12 +176,10 @@ def run_single(args):
     tf, mhz = C.c_double(), C.c_double()
     _capi.check(lib.mppi_measure_fp32_peak(0, C.byref(tf), C.byref(mhz)), "mppi_measure_fp32_peak")
     results = {}
-    sampler = None
-    for prec in ("f32", "f64", args.precision):          # headline precision last (its clocks are sampled)
+    sampler = ClockSampler(0)                            # clocks / throttle reasons DURING all timed regions
+    for prec in ("f32", "f64", args.precision):          # headline precision last
         m = mp.MPPI(horizon=T, samples=K, precision=prec, seed=0)
         m.goal = GOAL
-        if prec == args.precision:
-            sampler = ClockSampler(0)
         r = m.bench(X0, steps=args.steps, warmup=args.warmup, flush_l2=True, per_kernel=True)
         # e2e: the public call with HOST buffers, copies inside the timed region.
         # (1) through the Python mirror of the reference class (MPPI.get_path, what Controller calls)
@@ -214,7 +212,7 @@ def run_single(args):
         r["stats"] = m.stats()
         results[prec] = r
         m.close()
-    clocks = sampler.stop() if sampler else {}
+    clocks = sampler.stop()
     r = results[args.precision]
     ms = r["step_ms"]
     value = K / (ms * 1e-3)
