@@ -19,6 +19,9 @@
 namespace mppi {
 
 constexpr int kUnrollT2 = MPPI_UNROLL_T2;   // step pairs per iteration of the rollout loop
+constexpr int kWsBlockTag = 96;      // `block` value that selects the warp-specialised rollout kernel (32 rollouts, 96 threads)
+constexpr int kWsThreads = 96;
+constexpr int kWsTile = 32;
 constexpr int kMaxCand = 16;        // SCREEN: candidate slots per (CTA, t)
 constexpr int kMaxRefine = 256;     // SCREEN: fp64 re-evaluations per t after the global filter
 constexpr int kRecordStride = 6;    // doubles per t in an exchange record: m, S, N0, N1, E0, E1

@@ -190,12 +190,30 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
   for (int kind = 0; kind < 3; ++kind) {
     KindCfg best;
     double best_cost = 1e300;
-    for (int block = (fast ? 32 : 64); block <= (fast ? 128 : 64); block *= 2) {
-      if (envb && atoi(envb) != block && fast) continue;
+    // candidate tile shapes: 32/64/128 rollouts per CTA (one thread each), or the warp-specialised kernel
+    // (tag 96: 32 rollouts, 1 consumer + 2 producer warps) which is preferred for the fp32 FAST path.
+    // MPPI_B200_BLOCK=<32|64|128|96> forces one shape, MPPI_B200_WS=0 disables the warp-specialised kernel.
+    const char* envws = getenv("MPPI_B200_WS");
+    const bool ws_ok = fast && kind != ROLLOUT_F64_SOFTMIN && !(envws && atoi(envws) == 0);
+    int shapes[4], nshapes = 0;
+    if (!fast) {
+      shapes[nshapes++] = 64;
+    } else if (envb && (atoi(envb) == 32 || atoi(envb) == 64 || atoi(envb) == 128 || (atoi(envb) == kWsBlockTag && ws_ok))) {
+      shapes[nshapes++] = atoi(envb);
+    } else if (ws_ok) {
+      shapes[nshapes++] = kWsBlockTag;
+    } else {
+      shapes[nshapes++] = 32;
+      shapes[nshapes++] = 64;
+      shapes[nshapes++] = 128;
+    }
+    for (int si = 0; si < nshapes; ++si) {
+      const int block = shapes[si];
       KindCfg c;
       c.fast = fast;
       c.block = block;
-      c.ntiles = (sp.K + block - 1) / block;
+      const int rollouts = (block == kWsBlockTag) ? kWsTile : block;
+      c.ntiles = (sp.K + rollouts - 1) / rollouts;
       c.smem = rollout_smem(kind, sp.T, block, gin);
       if (c.smem > 227 * 1024) continue;
       cudaError_t ce = rollout_prepare(kind, sp.model, has_grid, block, fast, c.smem, &c.ctas_per_sm, &c.regs);
@@ -206,7 +224,7 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
       const long long resident = (long long)e->num_sms * c.ctas_per_sm;
       c.grid = (int)((c.ntiles < resident) ? c.ntiles : resident);
       // busiest-SM thread-work: tiles are dealt round-robin over the SMs
-      const double cost = (double)((c.ntiles + e->num_sms - 1) / e->num_sms) * block;
+      const double cost = (double)((c.ntiles + e->num_sms - 1) / e->num_sms) * rollouts;
       c.ready = true;
       if (cost < best_cost || (cost == best_cost && block > best.block)) {
         best = c;

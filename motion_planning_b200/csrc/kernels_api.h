@@ -12,7 +12,7 @@ enum RolloutKind { ROLLOUT_F32_SOFTMIN = 0, ROLLOUT_F32_SCREEN = 1, ROLLOUT_F64_
 cudaError_t rollout_prepare(int kind, int model, bool has_grid, int block, bool fast, size_t smem, int* ctas_per_sm, int* regs);
 cudaError_t rollout_launch(int kind, int model, bool has_grid, int block, bool fast, int grid, size_t smem, cudaStream_t st,
                            const RolloutArgs& a);
-size_t rollout_smem(int kind, int T, int block, int grid_bytes_in_smem);
+size_t rollout_smem(int kind, int T, int block, int grid_bytes_in_smem);   // block == kWsBlockTag: warp-specialised kernel
 
 cudaError_t reduce_softmin_launch(bool f64, int T, cudaStream_t st, const ReduceArgs& a);
 cudaError_t reduce_screen_launch(int model, bool has_grid, int T, cudaStream_t st, const ReduceArgs& a);

@@ -5,6 +5,7 @@
 #include "kernels_api.h"
 #include "reduce_kernels.cuh"
 #include "rollout_kernel.cuh"
+#include "rollout_ws_kernel.cuh"
 
 namespace mppi {
 
@@ -53,6 +54,7 @@ cudaError_t rollout_launch(int kind, int model, bool has_grid, int block, bool f
 }
 
 size_t rollout_smem(int kind, int T, int block, int grid_bytes_in_smem) {
+  if (block == kWsBlockTag) return rollout_ws_smem_bytes(T, grid_bytes_in_smem);
   return kind == ROLLOUT_F64_SOFTMIN ? rollout_smem_bytes<double>(T, block, grid_bytes_in_smem)
                                      : rollout_smem_bytes<float>(T, block, grid_bytes_in_smem);
 }

@@ -62,6 +62,99 @@ __device__ __noinline__ int screen_tighten(uint2* list, int cnt_old, const R* to
   return n;
 }
 
+// One row t of the transposed pass over the BLOCK rollouts of a tile (executed by ONE lane): cost-to-go
+// V[t,k] = Tot[k] - P[t-1,k], running minimum, then the online soft-min partial (MODE_SOFTMIN) or the
+// candidate list of the fp32 screen (MODE_SCREEN).  Shared by rollout_kernel and rollout_ws_kernel.
+template <typename R, int MODE, int BLOCK>
+__device__ __forceinline__ void transposed_row(const RolloutArgs& a, int t, int tile, int cta, int nCTA, const R* P,
+                                               typename Math<R>::Vec4* run, int* ccount, double* ed, bool cost_to_go,
+                                               R neg_inv_lam, R margin, float std0, float std1, unsigned int step) {
+  typedef typename Math<R>::Vec4 Vec4;
+  constexpr int PS = BLOCK + 1;
+  const StaticParams& sp = a.sp;
+  const int T = sp.T;
+  const R* tot = P + (size_t)(T - 1) * PS;
+  const R* pre = (t > 0 && cost_to_go) ? P + (size_t)(t - 1) * PS : nullptr;
+  const int tile_base = tile * BLOCK;
+  const int nk = min(BLOCK, sp.K - tile_base);
+  R m = Math<R>::inf();
+  if (pre) {
+#pragma unroll 8
+    for (int k = 0; k < BLOCK; ++k) m = Math<R>::min_(m, tot[k] - pre[k]);   // cost-to-go, :175
+  } else {
+#pragma unroll 8
+    for (int k = 0; k < BLOCK; ++k) m = Math<R>::min_(m, tot[k]);
+  }
+  if (sp.capture) {
+    R* vc = reinterpret_cast<R*>(a.vcap) + (size_t)t * sp.K + tile_base;
+    for (int k = 0; k < nk; ++k) vc[k] = tot[k] - (pre ? pre[k] : R(0));
+  }
+  if (sp.noise_external) {   // floor sums straight from the replayed noise
+    const double* e0p = a.eps_ext + ((size_t)t * 2 + 0) * sp.K + tile_base;
+    const double* e1p = a.eps_ext + ((size_t)t * 2 + 1) * sp.K + tile_base;
+    double s0 = 0.0, s1 = 0.0;
+    for (int k = 0; k < nk; ++k) {
+      s0 += e0p[k];
+      s1 += e1p[k];
+    }
+    ed[2 * t] += s0;
+    ed[2 * t + 1] += s1;
+  }
+  Vec4 rr = run[t];
+  const R mnew = Math<R>::min_(rr.x, m);
+  if (MODE == MODE_SOFTMIN) {
+    // online softmin: weights relative to the running minimum of this CTA (:189-196)
+    R S = R(0), N0 = R(0), N1 = R(0);
+    for (int k = 0; k < BLOCK; ++k) {
+      const R arg = ((tot[k] - (pre ? pre[k] : R(0))) - mnew) * neg_inv_lam;   // <= 0
+      if (arg > R(-80)) {                                   // e^-80 ~ 2e-35: below any rounding
+        const R e = Math<R>::exp_(arg);
+        R e0, e1;
+        if (sp.noise_external) {
+          e0 = load_eps_ext<R>(a.eps_ext, t, 0, sp.K, tile_base + k);
+          e1 = load_eps_ext<R>(a.eps_ext, t, 1, sp.K, tile_base + k);
+        } else {
+          float f0, f1;
+          philox_eps(sp.seed, (unsigned long long)(sp.k_offset + tile_base + k), t, step, std0, std1, f0, f1);
+          e0 = R(f0);
+          e1 = R(f1);
+        }
+        S += e;
+        N0 = Math<R>::fma_(e, e0, N0);
+        N1 = Math<R>::fma_(e, e1, N1);
+      }
+    }
+    const R sc = (rr.x == mnew) ? R(1) : Math<R>::exp_((rr.x - mnew) * neg_inv_lam);
+    rr.y = Math<R>::fma_(rr.y, sc, S);
+    rr.z = Math<R>::fma_(rr.z, sc, N0);
+    rr.w = Math<R>::fma_(rr.w, sc, N1);
+    rr.x = mnew;
+    run[t] = rr;
+  } else {
+    // screen: keep every rollout within the window [m, lim] of the CTA's running minimum m.
+    // run[t] = (m, L): L is the tightest limit ever applied, so the list is guaranteed to hold
+    // EVERY rollout of this CTA with V <= L.  Normally lim = m + margin; if more than kMaxCand
+    // rollouts fall inside, the window is halved until they fit (the reduce kernel checks that L
+    // still covers the window of the GLOBAL minimum, else the step is redone in fp64).
+    R lim = mnew + margin;
+    uint2* list = a.cand + ((size_t)t * nCTA + cta) * kMaxCand;
+    const int cnt_old = ccount[t];
+    int cnt = cnt_old;
+    for (int k = 0; k < BLOCK; ++k) {
+      const R v = tot[k] - (pre ? pre[k] : R(0));
+      if (v <= lim) {
+        if (cnt < kMaxCand) list[cnt] = make_uint2((unsigned)(tile_base + k), __float_as_uint((float)v));
+        ++cnt;
+      }
+    }
+    if (cnt > kMaxCand) cnt = screen_tighten<R>(list, cnt_old, tot, pre, BLOCK, tile_base, mnew, lim);
+    rr.x = mnew;
+    rr.y = Math<R>::min_(rr.y, lim);
+    run[t] = rr;
+    ccount[t] = cnt;
+  }
+}
+
 template <typename R, int MODEL, int MODE, bool HAS_GRID, int BLOCK, bool FAST>
 __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ RolloutArgs a) {
   typedef typename Math<R>::Vec4 Vec4;
@@ -236,88 +329,8 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     // ---- transposed pass: lane l of warp w owns row t = 32*(w + NW*i) + l ----------------------
     for (int tb = warp * 32; tb < T; tb += NW * 32) {
       const int t = tb + lane;
-      if (t < T) {
-        const R* tot = P + (size_t)(T - 1) * PS;
-        const R* pre = (t > 0 && cost_to_go) ? P + (size_t)(t - 1) * PS : nullptr;
-        const int tile_base = tile * BLOCK;
-        const int nk = min(BLOCK, sp.K - tile_base);
-        R m = Math<R>::inf();
-        if (pre) {
-#pragma unroll 8
-          for (int k = 0; k < BLOCK; ++k) m = Math<R>::min_(m, tot[k] - pre[k]);   // cost-to-go, :175
-        } else {
-#pragma unroll 8
-          for (int k = 0; k < BLOCK; ++k) m = Math<R>::min_(m, tot[k]);
-        }
-        if (sp.capture) {
-          R* vc = reinterpret_cast<R*>(a.vcap) + (size_t)t * sp.K + tile_base;
-          for (int k = 0; k < nk; ++k) vc[k] = tot[k] - (pre ? pre[k] : R(0));
-        }
-        if (sp.noise_external) {   // floor sums straight from the replayed noise
-          const double* e0p = a.eps_ext + ((size_t)t * 2 + 0) * sp.K + tile_base;
-          const double* e1p = a.eps_ext + ((size_t)t * 2 + 1) * sp.K + tile_base;
-          double s0 = 0.0, s1 = 0.0;
-          for (int k = 0; k < nk; ++k) {
-            s0 += e0p[k];
-            s1 += e1p[k];
-          }
-          ed[2 * t] += s0;
-          ed[2 * t + 1] += s1;
-        }
-        Vec4 rr = run[t];
-        const R mnew = Math<R>::min_(rr.x, m);
-        if (MODE == MODE_SOFTMIN) {
-          // online softmin: weights relative to the running minimum of this CTA (:189-196)
-          R S = R(0), N0 = R(0), N1 = R(0);
-          for (int k = 0; k < BLOCK; ++k) {
-            const R arg = ((tot[k] - (pre ? pre[k] : R(0))) - mnew) * neg_inv_lam;   // <= 0
-            if (arg > R(-80)) {                                   // e^-80 ~ 2e-35: below any rounding
-              const R e = Math<R>::exp_(arg);
-              R e0, e1;
-              if (sp.noise_external) {
-                e0 = load_eps_ext<R>(a.eps_ext, t, 0, sp.K, tile_base + k);
-                e1 = load_eps_ext<R>(a.eps_ext, t, 1, sp.K, tile_base + k);
-              } else {
-                float f0, f1;
-                philox_eps(sp.seed, (unsigned long long)(sp.k_offset + tile_base + k), t, step, std0, std1, f0, f1);
-                e0 = R(f0);
-                e1 = R(f1);
-              }
-              S += e;
-              N0 = Math<R>::fma_(e, e0, N0);
-              N1 = Math<R>::fma_(e, e1, N1);
-            }
-          }
-          const R sc = (rr.x == mnew) ? R(1) : Math<R>::exp_((rr.x - mnew) * neg_inv_lam);
-          rr.y = Math<R>::fma_(rr.y, sc, S);
-          rr.z = Math<R>::fma_(rr.z, sc, N0);
-          rr.w = Math<R>::fma_(rr.w, sc, N1);
-          rr.x = mnew;
-          run[t] = rr;
-        } else {
-          // screen: keep every rollout within the window [m, lim] of the CTA's running minimum m.
-          // run[t] = (m, L): L is the tightest limit ever applied, so the list is guaranteed to hold
-          // EVERY rollout of this CTA with V <= L.  Normally lim = m + margin; if more than kMaxCand
-          // rollouts fall inside, the window is halved until they fit (the reduce kernel checks that L
-          // still covers the window of the GLOBAL minimum, else the step is redone in fp64).
-          R lim = mnew + margin;
-          uint2* list = a.cand + ((size_t)t * nCTA + cta) * kMaxCand;
-          const int cnt_old = ccount[t];
-          int cnt = cnt_old;
-          for (int k = 0; k < BLOCK; ++k) {
-            const R v = tot[k] - (pre ? pre[k] : R(0));
-            if (v <= lim) {
-              if (cnt < kMaxCand) list[cnt] = make_uint2((unsigned)(tile_base + k), __float_as_uint((float)v));
-              ++cnt;
-            }
-          }
-          if (cnt > kMaxCand) cnt = screen_tighten<R>(list, cnt_old, tot, pre, BLOCK, tile_base, mnew, lim);
-          rr.x = mnew;
-          rr.y = Math<R>::min_(rr.y, lim);
-          run[t] = rr;
-          ccount[t] = cnt;
-        }
-      }
+      if (t < T)
+        transposed_row<R, MODE, BLOCK>(a, t, tile, cta, nCTA, P, run, ccount, ed, cost_to_go, neg_inv_lam, margin, std0, std1, step);
     }
     __syncthreads();
     // fold the per-tile fixed-point sums into the CTA's 64-bit accumulators
