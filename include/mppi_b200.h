@@ -208,8 +208,11 @@ MPPI_API mppi_status mppi_measure_fp32_peak(int32_t device, double* tflops, doub
 
 /* bytes mppi_step moves per call: host->device (x0, goal) and device->host (result block). */
 MPPI_API mppi_status mppi_io_bytes(mppi_handle h, size_t* h2d, size_t* d2h);
-/* launch configuration of the rollout kernel (diagnostics): block, grid, tiles, dynamic smem, CTAs/SM, regs */
-MPPI_API mppi_status mppi_launch_info(mppi_handle h, int32_t info[6]);
+/* measurement aid: overwrite a 256 MiB device buffer (> L2) and synchronise, so the next step starts cache-cold. */
+MPPI_API mppi_status mppi_debug_flush_l2(mppi_handle h);
+/* launch configuration of the rollout kernel (diagnostics): block, grid, tiles, dynamic smem, CTAs/SM, regs,
+ * code path (0 general, 1 fast, 2 lean), reserved */
+MPPI_API mppi_status mppi_launch_info(mppi_handle h, int32_t info[8]);
 
 /* profiling aid: globaltimer stamps (ns) of the reduce-kernel phases of the last step, [T][8];
  * the first call arms the stamps. */

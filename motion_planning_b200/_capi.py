@@ -90,6 +90,7 @@ _SIGNATURES = {
     "mppi_measure_fp32_peak": [C.c_int32, _dp, _dp],
     "mppi_io_bytes": [_H, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
     "mppi_launch_info": [_H, C.POINTER(C.c_int32)],
+    "mppi_debug_flush_l2": [_H],
     "mppi_debug_reduce_timestamps": [_H, C.POINTER(C.c_uint64)],
     "mppi_last_error": [],
     "mppi_version": [],

@@ -19,13 +19,11 @@
 namespace mppi {
 
 constexpr int kUnrollT2 = MPPI_UNROLL_T2;   // step pairs per iteration of the rollout loop
-constexpr int kWsBlockTag = 96;      // `block` value that selects the warp-specialised rollout kernel (32 rollouts, 96 threads)
-constexpr int kWsThreads = 96;
-constexpr int kWsTile = 32;
 constexpr int kMaxCand = 16;        // SCREEN: candidate slots per (CTA, t)
 constexpr int kMaxRefine = 256;     // SCREEN: fp64 re-evaluations per t after the global filter
 constexpr int kRecordStride = 6;    // doubles per t in an exchange record: m, S, N0, N1, E0, E1
 constexpr double kZFixScale = 1048576.0;   // 2^20: fixed-point scale of the floor-term noise sums
+constexpr double kLeanMaxYawInc = 0.125;   // LEAN rollout kernel: admission bound on |dt * yaw rate| (half of it for Euler)
 
 enum RolloutMode { MODE_SOFTMIN = 0, MODE_SCREEN = 1 };
 
@@ -76,7 +74,36 @@ struct DynState {
   double last_max_dev;
   int overflow_total;    // steps that hit a candidate-list overflow since creation
   unsigned int xchg;     // p2p exchange epoch: +1 per step, never rewound (arrival flags carry xchg+1)
+  // fp32 mirrors of lam / noise_std kept by the host (LEAN rollout prologue: no fp64 division, no conversions)
+  float neg_inv_lam_f;
+  float noise_std_f[2];
+  float pad1;
 };
+// result block of one step in MAPPED pinned host memory: the finalize phase stores it straight into host memory
+// (zero-copy, one PCIe write burst) and publishes it by writing `seq` last; mppi_step polls `seq`.
+struct HostResult {
+  double out_u[2];
+  double out_x[3];
+  double max_dev;
+  int status;
+  int candidates;
+  int overflow_total;
+  int pad;
+  unsigned long long seq;
+};
+// x0 / goal of a step either travel as kernel ARGUMENTS (mppi_step: no H2D copy on the critical path) or live in
+// DynState (device-resident closed loop, sharded local/finish steps)
+struct StepInput {
+  double x0g[6];         // x0[3], goal[3]
+  int from_args;
+};
+__device__ __forceinline__ void load_step_input(const StepInput& in, const DynState* __restrict__ ds, double x0[3], double goal[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    x0[i] = in.from_args ? in.x0g[i] : ds->x0[i];
+    goal[i] = in.from_args ? in.x0g[3 + i] : ds->goal[i];
+  }
+}
 constexpr int kStatusRedoF64 = 100;   // MIXED: support list overflowed, host must redo the step in fp64
 
 // ---- small math layer ---------------------------------------------------------------------------
@@ -243,11 +270,14 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // 4 standard normals (fp32) = the z of (t=2*t2: ch0, ch1), (t=2*t2+1: ch0, ch1).  Box-Muller on the
 // SFU pipe (lg2, rsqrt/sqrt, sin, cos).  Bit-identical wherever it is called from (intrinsics only,
 // nothing for the compiler to contract).
+__device__ __forceinline__ float4 normal4_from_bits(uint4 r);
 __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long kglobal,
                                                  unsigned int t2, unsigned int step) {
   uint4 ctr = make_uint4((uint32_t)kglobal, (uint32_t)(kglobal >> 32), t2, step);
   uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-  uint4 r = philox4x32_10(ctr, key);
+  return normal4_from_bits(philox4x32_10(ctr, key));
+}
+__device__ __forceinline__ float4 normal4_from_bits(uint4 r) {
   const float S = 2.3283064365386963e-10f;   // 2^-32
   float u0 = __fmaf_rn((float)r.x, S, 1.1641532182693481e-10f);   // (0,1]
   float u2 = __fmaf_rn((float)r.z, S, 1.1641532182693481e-10f);
@@ -387,14 +417,16 @@ __device__ __forceinline__ R grid_cost(const CostConsts<R>& cc, const signed cha
 }
 
 template <typename R>
-__device__ __forceinline__ void make_consts(const StaticParams& sp, const DynState* __restrict__ ds,
+__device__ __forceinline__ void make_consts(const StaticParams& sp, const StepInput& in, const DynState* __restrict__ ds,
                                             ModelConsts<R>& mc, CostConsts<R>& cc) {
   mc.dt = R(sp.dt);
   mc.half_r = R(sp.wheel_r * 0.5);
   mc.r_over_L = R(sp.wheel_r / sp.wheel_L);
   mc.inv_L = R(1.0 / sp.wheel_L);
-  double x0 = ds->x0[0], y0 = ds->x0[1], th0 = ds->x0[2];
-  double gx = ds->goal[0], gy = ds->goal[1], gth = ds->goal[2];
+  double xs[3], gs[3];
+  load_step_input(in, ds, xs, gs);
+  const double x0 = xs[0], y0 = xs[1], th0 = xs[2];
+  const double gx = gs[0], gy = gs[1], gth = gs[2];
   cc.hqx = R(0.5 * sp.q[0]);
   cc.hqy = R(0.5 * sp.q[1]);
   cc.hqth = R(0.5 * sp.q[2]);

@@ -6,6 +6,8 @@
 // of the result block; all controller state (nominal U, Philox step counter) stays resident in HBM.
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -42,7 +44,7 @@ static void set_err(const char* fmt, ...) {
   } while (0)
 
 struct KindCfg {
-  bool fast = false;
+  int variant = ROLLOUT_GENERAL;
   int block = 0, grid = 0, ntiles = 0, ctas_per_sm = 0, regs = 0;
   size_t smem = 0;
   bool ready = false;
@@ -82,8 +84,13 @@ struct mppi_engine {
   // pinned host staging
   double* h_in = nullptr;      // x0[3], goal[3]
   DynState* h_out = nullptr;
+  // zero-copy result hand-over of mppi_step: mapped pinned block written by the finalize phase, published by seq
+  HostResult* h_res = nullptr;
+  HostResult* d_res = nullptr;   // device alias of h_res
+  unsigned long long seq = 0;
+  bool wait_block = false;       // MPPI_B200_WAIT=block: cudaStreamSynchronize instead of polling h_res->seq
   // graphs
-  cudaGraphExec_t g_step = nullptr, g_loop = nullptr;
+  cudaGraphExec_t g_loop = nullptr;   // device-resident closed loop (mppi_bench)
   bool dirty = true;
   // host mirrors
   double goal[3] = {0, 0, 0};
@@ -160,9 +167,8 @@ static void free_partials(mppi_engine* e) {
 }
 
 static mppi_status drop_graphs(mppi_engine* e) {
-  if (e->g_step) cudaGraphExecDestroy(e->g_step);
   if (e->g_loop) cudaGraphExecDestroy(e->g_loop);
-  e->g_step = e->g_loop = nullptr;
+  e->g_loop = nullptr;
   e->dirty = true;
   return MPPI_OK;
 }
@@ -183,40 +189,43 @@ static double max_yaw_increment(const StaticParams& sp) {
 static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
   StaticParams& sp = e->sp;
   const bool has_grid = sp.has_grid != 0;
-  // FAST kernels: in-register Philox noise and yaw increments small enough for the branch-free step
-  const bool fast = !sp.noise_external && max_yaw_increment(sp) <= 0.78;
+  // FAST kernels: in-register Philox noise and yaw increments small enough for the branch-free step;
+  // LEAN (fp32 families only): additionally Q[2] == 0 and |dt * yaw rate| <= 1/8 (rollout_lean_kernel.cuh).
+  // MPPI_B200_BLOCK=<64|128> forces one tile shape, MPPI_B200_VARIANT=<general|fast|lean> caps the code path
+  // (experiments / tests of the fallback paths).
+  const double yaw_inc = max_yaw_increment(sp);
+  int variant_max = ROLLOUT_LEAN;
+  if (const char* envv = getenv("MPPI_B200_VARIANT")) {
+    if (!strcmp(envv, "general")) variant_max = ROLLOUT_GENERAL;
+    else if (!strcmp(envv, "fast")) variant_max = ROLLOUT_FAST;
+  }
+  const bool fast = !sp.noise_external && yaw_inc <= 0.78 && variant_max >= ROLLOUT_FAST;
+  const bool lean = fast && sp.q[2] == 0.0 && yaw_inc <= (sp.model == MPPI_MODEL_UNICYCLE_EULER ? 0.5 : 1.0) * kLeanMaxYawInc && variant_max >= ROLLOUT_LEAN;
   const char* envb = getenv("MPPI_B200_BLOCK");
   *max_ctas = 0;
   for (int kind = 0; kind < 3; ++kind) {
     KindCfg best;
     double best_cost = 1e300;
-    // candidate tile shapes: 32/64/128 rollouts per CTA (one thread each), or the warp-specialised kernel
-    // (tag 96: 32 rollouts, 1 consumer + 2 producer warps) which is preferred for the fp32 FAST path.
-    // MPPI_B200_BLOCK=<32|64|128|96> forces one shape, MPPI_B200_WS=0 disables the warp-specialised kernel.
-    const char* envws = getenv("MPPI_B200_WS");
-    const bool ws_ok = fast && kind != ROLLOUT_F64_SOFTMIN && !(envws && atoi(envws) == 0);
-    int shapes[4], nshapes = 0;
-    if (!fast) {
+    const int variant = !fast ? ROLLOUT_GENERAL : ((lean && kind != ROLLOUT_F64_SOFTMIN) ? ROLLOUT_LEAN : ROLLOUT_FAST);
+    int shapes[2], nshapes = 0;
+    if (variant == ROLLOUT_GENERAL) {
       shapes[nshapes++] = 64;
-    } else if (envb && (atoi(envb) == 32 || atoi(envb) == 64 || atoi(envb) == 128 || (atoi(envb) == kWsBlockTag && ws_ok))) {
+    } else if (envb && (atoi(envb) == 64 || atoi(envb) == 128)) {
       shapes[nshapes++] = atoi(envb);
-    } else if (ws_ok) {
-      shapes[nshapes++] = kWsBlockTag;
     } else {
-      shapes[nshapes++] = 32;
       shapes[nshapes++] = 64;
       shapes[nshapes++] = 128;
     }
     for (int si = 0; si < nshapes; ++si) {
       const int block = shapes[si];
       KindCfg c;
-      c.fast = fast;
+      c.variant = variant;
       c.block = block;
-      const int rollouts = (block == kWsBlockTag) ? kWsTile : block;
+      const int rollouts = block;
       c.ntiles = (sp.K + rollouts - 1) / rollouts;
-      c.smem = rollout_smem(kind, sp.T, block, gin);
+      c.smem = rollout_smem(kind, sp.T, block, variant, gin);
       if (c.smem > 227 * 1024) continue;
-      cudaError_t ce = rollout_prepare(kind, sp.model, has_grid, block, fast, c.smem, &c.ctas_per_sm, &c.regs);
+      cudaError_t ce = rollout_prepare(kind, sp.model, has_grid, block, variant, c.smem, &c.ctas_per_sm, &c.regs);
       if (ce != cudaSuccess || c.ctas_per_sm < 1) {
         cudaGetLastError();
         continue;
@@ -292,6 +301,9 @@ static mppi_status upload_dyn_sampling(mppi_engine* e, const double sig[4], doub
   tmp.lam = lam;
   tmp.noise_std[0] = nstd[0];
   tmp.noise_std[1] = nstd[1];
+  tmp.neg_inv_lam_f = (float)(-1.0 / lam);
+  tmp.noise_std_f[0] = (float)nstd[0];
+  tmp.noise_std_f[1] = (float)nstd[1];
   CK(cudaMemcpy(e->d_dyn, &tmp, sizeof(DynState), cudaMemcpyHostToDevice));
   return MPPI_OK;
 }
@@ -407,7 +419,7 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
   CKF(cudaMalloc(&e->d_Ulast, 2 * T * sizeof(double)));
   CKF(cudaMalloc(&e->d_Utmp, 4 * T * sizeof(double)));
   CKF(cudaMalloc(&e->d_nomD, 4 * T * sizeof(double)));
-  CKF(cudaMalloc(&e->d_nomF, 4 * T * sizeof(float)));
+  CKF(cudaMalloc(&e->d_nomF, 8 * T * sizeof(float)));   // planar [4][T] + interleaved float4[T] (LEAN)
   CKF(cudaMalloc(&e->d_record, (size_t)T * kRecordStride * sizeof(double)));
   CKF(cudaMalloc(&e->d_record_tmp, (size_t)T * kRecordStride * sizeof(double)));
   CKF(cudaMalloc(&e->d_gather, (size_t)p.world_size * T * kRecordStride * sizeof(double)));
@@ -415,6 +427,10 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
   CKF(cudaMemset(e->d_done, 0, sizeof(unsigned int)));
   CKF(cudaMallocHost(&e->h_in, 6 * sizeof(double)));
   CKF(cudaMallocHost(&e->h_out, sizeof(DynState)));
+  CKF(cudaHostAlloc(&e->h_res, sizeof(HostResult), cudaHostAllocMapped));
+  memset(e->h_res, 0, sizeof(HostResult));
+  CKF(cudaHostGetDevicePointer((void**)&e->d_res, e->h_res, 0));
+  if (const char* w = getenv("MPPI_B200_WAIT")) e->wait_block = !strcmp(w, "block");
   CKF(cudaMemset(e->d_Umaster, 0, 2 * T * sizeof(double)));     // uvec_init = zeros, control/src/mppi:65
   CKF(cudaMemset(e->d_Ulast, 0, 2 * T * sizeof(double)));
   CKF(cudaMemset(e->d_record, 0, (size_t)T * kRecordStride * sizeof(double)));
@@ -430,6 +446,9 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
     }
     d.noise_std[0] = p.noise_std[0];
     d.noise_std[1] = p.noise_std[1];
+    d.neg_inv_lam_f = (float)(-1.0 / p.lambda);
+    d.noise_std_f[0] = (float)p.noise_std[0];
+    d.noise_std_f[1] = (float)p.noise_std[1];
     CKF(cudaMemcpy(e->d_dyn, &d, sizeof(d), cudaMemcpyHostToDevice));
   }
   e->U_prev.assign(2 * T, 0.0);
@@ -467,6 +486,7 @@ extern "C" mppi_status mppi_destroy(mppi_handle e) {
   cudaFree(e->d_flush);
   if (e->h_in) cudaFreeHost(e->h_in);
   if (e->h_out) cudaFreeHost(e->h_out);
+  if (e->h_res) cudaFreeHost(e->h_res);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return MPPI_OK;
@@ -521,7 +541,7 @@ extern "C" mppi_status mppi_set_noise_std(mppi_handle e, const double nstd[2]) {
   CKS(upload_dyn_sampling(e, e->p.sig, e->p.lambda, nstd));
   e->p.noise_std[0] = nstd[0];
   e->p.noise_std[1] = nstd[1];
-  return MPPI_OK;
+  return prep_nominal(e);   // the LEAN nominal block carries std * g
 }
 
 extern "C" mppi_status mppi_get_nominal(mppi_handle e, double* U) {
@@ -672,14 +692,17 @@ static FinalizeArgs make_fin(mppi_engine* e, bool closed_loop) {
 enum FuseMode { FUSE_NONE = 0, FUSE_STEP = 1, FUSE_LOOP = 2 };
 
 // rollout + reduce (+ finalize fused into the reduce kernel's last block when fuse != FUSE_NONE)
-static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, int fuse, KernelEvents* kev) {
+// `in` != nullptr: x0 / goal travel as kernel arguments and the result is published to e->h_res under e->seq
+static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, int fuse, KernelEvents* kev,
+                                const StepInput* in = nullptr) {
   const int kind = kind_of(precision);
   const KindCfg& c = e->cfg[kind];
   RolloutArgs ra;
   memset(&ra, 0, sizeof(ra));
   ra.sp = e->sp;
   ra.dyn = e->d_dyn;
-  ra.nom = (kind == ROLLOUT_F64_SOFTMIN) ? (const void*)e->d_nomD : (const void*)e->d_nomF;
+  ra.nom = (kind == ROLLOUT_F64_SOFTMIN) ? (const void*)e->d_nomD
+                                         : (const void*)(e->d_nomF + (c.variant == ROLLOUT_LEAN ? 4 * e->sp.T : 0));
   ra.grid = e->d_grid;
   ra.eps_ext = e->d_eps_ext;
   ra.part = e->d_part;
@@ -688,13 +711,45 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   ra.cand = e->d_cand;
   ra.vcap = e->d_vcap;
   ra.ntiles = c.ntiles;
+  if (in) ra.in = *in;
+  if (c.variant == ROLLOUT_LEAN) {
+    const StaticParams& sp = e->sp;
+    LeanStatic& ls = ra.lean;
+    ls.ca = (float)(0.5 * sp.dt * sp.wheel_r / sp.wheel_L);
+    ls.cg = (float)(sp.dt * sp.wheel_r * 0.5 / 6.0);
+    ls.ck = (float)(sp.dt * sp.wheel_r / sp.wheel_L);
+    ls.dt = (float)sp.dt;
+    ls.dt6 = (float)(sp.dt / 6.0);
+    ls.inv_L = (float)(1.0 / sp.wheel_L);
+    ls.um0 = (float)sp.u_max[0];
+    ls.um1 = (float)sp.u_max[1];
+    ls.hqx = (float)(0.5 * sp.q[0]);
+    ls.hqy = (float)(0.5 * sp.q[1]);
+    ls.p1x = (float)sp.p1[0];
+    ls.p1y = (float)sp.p1[1];
+    ls.p1th = (float)sp.p1[2];
+    ls.g_inv_res = (float)sp.g_inv_res;
+    ls.w_obs_100 = (float)(sp.w_obs / 100.0);
+    ls.margin = (float)sp.margin;
+    for (int i = 0; i < MPPI_PHILOX_ROUNDS; ++i) {
+      ls.pkx[i] = (uint32_t)sp.seed + (uint32_t)i * 0x9E3779B9u;
+      ls.pky[i] = (uint32_t)(sp.seed >> 32) + (uint32_t)i * 0xBB67AE85u;
+    }
+  }
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[0], st));
-  CK(rollout_launch(kind, e->sp.model, e->sp.has_grid != 0, c.block, c.fast, c.grid, c.smem, st, ra));
+  CK(rollout_launch(kind, e->sp.model, e->sp.has_grid != 0, c.block, c.variant, c.grid, c.smem, st, ra));
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[1], st));
   ReduceArgs rd;
   memset(&rd, 0, sizeof(rd));
   rd.sp = e->sp;
   rd.fin = make_fin(e, fuse == FUSE_LOOP);
+  if (in) {
+    rd.fin.in = *in;
+    if (fuse != FUSE_NONE) {
+      rd.fin.host_res = e->d_res;
+      rd.fin.seq = e->seq;
+    }
+  }
   if (fuse != FUSE_NONE && e->p2p_on) {   // sharded + p2p: the last block also exchanges and finalizes
     rd.fin.p2p = 1;
     rd.fin.gather = nullptr;
@@ -724,8 +779,13 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
 }
 
 // stand-alone finalize (sharded steps: after the exchange)
-static mppi_status launch_finalize(mppi_engine* e, cudaStream_t st, bool closed_loop, KernelEvents* kev, bool p2p = false) {
+static mppi_status launch_finalize(mppi_engine* e, cudaStream_t st, bool closed_loop, KernelEvents* kev, bool p2p = false,
+                                   bool publish = false) {
   FinalizeArgs fa = make_fin(e, closed_loop);
+  if (publish) {
+    fa.host_res = e->d_res;
+    fa.seq = e->seq;
+  }
   if (p2p) {   // records arrive in the local IPC buffer; parity is resolved on the device from dyn->xchg
     fa.p2p = 1;
     fa.gather = nullptr;
@@ -735,46 +795,68 @@ static mppi_status launch_finalize(mppi_engine* e, cudaStream_t st, bool closed_
   return MPPI_OK;
 }
 
+// the device-resident closed loop of mppi_bench: one graph = { rollout, reduce + finalize }
 static mppi_status build_graphs(mppi_engine* e) {
   if (!e->dirty) return MPPI_OK;
   drop_graphs(e);
-  for (int which = 0; which < 2; ++which) {
-    cudaGraph_t g = nullptr;
-    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-    mppi_status s = MPPI_OK;
-    if (which == 0) {
-      cudaError_t ce = cudaMemcpyAsync(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream);
-      if (ce != cudaSuccess) s = MPPI_ERR_CUDA;
-    }
-    if (s == MPPI_OK) s = launch_local(e, e->stream, e->p.precision, which == 1 ? FUSE_LOOP : FUSE_STEP, nullptr);
-    if (s == MPPI_OK && which == 0) {
-      cudaError_t ce = cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream);
-      if (ce != cudaSuccess) s = MPPI_ERR_CUDA;
-    }
-    cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
-    if (s != MPPI_OK || ce != cudaSuccess) {
-      if (g) cudaGraphDestroy(g);
-      if (s == MPPI_OK) set_err("cudaStreamEndCapture: %s", cudaGetErrorString(ce));
-      return MPPI_ERR_CUDA;
-    }
-    cudaGraphExec_t ge = nullptr;
-    ce = cudaGraphInstantiate(&ge, g, 0);
-    cudaGraphDestroy(g);
-    if (ce != cudaSuccess) {
-      set_err("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
-      return MPPI_ERR_CUDA;
-    }
-    if (which == 0)
-      e->g_step = ge;
-    else
-      e->g_loop = ge;
+  cudaGraph_t g = nullptr;
+  CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+  mppi_status s = launch_local(e, e->stream, e->p.precision, FUSE_LOOP, nullptr);
+  cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+  if (s != MPPI_OK || ce != cudaSuccess) {
+    if (g) cudaGraphDestroy(g);
+    if (s == MPPI_OK) set_err("cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+    return MPPI_ERR_CUDA;
   }
+  cudaGraphExec_t ge = nullptr;
+  ce = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (ce != cudaSuccess) {
+    set_err("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+    return MPPI_ERR_CUDA;
+  }
+  e->g_loop = ge;
   e->dirty = false;
   return MPPI_OK;
 }
 
+// wait until the finalize phase has published the result of step e->seq into mapped host memory.  Polling a
+// host-memory word costs ~0.1 us of latency against ~5 us for a blocking stream synchronisation; the stream is
+// queried now and then so that a faulted kernel cannot hang the caller.
+static mppi_status wait_result(mppi_engine* e) {
+  volatile unsigned long long* seq = &e->h_res->seq;
+  if (e->wait_block) {
+    CK(cudaStreamSynchronize(e->stream));
+  } else {
+    for (unsigned int spin = 1;; ++spin) {
+      if (*seq == e->seq) break;
+      if ((spin & 0xfffu) == 0) {
+        const cudaError_t q = cudaStreamQuery(e->stream);
+        if (q == cudaSuccess) break;             // everything retired: seq is checked below
+        if (q != cudaErrorNotReady) {
+          set_err("mppi_step: %s", cudaGetErrorString(q));
+          return MPPI_ERR_CUDA;
+        }
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  if (*seq != e->seq) {
+    set_err("mppi_step: the step retired without publishing its result (seq %llu != %llu)", (unsigned long long)*seq, e->seq);
+    return MPPI_ERR_STATE;
+  }
+  return MPPI_OK;
+}
+
+static StepInput step_input(const mppi_engine* e) {
+  StepInput in;
+  for (int i = 0; i < 6; ++i) in.x0g[i] = e->h_in[i];
+  in.from_args = 1;
+  return in;
+}
+
 static mppi_status finish_outputs(mppi_engine* e, double u_out[2], double x_next[3]) {
-  const DynState* o = e->h_out;
+  const HostResult* o = e->h_res;
   if (o->status == kStatusRedoF64) {
     // MIXED: a candidate list overflowed; redo this step entirely in fp64 (same noise: the step
     // counter was not advanced, U and x0 are untouched).
@@ -782,13 +864,14 @@ static mppi_status finish_outputs(mppi_engine* e, double u_out[2], double x_next
       set_err("MIXED overflow in a sharded step with an external exchange: rerun with precision F64");
       return MPPI_ERR_UNSUPPORTED;
     }
-    CKS(launch_local(e, e->stream, MPPI_PRECISION_F64, FUSE_STEP, nullptr));
-    CK(cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    const StepInput in = step_input(e);
+    e->seq += 1;
+    CKS(launch_local(e, e->stream, MPPI_PRECISION_F64, FUSE_STEP, nullptr, &in));
+    CKS(wait_result(e));
     e->last.refine_overflow += 1;
   }
-  e->last.refine_candidates = o->last_candidates;
-  e->last.refine_max_dev = o->last_max_dev;
+  e->last.refine_candidates = o->candidates;
+  e->last.refine_max_dev = o->max_dev;
   if (u_out) {
     u_out[0] = o->out_u[0];
     u_out[1] = o->out_u[1];
@@ -801,6 +884,10 @@ static mppi_status finish_outputs(mppi_engine* e, double u_out[2], double x_next
   if (o->status == MPPI_ERR_NONFINITE) {
     set_err("non-finite control update (NaN/Inf input propagated, as in the reference)");
     return MPPI_ERR_NONFINITE;
+  }
+  if (o->status == MPPI_ERR_STATE) {
+    set_err("peer-to-peer exchange timed out (a rank did not deliver its record)");
+    return MPPI_ERR_STATE;
   }
   return MPPI_OK;
 }
@@ -834,15 +921,11 @@ extern "C" mppi_status mppi_step(mppi_handle e, const double x0[3], double u_out
     return MPPI_ERR_STATE;
   }
   CKS(pre_step(e, x0));
-  if (e->own_stream) {
-    CKS(build_graphs(e));
-    CK(cudaGraphLaunch(e->g_step, e->stream));
-  } else {
-    CK(cudaMemcpyAsync(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    CKS(launch_local(e, e->stream, e->p.precision, FUSE_STEP, nullptr));
-    CK(cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream));
-  }
-  CK(cudaStreamSynchronize(e->stream));
+  // two launches, no copies: x0 / goal ride in the kernel arguments, the result comes back through mapped host memory
+  const StepInput in = step_input(e);
+  e->seq += 1;
+  CKS(launch_local(e, e->stream, e->p.precision, FUSE_STEP, nullptr, &in));
+  CKS(wait_result(e));
   return finish_outputs(e, u_out, x_next);
 }
 
@@ -936,9 +1019,9 @@ extern "C" mppi_status mppi_step_finish(mppi_handle e, double u_out[2], double x
     return MPPI_ERR_STATE;
   }
   e->local_pending = false;
-  CKS(launch_finalize(e, e->stream, false, nullptr));
-  CK(cudaMemcpyAsync(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
+  e->seq += 1;
+  CKS(launch_finalize(e, e->stream, false, nullptr, false, true));
+  CKS(wait_result(e));
   return finish_outputs(e, u_out, x_next);
 }
 
@@ -1211,12 +1294,25 @@ extern "C" mppi_status mppi_debug_reduce_timestamps(mppi_handle e, unsigned long
 
 extern "C" mppi_status mppi_io_bytes(mppi_handle e, size_t* h2d, size_t* d2h) {
   ENTER(e);
-  if (h2d) *h2d = 6 * sizeof(double);
-  if (d2h) *d2h = sizeof(DynState);
+  // x0 + goal ride in the argument buffers of the two kernels; the result block is stored into mapped host memory
+  if (h2d) *h2d = 2 * 6 * sizeof(double);
+  if (d2h) *d2h = sizeof(HostResult);
   return MPPI_OK;
 }
 
-extern "C" mppi_status mppi_launch_info(mppi_handle e, int32_t info[6]) {
+// measurement aid: overwrite a buffer larger than L2 so that the next step starts from a cold cache
+extern "C" mppi_status mppi_debug_flush_l2(mppi_handle e) {
+  ENTER(e);
+  if (!e->d_flush) {
+    e->flush_bytes = (size_t)256 << 20;   // > 126 MB L2
+    CK(cudaMalloc(&e->d_flush, e->flush_bytes));
+  }
+  CK(cudaMemsetAsync(e->d_flush, (int)(e->seq & 0xff), e->flush_bytes, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return MPPI_OK;
+}
+
+extern "C" mppi_status mppi_launch_info(mppi_handle e, int32_t info[8]) {
   ENTER(e);
   if (!info) return MPPI_ERR_INVALID;
   const KindCfg& c = e->cfg[kind_of(e->p.precision)];
@@ -1226,6 +1322,8 @@ extern "C" mppi_status mppi_launch_info(mppi_handle e, int32_t info[6]) {
   info[3] = (int32_t)c.smem;
   info[4] = c.ctas_per_sm;
   info[5] = c.regs;
+  info[6] = c.variant;
+  info[7] = 0;
   return MPPI_OK;
 }
 

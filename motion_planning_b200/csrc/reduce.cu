@@ -5,7 +5,7 @@
 #include "kernels_api.h"
 #include "reduce_kernels.cuh"
 #include "rollout_kernel.cuh"
-#include "rollout_ws_kernel.cuh"
+#include "rollout_lean_kernel.cuh"
 
 namespace mppi {
 
@@ -28,33 +28,33 @@ static cudaError_t launch_pdl(Fn f, int grid, int block, size_t smem, cudaStream
 }
 
 #define DECL_TU(name)                                                                                          \
-  cudaError_t rollout_##name##_prepare(int model, bool has_grid, int block, bool fast, size_t smem, int* ctas, int* regs); \
-  cudaError_t rollout_##name##_launch(int model, bool has_grid, int block, bool fast, int grid, size_t smem, cudaStream_t st, \
+  cudaError_t rollout_##name##_prepare(int model, bool has_grid, int block, int variant, size_t smem, int* ctas, int* regs); \
+  cudaError_t rollout_##name##_launch(int model, bool has_grid, int block, int variant, int grid, size_t smem, cudaStream_t st, \
                                       const RolloutArgs& a);
 DECL_TU(f32_softmin)
 DECL_TU(f32_screen)
 DECL_TU(f64_softmin)
 #undef DECL_TU
 
-cudaError_t rollout_prepare(int kind, int model, bool has_grid, int block, bool fast, size_t smem, int* ctas, int* regs) {
+cudaError_t rollout_prepare(int kind, int model, bool has_grid, int block, int variant, size_t smem, int* ctas, int* regs) {
   switch (kind) {
-    case ROLLOUT_F32_SOFTMIN: return rollout_f32_softmin_prepare(model, has_grid, block, fast, smem, ctas, regs);
-    case ROLLOUT_F32_SCREEN: return rollout_f32_screen_prepare(model, has_grid, block, fast, smem, ctas, regs);
-    default: return rollout_f64_softmin_prepare(model, has_grid, block, fast, smem, ctas, regs);
+    case ROLLOUT_F32_SOFTMIN: return rollout_f32_softmin_prepare(model, has_grid, block, variant, smem, ctas, regs);
+    case ROLLOUT_F32_SCREEN: return rollout_f32_screen_prepare(model, has_grid, block, variant, smem, ctas, regs);
+    default: return rollout_f64_softmin_prepare(model, has_grid, block, variant, smem, ctas, regs);
   }
 }
 
-cudaError_t rollout_launch(int kind, int model, bool has_grid, int block, bool fast, int grid, size_t smem, cudaStream_t st,
+cudaError_t rollout_launch(int kind, int model, bool has_grid, int block, int variant, int grid, size_t smem, cudaStream_t st,
                            const RolloutArgs& a) {
   switch (kind) {
-    case ROLLOUT_F32_SOFTMIN: return rollout_f32_softmin_launch(model, has_grid, block, fast, grid, smem, st, a);
-    case ROLLOUT_F32_SCREEN: return rollout_f32_screen_launch(model, has_grid, block, fast, grid, smem, st, a);
-    default: return rollout_f64_softmin_launch(model, has_grid, block, fast, grid, smem, st, a);
+    case ROLLOUT_F32_SOFTMIN: return rollout_f32_softmin_launch(model, has_grid, block, variant, grid, smem, st, a);
+    case ROLLOUT_F32_SCREEN: return rollout_f32_screen_launch(model, has_grid, block, variant, grid, smem, st, a);
+    default: return rollout_f64_softmin_launch(model, has_grid, block, variant, grid, smem, st, a);
   }
 }
 
-size_t rollout_smem(int kind, int T, int block, int grid_bytes_in_smem) {
-  if (block == kWsBlockTag) return rollout_ws_smem_bytes(T, grid_bytes_in_smem);
+size_t rollout_smem(int kind, int T, int block, int variant, int grid_bytes_in_smem) {
+  if (variant == ROLLOUT_LEAN) return rollout_lean_smem_bytes(T, block, grid_bytes_in_smem);
   return kind == ROLLOUT_F64_SOFTMIN ? rollout_smem_bytes<double>(T, block, grid_bytes_in_smem)
                                      : rollout_smem_bytes<float>(T, block, grid_bytes_in_smem);
 }

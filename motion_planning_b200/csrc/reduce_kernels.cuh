@@ -78,6 +78,29 @@ __device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch /* [
 
 __device__ void finalize_body(const FinalizeArgs& a, double* Us);
 
+// one thread: store the step's result block into mapped host memory and publish it (seq last, system-scope fences)
+__device__ __forceinline__ void publish_result(const FinalizeArgs& a, int status, const double* u, const double* xn, int cand,
+                                               double dev, int overflow_total) {
+  if (!a.host_res) return;
+  __threadfence();                       // DynState / nominal updates of this step are ordered before the hand-over
+  volatile HostResult* r = a.host_res;
+  if (u) {
+    r->out_u[0] = u[0];
+    r->out_u[1] = u[1];
+  }
+  if (xn) {
+    r->out_x[0] = xn[0];
+    r->out_x[1] = xn[1];
+    r->out_x[2] = xn[2];
+  }
+  r->max_dev = dev;
+  r->status = status;
+  r->candidates = cand;
+  r->overflow_total = overflow_total;
+  __threadfence_system();
+  r->seq = a.seq;
+}
+
 // "last block done": the block that finishes the last record runs the finalize phase, saving one
 // kernel boundary on the serial tail of the step (world_size 1 only; sharded steps exchange first)
 __device__ __forceinline__ bool last_block_done(unsigned int* counter, unsigned int nblocks) {
@@ -149,7 +172,10 @@ __device__ inline void last_block_epilogue(const ReduceArgs& a, double* scratch4
   if (a.p2p_push) {
     p2p_push_record(a);
     if (!p2p_wait_all(a.fin)) {
-      if (threadIdx.x == 0) a.fin.dyn->status = (int)MPPI_ERR_STATE;   // exchange timed out (a peer died)
+      if (threadIdx.x == 0) {   // exchange timed out (a peer died)
+        a.fin.dyn->status = (int)MPPI_ERR_STATE;
+        publish_result(a.fin, (int)MPPI_ERR_STATE, nullptr, nullptr, 0, 0.0, 0);
+      }
       return;
     }
   }
@@ -358,7 +384,7 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   // not write DynState, so these L2 round trips overlap its tail
   ModelConsts<double> mc;
   CostConsts<double> cc;
-  make_consts<double>(sp, a.fin.dyn, mc, cc);
+  make_consts<double>(sp, a.fin.in, a.fin.dyn, mc, cc);
   const double neg_inv_lam = -1.0 / a.fin.dyn->lam;
   const float std0 = (float)a.fin.dyn->noise_std[0], std1 = (float)a.fin.dyn->noise_std[1];
   const unsigned int philox_step = a.fin.dyn->step;
@@ -486,8 +512,8 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
 
 // ---- kernel 3: finalize.  one block of 256 threads ------------------------------------------------
 
-__device__ __forceinline__ void write_nominal_block(double lam, const double sig[4], int T, int t, double u0, double u1,
-                                                    float* nomF, double* nomD) {
+__device__ __forceinline__ void write_nominal_block(double lam, const double sig[4], const float nstd[2], int T, int t, double u0,
+                                                    double u1, float* nomF, double* nomD) {
   // g[t] = lam * (u . sig)   so that   lam * u.dot(sig).dot(eps) = g0 eps0 + g1 eps1   (control/src/mppi:184)
   const double g0 = lam * (u0 * sig[0] + u1 * sig[2]);
   const double g1 = lam * (u0 * sig[1] + u1 * sig[3]);
@@ -499,11 +525,15 @@ __device__ __forceinline__ void write_nominal_block(double lam, const double sig
   nomF[T + t] = (float)u1;
   nomF[2 * T + t] = (float)g0;
   nomF[3 * T + t] = (float)g1;
+  // LEAN block: interleaved per t, the noise std folded into the cost coefficients (rollout_lean_kernel.cuh)
+  reinterpret_cast<float4*>(nomF + 4 * T)[t] = make_float4((float)u0, (float)u1, (float)(g0 * (double)nstd[0]), (float)(g1 * (double)nstd[1]));
 }
 
 __global__ void prep_nominal_kernel(const DynState* dyn, int T, const double* Umaster, float* nomF, double* nomD) {
   const double sig[4] = {dyn->sig[0], dyn->sig[1], dyn->sig[2], dyn->sig[3]};
-  for (int t = threadIdx.x; t < T; t += blockDim.x) write_nominal_block(dyn->lam, sig, T, t, Umaster[t], Umaster[T + t], nomF, nomD);
+  const float nstd[2] = {(float)dyn->noise_std[0], (float)dyn->noise_std[1]};
+  for (int t = threadIdx.x; t < T; t += blockDim.x)
+    write_nominal_block(dyn->lam, sig, nstd, T, t, Umaster[t], Umaster[T + t], nomF, nomD);
 }
 
 template <int MODEL>
@@ -542,6 +572,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
   // the serial tail of the step: issue every global load it needs up front
   const double lam = a.dyn->lam;
   const double sigr[4] = {a.dyn->sig[0], a.dyn->sig[1], a.dyn->sig[2], a.dyn->sig[3]};
+  const float nstdr[2] = {(float)a.dyn->noise_std[0], (float)a.dyn->noise_std[1]};
   double x0r[3] = {0.0, 0.0, 0.0};
   unsigned int step_r = 0, xchg_r = 0;
   int cand_r = 0;
@@ -553,9 +584,14 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
     xchg_r = a.dyn->xchg;
     cand_r = __ldcg(&a.dyn->refine_candidates);
     dev_r = __ldcg(&a.dyn->refine_max_dev);
+    double goalr[3];
+    load_step_input(a.in, a.dyn, x0r, goalr);
     for (int i = 0; i < 3; ++i) {
-      x0r[i] = a.dyn->x0[i];
-      if (a.mode == 0 && (!isfinite(x0r[i]) || !isfinite(a.dyn->goal[i]))) bad = 1;
+      if (a.mode == 0 && (!isfinite(x0r[i]) || !isfinite(goalr[i]))) bad = 1;
+      if (a.mode == 0 && a.in.from_args) {   // keep DynState the single record of "the last step's input"
+        a.dyn->x0[i] = x0r[i];
+        a.dyn->goal[i] = goalr[i];
+      }
     }
   }
   const double* gather = a.p2p ? a.p2p_local + (size_t)(a.dyn->xchg & 1u) * sp.world * T * kRecordStride : a.gather;
@@ -616,6 +652,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       d->refine_candidates = 0;
       d->refine_overflow = 0;
       d->refine_max_dev = 0.0;
+      publish_result(a, kStatusRedoF64, nullptr, nullptr, cand_r, dev_r, d->overflow_total);
     }
     return;
   }
@@ -663,7 +700,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       const double u1 = (t + 1 < T) ? Uf[T + t + 1] : 0.0;
       a.Umaster[t] = u0;
       a.Umaster[T + t] = u1;
-      write_nominal_block(lam, sigr, T, t, u0, u1, a.nomF, a.nomD);
+      write_nominal_block(lam, sigr, nstdr, T, t, u0, u1, a.nomF, a.nomD);
     }
     if (tid == 0) {
       DynState* d = a.dyn;
@@ -687,6 +724,8 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       d->refine_candidates = 0;
       d->refine_overflow = 0;
       d->refine_max_dev = 0.0;
+      const double uo[2] = {Uf[0], Uf[T]};
+      publish_result(a, d->status, uo, xn, cand_r, dev_r, d->overflow_total);
     }
   }
 }

@@ -3,6 +3,18 @@
 #include "common.cuh"
 namespace mppi {
 
+// engine-lifetime fp32 constants of the LEAN rollout kernel, folded on the host (no fp64 math in its prologue)
+struct LeanStatic {
+  float ca, cg, ck;          // diff-drive: a = ca (u1-u0), g = cg (u0+u1), kth = ck (u1-u0)
+  float dt, dt6, inv_L;      // unicycle / bicycle
+  float um0, um1;
+  float hqx, hqy;            // Q/2
+  float p1x, p1y, p1th;
+  float g_inv_res, w_obs_100;
+  float margin;
+  uint32_t pkx[MPPI_PHILOX_ROUNDS], pky[MPPI_PHILOX_ROUNDS];   // Philox key schedule key + i * Weyl, per round
+};
+
 struct RolloutArgs {
   StaticParams sp;
   const DynState* dyn;
@@ -15,6 +27,8 @@ struct RolloutArgs {
   uint2* cand;                 // SCREEN: [T][nCTA][kMaxCand]  (k_local, float bits of V)
   void* vcap;                  // capture: Real[T][K]
   int ntiles;
+  StepInput in;                // x0 / goal of this step
+  LeanStatic lean;             // LEAN variant only
 };
 
 struct FinalizeArgs {
@@ -32,6 +46,9 @@ struct FinalizeArgs {
   // peer-to-peer exchange (world > 1, NVLink): wait for every rank's record to land in p2p_local
   int p2p;
   double* p2p_local;         // this rank's buffer: [2 parity][world][T*6] doubles, then flags [2][world] uint32
+  StepInput in;              // x0 / goal of this step (also used by the reduce kernel's fp64 re-evaluation)
+  HostResult* host_res;      // mapped pinned host memory (nullptr: results are fetched from DynState)
+  unsigned long long seq;    // value that publishes host_res
 };
 
 struct ReduceArgs {

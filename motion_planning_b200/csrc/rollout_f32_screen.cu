@@ -2,5 +2,5 @@
 #define TU_REAL float
 #define TU_MODE MODE_SCREEN
 #define TU_NAME(x) rollout_f32_screen_##x
-#define TU_HAS_WS 1
+#define TU_HAS_LEAN 1
 #include "rollout_tu.inc"

@@ -2,5 +2,5 @@
 #define TU_REAL float
 #define TU_MODE MODE_SOFTMIN
 #define TU_NAME(x) rollout_f32_softmin_##x
-#define TU_HAS_WS 1
+#define TU_HAS_LEAN 1
 #include "rollout_tu.inc"

@@ -22,6 +22,8 @@
 // accumulated exactly in fixed point (2^-20) with one REDUX (warp integer add) per channel and step;
 // integer sums make the term independent of the summation order / sharding.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "reduce_kernels_args.h"
 
@@ -37,7 +39,7 @@ __device__ __forceinline__ R load_eps_ext(const double* __restrict__ eps, int t,
 // running minimum), and if more than kMaxCand rollouts really are inside the window halve it until the
 // old entries plus this tile's rollouts fit; then rebuild the list.  One lane, sequential.
 template <typename R>
-__device__ __noinline__ int screen_tighten(uint2* list, int cnt_old, const R* tot, const R* pre, int block, int tile_base,
+__device__ __forceinline__ int screen_tighten(uint2* list, int cnt_old, const R* tot, const R* pre, int block, int tile_base,
                                            R mnew, R& lim) {
   int total = 0;
   for (int it = 0; it < 32; ++it) {
@@ -46,7 +48,7 @@ __device__ __noinline__ int screen_tighten(uint2* list, int cnt_old, const R* to
     if (it > 0) lim = mnew + (lim - mnew) * R(0.5);
     total = 0;
     for (int i = 0; i < cnt_old; ++i) total += (R(__uint_as_float(list[i].y)) <= lim) ? 1 : 0;
-    for (int k = 0; k < block; ++k) total += ((tot[k] - (pre ? pre[k] : R(0))) <= lim) ? 1 : 0;
+    for (int k = 0; k < block; ++k) total += ((tot[k] - pre[k]) <= lim) ? 1 : 0;
     if (total <= kMaxCand) break;
   }
   if (total > kMaxCand) lim = -Math<R>::inf();   // > kMaxCand exact ties: force the fp64 redo
@@ -56,38 +58,65 @@ __device__ __noinline__ int screen_tighten(uint2* list, int cnt_old, const R* to
     if (R(__uint_as_float(e.y)) <= lim) list[n++] = e;
   }
   for (int k = 0; k < block; ++k) {
-    const R v = tot[k] - (pre ? pre[k] : R(0));
+    const R v = tot[k] - pre[k];
     if (v <= lim && n < kMaxCand) list[n++] = make_uint2((unsigned)(tile_base + k), __float_as_uint((float)v));
   }
   return n;
 }
 
+// ---- cost tile geometry ---------------------------------------------------------------------------------
+// P holds T+1 rows of BLOCK Reals: row 0 is all zeros ("prefix before step 0"), row 1+t the running cost after
+// step t (row T = the rollout total).  Rows are padded by 16 bytes: the column-wise writes of the rollout loop
+// stay bank-conflict free AND the transposed pass can read 16-byte vectors (lane l reads row 32c+l: with a row
+// stride of BLOCK*sizeof(R)+16 bytes the 8 lanes of a quarter-warp phase hit 8 distinct 16-byte bank groups).
+template <typename R> struct Vec16;
+template <> struct Vec16<float> {
+  typedef float4 V;
+  static constexpr int N = 4;
+  static __device__ __forceinline__ float min_diff(const float4& a, const float4& b) {
+    return fminf(fminf(a.x - b.x, a.y - b.y), fminf(a.z - b.z, a.w - b.w));
+  }
+};
+template <> struct Vec16<double> {
+  typedef double2 V;
+  static constexpr int N = 2;
+  static __device__ __forceinline__ double min_diff(const double2& a, const double2& b) { return fmin(a.x - b.x, a.y - b.y); }
+};
+template <typename R, int BLOCK>
+struct CostTile {
+  static constexpr int PS = BLOCK + 16 / (int)sizeof(R);          // row stride in Reals
+  static __host__ __device__ constexpr size_t bytes(int T) { return (size_t)(T + 1) * PS * sizeof(R); }
+};
+
 // One row t of the transposed pass over the BLOCK rollouts of a tile (executed by ONE lane): cost-to-go
 // V[t,k] = Tot[k] - P[t-1,k], running minimum, then the online soft-min partial (MODE_SOFTMIN) or the
-// candidate list of the fp32 screen (MODE_SCREEN).  Shared by rollout_kernel and rollout_ws_kernel.
+// candidate list of the fp32 screen (MODE_SCREEN).  Two vectorised sweeps: (1) the minimum, (2) a bit mask of
+// the 16-byte groups that hold a rollout inside the window; only those groups are then visited element-wise
+// (in increasing k, so the partials do not depend on how the sweep is organised).
 template <typename R, int MODE, int BLOCK>
 __device__ __forceinline__ void transposed_row(const RolloutArgs& a, int t, int tile, int cta, int nCTA, const R* P,
                                                typename Math<R>::Vec4* run, int* ccount, double* ed, bool cost_to_go,
                                                R neg_inv_lam, R margin, float std0, float std1, unsigned int step) {
   typedef typename Math<R>::Vec4 Vec4;
-  constexpr int PS = BLOCK + 1;
+  typedef typename Vec16<R>::V V16;
+  constexpr int PS = CostTile<R, BLOCK>::PS;
+  constexpr int N = Vec16<R>::N;
+  constexpr int NG = BLOCK / N;                                   // 16-byte groups per row
+  typedef typename std::conditional<(NG <= 32), unsigned int, unsigned long long>::type Mask;
   const StaticParams& sp = a.sp;
   const int T = sp.T;
-  const R* tot = P + (size_t)(T - 1) * PS;
-  const R* pre = (t > 0 && cost_to_go) ? P + (size_t)(t - 1) * PS : nullptr;
+  const R* tot = P + (size_t)T * PS;                              // row T: rollout totals
+  const R* pre = P + (size_t)(cost_to_go ? t : 0) * PS;           // row t = prefix BEFORE step t (row 0 = zeros), :175
+  const V16* tot4 = reinterpret_cast<const V16*>(tot);
+  const V16* pre4 = reinterpret_cast<const V16*>(pre);
   const int tile_base = tile * BLOCK;
   const int nk = min(BLOCK, sp.K - tile_base);
   R m = Math<R>::inf();
-  if (pre) {
 #pragma unroll 8
-    for (int k = 0; k < BLOCK; ++k) m = Math<R>::min_(m, tot[k] - pre[k]);   // cost-to-go, :175
-  } else {
-#pragma unroll 8
-    for (int k = 0; k < BLOCK; ++k) m = Math<R>::min_(m, tot[k]);
-  }
+  for (int g = 0; g < NG; ++g) m = Math<R>::min_(m, Vec16<R>::min_diff(tot4[g], pre4[g]));
   if (sp.capture) {
     R* vc = reinterpret_cast<R*>(a.vcap) + (size_t)t * sp.K + tile_base;
-    for (int k = 0; k < nk; ++k) vc[k] = tot[k] - (pre ? pre[k] : R(0));
+    for (int k = 0; k < nk; ++k) vc[k] = tot[k] - pre[k];
   }
   if (sp.noise_external) {   // floor sums straight from the replayed noise
     const double* e0p = a.eps_ext + ((size_t)t * 2 + 0) * sp.K + tile_base;
@@ -102,26 +131,39 @@ __device__ __forceinline__ void transposed_row(const RolloutArgs& a, int t, int 
   }
   Vec4 rr = run[t];
   const R mnew = Math<R>::min_(rr.x, m);
+  // sweep 2: which groups hold a rollout with V <= lim?
+  //   SOFTMIN: e^-80 ~ 2e-35 is below any rounding   SCREEN: the window [m, m + margin] of the running minimum
+  const R lim = (MODE == MODE_SOFTMIN) ? mnew + R(80) / (-neg_inv_lam) * R(1.0001) : mnew + margin;
+  Mask hits = 0;
+#pragma unroll 8
+  for (int g = 0; g < NG; ++g)
+    if (Vec16<R>::min_diff(tot4[g], pre4[g]) <= lim) hits |= (Mask)1 << g;
   if (MODE == MODE_SOFTMIN) {
     // online softmin: weights relative to the running minimum of this CTA (:189-196)
     R S = R(0), N0 = R(0), N1 = R(0);
-    for (int k = 0; k < BLOCK; ++k) {
-      const R arg = ((tot[k] - (pre ? pre[k] : R(0))) - mnew) * neg_inv_lam;   // <= 0
-      if (arg > R(-80)) {                                   // e^-80 ~ 2e-35: below any rounding
-        const R e = Math<R>::exp_(arg);
-        R e0, e1;
-        if (sp.noise_external) {
-          e0 = load_eps_ext<R>(a.eps_ext, t, 0, sp.K, tile_base + k);
-          e1 = load_eps_ext<R>(a.eps_ext, t, 1, sp.K, tile_base + k);
-        } else {
-          float f0, f1;
-          philox_eps(sp.seed, (unsigned long long)(sp.k_offset + tile_base + k), t, step, std0, std1, f0, f1);
-          e0 = R(f0);
-          e1 = R(f1);
+    while (hits) {
+      const int g = (sizeof(Mask) == 4) ? __ffs((unsigned int)hits) - 1 : __ffsll((unsigned long long)hits) - 1;
+      hits &= hits - 1;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const int k = g * N + j;
+        const R arg = ((tot[k] - pre[k]) - mnew) * neg_inv_lam;   // <= 0
+        if (arg > R(-80)) {
+          const R e = Math<R>::exp_(arg);
+          R e0, e1;
+          if (sp.noise_external) {
+            e0 = load_eps_ext<R>(a.eps_ext, t, 0, sp.K, tile_base + k);
+            e1 = load_eps_ext<R>(a.eps_ext, t, 1, sp.K, tile_base + k);
+          } else {
+            float f0, f1;
+            philox_eps(sp.seed, (unsigned long long)(sp.k_offset + tile_base + k), t, step, std0, std1, f0, f1);
+            e0 = R(f0);
+            e1 = R(f1);
+          }
+          S += e;
+          N0 = Math<R>::fma_(e, e0, N0);
+          N1 = Math<R>::fma_(e, e1, N1);
         }
-        S += e;
-        N0 = Math<R>::fma_(e, e0, N0);
-        N1 = Math<R>::fma_(e, e1, N1);
       }
     }
     const R sc = (rr.x == mnew) ? R(1) : Math<R>::exp_((rr.x - mnew) * neg_inv_lam);
@@ -136,20 +178,26 @@ __device__ __forceinline__ void transposed_row(const RolloutArgs& a, int t, int 
     // EVERY rollout of this CTA with V <= L.  Normally lim = m + margin; if more than kMaxCand
     // rollouts fall inside, the window is halved until they fit (the reduce kernel checks that L
     // still covers the window of the GLOBAL minimum, else the step is redone in fp64).
-    R lim = mnew + margin;
+    R lim2 = lim;
     uint2* list = a.cand + ((size_t)t * nCTA + cta) * kMaxCand;
     const int cnt_old = ccount[t];
     int cnt = cnt_old;
-    for (int k = 0; k < BLOCK; ++k) {
-      const R v = tot[k] - (pre ? pre[k] : R(0));
-      if (v <= lim) {
-        if (cnt < kMaxCand) list[cnt] = make_uint2((unsigned)(tile_base + k), __float_as_uint((float)v));
-        ++cnt;
+    while (hits) {
+      const int g = (sizeof(Mask) == 4) ? __ffs((unsigned int)hits) - 1 : __ffsll((unsigned long long)hits) - 1;
+      hits &= hits - 1;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const int k = g * N + j;
+        const R v = tot[k] - pre[k];
+        if (v <= lim2) {
+          if (cnt < kMaxCand) list[cnt] = make_uint2((unsigned)(tile_base + k), __float_as_uint((float)v));
+          ++cnt;
+        }
       }
     }
-    if (cnt > kMaxCand) cnt = screen_tighten<R>(list, cnt_old, tot, pre, BLOCK, tile_base, mnew, lim);
+    if (cnt > kMaxCand) cnt = screen_tighten<R>(list, cnt_old, tot, pre, BLOCK, tile_base, mnew, lim2);
     rr.x = mnew;
-    rr.y = Math<R>::min_(rr.y, lim);
+    rr.y = Math<R>::min_(rr.y, lim2);
     run[t] = rr;
     ccount[t] = cnt;
   }
@@ -159,7 +207,7 @@ template <typename R, int MODEL, int MODE, bool HAS_GRID, int BLOCK, bool FAST>
 __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ RolloutArgs a) {
   typedef typename Math<R>::Vec4 Vec4;
   constexpr int NW = BLOCK / 32;
-  constexpr int PS = BLOCK + 1;   // padded row stride of the cost tile
+  constexpr int PS = CostTile<R, BLOCK>::PS;   // padded row stride of the cost tile
   const StaticParams& sp = a.sp;
   const int T = sp.T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -185,8 +233,8 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
   int* ccount = reinterpret_cast<int*>(smem_raw + off);                       // [T] SCREEN counts
   off += (size_t)T * sizeof(int);
   off = (off + 15) & ~(size_t)15;
-  R* P = reinterpret_cast<R*>(smem_raw + off);                                // [T][BLOCK+1]
-  off += (size_t)T * PS * sizeof(R);
+  R* P = reinterpret_cast<R*>(smem_raw + off);                                // [T+1][PS], row 0 = zeros
+  off += CostTile<R, BLOCK>::bytes(T);
   off = (off + 15) & ~(size_t)15;
   signed char* gcells = reinterpret_cast<signed char*>(smem_raw + off);       // grid copy (optional)
 
@@ -218,9 +266,10 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     ez32[2 * t + 1] = 0;
     ccount[t] = 0;
   }
+  for (int k = tid; k < PS; k += BLOCK) P[k] = R(0);
   ModelConsts<R> mc;
   CostConsts<R> cc;
-  make_consts<R>(sp, a.dyn, mc, cc);
+  make_consts<R>(sp, a.in, a.dyn, mc, cc);
   const R um0 = R(sp.u_max[0]), um1 = R(sp.u_max[1]);
   const float std0 = (float)a.dyn->noise_std[0], std1 = (float)a.dyn->noise_std[1];
   const unsigned int step = a.dyn->step;
@@ -262,7 +311,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
       R c = running_cost<R>(cc, dx, dy, th, nomG0[t], nomG1[t], e0, e1);     // :160-161,180-184
       if (HAS_GRID) c += grid_cost<R>(cc, cells, dx, dy);
       acc += c;
-      P[t * PS + tid] = acc;
+      P[(t + 1) * PS + tid] = acc;
     };
     // every lane flushes the step it owns in the 32-step chunk starting at `base`
     auto flush_chunk = [&](int base) {
@@ -323,7 +372,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     }
     acc += terminal_cost<R>(cc, dx, dy, th);                                 // :165-171
     if (!valid) acc = Math<R>::inf();
-    P[(T - 1) * PS + tid] = acc;   // row T-1 holds the rollout total Tot[k]
+    P[T * PS + tid] = acc;   // row T holds the rollout total Tot[k]
     __syncthreads();
 
     // ---- transposed pass: lane l of warp w owns row t = 32*(w + NW*i) + l ----------------------
@@ -367,7 +416,7 @@ inline size_t rollout_smem_bytes(int T, int block, int grid_bytes_padded_in_smem
   off += (size_t)T * 2 * sizeof(int);
   off += (size_t)T * sizeof(int);
   off = (off + 15) & ~(size_t)15;
-  off += (size_t)T * (block + 1) * sizeof(R);
+  off += (size_t)(T + 1) * (block + 16 / sizeof(R)) * sizeof(R);
   off = (off + 15) & ~(size_t)15;
   off += (size_t)grid_bytes_padded_in_smem;
   return off + 128;   // slack for the 128 B alignment of the dynamic segment

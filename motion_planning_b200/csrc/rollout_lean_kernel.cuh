@@ -1,0 +1,338 @@
+// rollout_lean_kernel.cuh -- the product instantiation of kernel 1 (fp32, in-register Philox noise).
+//
+// Same contract as rollout_kernel<float, ..., FAST> (rollout_kernel.cuh): noise -> rollout -> cost -> per-t
+// partials, identical Philox counters and partial-record formats; the reduce kernels cannot tell the two
+// apart.  The rollout kernel is ISSUE bound (one warp instruction per scheduler cycle),
+// so this variant is written to minimise executed instructions per state-step under the conditions the host
+// has checked for it (engine.cu: try_configure):
+//   * Q[2] == 0 (the reference's Q = diag(1e3, 1e3, 0), control/src/mppi:69): theta enters the running cost
+//     nowhere, so it is carried as a plain sum of yaw increments, wrapped once per four steps (branch-free,
+//     round-to-nearest turn count) and used only by the terminal cost (:165-171);
+//   * |dt * yaw rate| <= 1/8 for every admissible control: sin/cos of the HALF increment (|a| <= 1/16) are
+//     two-term polynomials, exact to fp32 rounding (next terms a^7/5040 < 1e-12, a^6/720 < 1e-10).
+// Differences from the generic FAST step:
+//   * nominal block interleaved as float4 per t (U0, U1, std0*g0, std1*g1): one broadcast LDS.128 per step;
+//     the sampled control is fmaf(std, z, U) and the noise term of the cost (:184) fmaf(std*g, z, .), so eps is
+//     never materialised;
+//   * model constants folded: a = (dt r / 2L)(u1-u0), g = (dt r / 12)(u0+u1), theta += (dt r / L)(u1-u0);
+//   * Simpson weights through the mid-point rotation only: c1 + 4 c2 + c4 = c2 (4 + 2 cos a) because
+//     c1 + c4 = 2 c2 cos a -- one rotation feeds the position update, a second one advances (cos, sin);
+//   * (cos, sin) is never re-derived from theta: one first-order renormalisation per four steps keeps the
+//     pair on the unit circle, the phase error stays at rounding level (~1e-6 rad over 128 steps);
+//   * floor-term sums: round(z * 2^18) by the magic-number trick (FFMA, no F2I on the SFU-class pipe), the
+//     rollout-valid mask folded into the scale; the 32 lanes' bias is removed after the warp REDUX.
+// Anything outside those conditions (Q[2] != 0, large yaw increments, replayed noise, fp64) runs rollout_kernel.
+#pragma once
+#include "rollout_kernel.cuh"
+
+namespace mppi {
+
+constexpr float kLeanFixScale = 262144.0f;        // 2^18: |z| < 6.8 -> |q| < 2^21 (magic-number rounding needs < 2^22)
+constexpr float kLeanMagic = 12582912.0f;         // 1.5 * 2^23
+constexpr unsigned kLeanBias32 = 0x68000000u;     // 32 * float_as_int(kLeanMagic) = 32 * 0x4B400000 (mod 2^32)
+
+// per-step constants: LeanStatic (host-folded) + what depends on x0 / goal / DynState
+struct LeanConsts {
+  float ca, cg, ck, dt, dt6, inv_L, um0, um1, hqx, hqy;
+  float std0, std1, ax2, ay2, th0;
+};
+
+// (half) yaw increment a, Simpson factor g = dt*speed/6 (Euler: dt*speed), theta <- theta + dt*yaw rate
+template <int MODEL>
+__device__ __forceinline__ void lean_controls(const LeanConsts& lc, float u0, float u1, float& a, float& g, float& th) {
+  if (MODEL == MPPI_MODEL_DIFF_DRIVE) {            // dd_dynamics, control/src/mppi:23-30
+    const float df = u1 - u0, sm = u0 + u1;
+    a = lc.ca * df;
+    g = lc.cg * sm;
+    th = fmaf(lc.ck, df, th);
+  } else if (MODEL == MPPI_MODEL_UNICYCLE_EULER) { // unicycle_dynamics + euler, control/src/mppi:33-36,57-58
+    a = lc.dt * u1;                                // the FULL increment: Euler rotates once per step
+    g = lc.dt * u0;
+    th += a;
+  } else {                                         // NEW bicycle: thdot = v tan(delta) / L
+    float sd, cd;
+    Math<float>::sincos_(u1, sd, cd);
+    const float kth = lc.dt * (u0 * (sd / cd) * lc.inv_L);
+    a = 0.5f * kth;
+    g = lc.dt6 * u0;
+    th += kth;
+  }
+}
+
+// Philox4x32-10 with the key schedule read from the kernel arguments (constant-bank operands of the XORs): the same
+// function as philox4x32_10(ctr, key) in common.cuh, minus 20 key additions per call
+__device__ __forceinline__ uint4 philox4x32_sched(uint4 c, const LeanStatic& ls) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int i = 0; i < MPPI_PHILOX_ROUNDS; ++i) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ ls.pkx[i], lo1, hi0 ^ c.w ^ ls.pky[i], lo0);
+  }
+  return c;
+}
+__device__ __forceinline__ float4 lean_normal4(const LeanStatic& ls, unsigned long long kglobal, unsigned int t2, unsigned int step) {
+  return normal4_from_bits(philox4x32_sched(make_uint4((uint32_t)kglobal, (uint32_t)(kglobal >> 32), t2, step), ls));
+}
+
+// sin/cos for |a| <= 1/16: two-term polynomials
+__device__ __forceinline__ void sincos_tiny(float a, float& s, float& c) {
+  const float z = a * a;
+  s = fmaf(a * z, fmaf(z, 8.3333333e-3f, -1.6666667e-1f), a);
+  c = fmaf(z, fmaf(z, 4.1666668e-2f, -0.5f), 1.0f);
+}
+
+// theta - 2 pi * rint(theta / 2 pi): the reference's wrap (control/src/mppi:52-53) for any number of turns,
+// branch-free on the FMA pipe (differs from the ceil form only AT theta = -pi, a null set)
+__device__ __forceinline__ float wrap_rint(float th) {
+  const float j = fmaf(th, 0.159154943f, kLeanMagic) - kLeanMagic;
+  return fmaf(-j, 6.28318548f, th);
+}
+
+template <int MODEL, int MODE, bool HAS_GRID, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) rollout_lean_kernel(const __grid_constant__ RolloutArgs a) {
+  typedef float R;
+  typedef float4 Vec4;
+  constexpr int NW = BLOCK / 32;
+  constexpr int PS = CostTile<R, BLOCK>::PS;
+  const StaticParams& sp = a.sp;
+  const int T = sp.T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nCTA = gridDim.x, cta = blockIdx.x;
+
+  // ---- shared memory carve-up ------------------------------------------------------------------
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);                      // 8 B
+  float* post = reinterpret_cast<float*>(smem_raw + 8);                       // 2 floats: constants only needed AFTER the T-step
+                                                                              // loop live here, not in registers or a stack frame
+  float4* nomL = reinterpret_cast<float4*>(smem_raw + 16);                    // [T] (U0, U1, std0*g0, std1*g1)
+  size_t off = 16 + (size_t)T * sizeof(float4);
+  Vec4* run = reinterpret_cast<Vec4*>(smem_raw + off);                        // running (m,S,N0,N1) / (m,L) per t
+  off += (size_t)T * sizeof(Vec4);
+  long long* ez64 = reinterpret_cast<long long*>(smem_raw + off);             // [T][2] CTA floor sums
+  off += (size_t)T * 2 * sizeof(long long);
+  int* ez32 = reinterpret_cast<int*>(smem_raw + off);                         // [T][2] per-tile floor sums
+  off += (size_t)T * 2 * sizeof(int);
+  int* ccount = reinterpret_cast<int*>(smem_raw + off);                       // [T] SCREEN counts
+  off += (size_t)T * sizeof(int);
+  off = (off + 15) & ~(size_t)15;
+  R* P = reinterpret_cast<R*>(smem_raw + off);                                // [T+1][PS], row 0 = zeros
+  off += CostTile<R, BLOCK>::bytes(T);
+  signed char* gcells = reinterpret_cast<signed char*>(smem_raw + off);       // grid copy (optional)
+
+  // ---- prologue: TMA bulk copies of the nominal block (+ grid) into shared memory -------------
+  const uint32_t nom_bytes = (uint32_t)(T * sizeof(float4));
+  const bool grid_smem = HAS_GRID && sp.grid_in_smem;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, nom_bytes + (grid_smem ? (uint32_t)sp.grid_bytes_padded : 0u));
+    tma_bulk_g2s(nomL, a.nom, nom_bytes, bar);
+    if (grid_smem) tma_bulk_g2s(gcells, a.grid, (uint32_t)sp.grid_bytes_padded, bar);
+  }
+  for (int t = tid; t < T; t += BLOCK) {
+    run[t] = make_float4(Math<R>::inf(), (MODE == MODE_SCREEN) ? Math<R>::inf() : 0.f, 0.f, 0.f);
+    ez64[2 * t] = 0;
+    ez64[2 * t + 1] = 0;
+    ez32[2 * t] = 0;
+    ez32[2 * t + 1] = 0;
+    ccount[t] = 0;
+  }
+  for (int k = tid; k < PS; k += BLOCK) P[k] = 0.f;
+  // every global load of the prologue is issued here, before the barrier wait; the engine-lifetime constants
+  // arrive pre-folded in the kernel arguments (LeanStatic)
+  const DynState* __restrict__ ds = a.dyn;
+  const unsigned int step = ds->step;
+  const R neg_inv_lam_ld = ds->neg_inv_lam_f;
+  const float std0_f = ds->noise_std_f[0], std1_f = ds->noise_std_f[1];
+  double xs[3], gs[3];
+  load_step_input(a.in, ds, xs, gs);
+  LeanConsts lc;
+  CostConsts<R> cc;     // grid / terminal constants in the layout grid_cost / terminal_cost expect
+  {
+    const LeanStatic& ls = a.lean;
+    lc.ca = ls.ca;
+    lc.cg = ls.cg;
+    lc.ck = ls.ck;
+    lc.dt = ls.dt;
+    lc.dt6 = ls.dt6;
+    lc.inv_L = ls.inv_L;
+    lc.um0 = ls.um0;
+    lc.um1 = ls.um1;
+    lc.hqx = ls.hqx;
+    lc.hqy = ls.hqy;
+    lc.std0 = std0_f;
+    lc.std1 = std1_f;
+    lc.ax2 = (float)(2.0 * (xs[0] - gs[0]));
+    lc.ay2 = (float)(2.0 * (xs[1] - gs[1]));
+    lc.th0 = (float)xs[2];
+    cc.hqx = ls.hqx;
+    cc.hqy = ls.hqy;
+    cc.hqth = 0.f;
+    cc.p1x = ls.p1x;
+    cc.p1y = ls.p1y;
+    cc.p1th = ls.p1th;
+    cc.ax2 = lc.ax2;
+    cc.ay2 = lc.ay2;
+    cc.th0 = lc.th0;
+    cc.gth2 = 0.f;   // staged in shared memory (post[0]) until the terminal cost needs it
+    if (tid == 0) {
+      post[0] = (float)(2.0 * gs[2]);
+      post[1] = neg_inv_lam_ld;
+    }
+    cc.g_inv_res = ls.g_inv_res;
+    cc.g_ox = (float)(xs[0] - sp.g_x0);
+    cc.g_oy = (float)(xs[1] - sp.g_y0);
+    cc.w_obs_100 = ls.w_obs_100;
+    cc.gW = sp.gW;
+    cc.gH = sp.gH;
+  }
+  const R margin = a.lean.margin;
+  const signed char* cells = grid_smem ? gcells : a.grid;
+  const bool cost_to_go = sp.weighting == MPPI_WEIGHT_COST_TO_GO;
+  float sth0, cth0;
+  Math<R>::sincos_(lc.th0, sth0, cth0);
+  // lane (t mod 32) keeps the warp sums of step t: per unrolled step i the owner test is lane - i == t4 (mod 32)
+  const int own0 = lane, own1 = (lane - 1) & 31, own2 = (lane - 2) & 31, own3 = (lane - 3) & 31;
+  mbar_wait(bar, 0);
+  __syncthreads();
+
+  for (int tile = cta; tile < a.ntiles; tile += nCTA) {
+    const int k_local = tile * BLOCK + tid;
+    const bool valid = k_local < sp.K;
+    const unsigned long long kglobal = (unsigned long long)(sp.k_offset + k_local);
+    const float qscale = valid ? kLeanFixScale : 0.f;     // invalid rollouts add exactly 0 to the floor sums
+    R dx = 0.f, dy = 0.f, th = lc.th0, acc = 0.f, cth = cth0, sth = sth0;
+    int eown0 = 0, eown1 = 0;
+    R* prow = P + PS + tid;                               // row 1 + t of this rollout's column
+
+    // one model step + running cost + prefix store (control/src/mppi:147-161); z0, z1 = the step's standard normals
+    auto one_step = [&](const float4 n, float z0, float z1, bool own, int row) {
+      // floor-term sums: exact fixed point (2^-18), one warp integer add (REDUX) per channel
+      int q0 = __float_as_int(fmaf(z0, qscale, kLeanMagic));
+      int q1 = __float_as_int(fmaf(z1, qscale, kLeanMagic));
+      q0 = __reduce_add_sync(0xffffffffu, q0);
+      q1 = __reduce_add_sync(0xffffffffu, q1);
+      eown0 = own ? q0 : eown0;
+      eown1 = own ? q1 : eown1;
+      // u_samp = clip(U[:,t] + eps), eps = std * z   (:147-152; eps itself stays unclipped)
+      const float u0 = fminf(fmaxf(fmaf(lc.std0, z0, n.x), -lc.um0), lc.um0);
+      const float u1 = fminf(fmaxf(fmaf(lc.std1, z1, n.y), -lc.um1), lc.um1);
+      float ah, g;
+      lean_controls<MODEL>(lc, u0, u1, ah, g, th);
+      float sa, ca;
+      sincos_tiny(ah, sa, ca);
+      if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {           // euler, :57-58: position with the OLD heading
+        dx = fmaf(g, cth, dx);
+        dy = fmaf(g, sth, dy);
+        const float cn = fmaf(cth, ca, -(sth * sa));
+        sth = fmaf(sth, ca, cth * sa);
+        cth = cn;
+      } else {                                            // rk4, :39-54 (Simpson in x, y; see header)
+        const float c2 = fmaf(cth, ca, -(sth * sa)), s2 = fmaf(sth, ca, cth * sa);
+        const float h = g * fmaf(2.0f, ca, 4.0f);
+        dx = fmaf(h, c2, dx);
+        dy = fmaf(h, s2, dy);
+        cth = fmaf(c2, ca, -(s2 * sa));
+        sth = fmaf(s2, ca, c2 * sa);
+      }
+      // get_cost in delta form (:180-184; common.cuh running_cost), increments summed before they meet acc
+      float c = n.w * z1;
+      c = fmaf(n.z, z0, c);
+      c = fmaf(lc.hqx * dx, dx + lc.ax2, c);
+      c = fmaf(lc.hqy * dy, dy + lc.ay2, c);
+      if (HAS_GRID) c += grid_cost<R>(cc, cells, dx, dy);
+      acc += c;
+      prow[row * PS] = acc;
+    };
+    auto flush_chunk = [&](int base) {
+      const int town = base + lane;
+      if (town < T) {
+        atomicAdd(&ez32[2 * town], (int)((unsigned)eown0 - kLeanBias32));   // remove the 32 lanes' bias
+        atomicAdd(&ez32[2 * town + 1], (int)((unsigned)eown1 - kLeanBias32));
+      }
+    };
+
+    float4 za = lean_normal4(a.lean, kglobal, 0u, step);
+    float4 zb = lean_normal4(a.lean, kglobal, 1u, step);
+    int t4 = 0;
+    for (; t4 + 4 <= T; t4 += 4) {
+      const float4 z0 = za, z1 = zb;
+      za = lean_normal4(a.lean, kglobal, (unsigned)(t4 >> 1) + 2u, step);   // one iteration ahead
+      zb = lean_normal4(a.lean, kglobal, (unsigned)(t4 >> 1) + 3u, step);
+      const int tm = t4 & 31;
+      const float4* nl = nomL + t4;
+      one_step(nl[0], z0.x, z0.y, own0 == tm, 0);
+      one_step(nl[1], z0.z, z0.w, own1 == tm, 1);
+      one_step(nl[2], z1.x, z1.y, own2 == tm, 2);
+      one_step(nl[3], z1.z, z1.w, own3 == tm, 3);
+      prow += 4 * PS;
+      // keep (cos, sin) on the unit circle and theta in (-pi, pi]
+      const float f = fmaf(fmaf(cth, cth, sth * sth), -0.5f, 1.5f);
+      cth *= f;
+      sth *= f;
+      th = wrap_rint(th);
+      if (tm == 28) flush_chunk(t4 & ~31);
+    }
+    if (t4 < T) {   // T = 4n + 2: one more pair
+      const int tm = t4 & 31;
+      const float4* nl = nomL + t4;
+      one_step(nl[0], za.x, za.y, own0 == tm, 0);
+      one_step(nl[1], za.z, za.w, own1 == tm, 1);
+      th = wrap_rint(th);
+    }
+    if (T & 31) flush_chunk(T & ~31);
+    cc.gth2 = post[0];
+    acc += terminal_cost<R>(cc, dx, dy, th);                                 // :165-171
+    if (!valid) acc = Math<R>::inf();
+    prow[(T - 1 - t4) * PS] = acc;   // row T holds the rollout total Tot[k] (addressed from the running row pointer: the
+                                     // tile-invariant form P + T*PS + tid gets hoisted and spilled)
+    __syncthreads();
+
+    // ---- transposed pass: lane l of warp w owns row t = 32*(w + NW*i) + l ----------------------
+    const R neg_inv_lam = post[1];
+    for (int tb = warp * 32; tb < T; tb += NW * 32) {
+      const int t = tb + lane;
+      if (t < T)
+        transposed_row<R, MODE, BLOCK>(a, t, tile, cta, nCTA, P, run, ccount, nullptr, cost_to_go, neg_inv_lam, margin, lc.std0,
+                                       lc.std1, step);
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * T; i += BLOCK) {
+      ez64[i] += (long long)ez32[i];
+      ez32[i] = 0;
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: one partial per (t, CTA) ------------------------------------------------------
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // floor sums leave in the 2^-20 units of the generic kernel (kZFixScale), so the reduce kernels see one format
+  constexpr double kToGeneric = kZFixScale / (double)kLeanFixScale;
+  for (int t = tid; t < T; t += BLOCK) {
+    const size_t idx = (size_t)t * nCTA + cta;
+    if (MODE == MODE_SOFTMIN)
+      reinterpret_cast<Vec4*>(a.part)[idx] = run[t];
+    else
+      a.cand_meta[idx] = make_float4(run[t].x, run[t].y, __int_as_float(ccount[t]), 0.f);
+    a.epart[2 * idx] = (double)ez64[2 * t] * kToGeneric;
+    a.epart[2 * idx + 1] = (double)ez64[2 * t + 1] * kToGeneric;
+  }
+}
+
+inline size_t rollout_lean_smem_bytes(int T, int block, int grid_bytes_padded_in_smem) {
+  size_t off = 16 + (size_t)T * sizeof(float4);
+  off += (size_t)T * sizeof(float4);               // run
+  off += (size_t)T * 2 * sizeof(long long);
+  off += (size_t)T * 2 * sizeof(int);
+  off += (size_t)T * sizeof(int);
+  off = (off + 15) & ~(size_t)15;
+  off += (size_t)(T + 1) * (block + 4) * sizeof(float);
+  off += (size_t)grid_bytes_padded_in_smem;
+  return off + 128;
+}
+
+}  // namespace mppi

@@ -327,9 +327,11 @@ class MPPI(object):
         return a.value, b.value
 
     def launch_info(self):
-        info = (C.c_int32 * 6)()
+        info = (C.c_int32 * 8)()
         _capi.check(self._lib.mppi_launch_info(self._h, info), "mppi_launch_info")
-        return dict(zip(["block", "grid", "tiles", "smem_bytes", "ctas_per_sm", "regs"], list(info)))
+        d = dict(zip(["block", "grid", "tiles", "smem_bytes", "ctas_per_sm", "regs"], list(info)[:6]))
+        d["variant"] = ("general", "fast", "lean")[info[6]]
+        return d
 
     def bench(self, x0, steps=20, warmup=3, flush_l2=True, per_kernel=True):
         t = _capi.MppiTiming()

@@ -18,7 +18,8 @@ out = {}
 for prec in ("mixed", "f32"):
     m = mp.MPPI(horizon=T, samples=K, precision=prec, seed=0); m.goal = np.array([0., -1., 0.])
     r = m.bench(np.zeros(3), steps=40, warmup=5, flush_l2=True, per_kernel=True)
-    out[prec] = (round(r["step_ms"] * 1e3, 2), round(r["rollout_ms"] * 1e3, 2), m.launch_info()["block"], m.launch_info()["regs"])
+    out[prec] = (round(r["step_ms"] * 1e3, 2), round(r["rollout_ms"] * 1e3, 2), m.launch_info()["block"], m.launch_info()["regs"], m.launch_info()["variant"],
+                 r["refine_candidates"], float("%%.2g" %% r["refine_max_dev"]))
     m.close()
 print(json.dumps(out))
 ''' % ROOT
@@ -27,7 +28,9 @@ for tag in tags:
     name = tag
     if tag.startswith("block"):
         env["MPPI_B200_BLOCK"] = tag[5:]
+    elif tag in ("fast", "general"):
+        env["MPPI_B200_VARIANT"] = tag
     elif tag:
         env["MPPI_B200_LIB"] = os.path.join(ROOT, "motion_planning_b200", "lib", "libmppi_b200_%s.so" % tag)
     r = subprocess.run([sys.executable, "-c", code, K, T], env=env, capture_output=True, text=True)
-    print("%-8s K=%s T=%s (step us, rollout us, block, regs): %s %s" % (name or "default", K, T, r.stdout.strip(), r.stderr.strip()[-300:]))
+    print("%-8s K=%s T=%s (step us, rollout us, block, regs, variant, candidates, max|V32-V64|): %s %s" % (name or "default", K, T, r.stdout.strip(), r.stderr.strip()[-300:]))
