@@ -78,7 +78,7 @@ cudaError_t reduce_screen_launch(int model, bool has_grid, int T, cudaStream_t s
       break;
     default: f = has_grid ? sfn_<MPPI_MODEL_BICYCLE, true>() : sfn_<MPPI_MODEL_BICYCLE, false>(); break;
   }
-  const size_t smem = (size_t)8 * 7 * T * sizeof(double);
+  const size_t smem = (size_t)(8 * 7 + 4) * T * sizeof(double);   // scan scratch of 8 warps + nominal block
   if (smem > 32 * 1024) {   // static + dynamic shared memory beyond 48 KB needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

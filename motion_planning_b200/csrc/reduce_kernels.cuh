@@ -104,15 +104,18 @@ __device__ __forceinline__ void publish_result(const FinalizeArgs& a, int status
 // "last block done": the block that finishes the last record runs the finalize phase, saving one
 // kernel boundary on the serial tail of the step (world_size 1 only; sharded steps exchange first)
 __device__ __forceinline__ bool last_block_done(unsigned int* counter, unsigned int nblocks) {
+  // precondition: the block's global results (its record, statistics) were written by THREAD 0 only, so one
+  // fence + one atomic by that thread order them before the ticket; the others just learn the outcome
   __shared__ unsigned int ticket;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) ticket = atomicAdd(counter, 1u);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    ticket = atomicAdd(counter, 1u);
+  }
   __syncthreads();
   const bool last = (ticket == nblocks - 1);
   if (last) {
     if (threadIdx.x == 0) *counter = 0u;
-    __threadfence();
+    __threadfence();   // acquire side: the other blocks' records are visible to every thread of the last block
   }
   return last;
 }
@@ -260,7 +263,8 @@ template <int MODEL, bool HAS_GRID>
 __device__ double resim_cost_to_go_f64(const StaticParams& sp, const DynState* dyn, const double* __restrict__ nomD,
                                        const signed char* __restrict__ grid, const double* __restrict__ eps_ext,
                                        const ModelConsts<double>& mc, const CostConsts<double>& cc, float std0, float std1,
-                                       unsigned int step, int k_local, int t_target, double* sm) {
+                                       unsigned int step, int k_local, int t_target, double* sm, int t_eps = 0,
+                                       double* eps_out = nullptr) {
   const int T = sp.T, lane = threadIdx.x & 31;
   double* s_kth = sm;          // yaw increment per step, then exclusive theta
   double* s_spd = sm + T;      // forward speed
@@ -356,73 +360,99 @@ __device__ double resim_cost_to_go_f64(const StaticParams& sp, const DynState* d
       vsum += c;
     }
   }
+  if (eps_out && lane == 0) {   // the rollout's noise at step t_eps (the softmin numerator needs exactly this sample)
+    eps_out[0] = s_e0[t_eps];
+    eps_out[1] = s_e1[t_eps];
+  }
   __syncwarp();
   return warp_sum<double>(vsum);
 }
 
-// ---- kernel 2b: SCREEN -> fp64 refinement.  grid = T blocks of 128 threads -----------------------
-// dynamic smem: 8 warps * 7 * T doubles (reused by the fused finalize phase)
+// ---- kernel 2b: SCREEN -> fp64 refinement.  grid = T blocks of 256 threads ------------------------
+// dynamic smem: 8 warps * 7 * T doubles of scan scratch (reused by the fused finalize phase) + 4 * T doubles of
+// nominal block.  Everything the block needs that the rollout kernel does NOT write (DynState, the fp64 nominal
+// block) is fetched before the PDL dependency wait, i.e. while the rollout kernel is still draining.
 template <int MODEL, bool HAS_GRID>
 __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constant__ ReduceArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw2[];
   double* warp_scratch = reinterpret_cast<double*>(smem_raw2);
-  __shared__ double scratch[8];
-  __shared__ double scratch5[40];
+  __shared__ double red[8][3];
   __shared__ int sel_k[kMaxRefine];
   __shared__ float sel_v32[kMaxRefine];
   __shared__ double sel_v64[kMaxRefine];
+  __shared__ double sel_eps[kMaxRefine][2];
   __shared__ int nsel, overflow;
   const StaticParams& sp = a.sp;
   const int T = sp.T;
+  double* nomS = warp_scratch + (size_t)8 * 7 * T;   // [4][T] copy of the fp64 nominal block
   const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nth = blockDim.x;
   const int t_eval = (sp.weighting == MPPI_WEIGHT_COST_TO_GO) ? t : 0;
   if (tid == 0) {
     nsel = 0;
     overflow = 0;
   }
-  // everything the block needs from DynState is loaded BEFORE the dependency wait: the rollout kernel does
-  // not write DynState, so these L2 round trips overlap its tail
   ModelConsts<double> mc;
   CostConsts<double> cc;
   make_consts<double>(sp, a.fin.in, a.fin.dyn, mc, cc);
   const double neg_inv_lam = -1.0 / a.fin.dyn->lam;
   const float std0 = (float)a.fin.dyn->noise_std[0], std1 = (float)a.fin.dyn->noise_std[1];
   const unsigned int philox_step = a.fin.dyn->step;
-  griddep_wait();   // PDL: the block is resident before the rollout kernel has drained
+  for (int i = tid; i < 4 * T; i += nth) nomS[i] = a.nomD[i];
+  griddep_wait();   // PDL: the block is resident, with its constants loaded, before the rollout kernel has drained
   TS(0);
-  // phase A: global fp32 minimum + floor sums.  meta[t][cta] = (min, limit, count, -) is ONE 16-byte
-  // load per CTA, batched 4 deep; nothing else is touched for CTAs outside the global window.
+  // phase A: global fp32 minimum + floor sums.  meta[t][cta] = (min, limit, count, -) is ONE 16-byte load per CTA,
+  // batched 4 deep; the first batch stays in registers for phase B.
   const float4* meta = a.cand_meta + (size_t)t * a.nCTA;
   const double2* ep = reinterpret_cast<const double2*>(a.epart) + (size_t)t * a.nCTA;
-  const int nth = blockDim.x;
-  double m32 = Math<double>::inf(), E0 = 0, E1 = 0;
+  const float4 kNoMeta = make_float4(__int_as_float(0x7f800000), __int_as_float(0x7f800000), 0.f, 0.f);
+  float4 md0[4];
+  float m32 = __int_as_float(0x7f800000);
+  double E0 = 0, E1 = 0;
   for (int base = 0; base < a.nCTA; base += 4 * nth) {
-    float mx[4];
+    float4 md[4];
     double2 e[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = base + j * nth + tid;
-      mx[j] = (i < a.nCTA) ? meta[i].x : __int_as_float(0x7f800000);
+      md[j] = (i < a.nCTA) ? meta[i] : kNoMeta;
       e[j] = (i < a.nCTA) ? ep[i] : make_double2(0.0, 0.0);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      m32 = fmin(m32, (double)mx[j]);
+      if (base == 0) md0[j] = md[j];
+      m32 = fminf(m32, md[j].x);
       E0 += e[j].x;
       E1 += e[j].y;
     }
   }
-  m32 = block_min(m32, scratch);
+  // one shared-memory exchange for the minimum and both floor sums
+  m32 = warp_min<float>(m32);
+  E0 = warp_sum<double>(E0);
+  E1 = warp_sum<double>(E1);
+  if (lane == 0) {
+    red[warp][0] = (double)m32;
+    red[warp][1] = E0;
+    red[warp][2] = E1;
+  }
+  __syncthreads();
+  E0 = 0.0;
+  E1 = 0.0;
+  for (int w = 0; w < (nth >> 5); ++w) {
+    m32 = fminf(m32, (float)red[w][0]);
+    E0 += red[w][1];
+    E1 += red[w][2];
+  }
   TS(1);
   // phase B: compact the candidates inside the window of the GLOBAL minimum; a CTA whose list does
   // not cover that window (it had to tighten its own window) is an overflow
-  const float lim = (float)m32 + (float)sp.margin;
+  const float lim = m32 + (float)sp.margin;
   for (int base = 0; base < a.nCTA; base += 4 * nth) {
     float4 md[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = base + j * nth + tid;
-      md[j] = (i < a.nCTA) ? meta[i] : make_float4(__int_as_float(0x7f800000), __int_as_float(0x7f800000), 0.f, 0.f);
+      md[j] = (base == 0) ? md0[j] : ((i < a.nCTA) ? meta[i] : kNoMeta);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -450,57 +480,48 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   TS(2);
   const int n = min(nsel, kMaxRefine);
   // phase C: fp64 re-evaluation, one warp per candidate
-  double dev = 0.0;
   for (int c = warp; c < n; c += 8) {
-    const double v64 = resim_cost_to_go_f64<MODEL, HAS_GRID>(sp, a.fin.dyn, a.nomD, a.grid, a.eps_ext, mc, cc, std0, std1, philox_step,
-                                                              sel_k[c], t_eval,
-                                                              warp_scratch + (size_t)warp * 7 * T);
+    const double v64 = resim_cost_to_go_f64<MODEL, HAS_GRID>(sp, a.fin.dyn, nomS, a.grid, a.eps_ext, mc, cc, std0, std1, philox_step,
+                                                              sel_k[c], t_eval, warp_scratch + (size_t)warp * 7 * T, t, sel_eps[c]);
     if (lane == 0) sel_v64[c] = v64;
-    dev = fmax(dev, fabs(v64 - (double)sel_v32[c]));
   }
   __syncthreads();
   TS(3);
-  // phase D: exact softmin over the support (control/src/mppi:189-196)
-  double m64 = Math<double>::inf();
-  for (int c = 0; c < n; ++c) m64 = fmin(m64, sel_v64[c]);
-  double S = 0, N0 = 0, N1 = 0;
-  for (int c = tid; c < n; c += blockDim.x) {
-    const double e = exp((sel_v64[c] - m64) * neg_inv_lam);
-    double e0, e1;
-    if (sp.noise_external) {
-      e0 = a.eps_ext[((size_t)t * 2 + 0) * sp.K + sel_k[c]];
-      e1 = a.eps_ext[((size_t)t * 2 + 1) * sp.K + sel_k[c]];
-    } else {
-      float f0, f1;
-      philox_eps(sp.seed, (unsigned long long)(sp.k_offset + sel_k[c]), t, philox_step, std0, std1, f0, f1);
-      e0 = f0;
-      e1 = f1;
+  // phase D (one warp): exact softmin over the support (control/src/mppi:189-196) and the block's record
+  if (warp == 0) {
+    double m64 = Math<double>::inf(), dev = 0.0;
+    for (int c = lane; c < n; c += 32) {
+      m64 = fmin(m64, sel_v64[c]);
+      dev = fmax(dev, fabs(sel_v64[c] - (double)sel_v32[c]));
     }
-    S += e;
-    N0 += e * e0;
-    N1 += e * e1;
-  }
-  double v5[5] = {S, N0, N1, E0, E1};
-  block_sum_n<5>(v5, scratch5);
-  dev = warp_min<double>(-dev);   // dev is warp-uniform already; negate for the max
-  if (lane == 0) scratch[warp] = dev;
-  __syncthreads();
-  dev = 0.0;
-  for (int w = 0; w < 8; ++w) dev = fmax(dev, -scratch[w]);
-  if (tid == 0) {
-    double s0, s1;
-    floor_scale(sp, a.fin.dyn, s0, s1);
-    double* r = a.record + (size_t)t * kRecordStride;
-    r[0] = m64;
-    r[1] = overflow ? -1.0 : v5[0];   // S < 0 marks a candidate-list overflow for every rank that merges this record
-    r[2] = v5[1];
-    r[3] = v5[2];
-    r[4] = v5[3] * s0;
-    r[5] = v5[4] * s1;
-    atomicAdd(&a.fin.dyn->refine_candidates, n);
-    if (overflow) atomicOr(&a.fin.dyn->refine_overflow, 1);
-    // max of non-negative doubles == max of their bit patterns
-    atomicMax(reinterpret_cast<unsigned long long*>(&a.fin.dyn->refine_max_dev), (unsigned long long)__double_as_longlong(dev));
+    m64 = warp_min<double>(m64);
+    dev = -warp_min<double>(-dev);
+    double S = 0, N0 = 0, N1 = 0;
+    for (int c = lane; c < n; c += 32) {
+      const double e = exp((sel_v64[c] - m64) * neg_inv_lam);
+      const double e0 = sel_eps[c][0], e1 = sel_eps[c][1];   // eps[t] of the candidate, kept from its re-evaluation
+      S += e;
+      N0 += e * e0;
+      N1 += e * e1;
+    }
+    S = warp_sum<double>(S);
+    N0 = warp_sum<double>(N0);
+    N1 = warp_sum<double>(N1);
+    if (lane == 0) {
+      const double s0 = sp.noise_external ? 1.0 : (double)std0 / kZFixScale;   // integer floor sums of z -> sums of eps
+      const double s1 = sp.noise_external ? 1.0 : (double)std1 / kZFixScale;
+      double* r = a.record + (size_t)t * kRecordStride;
+      r[0] = m64;
+      r[1] = overflow ? -1.0 : S;   // S < 0 marks a candidate-list overflow for every rank that merges this record
+      r[2] = N0;
+      r[3] = N1;
+      r[4] = E0 * s0;
+      r[5] = E1 * s1;
+      atomicAdd(&a.fin.dyn->refine_candidates, n);
+      if (overflow) atomicOr(&a.fin.dyn->refine_overflow, 1);
+      // max of non-negative doubles == max of their bit patterns
+      atomicMax(reinterpret_cast<unsigned long long*>(&a.fin.dyn->refine_max_dev), (unsigned long long)__double_as_longlong(dev));
+    }
   }
   TS(4);
   if ((a.fuse_finalize || a.p2p_push) && last_block_done(a.done_counter, gridDim.x)) {
@@ -562,12 +583,14 @@ __device__ inline void model_step_dispatch_f64(const StaticParams& sp, const dou
 
 // needs 4*T doubles of shared scratch `Us`; any blockDim that is a multiple of 32
 __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
-  double* Uf = Us + 2 * a.sp.T;                        // [2][T] filtered
   __shared__ double coef[2][2][4];
   __shared__ int bad;
   const StaticParams& sp = a.sp;
   const int T = sp.T, W = T - 1, h = W / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  // the OWNER thread carries the scalar part of the step (perform_action, DynState, the host hand-over); it is the
+  // last thread of the block, which has no per-t work for T < blockDim, so that part overlaps the per-t stores
+  const bool owner = tid == (int)blockDim.x - 1;
   __shared__ int any_ovf;
   // the serial tail of the step: issue every global load it needs up front
   const double lam = a.dyn->lam;
@@ -577,7 +600,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
   unsigned int step_r = 0, xchg_r = 0;
   int cand_r = 0;
   double dev_r = 0.0;
-  if (tid == 0) {
+  if (owner) {
     bad = 0;
     any_ovf = 0;
     step_r = a.dyn->step;
@@ -644,7 +667,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
     // every rank sees the same records, so every rank leaves U, the step counter and x0 untouched and
     // asks its host to redo this step with the fp64 pipeline (same noise: the Philox step counter is
     // not advanced; the exchange epoch is).
-    if (tid == 0) {
+    if (owner) {
       DynState* d = a.dyn;
       d->status = kStatusRedoF64;
       d->overflow_total += 1;
@@ -683,49 +706,52 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < 2 * T; idx += blockDim.x) {
-    const int c = idx / T, t = idx - c * T;
+  // filtered and clipped U[c][t] (:202-206): evaluate fit A (t <= h) or fit B at its abscissa
+  auto sg_eval = [&](int c, int t) -> double {
     const int fit = (t <= h) ? 0 : 1;
     const double z = (double)(t - fit - h);
     const double* k = coef[c][fit];
     const double v = k[0] + k[1] * z + k[2] * (z * z - a.sg_a) + k[3] * (z * z * z - a.sg_b * z);
-    Uf[c * T + t] = clamp_<double>(v, sp.u_max[c]);                          // :205-206
+    return clamp_<double>(v, sp.u_max[c]);
+  };
+  // -- perform_action (:210-213), DynState, hand-over to the host: the owner thread, concurrently with the stores below
+  if (a.mode == 0 && owner) {
+    DynState* d = a.dyn;
+    const double uo[2] = {sg_eval(0, 0), sg_eval(1, 0)};
+    double xn[3];
+    model_step_dispatch_f64(sp, x0r, uo[0], uo[1], xn);
+    d->out_u[0] = uo[0];
+    d->out_u[1] = uo[1];
+    d->out_x[0] = xn[0];
+    d->out_x[1] = xn[1];
+    d->out_x[2] = xn[2];
+    const int status = bad ? (int)MPPI_ERR_NONFINITE : (int)MPPI_OK;
+    const int ovf_total = d->overflow_total;
+    d->status = status;
+    d->step = step_r + 1u;
+    d->xchg = xchg_r + 1u;
+    if (a.closed_loop) {
+      d->x0[0] = xn[0];
+      d->x0[1] = xn[1];
+      d->x0[2] = xn[2];
+    }
+    d->last_candidates = cand_r;
+    d->last_max_dev = dev_r;
+    d->refine_candidates = 0;
+    d->refine_overflow = 0;
+    d->refine_max_dev = 0.0;
+    publish_result(a, status, uo, xn, cand_r, dev_r, ovf_total);
   }
-  __syncthreads();
-  // -- outputs, perform_action (:210-213), shift (:100-101), next nominal block -----------------
-  for (int idx = tid; idx < 2 * T; idx += blockDim.x) a.Ulast[idx] = Uf[idx];
-  if (a.mode == 0) {
-    for (int t = tid; t < T; t += blockDim.x) {
-      const double u0 = (t + 1 < T) ? Uf[t + 1] : 0.0;
-      const double u1 = (t + 1 < T) ? Uf[T + t + 1] : 0.0;
+  // -- update_action result, receding-horizon shift (:100-101), next nominal block: one pass, no further barrier
+  for (int t = tid; t < T; t += blockDim.x) {
+    a.Ulast[t] = sg_eval(0, t);
+    a.Ulast[T + t] = sg_eval(1, t);
+    if (a.mode == 0) {
+      const double u0 = (t + 1 < T) ? sg_eval(0, t + 1) : 0.0;
+      const double u1 = (t + 1 < T) ? sg_eval(1, t + 1) : 0.0;
       a.Umaster[t] = u0;
       a.Umaster[T + t] = u1;
       write_nominal_block(lam, sigr, nstdr, T, t, u0, u1, a.nomF, a.nomD);
-    }
-    if (tid == 0) {
-      DynState* d = a.dyn;
-      double xn[3];
-      model_step_dispatch_f64(sp, x0r, Uf[0], Uf[T], xn);
-      d->out_u[0] = Uf[0];
-      d->out_u[1] = Uf[T];
-      d->out_x[0] = xn[0];
-      d->out_x[1] = xn[1];
-      d->out_x[2] = xn[2];
-      d->status = bad ? (int)MPPI_ERR_NONFINITE : (int)MPPI_OK;
-      d->step = step_r + 1u;
-      d->xchg = xchg_r + 1u;
-      if (a.closed_loop) {
-        d->x0[0] = xn[0];
-        d->x0[1] = xn[1];
-        d->x0[2] = xn[2];
-      }
-      d->last_candidates = cand_r;
-      d->last_max_dev = dev_r;
-      d->refine_candidates = 0;
-      d->refine_overflow = 0;
-      d->refine_max_dev = 0.0;
-      const double uo[2] = {Uf[0], Uf[T]};
-      publish_result(a, d->status, uo, xn, cand_r, dev_r, d->overflow_total);
     }
   }
 }

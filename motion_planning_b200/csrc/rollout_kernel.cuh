@@ -96,7 +96,10 @@ struct CostTile {
 template <typename R, int MODE, int BLOCK>
 __device__ __forceinline__ void transposed_row(const RolloutArgs& a, int t, int tile, int cta, int nCTA, const R* P,
                                                typename Math<R>::Vec4* run, int* ccount, double* ed, bool cost_to_go,
-                                               R neg_inv_lam, R margin, float std0, float std1, unsigned int step) {
+                                               R neg_inv_lam, R margin, float std0, float std1, unsigned int step,
+                                               bool direct_out = false, double fsum0 = 0.0, double fsum1 = 0.0) {
+  // direct_out (a CTA that owns exactly one tile): the lane stores the (t, CTA) partial straight to global memory,
+  // with the floor sums fsum0/1 of the row -- no shared-memory round trip, no epilogue pass
   typedef typename Math<R>::Vec4 Vec4;
   typedef typename Vec16<R>::V V16;
   constexpr int PS = CostTile<R, BLOCK>::PS;
@@ -111,9 +114,14 @@ __device__ __forceinline__ void transposed_row(const RolloutArgs& a, int t, int 
   const V16* pre4 = reinterpret_cast<const V16*>(pre);
   const int tile_base = tile * BLOCK;
   const int nk = min(BLOCK, sp.K - tile_base);
-  R m = Math<R>::inf();
-#pragma unroll 8
-  for (int g = 0; g < NG; ++g) m = Math<R>::min_(m, Vec16<R>::min_diff(tot4[g], pre4[g]));
+  // the sweep: one 16-byte vector of totals (broadcast) and one of prefixes per group; the group minima stay in
+  // registers (NG <= 64 values), so the window test below touches no memory
+  R gmin[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) gmin[g] = Vec16<R>::min_diff(tot4[g], pre4[g]);
+  R m = gmin[0];
+#pragma unroll
+  for (int g = 1; g < NG; ++g) m = Math<R>::min_(m, gmin[g]);
   if (sp.capture) {
     R* vc = reinterpret_cast<R*>(a.vcap) + (size_t)t * sp.K + tile_base;
     for (int k = 0; k < nk; ++k) vc[k] = tot[k] - pre[k];
@@ -131,23 +139,26 @@ __device__ __forceinline__ void transposed_row(const RolloutArgs& a, int t, int 
   }
   Vec4 rr = run[t];
   const R mnew = Math<R>::min_(rr.x, m);
-  // sweep 2: which groups hold a rollout with V <= lim?
+  // which groups hold a rollout with V <= lim?
   //   SOFTMIN: e^-80 ~ 2e-35 is below any rounding   SCREEN: the window [m, m + margin] of the running minimum
   const R lim = (MODE == MODE_SOFTMIN) ? mnew + R(80) / (-neg_inv_lam) * R(1.0001) : mnew + margin;
   Mask hits = 0;
-#pragma unroll 8
+#pragma unroll
   for (int g = 0; g < NG; ++g)
-    if (Vec16<R>::min_diff(tot4[g], pre4[g]) <= lim) hits |= (Mask)1 << g;
+    if (gmin[g] <= lim) hits |= (Mask)1 << g;
   if (MODE == MODE_SOFTMIN) {
     // online softmin: weights relative to the running minimum of this CTA (:189-196)
     R S = R(0), N0 = R(0), N1 = R(0);
     while (hits) {
       const int g = (sizeof(Mask) == 4) ? __ffs((unsigned int)hits) - 1 : __ffsll((unsigned long long)hits) - 1;
       hits &= hits - 1;
+      const V16 tv = tot4[g], pv = pre4[g];
+      const R* tvp = reinterpret_cast<const R*>(&tv);
+      const R* pvp = reinterpret_cast<const R*>(&pv);
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         const int k = g * N + j;
-        const R arg = ((tot[k] - pre[k]) - mnew) * neg_inv_lam;   // <= 0
+        const R arg = ((tvp[j] - pvp[j]) - mnew) * neg_inv_lam;   // <= 0
         if (arg > R(-80)) {
           const R e = Math<R>::exp_(arg);
           R e0, e1;
@@ -171,7 +182,13 @@ __device__ __forceinline__ void transposed_row(const RolloutArgs& a, int t, int 
     rr.z = Math<R>::fma_(rr.z, sc, N0);
     rr.w = Math<R>::fma_(rr.w, sc, N1);
     rr.x = mnew;
-    run[t] = rr;
+    if (direct_out) {
+      const size_t idx = (size_t)t * nCTA + cta;
+      reinterpret_cast<Vec4*>(a.part)[idx] = rr;
+      reinterpret_cast<double2*>(a.epart)[idx] = make_double2(fsum0, fsum1);
+    } else {
+      run[t] = rr;
+    }
   } else {
     // screen: keep every rollout within the window [m, lim] of the CTA's running minimum m.
     // run[t] = (m, L): L is the tightest limit ever applied, so the list is guaranteed to hold
@@ -185,10 +202,13 @@ __device__ __forceinline__ void transposed_row(const RolloutArgs& a, int t, int 
     while (hits) {
       const int g = (sizeof(Mask) == 4) ? __ffs((unsigned int)hits) - 1 : __ffsll((unsigned long long)hits) - 1;
       hits &= hits - 1;
+      const V16 tv = tot4[g], pv = pre4[g];
+      const R* tvp = reinterpret_cast<const R*>(&tv);
+      const R* pvp = reinterpret_cast<const R*>(&pv);
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         const int k = g * N + j;
-        const R v = tot[k] - pre[k];
+        const R v = tvp[j] - pvp[j];
         if (v <= lim2) {
           if (cnt < kMaxCand) list[cnt] = make_uint2((unsigned)(tile_base + k), __float_as_uint((float)v));
           ++cnt;
@@ -198,8 +218,14 @@ __device__ __forceinline__ void transposed_row(const RolloutArgs& a, int t, int 
     if (cnt > kMaxCand) cnt = screen_tighten<R>(list, cnt_old, tot, pre, BLOCK, tile_base, mnew, lim2);
     rr.x = mnew;
     rr.y = Math<R>::min_(rr.y, lim2);
-    run[t] = rr;
-    ccount[t] = cnt;
+    if (direct_out) {
+      const size_t idx = (size_t)t * nCTA + cta;
+      a.cand_meta[idx] = make_float4((float)rr.x, (float)rr.y, __int_as_float(cnt), 0.f);
+      reinterpret_cast<double2*>(a.epart)[idx] = make_double2(fsum0, fsum1);
+    } else {
+      run[t] = rr;
+      ccount[t] = cnt;
+    }
   }
 }
 

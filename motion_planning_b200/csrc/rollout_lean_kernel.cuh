@@ -20,7 +20,9 @@
 //   * (cos, sin) is never re-derived from theta: one first-order renormalisation per four steps keeps the
 //     pair on the unit circle, the phase error stays at rounding level (~1e-6 rad over 128 steps);
 //   * floor-term sums: round(z * 2^18) by the magic-number trick (FFMA, no F2I on the SFU-class pipe), the
-//     rollout-valid mask folded into the scale; the 32 lanes' bias is removed after the warp REDUX.
+//     rollout-valid mask folded into the scale; the warp REDUX results (uniform registers) of four steps leave
+//     through two 16-byte shared-memory stores of one lane into per-warp slots -- no selects, no atomics; the
+//     32 lanes' bias is removed when the slots are summed.
 // Anything outside those conditions (Q[2] != 0, large yaw increments, replayed noise, fp64) runs rollout_kernel.
 #pragma once
 #include "rollout_kernel.cuh"
@@ -90,7 +92,7 @@ __device__ __forceinline__ float wrap_rint(float th) {
 }
 
 template <int MODEL, int MODE, bool HAS_GRID, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) rollout_lean_kernel(const __grid_constant__ RolloutArgs a) {
+__global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const __grid_constant__ RolloutArgs a) {
   typedef float R;
   typedef float4 Vec4;
   constexpr int NW = BLOCK / 32;
@@ -111,8 +113,8 @@ __global__ void __launch_bounds__(BLOCK) rollout_lean_kernel(const __grid_consta
   off += (size_t)T * sizeof(Vec4);
   long long* ez64 = reinterpret_cast<long long*>(smem_raw + off);             // [T][2] CTA floor sums
   off += (size_t)T * 2 * sizeof(long long);
-  int* ez32 = reinterpret_cast<int*>(smem_raw + off);                         // [T][2] per-tile floor sums
-  off += (size_t)T * 2 * sizeof(int);
+  int* ezw = reinterpret_cast<int*>(smem_raw + off);                          // [NW][T][2] per-warp floor sums of the tile
+  off += (size_t)NW * T * 2 * sizeof(int);                                    //   (biased, see kLeanBias32; no atomics)
   int* ccount = reinterpret_cast<int*>(smem_raw + off);                       // [T] SCREEN counts
   off += (size_t)T * sizeof(int);
   off = (off + 15) & ~(size_t)15;
@@ -137,8 +139,6 @@ __global__ void __launch_bounds__(BLOCK) rollout_lean_kernel(const __grid_consta
     run[t] = make_float4(Math<R>::inf(), (MODE == MODE_SCREEN) ? Math<R>::inf() : 0.f, 0.f, 0.f);
     ez64[2 * t] = 0;
     ez64[2 * t + 1] = 0;
-    ez32[2 * t] = 0;
-    ez32[2 * t + 1] = 0;
     ccount[t] = 0;
   }
   for (int k = tid; k < PS; k += BLOCK) P[k] = 0.f;
@@ -195,29 +195,33 @@ __global__ void __launch_bounds__(BLOCK) rollout_lean_kernel(const __grid_consta
   const bool cost_to_go = sp.weighting == MPPI_WEIGHT_COST_TO_GO;
   float sth0, cth0;
   Math<R>::sincos_(lc.th0, sth0, cth0);
-  // lane (t mod 32) keeps the warp sums of step t: per unrolled step i the owner test is lane - i == t4 (mod 32)
-  const int own0 = lane, own1 = (lane - 1) & 31, own2 = (lane - 2) & 31, own3 = (lane - 3) & 31;
+  int* ezrow = ezw + (size_t)warp * T * 2;   // this warp's [T][2] slots
   mbar_wait(bar, 0);
   __syncthreads();
 
+  const bool multi_tile = a.ntiles > nCTA;
+  // floor sums leave in the 2^-20 units of the generic kernel (kZFixScale), so the reduce kernels see one format
+  constexpr double kToGeneric = kZFixScale / (double)kLeanFixScale;
+  // floor sum i = 2 t + channel of the tile just finished: the warps' slots minus the 32 lanes' bias each
+  auto tile_floor_sum = [&](int i) -> long long {
+    long long sum = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) sum += (long long)(int)((unsigned)ezw[(size_t)w * T * 2 + i] - kLeanBias32);
+    return sum;
+  };
   for (int tile = cta; tile < a.ntiles; tile += nCTA) {
     const int k_local = tile * BLOCK + tid;
     const bool valid = k_local < sp.K;
     const unsigned long long kglobal = (unsigned long long)(sp.k_offset + k_local);
     const float qscale = valid ? kLeanFixScale : 0.f;     // invalid rollouts add exactly 0 to the floor sums
     R dx = 0.f, dy = 0.f, th = lc.th0, acc = 0.f, cth = cth0, sth = sth0;
-    int eown0 = 0, eown1 = 0;
     R* prow = P + PS + tid;                               // row 1 + t of this rollout's column
 
     // one model step + running cost + prefix store (control/src/mppi:147-161); z0, z1 = the step's standard normals
-    auto one_step = [&](const float4 n, float z0, float z1, bool own, int row) {
-      // floor-term sums: exact fixed point (2^-18), one warp integer add (REDUX) per channel
-      int q0 = __float_as_int(fmaf(z0, qscale, kLeanMagic));
-      int q1 = __float_as_int(fmaf(z1, qscale, kLeanMagic));
-      q0 = __reduce_add_sync(0xffffffffu, q0);
-      q1 = __reduce_add_sync(0xffffffffu, q1);
-      eown0 = own ? q0 : eown0;
-      eown1 = own ? q1 : eown1;
+    auto one_step = [&](const float4 n, float z0, float z1, int& q0, int& q1, int row) {
+      // floor-term sums: exact fixed point (2^-18), one warp integer add (REDUX, warp-uniform result) per channel
+      q0 = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(z0, qscale, kLeanMagic)));
+      q1 = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(z1, qscale, kLeanMagic)));
       // u_samp = clip(U[:,t] + eps), eps = std * z   (:147-152; eps itself stays unclipped)
       const float u0 = fminf(fmaxf(fmaf(lc.std0, z0, n.x), -lc.um0), lc.um0);
       const float u1 = fminf(fmaxf(fmaf(lc.std1, z1, n.y), -lc.um1), lc.um1);
@@ -248,14 +252,6 @@ __global__ void __launch_bounds__(BLOCK) rollout_lean_kernel(const __grid_consta
       acc += c;
       prow[row * PS] = acc;
     };
-    auto flush_chunk = [&](int base) {
-      const int town = base + lane;
-      if (town < T) {
-        atomicAdd(&ez32[2 * town], (int)((unsigned)eown0 - kLeanBias32));   // remove the 32 lanes' bias
-        atomicAdd(&ez32[2 * town + 1], (int)((unsigned)eown1 - kLeanBias32));
-      }
-    };
-
     float4 za = lean_normal4(a.lean, kglobal, 0u, step);
     float4 zb = lean_normal4(a.lean, kglobal, 1u, step);
     int t4 = 0;
@@ -263,31 +259,36 @@ __global__ void __launch_bounds__(BLOCK) rollout_lean_kernel(const __grid_consta
       const float4 z0 = za, z1 = zb;
       za = lean_normal4(a.lean, kglobal, (unsigned)(t4 >> 1) + 2u, step);   // one iteration ahead
       zb = lean_normal4(a.lean, kglobal, (unsigned)(t4 >> 1) + 3u, step);
-      const int tm = t4 & 31;
       const float4* nl = nomL + t4;
-      one_step(nl[0], z0.x, z0.y, own0 == tm, 0);
-      one_step(nl[1], z0.z, z0.w, own1 == tm, 1);
-      one_step(nl[2], z1.x, z1.y, own2 == tm, 2);
-      one_step(nl[3], z1.z, z1.w, own3 == tm, 3);
+      int4 qa, qb;
+      one_step(nl[0], z0.x, z0.y, qa.x, qa.y, 0);
+      one_step(nl[1], z0.z, z0.w, qa.z, qa.w, 1);
+      one_step(nl[2], z1.x, z1.y, qb.x, qb.y, 2);
+      one_step(nl[3], z1.z, z1.w, qb.z, qb.w, 3);
+      if (lane == 0) {   // the warp sums of the four steps: two 16-byte stores by one lane
+        *reinterpret_cast<int4*>(ezrow + 2 * t4) = qa;
+        *reinterpret_cast<int4*>(ezrow + 2 * t4 + 4) = qb;
+      }
       prow += 4 * PS;
       // keep (cos, sin) on the unit circle and theta in (-pi, pi]
       const float f = fmaf(fmaf(cth, cth, sth * sth), -0.5f, 1.5f);
       cth *= f;
       sth *= f;
       th = wrap_rint(th);
-      if (tm == 28) flush_chunk(t4 & ~31);
     }
     if (t4 < T) {   // T = 4n + 2: one more pair
-      const int tm = t4 & 31;
       const float4* nl = nomL + t4;
-      one_step(nl[0], za.x, za.y, own0 == tm, 0);
-      one_step(nl[1], za.z, za.w, own1 == tm, 1);
+      int4 qa;
+      one_step(nl[0], za.x, za.y, qa.x, qa.y, 0);
+      one_step(nl[1], za.z, za.w, qa.z, qa.w, 1);
+      if (lane == 0) *reinterpret_cast<int4*>(ezrow + 2 * t4) = qa;
       th = wrap_rint(th);
     }
-    if (T & 31) flush_chunk(T & ~31);
     cc.gth2 = post[0];
     acc += terminal_cost<R>(cc, dx, dy, th);                                 // :165-171
     if (!valid) acc = Math<R>::inf();
+    // PDL: the reduce kernel may start getting resident now (it still waits for this grid to complete)
+    if (tile + nCTA >= a.ntiles) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     prow[(T - 1 - t4) * PS] = acc;   // row T holds the rollout total Tot[k] (addressed from the running row pointer: the
                                      // tile-invariant form P + T*PS + tid gets hoisted and spilled)
     __syncthreads();
@@ -296,22 +297,23 @@ __global__ void __launch_bounds__(BLOCK) rollout_lean_kernel(const __grid_consta
     const R neg_inv_lam = post[1];
     for (int tb = warp * 32; tb < T; tb += NW * 32) {
       const int t = tb + lane;
-      if (t < T)
+      if (t < T) {
+        const bool direct = !multi_tile;
+        const double f0 = direct ? (double)tile_floor_sum(2 * t) * kToGeneric : 0.0;
+        const double f1 = direct ? (double)tile_floor_sum(2 * t + 1) * kToGeneric : 0.0;
         transposed_row<R, MODE, BLOCK>(a, t, tile, cta, nCTA, P, run, ccount, nullptr, cost_to_go, neg_inv_lam, margin, lc.std0,
-                                       lc.std1, step);
+                                       lc.std1, step, direct, f0, f1);
+      }
     }
-    __syncthreads();
-    for (int i = tid; i < 2 * T; i += BLOCK) {
-      ez64[i] += (long long)ez32[i];
-      ez32[i] = 0;
+    if (multi_tile) {   // a persistent CTA folds its per-tile sums into 64-bit accumulators
+      __syncthreads();
+      for (int i = tid; i < 2 * T; i += BLOCK) ez64[i] += tile_floor_sum(i);
+      __syncthreads();
     }
-    __syncthreads();
   }
+  if (!multi_tile) return;   // one tile per CTA: every row's partial already went out from the transposed pass
 
-  // ---- epilogue: one partial per (t, CTA) ------------------------------------------------------
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  // floor sums leave in the 2^-20 units of the generic kernel (kZFixScale), so the reduce kernels see one format
-  constexpr double kToGeneric = kZFixScale / (double)kLeanFixScale;
+  // ---- epilogue of a persistent CTA: one partial per (t, CTA) ---------------------------------------
   for (int t = tid; t < T; t += BLOCK) {
     const size_t idx = (size_t)t * nCTA + cta;
     if (MODE == MODE_SOFTMIN)
@@ -327,7 +329,7 @@ inline size_t rollout_lean_smem_bytes(int T, int block, int grid_bytes_padded_in
   size_t off = 16 + (size_t)T * sizeof(float4);
   off += (size_t)T * sizeof(float4);               // run
   off += (size_t)T * 2 * sizeof(long long);
-  off += (size_t)T * 2 * sizeof(int);
+  off += (size_t)(block / 32) * T * 2 * sizeof(int);
   off += (size_t)T * sizeof(int);
   off = (off + 15) & ~(size_t)15;
   off += (size_t)(T + 1) * (block + 4) * sizeof(float);

@@ -79,6 +79,39 @@ def _diag3(M, name):
     return np.diag(M).copy()
 
 
+class _Log(object):
+    """Append-only (n, d) float64 log with amortised O(1) append; `.array` is the (n, d) view.
+    (The reference re-concatenates `path` / `uvec` every step, control/src/mppi:95-97: O(n) per step.)"""
+
+    def __init__(self, first_row):
+        first_row = np.asarray(first_row, dtype=np.float64).reshape(1, -1)
+        self._buf = np.empty((64, first_row.shape[1]))
+        self._buf[0] = first_row[0]
+        self._n = 1
+
+    @classmethod
+    def from_array(cls, a):
+        a = np.asarray(a, dtype=np.float64)
+        if a.ndim != 2 or a.shape[0] < 1:
+            raise ValueError("expected an (n, d) array with n >= 1")
+        log = cls(a[0])
+        for row in a[1:]:
+            log.append(row)
+        return log
+
+    def append(self, row):
+        if self._n == self._buf.shape[0]:
+            grown = np.empty((2 * self._n, self._buf.shape[1]))
+            grown[:self._n] = self._buf
+            self._buf = grown
+        self._buf[self._n] = row
+        self._n += 1
+
+    @property
+    def array(self):
+        return self._buf[:self._n]
+
+
 class MPPI(object):
     def __init__(self, model=rk4, horizon=100, samples=10, thresh=0.05, **engine):
         """Reference signature (control/src/mppi:62) + keyword-only engine options:
@@ -146,12 +179,28 @@ class MPPI(object):
         _capi.check(self._lib.mppi_create(C.byref(p), C.byref(h)), "mppi_create")
         self._h = h
         self._cost_key = (tuple(q), tuple(p1), tuple(np.asarray(self.R, dtype=np.float64).reshape(4)))
+        self._cost_bytes = self._cost_fingerprint()
         self._sig, self._lam = np.array([[.9, 0.0], [0.0, .9]]), .001
+        self._sig_bytes = self._sig.tobytes()
+        self._goal_bytes = None
+        # fixed I/O buffers of the hot call (pointers resolved once)
+        self._xin, self._gin, self._uout, self._xout = np.empty(3), np.empty(3), np.empty(2), np.empty(3)
+        self._pxin, self._pgin, self._puout, self._pxout = (_capi.dptr(a) for a in (self._xin, self._gin, self._uout, self._xout))
         if self._noise_std_override is not None:
             _capi.check(self._lib.mppi_set_noise_std(self._h, _capi.dptr(self._noise_std_override)), "mppi_set_noise_std")
 
+    def _cost_fingerprint(self):
+        try:
+            return self.Q.tobytes() + self.P1.tobytes() + self.R.tobytes()
+        except AttributeError:       # somebody assigned a list: take the slow path
+            return None
+
     def _sync_cost(self):
         """Q / R / P1 are public attributes in the reference; re-create the engine if they changed."""
+        fp = self._cost_fingerprint()
+        if fp is not None and fp == self._cost_bytes:
+            return
+        self._cost_bytes = fp
         key = (tuple(_diag3(self.Q, "Q")), tuple(_diag3(self.P1, "P1")),
                tuple(np.asarray(self.R, dtype=np.float64).reshape(4)))
         if key != self._cost_key:
@@ -161,7 +210,10 @@ class MPPI(object):
             self.latest_uvec = U
 
     def _sync_sampling(self, sig, lam):
+        if lam == self._lam and isinstance(sig, np.ndarray) and sig.dtype == np.float64 and sig.tobytes() == self._sig_bytes:
+            return
         sig = _capi.f64(sig, (2, 2))
+        self._sig_bytes = sig.tobytes()
         if lam != self._lam or not np.array_equal(sig, self._sig):
             _capi.check(self._lib.mppi_set_sampling(self._h, _capi.dptr(sig), float(lam)), "mppi_set_sampling")
             if self._noise_std_override is not None:
@@ -201,18 +253,40 @@ class MPPI(object):
         self.uvec = np.array([self.uvec_init[:, 0]])
         self.path = np.array([self.start])
 
+    # `path` (n,3) and `uvec` (n,2) grow by one row per step (control/src/mppi:95-97); they are ndarray attributes in
+    # the reference, here ndarray VIEWS of append-only logs (assigning an array re-seeds the log)
+    @property
+    def path(self):
+        return self._path_log.array
+
+    @path.setter
+    def path(self, a):
+        self._path_log = _Log.from_array(a)
+
+    @property
+    def uvec(self):
+        return self._uvec_log.array
+
+    @uvec.setter
+    def uvec(self, a):
+        self._uvec_log = _Log.from_array(a)
+
     def get_path(self, state, goal, sig=np.array([[.9, 0.0], [0.0, .9]]), lam=.001):
         """control/src/mppi:85-102 -- one MPPI step on the GPU; returns the predicted next state."""
         self._sync_cost()
         self._sync_sampling(sig, lam)
-        state = _capi.f64(state, (3,))
-        goal = _capi.f64(goal, (3,))
-        _capi.check(self._lib.mppi_set_goal(self._h, _capi.dptr(goal)), "mppi_set_goal")
-        u = np.empty(2)
-        x = np.empty(3)
-        _capi.check(self._lib.mppi_step(self._h, _capi.dptr(state), _capi.dptr(u), _capi.dptr(x)), "mppi_step")
-        self.path = np.concatenate((self.path, np.array([x])))                  # :95
-        self.uvec = np.concatenate((self.uvec, np.array([u])))                  # :96-97
+        self._xin[:] = state
+        self._gin[:] = goal
+        gb = self._gin.tobytes()
+        if gb != self._goal_bytes:
+            _capi.check(self._lib.mppi_set_goal(self._h, self._pgin), "mppi_set_goal")
+            self._goal_bytes = gb
+        st = self._lib.mppi_step(self._h, self._pxin, self._puout, self._pxout)
+        if st != _capi.MPPI_OK:
+            _capi.check(st, "mppi_step")
+        x = self._xout.copy()
+        self._path_log.append(x)                                                # :95
+        self._uvec_log.append(self._uout)                                       # :96-97
         self.fin_time.append(self.fin_time[-1] + self.dt)                       # :98
         return x
 
@@ -336,6 +410,7 @@ class MPPI(object):
     def bench(self, x0, steps=20, warmup=3, flush_l2=True, per_kernel=True):
         t = _capi.MppiTiming()
         _capi.check(self._lib.mppi_set_goal(self._h, _capi.dptr(_capi.f64(self.goal, (3,)))), "mppi_set_goal")
+        self._goal_bytes = None   # the engine's goal no longer matches what get_path last sent
         _capi.check(self._lib.mppi_bench(self._h, _capi.dptr(_capi.f64(x0, (3,))), steps, warmup, int(flush_l2),
                                          int(per_kernel), C.byref(t)), "mppi_bench")
         return {k: getattr(t, k) for k, _ in t._fields_}

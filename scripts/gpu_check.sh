@@ -18,3 +18,4 @@ done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout -s 4 -c 1 \
   -o $O/prof_rollout_mixed_${TAG} -f python profiles/profile_step.py mixed 65536 64 4 > $O/ncu_full_${TAG}.log 2>&1
 tail -3 $O/ncu_full_${TAG}.log
+python profiles/reduce_timeline.py mixed > $O/reduce_timeline_${TAG}.txt 2>&1; cat $O/reduce_timeline_${TAG}.txt
