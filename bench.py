@@ -183,14 +183,19 @@ def run_single(args):
         r = m.bench(X0, steps=args.steps, warmup=args.warmup, flush_l2=True, per_kernel=True)
         # e2e: the public call with HOST buffers, copies inside the timed region.
         # (1) through the Python mirror of the reference class (MPPI.get_path, what Controller calls)
+        # Every timed call starts from a cold L2 and an idle GPU (mppi_debug_flush_l2 outside the timed intervals).
+        flush = lambda: _capi.check(lib.mppi_debug_flush_l2(m._h), "mppi_debug_flush_l2")  # noqa: E731
         m.initialize()
         s = X0.copy()
         for _ in range(args.warmup):
             s = m.get_path(s, GOAL)
-        t0 = time.perf_counter()
+        acc = 0.0
         for _ in range(args.steps):
+            flush()
+            t0 = time.perf_counter()
             s = m.get_path(s, GOAL)
-        r["e2e_shim_ms"] = (time.perf_counter() - t0) / args.steps * 1e3
+            acc += time.perf_counter() - t0
+        r["e2e_shim_ms"] = acc / args.steps * 1e3
         # (2) through the C ABI directly (mppi_step with host double[3] in, double[2]+double[3] out): what a
         #     C/C++ host pays; same copies, no interpreter overhead around the call
         m.initialize()
@@ -201,12 +206,20 @@ def run_single(args):
         for _ in range(args.warmup):
             step(h, px, pu, pn)
             x[:] = xn
-        t0 = time.perf_counter()
+        acc = 0.0
         for _ in range(args.steps):
+            flush()
+            t0 = time.perf_counter()
             if step(h, px, pu, pn) != 0:
                 raise RuntimeError("mppi_step failed")
+            acc += time.perf_counter() - t0
             x[:] = xn
-        r["e2e_ms"] = (time.perf_counter() - t0) / args.steps * 1e3
+        r["e2e_ms"] = acc / args.steps * 1e3
+        t0 = time.perf_counter()               # the same loop back to back (warm L2), for reference
+        for _ in range(args.steps):
+            step(h, px, pu, pn)
+            x[:] = xn
+        r["e2e_warm_ms"] = (time.perf_counter() - t0) / args.steps * 1e3
         r["io"] = m.io_bytes()
         r["launch"] = m.launch_info()
         r["stats"] = m.stats()
@@ -222,7 +235,7 @@ def run_single(args):
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
         ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
-        key = [k for k in ncu if k.startswith("rollout_kernel") and ("precision %s" % args.precision) in k]
+        key = [k for k in ncu if k.startswith("rollout") and ("precision %s" % args.precision) in k]
         if key:
             m_ = ncu[key[0]]
             mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -246,14 +259,16 @@ def run_single(args):
         "state_steps_per_s": value * T,
         "e2e": {"value": K / (r["e2e_ms"] * 1e-3), "unit": "rollouts/s", "h2d_bytes_per_step": r["io"][0],
                 "d2h_bytes_per_step": r["io"][1], "ms_per_step": r["e2e_ms"],
-                "call": "mppi_step (C ABI) with host x0 in / (u, x_next) out, closed loop on the host",
+                "call": "mppi_step (C ABI) with host x0 in / (u, x_next) out, closed loop on the host; x0 and goal ride in the "
+                        "kernel arguments, the result block is stored by the finalize phase into mapped pinned host memory",
+                "l2": "flushed before every timed call (outside the timed interval)", "warm_l2_ms_per_step": r["e2e_warm_ms"],
                 "python_shim_ms_per_step": r["e2e_shim_ms"], "python_shim_value": K / (r["e2e_shim_ms"] * 1e-3)},
         "gpu_launches": r["launches"],
         "kernels_ms": {"rollout": r["rollout_ms"], "reduce": r["reduce_ms"], "finalize": r["finalize_ms"]},
         "roofline": {"bound": "fp32_alu", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
                      "frac": achieved / tf.value if tf.value else None, "traffic": traffic,
                      "traffic_note": "DRAM bytes per launch from profiles/r01_ncu_summary.json (ncu --set full); the ~2 MB of per-CTA partials stay in L2",
-                     "kernel": "rollout_kernel", "flop_per_state_step": F_ALG,
+                     "kernel": "rollout_%s_kernel" % r["launch"].get("variant", "?"), "flop_per_state_step": F_ALG,
                      "peak_source": "FFMA chain measured in this run (mppi_measure_fp32_peak); MEASURED_PEAKS.json has no fp32 entry",
                      "hbm_view": {"algorithmic_bytes": hbm_alg_bytes,
                                   "achieved_GBps": hbm_alg_bytes / (r["rollout_ms"] * 1e-3) / 1e9,
@@ -277,6 +292,8 @@ def run_multi(args):
     from motion_planning_b200.distributed import ShardedMPPI
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K_total, T = K_PER_GPU * world, T_HORIZON

@@ -200,7 +200,7 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
     else if (!strcmp(envv, "fast")) variant_max = ROLLOUT_FAST;
   }
   const bool fast = !sp.noise_external && yaw_inc <= 0.78 && variant_max >= ROLLOUT_FAST;
-  const bool lean = fast && sp.q[2] == 0.0 && yaw_inc <= (sp.model == MPPI_MODEL_UNICYCLE_EULER ? 0.5 : 1.0) * kLeanMaxYawInc && variant_max >= ROLLOUT_LEAN;
+  const bool lean = fast && sp.q[2] == 0.0 && (sp.model != MPPI_MODEL_BICYCLE || sp.u_max[1] <= 0.785) && yaw_inc <= (sp.model == MPPI_MODEL_UNICYCLE_EULER ? 0.5 : 1.0) * kLeanMaxYawInc && variant_max >= ROLLOUT_LEAN;
   const char* envb = getenv("MPPI_B200_BLOCK");
   *max_ctas = 0;
   for (int kind = 0; kind < 3; ++kind) {

@@ -23,6 +23,7 @@
 //     rollout-valid mask folded into the scale; the warp REDUX results (uniform registers) of four steps leave
 //     through two 16-byte shared-memory stores of one lane into per-warp slots -- no selects, no atomics; the
 //     32 lanes' bias is removed when the slots are summed.
+//   (bicycle: additionally |delta| <= u_max[1] <= pi/4, so tan(delta) needs no range reduction.)
 // Anything outside those conditions (Q[2] != 0, large yaw increments, replayed noise, fp64) runs rollout_kernel.
 #pragma once
 #include "rollout_kernel.cuh"
@@ -53,8 +54,8 @@ __device__ __forceinline__ void lean_controls(const LeanConsts& lc, float u0, fl
     th += a;
   } else {                                         // NEW bicycle: thdot = v tan(delta) / L
     float sd, cd;
-    Math<float>::sincos_(u1, sd, cd);
-    const float kth = lc.dt * (u0 * (sd / cd) * lc.inv_L);
+    Math<float>::sincos_poly_(u1, sd, cd);         // |delta| <= u_max[1] <= pi/4 is an admission condition of this kernel
+    const float kth = lc.dt * (u0 * __fdividef(sd, cd) * lc.inv_L);
     a = 0.5f * kth;
     g = lc.dt6 * u0;
     th += kth;
@@ -75,6 +76,16 @@ __device__ __forceinline__ uint4 philox4x32_sched(uint4 c, const LeanStatic& ls)
 }
 __device__ __forceinline__ float4 lean_normal4(const LeanStatic& ls, unsigned long long kglobal, unsigned int t2, unsigned int step) {
   return normal4_from_bits(philox4x32_sched(make_uint4((uint32_t)kglobal, (uint32_t)(kglobal >> 32), t2, step), ls));
+}
+
+// NEW occupancy-grid term, same cell as grid_cost<float> in common.cuh (floor, outside = 100) with the
+// floor done by the float->int conversion and the range test on unsigned integers
+__device__ __forceinline__ float lean_grid_cost(const CostConsts<float>& cc, const signed char* __restrict__ cells, float dx, float dy) {
+  const int ix = __float2int_rd((dx + cc.g_ox) * cc.g_inv_res);
+  const int iy = __float2int_rd((dy + cc.g_oy) * cc.g_inv_res);
+  int v = 100;
+  if ((unsigned)ix < (unsigned)cc.gW && (unsigned)iy < (unsigned)cc.gH) v = cells[iy * cc.gW + ix];
+  return cc.w_obs_100 * (float)v;
 }
 
 // sin/cos for |a| <= 1/16: two-term polynomials
@@ -248,7 +259,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
       c = fmaf(n.z, z0, c);
       c = fmaf(lc.hqx * dx, dx + lc.ax2, c);
       c = fmaf(lc.hqy * dy, dy + lc.ay2, c);
-      if (HAS_GRID) c += grid_cost<R>(cc, cells, dx, dy);
+      if (HAS_GRID) c += lean_grid_cost(cc, cells, dx, dy);
       acc += c;
       prow[row * PS] = acc;
     };

@@ -105,6 +105,7 @@ class ShardedMPPI(object):
         if self.exchange == "p2p":
             return m.get_path(state, goal, sig, lam)      # plain mppi_step: the exchange is inside the graph
         _capi.check(lib.mppi_set_goal(h, _capi.dptr(_capi.f64(goal, (3,)))), "mppi_set_goal")
+        m._goal_bytes = None
         _capi.check(lib.mppi_step_local(h, _capi.dptr(_capi.f64(state, (3,)))), "mppi_step_local")
         if self.exchange == "nccl":
             with self._torch.cuda.stream(self.stream):
@@ -116,8 +117,8 @@ class ShardedMPPI(object):
             _capi.check(lib.mppi_write_gather(h, _capi.dptr(allrec)), "mppi_write_gather")
         u, x = np.empty(2), np.empty(3)
         _capi.check(lib.mppi_step_finish(h, _capi.dptr(u), _capi.dptr(x)), "mppi_step_finish")
-        m.path = np.concatenate((m.path, np.array([x])))
-        m.uvec = np.concatenate((m.uvec, np.array([u])))
+        m._path_log.append(x)
+        m._uvec_log.append(u)
         m.fin_time.append(m.fin_time[-1] + m.dt)
         return x
 

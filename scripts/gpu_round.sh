@@ -1,6 +1,6 @@
 #!/bin/bash
-# One full GPU visit: tests, bench (both arms), C++ facade demo, ncu launch lists + full captures.
-# usage (here): gpurun --timeout 1800 -- 'bash scripts/gpu_round.sh [tag]'
+# One full GPU visit: tests, bench (both arms), C++ facade demo, microbenchmark, ncu launch lists + full captures,
+# reduce timeline, all-config sweep.  usage (here): gpurun --timeout 1800 -- 'bash scripts/gpu_round.sh [tag]'
 TAG=${1:-r01}
 O=gpurun_out
 mkdir -p $O
@@ -14,16 +14,23 @@ tail -c 1500 $O/bench_${TAG}.json; tail -3 $O/bench_${TAG}.err
 g++ -std=c++17 -Iinclude examples/ros_control_node.cpp -Lmotion_planning_b200/lib -lmppi_b200 \
   -Wl,-rpath,$PWD/motion_planning_b200/lib -o /tmp/ros_node 2>&1 | grep -v Wcomment | head -5
 timeout 300 /tmp/ros_node 4096 64 3000 > $O/cpp_node_${TAG}.log 2>&1; tail -2 $O/cpp_node_${TAG}.log
+./profiles/microbench/pipes > $O/pipes_${TAG}.txt 2>&1
 for P in mixed f32 f64; do
   timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -c 40 --csv \
     --log-file $O/launches_${P}_${TAG}.csv python profiles/profile_step.py $P 65536 64 5 > $O/ncu_${P}_${TAG}.log 2>&1
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 4 -c 1 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout -s 4 -c 1 \
   -o $O/prof_rollout_mixed_${TAG} -f python profiles/profile_step.py mixed 65536 64 4 > $O/ncu_full_${TAG}.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:reduce_screen -s 4 -c 1 \
   -o $O/prof_reduce_mixed_${TAG} -f python profiles/profile_step.py mixed 65536 64 4 >> $O/ncu_full_${TAG}.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 4 -c 1 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout -s 4 -c 1 \
   -o $O/prof_rollout_f32_${TAG} -f python profiles/profile_step.py f32 65536 64 4 >> $O/ncu_full_${TAG}.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout -s 4 -c 1 \
+  -o $O/prof_rollout_c5_${TAG} -f python profiles/profile_step.py mixed 262144 128 4 >> $O/ncu_full_${TAG}.log 2>&1
 python profiles/reduce_timeline.py mixed > $O/reduce_timeline_${TAG}.txt 2>&1
 python profiles/sweep_configs.py 30 > $O/sweep_${TAG}.jsonl 2>&1
 ls $O | wc -l
+for TOOL in memcheck racecheck synccheck; do
+  timeout 600 compute-sanitizer --tool $TOOL python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -12 > $O/sanitizer_${TOOL}_${TAG}.log
+  tail -2 $O/sanitizer_${TOOL}_${TAG}.log
+done
