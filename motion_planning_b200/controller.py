@@ -1,0 +1,197 @@
+"""ROS-free mirror of the reference's `Controller` (control/src/mppi:296-389): the caller of the hot path.
+
+The reference node subscribes to `odom`, runs one `MPPI.get_path` per message and publishes a `Twist`
+on `cmd_vel`.  This class keeps that state machine line for line -- same attributes (`mppi`, `done`,
+`parallel_park`, `waypoints`, `idx`, `init`, `state`), same `pos_cb` / `wheelsToTwist` -- with the two
+ROS edges replaced by plain Python:
+
+    rospy.Subscriber('odom', Odometry, pos_cb)      ->  call pos_cb(odom) yourself; `odom` is anything
+                                                         shaped like nav_msgs/Odometry (pose.pose.position,
+                                                         pose.pose.orientation) or a plain (x, y, theta)
+    rospy.Publisher('cmd_vel', Twist).publish(tw)   ->  `publish(vx, wz)` callback; pos_cb also returns it
+    rospy.get_param("waypoints")                    ->  constructor argument `waypoints` (falsy = parallel park)
+    rospy.loginfo                                   ->  `log` callback (default: silent)
+
+A rospy node keeps working unchanged: `Controller.pos_cb` accepts the Odometry message itself and the
+node's `publish` callback fills the Twist.
+
+Planner hand-off: the reference reads its waypoints from a yaml file
+(control/config/waypoints.yaml:1) and never wires the planners in; `set_waypoints` /
+`waypoints_from_path` accept what the planners produce -- the vertex list of `trace_path`
+(global_planner/src/global_planner/heuristic.cpp:199-223) or the cell path of D* Lite
+(incremental.cpp:291-336) -- and feed it to the same state machine.
+"""
+import math
+
+import numpy as np
+
+from .mppi import MPPI, WHEEL_BASE, WHEEL_RADIUS
+
+
+def yaw_from_quaternion(x, y, z, w):
+    """Yaw of tf.transformations.euler_from_quaternion(q)[2] (axes 'sxyz'; call site control/src/mppi:333-334)
+    for a unit quaternion: atan2(2(wz + xy), 1 - 2(y^2 + z^2))."""
+    return math.atan2(2.0 * (w * z + x * y), 1.0 - 2.0 * (y * y + z * z))
+
+
+def _pose_of(odom):
+    """(x, y, theta) of an Odometry-shaped message (control/src/mppi:330-334) or of a plain triple."""
+    pose = getattr(odom, "pose", None)
+    if pose is None:
+        x, y, theta = odom
+        return float(x), float(y), float(theta)
+    p, q = pose.pose.position, pose.pose.orientation
+    return float(p.x), float(p.y), yaw_from_quaternion(q.x, q.y, q.z, q.w)
+
+
+def waypoints_from_path(path, min_spacing=0.0, origin=(0.0, 0.0), resolution=None):
+    """Waypoint list for `Controller` from a planner path.
+
+    path        (n,2) vertices in metres (trace_path output) or, with `resolution`, integer grid cells
+                (ix, iy) of a grid path, converted to cell centres with the map package's convention
+                x = x_min + (ix + 0.5) res (map/src/map/grid.cpp:106-119).
+    min_spacing drop vertices closer than this to the previously kept one (a cell-by-cell grid path would
+                otherwise hand the controller goals already inside `thresh`); the last vertex is always kept.
+    """
+    p = np.asarray(path, dtype=np.float64).reshape(-1, 2)
+    if resolution is not None:
+        p = np.asarray(origin, dtype=np.float64)[None, :] + (p + 0.5) * float(resolution)
+    if len(p) == 0:
+        return []
+    keep = [p[0]]
+    for v in p[1:-1]:
+        if np.linalg.norm(v - keep[-1]) >= min_spacing:
+            keep.append(v)
+    if len(p) > 1:
+        if len(keep) > 1 and np.linalg.norm(p[-1] - keep[-1]) < min_spacing:
+            keep[-1] = p[-1]
+        else:
+            keep.append(p[-1])
+    return [[float(v[0]), float(v[1])] for v in keep]
+
+
+class Controller(object):
+    def __init__(self, mppi=None, waypoints=None, publish=None, log=None):
+        """control/src/mppi:297-319.  `mppi` defaults to `MPPI()` (K=10, T=100: what the node runs, :298)."""
+        self.mppi = mppi if mppi is not None else MPPI()
+        self._publish = publish
+        self._log = log
+        self.done = False
+        if not waypoints:                                   # :305-309
+            self.parallel_park = True
+        else:
+            self.parallel_park = False
+            self.waypoints = [list(w) for w in waypoints]
+        self.idx = 0
+        self.init = True
+        self.state = self.mppi.start
+        self.cmd = (0.0, 0.0)
+        self._emit(0.0, 0.0)                                # :313-316: a zero Twist at start-up
+
+    # ---- ROS edges ------------------------------------------------------------------------------
+    def _emit(self, vx, wz):
+        self.cmd = (vx, wz)
+        if self._publish is not None:
+            self._publish(vx, wz)
+
+    def _info(self, msg):
+        if self._log is not None:
+            self._log(msg)
+
+    def set_waypoints(self, waypoints):
+        """Planner hand-off: replace the waypoint list; the next `pos_cb` re-initialises towards waypoints[0]."""
+        if not waypoints:
+            self.parallel_park = True
+        else:
+            self.parallel_park = False
+            self.waypoints = [list(w) for w in waypoints]
+        self.idx = 0
+        self.init = True
+        self.done = False
+
+    # ---- reference methods ----------------------------------------------------------------------
+    def wheelsToTwist(self, wheel_vels):
+        """control/src/mppi:320-326."""
+        ul = wheel_vels[0]
+        ur = wheel_vels[1]
+        vx = WHEEL_RADIUS * (ul + ur) / 2.0
+        wz = WHEEL_RADIUS * (-ul + ur) / WHEEL_BASE
+        return vx, wz
+
+    def _goal_towards(self, wpt):
+        """Goal = (wx, wy, heading from the current start to the waypoint), control/src/mppi:347-352."""
+        theta = np.arctan2(wpt[1] - self.mppi.start[1], wpt[0] - self.mppi.start[0])
+        return np.array([wpt[0], wpt[1], theta])
+
+    def pos_cb(self, odom):
+        """control/src/mppi:328-386: one odometry message -> one MPPI step -> one Twist (returned as (vx, wz))."""
+        m = self.mppi
+        x, y, theta = _pose_of(odom)
+        m.start = np.array([x, y, theta])                   # :335
+        if self.parallel_park:
+            m.goal = np.array([0.0, -1.0, 0.0])             # :337
+        if np.linalg.norm(m.start[:2] - m.goal[:2]) > m.thresh and not self.init:
+            self.state = m.get_path(m.start, m.goal)        # :341 -- the hot path
+            self.done = False
+        elif self.init:                                     # :344-354
+            m.initialize()
+            if not self.parallel_park:
+                m.goal = self._goal_towards(self.waypoints[self.idx])
+                self.state = m.start
+            self.init = False
+            self._info("NEXT WAYPOINT: {}".format(m.goal[:2]))
+        else:
+            if not self.parallel_park:                      # :357-373: goal reached, next waypoint (cyclic)
+                if self.idx + 1 >= len(self.waypoints):
+                    self.idx = 0
+                else:
+                    self.idx += 1
+                m.initialize()
+                self._info("WAYPOINT REACHED: {} \n NEXT WAYPOINT: {}".format(m.goal[:2], self.waypoints[self.idx]))
+                m.goal = self._goal_towards(self.waypoints[self.idx])
+                self.state = m.start
+            else:
+                self.done = True                            # :375
+        if not self.done:                                   # :378-381
+            u = m.uvec[-1, :]
+        else:
+            u = np.array([0.0, 0.0])
+        vx, wz = self.wheelsToTwist(u)
+        self._emit(vx, wz)
+        return vx, wz
+
+
+class FakeDiffDrive(object):
+    """Stand-in for the simulation half of control/launch/mppi_pentagon.launch:5-8,25-31 (rigid2d's fake
+    encoders + odometer, which are not part of the reference repository): integrates the published Twist
+    exactly over `dt` (constant-twist arc) and reports the pose as the next odometry."""
+
+    def __init__(self, pose=(0.0, 0.0, 0.0), dt=0.01):
+        self.pose = np.array(pose, dtype=np.float64)
+        self.dt = float(dt)
+
+    def step(self, vx, wz):
+        x, y, th = self.pose
+        a = wz * self.dt
+        if abs(a) < 1e-12:
+            x += vx * self.dt * math.cos(th)
+            y += vx * self.dt * math.sin(th)
+        else:
+            r = vx / wz
+            x += r * (math.sin(th + a) - math.sin(th))
+            y -= r * (math.cos(th + a) - math.cos(th))
+        th = math.atan2(math.sin(th + a), math.cos(th + a))
+        self.pose = np.array([x, y, th])
+        return self.pose
+
+
+def run_closed_loop(controller, plant, n_callbacks):
+    """Drive `controller` from `plant` for n odometry callbacks; returns the (n,3) poses fed in and the (n,2) twists out."""
+    poses, twists = [], []
+    for _ in range(int(n_callbacks)):
+        pose = plant.pose.copy()
+        vx, wz = controller.pos_cb(pose)
+        plant.step(vx, wz)
+        poses.append(pose)
+        twists.append((vx, wz))
+    return np.array(poses), np.array(twists)
