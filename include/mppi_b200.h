@@ -217,6 +217,10 @@ MPPI_API mppi_status mppi_launch_info(mppi_handle h, int32_t info[8]);
 /* profiling aid: globaltimer stamps (ns) of the reduce-kernel phases of the last step, [T][8];
  * the first call arms the stamps. */
 MPPI_API mppi_status mppi_debug_reduce_timestamps(mppi_handle h, unsigned long long* out);
+/* Profiling aid, meaningful only in libraries built with -DMPPI_EXP_TIMELINE: %globaltimer stamps (ns) of the
+ * rollout kernel's CTAs in the last step, out[n_ctas][8] = entry, loads issued, prologue done, loop done, total
+ * stored, barrier passed, tile done, SM id.  The first call (out may be NULL) arms the stamps. */
+MPPI_API mppi_status mppi_debug_rollout_timestamps(mppi_handle h, unsigned long long* out, size_t n_ctas);
 
 MPPI_API const char* mppi_last_error(void);
 MPPI_API const char* mppi_version(void);

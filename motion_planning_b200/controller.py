@@ -29,9 +29,15 @@ from .mppi import MPPI, WHEEL_BASE, WHEEL_RADIUS
 
 
 def yaw_from_quaternion(x, y, z, w):
-    """Yaw of tf.transformations.euler_from_quaternion(q)[2] (axes 'sxyz'; call site control/src/mppi:333-334)
-    for a unit quaternion: atan2(2(wz + xy), 1 - 2(y^2 + z^2))."""
-    return math.atan2(2.0 * (w * z + x * y), 1.0 - 2.0 * (y * y + z * z))
+    """Yaw of tf.transformations.euler_from_quaternion([x, y, z, w])[2] (axes 'sxyz'; call site control/src/mppi:333-334).
+    Same arithmetic as tf's route through quaternion_matrix, reduced to the two matrix entries the yaw needs: the
+    quaternion is scaled by sqrt(2 / |q|^2) (so it need not be normalised), M10 = qx qy + qz qw, M00 = 1 - qy qy - qz qz."""
+    nq = x * x + y * y + z * z + w * w
+    if nq < 8.881784197001252e-16:              # tf: 4 * machine epsilon -> identity
+        return 0.0
+    s = math.sqrt(2.0 / nq)
+    x, y, z, w = x * s, y * s, z * s, w * s
+    return math.atan2(x * y + z * w, 1.0 - y * y - z * z)
 
 
 def _pose_of(odom):

@@ -278,6 +278,9 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsign
   return normal4_from_bits(philox4x32_10(ctr, key));
 }
 __device__ __forceinline__ float4 normal4_from_bits(uint4 r) {
+#ifdef MPPI_EXP_NOMUFU   // measurement only (profiles/variants.py): uniform noise without the SFU pipe -- NOT a product path
+  return make_float4(fmaf((float)r.x, 8e-10f, -1.7f), fmaf((float)r.y, 8e-10f, -1.7f), fmaf((float)r.z, 8e-10f, -1.7f), fmaf((float)r.w, 8e-10f, -1.7f));
+#endif
   const float S = 2.3283064365386963e-10f;   // 2^-32
   float u0 = __fmaf_rn((float)r.x, S, 1.1641532182693481e-10f);   // (0,1]
   float u2 = __fmaf_rn((float)r.z, S, 1.1641532182693481e-10f);

@@ -64,6 +64,8 @@ struct mppi_engine {
   double *d_record = nullptr, *d_gather = nullptr, *d_record_tmp = nullptr;
   unsigned int* d_done = nullptr;
   unsigned long long* d_debug_ts = nullptr;
+  unsigned long long* d_debug_rts = nullptr;   // rollout kernel stamps (MPPI_EXP_TIMELINE builds)
+  size_t debug_rts_ctas = 0;
   // peer-to-peer exchange
   double* d_p2p = nullptr;          // local buffer (exported through CUDA IPC)
   size_t p2p_bytes = 0;
@@ -190,7 +192,7 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
   StaticParams& sp = e->sp;
   const bool has_grid = sp.has_grid != 0;
   // FAST kernels: in-register Philox noise and yaw increments small enough for the branch-free step;
-  // LEAN (fp32 families only): additionally Q[2] == 0 and |dt * yaw rate| <= 1/8 (rollout_lean_kernel.cuh).
+  // LEAN (fp32 families only): additionally Q[2] == 0, Q[0] == Q[1] > 0 and |dt * yaw rate| <= 1/8 (rollout_lean_kernel.cuh).
   // MPPI_B200_BLOCK=<64|128> forces one tile shape, MPPI_B200_VARIANT=<general|fast|lean> caps the code path
   // (experiments / tests of the fallback paths).
   const double yaw_inc = max_yaw_increment(sp);
@@ -200,7 +202,7 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
     else if (!strcmp(envv, "fast")) variant_max = ROLLOUT_FAST;
   }
   const bool fast = !sp.noise_external && yaw_inc <= 0.78 && variant_max >= ROLLOUT_FAST;
-  const bool lean = fast && sp.q[2] == 0.0 && (sp.model != MPPI_MODEL_BICYCLE || sp.u_max[1] <= 0.785) && yaw_inc <= (sp.model == MPPI_MODEL_UNICYCLE_EULER ? 0.5 : 1.0) * kLeanMaxYawInc && variant_max >= ROLLOUT_LEAN;
+  const bool lean = fast && sp.q[2] == 0.0 && sp.q[0] == sp.q[1] && sp.q[0] > 0.0 && sp.u_max[0] > 0.0 && sp.u_max[1] > 0.0 && (sp.model != MPPI_MODEL_BICYCLE || sp.u_max[1] <= 0.785) && yaw_inc <= (sp.model == MPPI_MODEL_UNICYCLE_EULER ? 0.5 : 1.0) * kLeanMaxYawInc && variant_max >= ROLLOUT_LEAN;
   const char* envb = getenv("MPPI_B200_BLOCK");
   *max_ctas = 0;
   for (int kind = 0; kind < 3; ++kind) {
@@ -309,7 +311,7 @@ static mppi_status upload_dyn_sampling(mppi_engine* e, const double sig[4], doub
 }
 
 static mppi_status prep_nominal(mppi_engine* e) {
-  CK(prep_nominal_launch(e->stream, e->d_dyn, e->sp.T, e->d_Umaster, e->d_nomF, e->d_nomD));
+  CK(prep_nominal_launch(e->stream, e->d_dyn, e->sp, e->d_Umaster, e->d_nomF, e->d_nomD));
   CK(cudaStreamSynchronize(e->stream));
   return MPPI_OK;
 }
@@ -477,6 +479,7 @@ extern "C" mppi_status mppi_destroy(mppi_handle e) {
   cudaFree(e->d_gather);
   cudaFree(e->d_done);
   cudaFree(e->d_debug_ts);
+  cudaFree(e->d_debug_rts);
   for (void* q : e->p2p_opened) cudaIpcCloseMemHandle(q);
   cudaFree(e->d_p2p_peers);
   cudaFree(e->d_p2p);
@@ -712,23 +715,46 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   ra.vcap = e->d_vcap;
   ra.ntiles = c.ntiles;
   if (in) ra.in = *in;
+  ra.debug_ts = e->d_debug_rts;
   if (c.variant == ROLLOUT_LEAN) {
     const StaticParams& sp = e->sp;
     LeanStatic& ls = ra.lean;
-    ls.ca = (float)(0.5 * sp.dt * sp.wheel_r / sp.wheel_L);
-    ls.cg = (float)(sp.dt * sp.wheel_r * 0.5 / 6.0);
-    ls.ck = (float)(sp.dt * sp.wheel_r / sp.wheel_L);
-    ls.dt = (float)sp.dt;
-    ls.dt6 = (float)(sp.dt / 6.0);
-    ls.inv_L = (float)(1.0 / sp.wheel_L);
-    ls.um0 = (float)sp.u_max[0];
-    ls.um1 = (float)sp.u_max[1];
-    ls.hqx = (float)(0.5 * sp.q[0]);
-    ls.hqy = (float)(0.5 * sp.q[1]);
-    ls.p1x = (float)sp.p1[0];
-    ls.p1y = (float)sp.p1[1];
+    const double hq = 0.5 * sp.q[0], sq = std::sqrt(hq);
+    const double um0 = sp.u_max[0], um1 = sp.u_max[1];
+    double A0 = 0, A1 = 0, Ac = 0, G0 = 0, G1 = 0, Gc = 0, bk = 0;
+    if (sp.model == MPPI_MODEL_DIFF_DRIVE) {          // u = u_max (2 s - 1); a = (dt r / 2L)(u1 - u0), g = (dt r / 12)(u0 + u1)
+      const double ca = 0.5 * sp.dt * sp.wheel_r / sp.wheel_L, cg = sq * sp.dt * sp.wheel_r * 0.5 / 6.0;
+      A0 = -2.0 * ca * um0;
+      A1 = 2.0 * ca * um1;
+      Ac = ca * (um0 - um1);
+      G0 = 2.0 * cg * um0;
+      G1 = 2.0 * cg * um1;
+      Gc = -cg * (um0 + um1);
+    } else if (sp.model == MPPI_MODEL_UNICYCLE_EULER) {   // a = dt u1 (full increment), g = dt u0
+      A1 = 2.0 * sp.dt * um1;
+      Ac = -sp.dt * um1;
+      G0 = 2.0 * sq * sp.dt * um0;
+      Gc = -sq * sp.dt * um0;
+    } else {                                          // bicycle: a = (dt / 2L) v tan(delta), g = (dt / 6) v
+      bk = 0.5 * sp.dt / sp.wheel_L;
+      G0 = sq * sp.dt / 6.0;
+    }
+    ls.A0 = (float)A0;
+    ls.A1 = (float)A1;
+    ls.Ac = (float)Ac;
+    ls.G0 = (float)G0;
+    ls.G1 = (float)G1;
+    ls.Gc = (float)Gc;
+    ls.um0 = (float)um0;
+    ls.um1 = (float)um1;
+    ls.bk = (float)bk;
+    ls.inv2um0 = (float)(0.5 / um0);
+    ls.inv2um1 = (float)(0.5 / um1);
+    ls.sq = (float)sq;
+    ls.p1x = (float)(sp.p1[0] / hq);
+    ls.p1y = (float)(sp.p1[1] / hq);
     ls.p1th = (float)sp.p1[2];
-    ls.g_inv_res = (float)sp.g_inv_res;
+    ls.g_inv_res = (float)(sp.g_inv_res / sq);
     ls.w_obs_100 = (float)(sp.w_obs / 100.0);
     ls.margin = (float)sp.margin;
     for (int i = 0; i < MPPI_PHILOX_ROUNDS; ++i) {
@@ -1289,6 +1315,24 @@ extern "C" mppi_status mppi_debug_reduce_timestamps(mppi_handle e, unsigned long
     drop_graphs(e);
   }
   if (out) CK(cudaMemcpy(out, e->d_debug_ts, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return MPPI_OK;
+}
+
+// profiling aid (libraries built with -DMPPI_EXP_TIMELINE): globaltimer stamps of the rollout kernel's CTAs, [n_ctas][8]
+// (entry, loads issued, prologue done, loop done, total stored, barrier, tile done, SM id); first call arms
+extern "C" mppi_status mppi_debug_rollout_timestamps(mppi_handle e, unsigned long long* out, size_t n_ctas) {
+  ENTER(e);
+  CK(cudaStreamSynchronize(e->stream));
+  if (!e->d_debug_rts) {
+    e->debug_rts_ctas = e->part_capacity_ctas;
+    CK(cudaMalloc(&e->d_debug_rts, e->debug_rts_ctas * 8 * sizeof(unsigned long long)));
+    CK(cudaMemset(e->d_debug_rts, 0, e->debug_rts_ctas * 8 * sizeof(unsigned long long)));
+    drop_graphs(e);
+  }
+  if (out) {
+    if (n_ctas > e->debug_rts_ctas) n_ctas = e->debug_rts_ctas;
+    CK(cudaMemcpy(out, e->d_debug_rts, n_ctas * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
   return MPPI_OK;
 }
 

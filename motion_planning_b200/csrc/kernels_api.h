@@ -23,7 +23,7 @@ size_t rollout_smem(int kind, int T, int block, int variant, int grid_bytes_in_s
 cudaError_t reduce_softmin_launch(bool f64, int T, cudaStream_t st, const ReduceArgs& a);
 cudaError_t reduce_screen_launch(int model, bool has_grid, int T, cudaStream_t st, const ReduceArgs& a);
 cudaError_t finalize_launch(cudaStream_t st, const FinalizeArgs& a);
-cudaError_t prep_nominal_launch(cudaStream_t st, const DynState* dyn, int T, const double* Umaster, float* nomF, double* nomD);   // nomF: 8*T floats
+cudaError_t prep_nominal_launch(cudaStream_t st, const DynState* dyn, const StaticParams& sp, const double* Umaster, float* nomF, double* nomD);   // nomF: 8*T floats
 cudaError_t noise_export_launch(cudaStream_t st, const StaticParams& sp, const DynState* dyn, unsigned step, double* eps);
 cudaError_t weights_from_v_launch(cudaStream_t st, const StaticParams& sp, const DynState* dyn, const double* V,
                                   const double* eps, double* record);

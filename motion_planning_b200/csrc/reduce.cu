@@ -92,8 +92,9 @@ cudaError_t finalize_launch(cudaStream_t st, const FinalizeArgs& a) {
   return cudaGetLastError();
 }
 
-cudaError_t prep_nominal_launch(cudaStream_t st, const DynState* dyn, int T, const double* Umaster, float* nomF, double* nomD) {
-  prep_nominal_kernel<<<1, 128, 0, st>>>(dyn, T, Umaster, nomF, nomD);
+cudaError_t prep_nominal_launch(cudaStream_t st, const DynState* dyn, const StaticParams& sp, const double* Umaster, float* nomF,
+                                double* nomD) {
+  prep_nominal_kernel<<<1, 128, 0, st>>>(dyn, sp.T, sp.u_max[0], sp.u_max[1], Umaster, nomF, nomD);
   return cudaGetLastError();
 }
 

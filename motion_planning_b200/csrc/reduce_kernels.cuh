@@ -533,8 +533,8 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
 
 // ---- kernel 3: finalize.  one block of 256 threads ------------------------------------------------
 
-__device__ __forceinline__ void write_nominal_block(double lam, const double sig[4], const float nstd[2], int T, int t, double u0,
-                                                    double u1, float* nomF, double* nomD) {
+__device__ __forceinline__ void write_nominal_block(double lam, const double sig[4], const float nstd[2], const double umax[2], int T,
+                                                    int t, double u0, double u1, float* nomF, double* nomD) {
   // g[t] = lam * (u . sig)   so that   lam * u.dot(sig).dot(eps) = g0 eps0 + g1 eps1   (control/src/mppi:184)
   const double g0 = lam * (u0 * sig[0] + u1 * sig[2]);
   const double g1 = lam * (u0 * sig[1] + u1 * sig[3]);
@@ -546,15 +546,18 @@ __device__ __forceinline__ void write_nominal_block(double lam, const double sig
   nomF[T + t] = (float)u1;
   nomF[2 * T + t] = (float)g0;
   nomF[3 * T + t] = (float)g1;
-  // LEAN block: interleaved per t, the noise std folded into the cost coefficients (rollout_lean_kernel.cuh)
-  reinterpret_cast<float4*>(nomF + 4 * T)[t] = make_float4((float)u0, (float)u1, (float)(g0 * (double)nstd[0]), (float)(g1 * (double)nstd[1]));
+  // LEAN block: interleaved per t; the controls in clip units u' = u / (2 u_max) + 1/2 (so that the clip :151-152 is the
+  // saturate modifier of one FFMA), the noise std folded into the cost coefficients (rollout_lean_kernel.cuh)
+  reinterpret_cast<float4*>(nomF + 4 * T)[t] = make_float4((float)(u0 / (2.0 * umax[0]) + 0.5), (float)(u1 / (2.0 * umax[1]) + 0.5),
+                                                           (float)(g0 * (double)nstd[0]), (float)(g1 * (double)nstd[1]));
 }
 
-__global__ void prep_nominal_kernel(const DynState* dyn, int T, const double* Umaster, float* nomF, double* nomD) {
+__global__ void prep_nominal_kernel(const DynState* dyn, int T, double um0, double um1, const double* Umaster, float* nomF, double* nomD) {
+  const double umax[2] = {um0, um1};
   const double sig[4] = {dyn->sig[0], dyn->sig[1], dyn->sig[2], dyn->sig[3]};
   const float nstd[2] = {(float)dyn->noise_std[0], (float)dyn->noise_std[1]};
   for (int t = threadIdx.x; t < T; t += blockDim.x)
-    write_nominal_block(dyn->lam, sig, nstd, T, t, Umaster[t], Umaster[T + t], nomF, nomD);
+    write_nominal_block(dyn->lam, sig, nstd, umax, T, t, Umaster[t], Umaster[T + t], nomF, nomD);
 }
 
 template <int MODEL>
@@ -751,7 +754,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       const double u1 = (t + 1 < T) ? sg_eval(1, t + 1) : 0.0;
       a.Umaster[t] = u0;
       a.Umaster[T + t] = u1;
-      write_nominal_block(lam, sigr, nstdr, T, t, u0, u1, a.nomF, a.nomD);
+      write_nominal_block(lam, sigr, nstdr, a.sp.u_max, T, t, u0, u1, a.nomF, a.nomD);
     }
   }
 }

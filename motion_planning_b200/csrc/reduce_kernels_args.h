@@ -5,12 +5,14 @@ namespace mppi {
 
 // engine-lifetime fp32 constants of the LEAN rollout kernel, folded on the host (no fp64 math in its prologue)
 struct LeanStatic {
-  float ca, cg, ck;          // diff-drive: a = ca (u1-u0), g = cg (u0+u1), kth = ck (u1-u0)
-  float dt, dt6, inv_L;      // unicycle / bicycle
-  float um0, um1;
-  float hqx, hqy;            // Q/2
-  float p1x, p1y, p1th;
-  float g_inv_res, w_obs_100;
+  // controls in clip units s = u / (2 u_max) + 1/2 in [0, 1]; positions in cost units d' = sq * d, sq = sqrt(Q/2)
+  float A0, A1, Ac;          // half yaw increment a = A0 s0 + A1 s1 + Ac (Euler: the full increment)
+  float G0, G1, Gc;          // Simpson factor sq * dt * speed / 6 (Euler: sq * dt * speed) = G0 s0 + G1 s1 + Gc; bicycle: G0 * v
+  float um0, um1, bk;        // bicycle: v = 2 um0 s0 - um0, delta = 2 um1 s1 - um1, a = bk * v * tan(delta)
+  float inv2um0, inv2um1;    // 1 / (2 u_max)
+  float sq;                  // sqrt(Q[0] / 2) (== sqrt(Q[1] / 2): admission condition)
+  float p1x, p1y, p1th;      // P1 / (Q/2) for x, y (terminal cost on cost-unit positions); P1[2]
+  float g_inv_res, w_obs_100;   // cells per cost unit
   float margin;
   uint32_t pkx[MPPI_PHILOX_ROUNDS], pky[MPPI_PHILOX_ROUNDS];   // Philox key schedule key + i * Weyl, per round
 };
@@ -29,6 +31,7 @@ struct RolloutArgs {
   int ntiles;
   StepInput in;                // x0 / goal of this step
   LeanStatic lean;             // LEAN variant only
+  unsigned long long* debug_ts;   // -DMPPI_EXP_TIMELINE builds only: [nCTA][8] globaltimer stamps + SM id (profiling aid)
 };
 
 struct FinalizeArgs {

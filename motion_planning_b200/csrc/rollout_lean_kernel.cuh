@@ -8,13 +8,19 @@
 //   * Q[2] == 0 (the reference's Q = diag(1e3, 1e3, 0), control/src/mppi:69): theta enters the running cost
 //     nowhere, so it is carried as a plain sum of yaw increments, wrapped once per four steps (branch-free,
 //     round-to-nearest turn count) and used only by the terminal cost (:165-171);
-//   * |dt * yaw rate| <= 1/8 for every admissible control: sin/cos of the HALF increment (|a| <= 1/16) are
-//     two-term polynomials, exact to fp32 rounding (next terms a^7/5040 < 1e-12, a^6/720 < 1e-10).
+//   * |dt * yaw rate| <= 1/8 for every admissible control: sin/cos of the HALF increment (|a| <= 1/16) are short
+//     polynomials (sin: a (1 - a^2/6), phase error 0.008 a^5 < 8e-9 rad per rotation; cos: next term a^6/720 < 1e-10).
 // Differences from the generic FAST step:
-//   * nominal block interleaved as float4 per t (U0, U1, std0*g0, std1*g1): one broadcast LDS.128 per step;
-//     the sampled control is fmaf(std, z, U) and the noise term of the cost (:184) fmaf(std*g, z, .), so eps is
-//     never materialised;
-//   * model constants folded: a = (dt r / 2L)(u1-u0), g = (dt r / 12)(u0+u1), theta += (dt r / L)(u1-u0);
+//   * nominal block interleaved as float4 per t (U0', U1', std0*g0, std1*g1): one broadcast LDS.128 per step; the
+//     controls live in CLIP UNITS s = u / (2 u_max) + 1/2, so sample + clip (:147-152) is ONE instruction,
+//     s = sat(fmaf(std / (2 u_max), z, U')) (FFMA.SAT instead of FFMA + 2 FMNMX on the half-rate ALU pipe), and the
+//     noise term of the cost (:184) is fmaf(std*g, z, .): neither eps nor u is ever materialised;
+//   * model constants folded into affine maps of the clip-unit controls: half yaw increment a = A0 s0 + A1 s1 + Ac,
+//     Simpson factor g = G0 s0 + G1 s1 + Gc;
+//   * positions carried in COST UNITS d' = sqrt(Q/2) d (admission: Q[0] == Q[1] > 0, the reference's Q): the running
+//     cost in delta form is d'(d' + a') per axis -- FADD + FFMA instead of FMUL + FADD + FFMA;
+//   * theta is not carried at all by the wrapping models (rk4 wraps every step, :52-53, so theta_T = atan2(sin, cos) of
+//     the carried pair, once per rollout); the Euler model (no wrap, :57-58) keeps a plain sum;
 //   * Simpson weights through the mid-point rotation only: c1 + 4 c2 + c4 = c2 (4 + 2 cos a) because
 //     c1 + c4 = 2 c2 cos a -- one rotation feeds the position update, a second one advances (cos, sin);
 //   * (cos, sin) is never re-derived from theta: one first-order renormalisation per four steps keeps the
@@ -36,29 +42,29 @@ constexpr unsigned kLeanBias32 = 0x68000000u;     // 32 * float_as_int(kLeanMagi
 
 // per-step constants: LeanStatic (host-folded) + what depends on x0 / goal / DynState
 struct LeanConsts {
-  float ca, cg, ck, dt, dt6, inv_L, um0, um1, hqx, hqy;
-  float std0, std1, ax2, ay2, th0;
+  float A0, A1, Ac, G0, G1, Gc;      // affine maps of the clip-unit controls (see LeanStatic)
+  float um0, um0x2, um1, um1x2, bk;  // bicycle only
+  float k0, k1;                      // std / (2 u_max)
+  float std0, std1, ax2, ay2, th0;   // ax2, ay2 = 2 (x0 - goal) in cost units
 };
 
-// (half) yaw increment a, Simpson factor g = dt*speed/6 (Euler: dt*speed), theta <- theta + dt*yaw rate
+// (half) yaw increment a and Simpson factor g = scale * dt * speed / 6 (Euler: scale * dt * speed) from the clip-unit
+// controls s0, s1 in [0, 1]; only the Euler model carries theta
 template <int MODEL>
-__device__ __forceinline__ void lean_controls(const LeanConsts& lc, float u0, float u1, float& a, float& g, float& th) {
+__device__ __forceinline__ void lean_controls(const LeanConsts& lc, float s0, float s1, float& a, float& g, float& th) {
   if (MODEL == MPPI_MODEL_DIFF_DRIVE) {            // dd_dynamics, control/src/mppi:23-30
-    const float df = u1 - u0, sm = u0 + u1;
-    a = lc.ca * df;
-    g = lc.cg * sm;
-    th = fmaf(lc.ck, df, th);
+    a = fmaf(lc.A1, s1, fmaf(lc.A0, s0, lc.Ac));
+    g = fmaf(lc.G1, s1, fmaf(lc.G0, s0, lc.Gc));
   } else if (MODEL == MPPI_MODEL_UNICYCLE_EULER) { // unicycle_dynamics + euler, control/src/mppi:33-36,57-58
-    a = lc.dt * u1;                                // the FULL increment: Euler rotates once per step
-    g = lc.dt * u0;
+    a = fmaf(lc.A1, s1, lc.Ac);                    // the FULL increment: Euler rotates once per step
+    g = fmaf(lc.G0, s0, lc.Gc);
     th += a;
   } else {                                         // NEW bicycle: thdot = v tan(delta) / L
+    const float v = fmaf(s0, lc.um0x2, -lc.um0), dl = fmaf(s1, lc.um1x2, -lc.um1);
     float sd, cd;
-    Math<float>::sincos_poly_(u1, sd, cd);         // |delta| <= u_max[1] <= pi/4 is an admission condition of this kernel
-    const float kth = lc.dt * (u0 * __fdividef(sd, cd) * lc.inv_L);
-    a = 0.5f * kth;
-    g = lc.dt6 * u0;
-    th += kth;
+    Math<float>::sincos_poly_(dl, sd, cd);         // |delta| <= u_max[1] <= pi/4 is an admission condition of this kernel
+    a = lc.bk * (v * __fdividef(sd, cd));
+    g = lc.G0 * v;
   }
 }
 
@@ -79,7 +85,8 @@ __device__ __forceinline__ float4 lean_normal4(const LeanStatic& ls, unsigned lo
 }
 
 // NEW occupancy-grid term, same cell as grid_cost<float> in common.cuh (floor, outside = 100) with the
-// floor done by the float->int conversion and the range test on unsigned integers
+// floor done by the float->int conversion and the range test on unsigned integers; dx, dy, g_ox, g_oy in cost units and
+// g_inv_res per cost unit
 __device__ __forceinline__ float lean_grid_cost(const CostConsts<float>& cc, const signed char* __restrict__ cells, float dx, float dy) {
   const int ix = __float2int_rd((dx + cc.g_ox) * cc.g_inv_res);
   const int iy = __float2int_rd((dy + cc.g_oy) * cc.g_inv_res);
@@ -88,19 +95,25 @@ __device__ __forceinline__ float lean_grid_cost(const CostConsts<float>& cc, con
   return cc.w_obs_100 * (float)v;
 }
 
-// sin/cos for |a| <= 1/16: two-term polynomials
+// sin/cos for |a| <= 1/16 (see the header for the error budget)
 __device__ __forceinline__ void sincos_tiny(float a, float& s, float& c) {
   const float z = a * a;
-  s = fmaf(a * z, fmaf(z, 8.3333333e-3f, -1.6666667e-1f), a);
+  s = a * fmaf(z, -1.6666667e-1f, 1.0f);
   c = fmaf(z, fmaf(z, 4.1666668e-2f, -0.5f), 1.0f);
 }
 
-// theta - 2 pi * rint(theta / 2 pi): the reference's wrap (control/src/mppi:52-53) for any number of turns,
-// branch-free on the FMA pipe (differs from the ceil form only AT theta = -pi, a null set)
-__device__ __forceinline__ float wrap_rint(float th) {
-  const float j = fmaf(th, 0.159154943f, kLeanMagic) - kLeanMagic;
-  return fmaf(-j, 6.28318548f, th);
-}
+#ifdef MPPI_EXP_TIMELINE   // measurement only (profiles/rollout_timeline.py) -- NOT compiled into the product library
+#define RTS(slot)                                                                  \
+  do {                                                                             \
+    if (a.debug_ts && threadIdx.x == 0) {                                          \
+      unsigned long long t_;                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                       \
+      a.debug_ts[(size_t)blockIdx.x * 8 + (slot)] = t_;                            \
+    }                                                                              \
+  } while (0)
+#else
+#define RTS(slot) do { } while (0)
+#endif
 
 template <int MODEL, int MODE, bool HAS_GRID, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const __grid_constant__ RolloutArgs a) {
@@ -113,6 +126,14 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nCTA = gridDim.x, cta = blockIdx.x;
 
+  RTS(0);
+#ifdef MPPI_EXP_TIMELINE
+  if (a.debug_ts && threadIdx.x == 0) {
+    unsigned int smid_;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));
+    a.debug_ts[(size_t)blockIdx.x * 8 + 7] = smid_;
+  }
+#endif
   // ---- shared memory carve-up ------------------------------------------------------------------
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);                      // 8 B
@@ -162,28 +183,31 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
   double xs[3], gs[3];
   load_step_input(a.in, ds, xs, gs);
   LeanConsts lc;
-  CostConsts<R> cc;     // grid / terminal constants in the layout grid_cost / terminal_cost expect
+  CostConsts<R> cc;     // grid / terminal constants in the layout lean_grid_cost / terminal_cost expect, in cost units
   {
     const LeanStatic& ls = a.lean;
-    lc.ca = ls.ca;
-    lc.cg = ls.cg;
-    lc.ck = ls.ck;
-    lc.dt = ls.dt;
-    lc.dt6 = ls.dt6;
-    lc.inv_L = ls.inv_L;
+    lc.A0 = ls.A0;
+    lc.A1 = ls.A1;
+    lc.Ac = ls.Ac;
+    lc.G0 = ls.G0;
+    lc.G1 = ls.G1;
+    lc.Gc = ls.Gc;
     lc.um0 = ls.um0;
+    lc.um0x2 = 2.0f * ls.um0;
     lc.um1 = ls.um1;
-    lc.hqx = ls.hqx;
-    lc.hqy = ls.hqy;
+    lc.um1x2 = 2.0f * ls.um1;
+    lc.bk = ls.bk;
+    lc.k0 = std0_f * ls.inv2um0;
+    lc.k1 = std1_f * ls.inv2um1;
     lc.std0 = std0_f;
     lc.std1 = std1_f;
-    lc.ax2 = (float)(2.0 * (xs[0] - gs[0]));
-    lc.ay2 = (float)(2.0 * (xs[1] - gs[1]));
+    lc.ax2 = (float)(2.0 * (xs[0] - gs[0]) * (double)ls.sq);
+    lc.ay2 = (float)(2.0 * (xs[1] - gs[1]) * (double)ls.sq);
     lc.th0 = (float)xs[2];
-    cc.hqx = ls.hqx;
-    cc.hqy = ls.hqy;
+    cc.hqx = 1.f;
+    cc.hqy = 1.f;
     cc.hqth = 0.f;
-    cc.p1x = ls.p1x;
+    cc.p1x = ls.p1x;      // P1 / (Q/2): the terminal cost takes the positions in cost units too
     cc.p1y = ls.p1y;
     cc.p1th = ls.p1th;
     cc.ax2 = lc.ax2;
@@ -195,8 +219,8 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
       post[1] = neg_inv_lam_ld;
     }
     cc.g_inv_res = ls.g_inv_res;
-    cc.g_ox = (float)(xs[0] - sp.g_x0);
-    cc.g_oy = (float)(xs[1] - sp.g_y0);
+    cc.g_ox = (float)((xs[0] - sp.g_x0) * (double)ls.sq);
+    cc.g_oy = (float)((xs[1] - sp.g_y0) * (double)ls.sq);
     cc.w_obs_100 = ls.w_obs_100;
     cc.gW = sp.gW;
     cc.gH = sp.gH;
@@ -207,8 +231,10 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
   float sth0, cth0;
   Math<R>::sincos_(lc.th0, sth0, cth0);
   int* ezrow = ezw + (size_t)warp * T * 2;   // this warp's [T][2] slots
+  RTS(1);
   mbar_wait(bar, 0);
   __syncthreads();
+  RTS(2);
 
   const bool multi_tile = a.ntiles > nCTA;
   // floor sums leave in the 2^-20 units of the generic kernel (kZFixScale), so the reduce kernels see one format
@@ -231,13 +257,17 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
     // one model step + running cost + prefix store (control/src/mppi:147-161); z0, z1 = the step's standard normals
     auto one_step = [&](const float4 n, float z0, float z1, int& q0, int& q1, int row) {
       // floor-term sums: exact fixed point (2^-18), one warp integer add (REDUX, warp-uniform result) per channel
+#ifdef MPPI_EXP_NOREDUX   // measurement only (profiles/variants.py): what the floor-term sums cost -- NOT a product path
+      q0 = q1 = 0;
+#else
       q0 = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(z0, qscale, kLeanMagic)));
       q1 = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(z1, qscale, kLeanMagic)));
-      // u_samp = clip(U[:,t] + eps), eps = std * z   (:147-152; eps itself stays unclipped)
-      const float u0 = fminf(fmaxf(fmaf(lc.std0, z0, n.x), -lc.um0), lc.um0);
-      const float u1 = fminf(fmaxf(fmaf(lc.std1, z1, n.y), -lc.um1), lc.um1);
+#endif
+      // u_samp = clip(U[:,t] + eps), eps = std * z, in clip units: one FFMA.SAT each (:147-152; eps itself stays unclipped)
+      const float s0 = __saturatef(fmaf(lc.k0, z0, n.x));
+      const float s1 = __saturatef(fmaf(lc.k1, z1, n.y));
       float ah, g;
-      lean_controls<MODEL>(lc, u0, u1, ah, g, th);
+      lean_controls<MODEL>(lc, s0, s1, ah, g, th);
       float sa, ca;
       sincos_tiny(ah, sa, ca);
       if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {           // euler, :57-58: position with the OLD heading
@@ -254,11 +284,11 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
         cth = fmaf(c2, ca, -(s2 * sa));
         sth = fmaf(s2, ca, c2 * sa);
       }
-      // get_cost in delta form (:180-184; common.cuh running_cost), increments summed before they meet acc
+      // get_cost in delta form and cost units (:180-184; common.cuh running_cost), increments summed before they meet acc
       float c = n.w * z1;
       c = fmaf(n.z, z0, c);
-      c = fmaf(lc.hqx * dx, dx + lc.ax2, c);
-      c = fmaf(lc.hqy * dy, dy + lc.ay2, c);
+      c = fmaf(dx, dx + lc.ax2, c);
+      c = fmaf(dy, dy + lc.ay2, c);
       if (HAS_GRID) c += lean_grid_cost(cc, cells, dx, dy);
       acc += c;
       prow[row * PS] = acc;
@@ -281,11 +311,10 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
         *reinterpret_cast<int4*>(ezrow + 2 * t4 + 4) = qb;
       }
       prow += 4 * PS;
-      // keep (cos, sin) on the unit circle and theta in (-pi, pi]
+      // keep (cos, sin) on the unit circle
       const float f = fmaf(fmaf(cth, cth, sth * sth), -0.5f, 1.5f);
       cth *= f;
       sth *= f;
-      th = wrap_rint(th);
     }
     if (t4 < T) {   // T = 4n + 2: one more pair
       const float4* nl = nomL + t4;
@@ -293,16 +322,20 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
       one_step(nl[0], za.x, za.y, qa.x, qa.y, 0);
       one_step(nl[1], za.z, za.w, qa.z, qa.w, 1);
       if (lane == 0) *reinterpret_cast<int4*>(ezrow + 2 * t4) = qa;
-      th = wrap_rint(th);
     }
+    RTS(3);
+    // rk4 wraps theta into (-pi, pi] after every step (:52-53): theta_T is the angle of the carried pair
+    if (MODEL != MPPI_MODEL_UNICYCLE_EULER) th = atan2f(sth, cth);
     cc.gth2 = post[0];
     acc += terminal_cost<R>(cc, dx, dy, th);                                 // :165-171
     if (!valid) acc = Math<R>::inf();
     // PDL: the reduce kernel may start getting resident now (it still waits for this grid to complete)
     if (tile + nCTA >= a.ntiles) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    RTS(4);
     prow[(T - 1 - t4) * PS] = acc;   // row T holds the rollout total Tot[k] (addressed from the running row pointer: the
                                      // tile-invariant form P + T*PS + tid gets hoisted and spilled)
     __syncthreads();
+    RTS(5);
 
     // ---- transposed pass: lane l of warp w owns row t = 32*(w + NW*i) + l ----------------------
     const R neg_inv_lam = post[1];
@@ -316,6 +349,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
                                        lc.std1, step, direct, f0, f1);
       }
     }
+    RTS(6);
     if (multi_tile) {   // a persistent CTA folds its per-tile sums into 64-bit accumulators
       __syncthreads();
       for (int i = tid; i < 2 * T; i += BLOCK) ez64[i] += tile_floor_sum(i);

@@ -11,13 +11,15 @@
 #define ITER 2048
 
 enum Op { FFMA3, FFMA_IMM, FMUL_, FADD_, IMADW, LOP3_, FMNMX_, SEL_, MUFU_LG2, MUFU_SQRT, MUFU_SIN, MUFU_COS, MUFU_EX2, MUFU_RCP,
-          MUFU_RSQ, I2FP_, F2I_, FRND_, REDUX_, SHFL_, MIX_FFMA_LOP3, MIX_FFMA_FMNMX, MIX_FFMA_MUFU, LDS128_BCAST, NOPS };
+          MUFU_RSQ, I2FP_, F2I_, FRND_, REDUX_, SHFL_, MIX_FFMA_LOP3, MIX_FFMA_FMNMX, MIX_FFMA_MUFU, LDS128_BCAST, PHILOX_RND, IMAD_LO, IMAD_HI, MIX_FFMA_IMADW, MIX_FFMA3_IMADW, MIX_LOP3_IMADW, FFMA_SAT, NOPS };
 static const char* names[] = {"FFMA (3 registers)", "FFMA (immediate/const operands)", "FMUL", "FADD", "IMAD.WIDE.U32", "LOP3 (xor3)", "FMNMX",
                               "SEL", "MUFU.LG2", "sqrt.approx (MUFU.SQRT/RSQ)", "sin.approx (FMUL+MUFU.SIN)", "cos.approx (FMUL+MUFU.COS)",
                               "MUFU.EX2", "MUFU.RCP", "MUFU.RSQ", "I2FP.F32.U32", "F2I (rn)", "FRND (rint)", "REDUX.SUM",
                               "SHFL.BFLY", "FFMA + LOP3 interleaved (1:1)", "FFMA + FMNMX interleaved (1:1)", "FFMA + MUFU.LG2 (3:1)",
-                              "LDS.128 broadcast"};
-static const int ops_per_iter[] = {8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 16, 16, 8, 8};
+                              "LDS.128 broadcast", "Philox half-round (IMAD.WIDE + LOP3)", "IMAD (32-bit low)", "IMAD.HI.U32",
+                              "FFMA + (IMAD.WIDE+LOP3) interleaved (1:1:1)", "3 FFMA + (IMAD.WIDE+LOP3)", "LOP3 + (IMAD.WIDE+LOP3)",
+                              "FFMA.SAT"};
+static const int ops_per_iter[] = {8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 16, 16, 8, 8, 16, 8, 8, 24, 40, 24, 8};
 
 template <int OP>
 __global__ void __launch_bounds__(1024, 1) bench(float* out, long long* cycles, float seed, int iseed) {
@@ -64,6 +66,13 @@ __global__ void __launch_bounds__(1024, 1) bench(float* out, long long* cycles, 
         if (i % 4 == 3) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
         else a[i] = fmaf(a[i], b2, c2);
       }
+      if (OP == PHILOX_RND) { const unsigned long long p = (unsigned long long)u[i] * 0xD2511F53u; u[i] = (unsigned)(p >> 32) ^ (unsigned)p ^ (unsigned)iseed; }
+      if (OP == IMAD_LO) u[i] = u[i] * 0xD2511F53u + (unsigned)iseed;
+      if (OP == IMAD_HI) u[i] = __umulhi(u[i], 0xD2511F53u) + (unsigned)iseed;
+      if (OP == MIX_FFMA_IMADW) { a[i] = fmaf(a[i], b2, c2); const unsigned long long p = (unsigned long long)u[i] * 0xD2511F53u; u[i] = (unsigned)(p >> 32) ^ (unsigned)p ^ (unsigned)iseed; }
+      if (OP == MIX_FFMA3_IMADW) { a[i] = fmaf(a[i], b2, c2); a[i] = fmaf(a[i], c2, b2); a[i] = fmaf(a[i], b2, c2); const unsigned long long p = (unsigned long long)u[i] * 0xD2511F53u; u[i] = (unsigned)(p >> 32) ^ (unsigned)p ^ (unsigned)iseed; }
+      if (OP == MIX_LOP3_IMADW) { u[(i + 4) & 7] = u[(i + 4) & 7] ^ u[(i + 5) & 7] ^ (unsigned)it; const unsigned long long p = (unsigned long long)u[i] * 0xD2511F53u; u[i] = (unsigned)(p >> 32) ^ (unsigned)p ^ (unsigned)iseed; }
+      if (OP == FFMA_SAT) a[i] = __saturatef(fmaf(a[i], b2, c2));
       if (OP == LDS128_BCAST) { float4 v = sm4[(it + i) & 63]; a[i] += v.x + v.w; }
     }
   }
@@ -122,5 +131,12 @@ int main() {
   run<MIX_FFMA_FMNMX>(nsm, out, cyc);
   run<MIX_FFMA_MUFU>(nsm, out, cyc);
   run<LDS128_BCAST>(nsm, out, cyc);
+  run<PHILOX_RND>(nsm, out, cyc);
+  run<IMAD_LO>(nsm, out, cyc);
+  run<IMAD_HI>(nsm, out, cyc);
+  run<MIX_FFMA_IMADW>(nsm, out, cyc);
+  run<MIX_FFMA3_IMADW>(nsm, out, cyc);
+  run<MIX_LOP3_IMADW>(nsm, out, cyc);
+  run<FFMA_SAT>(nsm, out, cyc);
   return 0;
 }

@@ -18,7 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
-from oracle import ref_loader  # noqa: E402
+from oracle import ref_controller, ref_loader  # noqa: E402
 
 CASES = [
     # name,            K,    T,   x0,              goal,             iters, store_big
@@ -64,6 +64,46 @@ def run_case(name, K, T, x0, goal, iters, store_big):
     print(name, "u0[0] =", repr(u0s[0]))
 
 
+# the caller of the hot path: the reference ROS node (control/src/mppi:296-389) driven without ROS (oracle/ref_controller.py)
+CONTROLLER_CASES = [
+    # name,                   waypoints ("waypoints" ROS parameter; None = parallel park), K,  T, pose0,           callbacks
+    ("waypoints_k32_t16", [[0.1, 0.0], [0.1, 0.1], [0.0, 0.0]], 32, 16, (0.0, 0.0, 0.0), 100),
+    ("park_k32_t16", None, 32, 16, (0.0, -0.93, 0.4), 60),
+]
+
+
+def unicycle_plant(pose0, dt):
+    """Constant-twist arc over dt (the simulated robot of control/launch/mppi_pentagon.launch; generator-side copy so the
+    fixture does not depend on product code)."""
+    import math
+    st = {"p": np.array(pose0, dtype=np.float64)}
+
+    def step(vx, wz):
+        x, y, th = st["p"]
+        a = wz * dt
+        if abs(a) < 1e-12:
+            x += vx * dt * math.cos(th)
+            y += vx * dt * math.sin(th)
+        else:
+            r = vx / wz
+            x += r * (math.sin(th + a) - math.sin(th))
+            y -= r * (math.cos(th + a) - math.cos(th))
+        th = math.atan2(math.sin(th + a), math.cos(th + a))
+        st["p"] = np.array([x, y, th])
+        return st["p"]
+    return step
+
+
+def run_controller_case(name, waypoints, K, T, pose0, n):
+    ref, node, log = ref_controller.load_node(waypoints, dict(horizon=T, samples=K))
+    # the noise is NOT stored: it is the legacy global NumPy stream seeded with 0 at module load (control/src/mppi:15),
+    # T draws of shape (2,K) per get_path (:143-146) -- the tests re-draw it (MPPI.draw_noise) callback by callback
+    poses, twists, flags, nominal = ref_controller.run_node(node, unicycle_plant(pose0, 1.0 / T), pose0, n)
+    np.savez_compressed(os.path.join(HERE, "node_%s.npz" % name), K=K, T=T, waypoints=np.array(waypoints if waypoints else []),
+                        poses=poses, twists=twists, flags=flags, nominal=nominal, uvec_rows=node.mppi.uvec.shape[0], n_log=len(log), numpy_version=np.__version__)
+    print(name, "final flags", flags[-1], "any done", int(flags[:, 2].max()), "max idx", int(flags[:, 0].max()), "last twist", twists[-1])
+
+
 def rng_kat():
     np.random.seed(0)
     a = np.random.normal(size=4)
@@ -74,6 +114,11 @@ def rng_kat():
 if __name__ == "__main__":
     if ref_loader.available() != "source":
         sys.exit("needs /root/reference (build container only)")
-    for c in CASES:
-        run_case(*c)
-    rng_kat()
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only in ("", "mppi"):
+        for c in CASES:
+            run_case(*c)
+        rng_kat()
+    if only in ("", "controller"):
+        for c in CONTROLLER_CASES:
+            run_controller_case(*c)
