@@ -46,6 +46,7 @@ static void set_err(const char* fmt, ...) {
 struct KindCfg {
   int variant = ROLLOUT_GENERAL;
   int block = 0, grid = 0, ntiles = 0, ctas_per_sm = 0, regs = 0;
+  int nparts = 0;   // partial records per time step the rollout kernel writes (== grid, or 7 per CTA for the SM-wide kernel)
   size_t smem = 0;
   bool ready = false;
 };
@@ -77,6 +78,7 @@ struct mppi_engine {
   float4* d_cand_meta = nullptr;
   uint2* d_cand = nullptr;
   size_t part_capacity_ctas = 0;
+  int lean_split = 0;   // MPPI_B200_SPLIT: first step of the second pair of warps of the SM-wide kernel's shared tile (0 = default)
   signed char* d_grid = nullptr;
   double* d_eps_ext = nullptr;
   void* d_vcap = nullptr;
@@ -209,22 +211,25 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
     KindCfg best;
     double best_cost = 1e300;
     const int variant = !fast ? ROLLOUT_GENERAL : ((lean && kind != ROLLOUT_F64_SOFTMIN) ? ROLLOUT_LEAN : ROLLOUT_FAST);
-    int shapes[2], nshapes = 0;
+    int shapes[3], nshapes = 0;
     if (variant == ROLLOUT_GENERAL) {
       shapes[nshapes++] = 64;
-    } else if (envb && (atoi(envb) == 64 || atoi(envb) == 128)) {
+    } else if (envb && (atoi(envb) == 64 || atoi(envb) == 128 || (atoi(envb) == 512 && variant == ROLLOUT_LEAN))) {
       shapes[nshapes++] = atoi(envb);
     } else {
       shapes[nshapes++] = 64;
       shapes[nshapes++] = 128;
+      if (variant == ROLLOUT_LEAN) shapes[nshapes++] = 512;
     }
     for (int si = 0; si < nshapes; ++si) {
       const int block = shapes[si];
       KindCfg c;
       c.variant = variant;
       c.block = block;
-      const int rollouts = block;
+      const bool sm_wide = block == 512;   // rollout_lean_sm_kernel: 7 tiles of 64 per CTA, at most one CTA per SM
+      const int rollouts = sm_wide ? 64 * 7 : block;
       c.ntiles = (sp.K + rollouts - 1) / rollouts;
+      if (sm_wide && c.ntiles > e->num_sms) continue;
       c.smem = rollout_smem(kind, sp.T, block, variant, gin);
       if (c.smem > 227 * 1024) continue;
       cudaError_t ce = rollout_prepare(kind, sp.model, has_grid, block, variant, c.smem, &c.ctas_per_sm, &c.regs);
@@ -234,8 +239,14 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
       }
       const long long resident = (long long)e->num_sms * c.ctas_per_sm;
       c.grid = (int)((c.ntiles < resident) ? c.ntiles : resident);
-      // busiest-SM thread-work: tiles are dealt round-robin over the SMs
-      const double cost = (double)((c.ntiles + e->num_sms - 1) / e->num_sms) * rollouts;
+      c.nparts = sm_wide ? (sp.K + 63) / 64 : c.grid;
+      // the kernel is issue bound and ends with its busiest scheduler: cost = warps' worth of T-step loops on the busiest
+      // scheduler of the busiest SM (tiles are dealt round-robin over the SMs, a CTA's warps over the four schedulers);
+      // the SM-wide kernel cuts its seventh tile in time and carries 3.5 on every scheduler
+      const int tiles_per_sm = (c.ntiles + e->num_sms - 1) / e->num_sms;
+      const double sched = sm_wide ? 3.5 : (double)((tiles_per_sm * (block / 32) + 3) / 4);
+      // ties: less thread-work on the busiest SM, then the larger tile
+      const double cost = sched * 1e6 + (double)tiles_per_sm * rollouts;
       c.ready = true;
       if (cost < best_cost || (cost == best_cost && block > best.block)) {
         best = c;
@@ -243,7 +254,7 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
       }
     }
     e->cfg[kind] = best;
-    if (best.ready && (size_t)best.grid > *max_ctas) *max_ctas = best.grid;
+    if (best.ready && (size_t)best.nparts > *max_ctas) *max_ctas = best.nparts;
   }
   return e->cfg[kind_of(e->p.precision)].ready && e->cfg[ROLLOUT_F64_SOFTMIN].ready;
 }
@@ -433,6 +444,7 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
   memset(e->h_res, 0, sizeof(HostResult));
   CKF(cudaHostGetDevicePointer((void**)&e->d_res, e->h_res, 0));
   if (const char* w = getenv("MPPI_B200_WAIT")) e->wait_block = !strcmp(w, "block");
+  if (const char* w = getenv("MPPI_B200_SPLIT")) e->lean_split = atoi(w);
   CKF(cudaMemset(e->d_Umaster, 0, 2 * T * sizeof(double)));     // uvec_init = zeros, control/src/mppi:65
   CKF(cudaMemset(e->d_Ulast, 0, 2 * T * sizeof(double)));
   CKF(cudaMemset(e->d_record, 0, (size_t)T * kRecordStride * sizeof(double)));
@@ -713,7 +725,7 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   ra.cand_meta = e->d_cand_meta;
   ra.cand = e->d_cand;
   ra.vcap = e->d_vcap;
-  ra.ntiles = c.ntiles;
+  ra.ntiles = (c.block == 512) ? c.nparts : c.ntiles;   // SM-wide kernel: the number of 64-rollout tiles
   if (in) ra.in = *in;
   ra.debug_ts = e->d_debug_rts;
   if (c.variant == ROLLOUT_LEAN) {
@@ -757,6 +769,7 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
     ls.g_inv_res = (float)(sp.g_inv_res / sq);
     ls.w_obs_100 = (float)(sp.w_obs / 100.0);
     ls.margin = (float)sp.margin;
+    ls.split = e->lean_split > 0 ? e->lean_split : ((sp.T * 9 / 16 + 3) & ~3);
     for (int i = 0; i < MPPI_PHILOX_ROUNDS; ++i) {
       ls.pkx[i] = (uint32_t)sp.seed + (uint32_t)i * 0x9E3779B9u;
       ls.pky[i] = (uint32_t)(sp.seed >> 32) + (uint32_t)i * 0xBB67AE85u;
@@ -794,7 +807,7 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   rd.grid = e->d_grid;
   rd.eps_ext = e->d_eps_ext;
   rd.record = e->d_record;
-  rd.nCTA = c.grid;
+  rd.nCTA = c.nparts;
   if (kind == ROLLOUT_F32_SCREEN)
     CK(reduce_screen_launch(e->sp.model, e->sp.has_grid != 0, e->sp.T, st, rd));
   else
@@ -1324,7 +1337,7 @@ extern "C" mppi_status mppi_debug_rollout_timestamps(mppi_handle e, unsigned lon
   ENTER(e);
   CK(cudaStreamSynchronize(e->stream));
   if (!e->d_debug_rts) {
-    e->debug_rts_ctas = e->part_capacity_ctas;
+    e->debug_rts_ctas = e->part_capacity_ctas;   // one row per partial record (CTA, or tile of the SM-wide kernel)
     CK(cudaMalloc(&e->d_debug_rts, e->debug_rts_ctas * 8 * sizeof(unsigned long long)));
     CK(cudaMemset(e->d_debug_rts, 0, e->debug_rts_ctas * 8 * sizeof(unsigned long long)));
     drop_graphs(e);
@@ -1367,7 +1380,7 @@ extern "C" mppi_status mppi_launch_info(mppi_handle e, int32_t info[8]) {
   info[4] = c.ctas_per_sm;
   info[5] = c.regs;
   info[6] = c.variant;
-  info[7] = 0;
+  info[7] = c.nparts;
   return MPPI_OK;
 }
 

@@ -54,6 +54,7 @@ cudaError_t rollout_launch(int kind, int model, bool has_grid, int block, int va
 }
 
 size_t rollout_smem(int kind, int T, int block, int variant, int grid_bytes_in_smem) {
+  if (variant == ROLLOUT_LEAN && block == 512) return rollout_lean_sm_smem_bytes(T, grid_bytes_in_smem);
   if (variant == ROLLOUT_LEAN) return rollout_lean_smem_bytes(T, block, grid_bytes_in_smem);
   return kind == ROLLOUT_F64_SOFTMIN ? rollout_smem_bytes<double>(T, block, grid_bytes_in_smem)
                                      : rollout_smem_bytes<float>(T, block, grid_bytes_in_smem);

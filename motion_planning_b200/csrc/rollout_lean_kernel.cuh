@@ -370,6 +370,291 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
   }
 }
 
+// ---- SM-wide balanced variant (one CTA of 16 warps per SM) -----------------------------------------------------------
+// The T-step loop is issue bound and a warp's rate is 1 / (warps on its scheduler), so the kernel ends when the
+// busiest scheduler does.  BASELINE config 2 puts 65536 / 148 = 13.8 warps on an SM: with independent 64-thread CTAs
+// the four schedulers hold 4, 4, 3, 3 warps and the two with three idle a quarter of the time (measured with the
+// %globaltimer stamps of profiles/rollout_timeline.py: loop 12.2 us on the 3-warp schedulers, 16.7 us on the 4-warp
+// ones).  Here one CTA owns the whole SM and the 14th/13th warp's work is CUT IN TIME: warps 0-11 (three per
+// scheduler) roll six tiles of 64 rollouts as before; the seventh tile is rolled by warps 12, 13 (schedulers 0, 1) for
+// the steps [0, split) and by warps 14, 15 (schedulers 2, 3) for [split, T), the rollout state (6 floats) handed over
+// through shared memory under a named barrier.  Every scheduler now carries 3.5 warps' worth of steps.
+// Each tile keeps its own cost tile / partial record, so the reduce kernels see 7 partials per CTA in the usual format.
+constexpr int kSmFullTiles = 6;
+constexpr int kSmTiles = kSmFullTiles + 1;
+constexpr int kSmThreads = 64 * (kSmFullTiles + 2);   // 512
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__host__ __device__ inline size_t rollout_lean_sm_tile_bytes(int T) {   // per-tile shared memory of the SM-wide kernel
+  size_t off = (size_t)T * sizeof(float4);          // run
+  off += (size_t)2 * T * 2 * sizeof(int);           // per-warp floor sums
+  off += (size_t)T * sizeof(int);                   // SCREEN counts
+  off = (off + 15) & ~(size_t)15;
+  off += (size_t)(T + 1) * (64 + 4) * sizeof(float);   // cost tile
+  return (off + 15) & ~(size_t)15;
+}
+
+template <int MODEL, int MODE, bool HAS_GRID>
+__global__ void __launch_bounds__(kSmThreads, 1) rollout_lean_sm_kernel(const __grid_constant__ RolloutArgs a) {
+  typedef float R;
+  typedef float4 Vec4;
+  constexpr int BLOCK = 64;
+  constexpr int PS = CostTile<R, BLOCK>::PS;
+  const StaticParams& sp = a.sp;
+  const int T = sp.T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // role 0: a full rollout; role 1: steps [0, split) of the shared tile; role 2: steps [split, T) of the shared tile
+  const int sub = (warp < 2 * kSmFullTiles) ? (warp >> 1) : kSmFullTiles;
+  const int role = (warp < 2 * kSmFullTiles) ? 0 : ((warp < 2 * kSmFullTiles + 2) ? 1 : 2);
+  const int wslot = warp & 1;
+  const int col = wslot * 32 + lane;                       // this thread's rollout within its tile
+  const int vtile = blockIdx.x * kSmTiles + sub;           // tile index == partial-record index
+  const int nvt = a.ntiles;                                // tiles that hold rollouts = ceil(K / 64); the last CTA may own fewer than 7
+
+#ifdef MPPI_EXP_TIMELINE
+#define RTS2(slot)                                                                 \
+  do {                                                                             \
+    if (a.debug_ts && col == 0 && role != 1) {                                     \
+      unsigned long long t_;                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                       \
+      a.debug_ts[(size_t)vtile * 8 + (slot)] = t_;                                 \
+    }                                                                              \
+  } while (0)
+  if (a.debug_ts && col == 0 && role != 1) {
+    unsigned int smid_;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));
+    a.debug_ts[(size_t)vtile * 8 + 7] = smid_;
+  }
+#else
+#define RTS2(slot) do { } while (0)
+#endif
+  RTS2(0);
+  // ---- shared memory carve-up ------------------------------------------------------------------
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  float* post = reinterpret_cast<float*>(smem_raw + 8);
+  float4* nomL = reinterpret_cast<float4*>(smem_raw + 16);
+  size_t off = 16 + (size_t)T * sizeof(float4);
+  float* hand = reinterpret_cast<float*>(smem_raw + off);                     // [6][64] hand-over of the shared tile
+  off += (size_t)6 * BLOCK * sizeof(float);
+  const size_t tile_bytes = rollout_lean_sm_tile_bytes(T);
+  unsigned char* tbase = smem_raw + off + (size_t)sub * tile_bytes;
+  Vec4* run = reinterpret_cast<Vec4*>(tbase);
+  int* ezw = reinterpret_cast<int*>(tbase + (size_t)T * sizeof(Vec4));        // [2][T][2]
+  int* ccount = ezw + 2 * T * 2;
+  R* P = reinterpret_cast<R*>(tbase + ((((size_t)T * sizeof(Vec4) + (size_t)2 * T * 2 * sizeof(int) + (size_t)T * sizeof(int)) + 15) & ~(size_t)15));
+  signed char* gcells = reinterpret_cast<signed char*>(smem_raw + off + (size_t)kSmTiles * tile_bytes);
+
+  // ---- prologue ---------------------------------------------------------------------------------
+  const uint32_t nom_bytes = (uint32_t)(T * sizeof(float4));
+  const bool grid_smem = HAS_GRID && sp.grid_in_smem;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, nom_bytes + (grid_smem ? (uint32_t)sp.grid_bytes_padded : 0u));
+    tma_bulk_g2s(nomL, a.nom, nom_bytes, bar);
+    if (grid_smem) tma_bulk_g2s(gcells, a.grid, (uint32_t)sp.grid_bytes_padded, bar);
+  }
+  if (role != 1) {   // the tile's 64 finishing threads initialise its records (the shared tile: warps 14, 15)
+    for (int t = col; t < T; t += BLOCK) {
+      run[t] = make_float4(Math<R>::inf(), (MODE == MODE_SCREEN) ? Math<R>::inf() : 0.f, 0.f, 0.f);
+      ccount[t] = 0;
+    }
+    for (int k = col; k < PS; k += BLOCK) P[k] = 0.f;
+  }
+  const DynState* __restrict__ ds = a.dyn;
+  const unsigned int step = ds->step;
+  const R neg_inv_lam_ld = ds->neg_inv_lam_f;
+  const float std0_f = ds->noise_std_f[0], std1_f = ds->noise_std_f[1];
+  double xs[3], gs[3];
+  load_step_input(a.in, ds, xs, gs);
+  LeanConsts lc;
+  CostConsts<R> cc;
+  {
+    const LeanStatic& ls = a.lean;
+    lc.A0 = ls.A0;
+    lc.A1 = ls.A1;
+    lc.Ac = ls.Ac;
+    lc.G0 = ls.G0;
+    lc.G1 = ls.G1;
+    lc.Gc = ls.Gc;
+    lc.um0 = ls.um0;
+    lc.um0x2 = 2.0f * ls.um0;
+    lc.um1 = ls.um1;
+    lc.um1x2 = 2.0f * ls.um1;
+    lc.bk = ls.bk;
+    lc.k0 = std0_f * ls.inv2um0;
+    lc.k1 = std1_f * ls.inv2um1;
+    lc.std0 = std0_f;
+    lc.std1 = std1_f;
+    lc.ax2 = (float)(2.0 * (xs[0] - gs[0]) * (double)ls.sq);
+    lc.ay2 = (float)(2.0 * (xs[1] - gs[1]) * (double)ls.sq);
+    lc.th0 = (float)xs[2];
+    cc.hqx = 1.f;
+    cc.hqy = 1.f;
+    cc.hqth = 0.f;
+    cc.p1x = ls.p1x;
+    cc.p1y = ls.p1y;
+    cc.p1th = ls.p1th;
+    cc.ax2 = lc.ax2;
+    cc.ay2 = lc.ay2;
+    cc.th0 = lc.th0;
+    cc.gth2 = 0.f;
+    if (tid == 0) {
+      post[0] = (float)(2.0 * gs[2]);
+      post[1] = neg_inv_lam_ld;
+    }
+    cc.g_inv_res = ls.g_inv_res;
+    cc.g_ox = (float)((xs[0] - sp.g_x0) * (double)ls.sq);
+    cc.g_oy = (float)((xs[1] - sp.g_y0) * (double)ls.sq);
+    cc.w_obs_100 = ls.w_obs_100;
+    cc.gW = sp.gW;
+    cc.gH = sp.gH;
+  }
+  const R margin = a.lean.margin;
+  const signed char* cells = grid_smem ? gcells : a.grid;
+  const bool cost_to_go = sp.weighting == MPPI_WEIGHT_COST_TO_GO;
+  int split = a.lean.split & ~3;                           // first step of the second part (a multiple of 4)
+  split = max(4, min(split, (T - 1) & ~3));
+  const int t_begin = (role == 2) ? split : 0;
+  const int t_end = (role == 1) ? split : T;
+  const int k_local = vtile * BLOCK + col;
+  const bool valid = k_local < sp.K;
+  const unsigned long long kglobal = (unsigned long long)(sp.k_offset + k_local);
+  const float qscale = valid ? kLeanFixScale : 0.f;
+  // the first normals of this warp's range, drawn before anything is waited for
+  float4 za = lean_normal4(a.lean, kglobal, (unsigned)(t_begin >> 1), step);
+  float4 zb = lean_normal4(a.lean, kglobal, (unsigned)(t_begin >> 1) + 1u, step);
+  R dx = 0.f, dy = 0.f, th = lc.th0, acc = 0.f, cth, sth;
+  Math<R>::sincos_(lc.th0, sth, cth);
+  int* ezrow = ezw + (size_t)wslot * T * 2;
+  RTS2(1);
+  mbar_wait(bar, 0);
+  __syncthreads();
+  RTS2(2);
+  if (vtile >= nvt) {   // a tile past the last rollout (last CTA only): nothing to roll, no record to write
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    return;
+  }
+  if (role == 2) {   // take over the rollouts warps 12, 13 have advanced to `split`
+    named_bar_sync(1, 128);
+    dx = hand[0 * BLOCK + col];
+    dy = hand[1 * BLOCK + col];
+    cth = hand[2 * BLOCK + col];
+    sth = hand[3 * BLOCK + col];
+    acc = hand[4 * BLOCK + col];
+    th = hand[5 * BLOCK + col];
+  }
+  R* prow = P + (size_t)(1 + t_begin) * PS + col;          // row 1 + t of this rollout's column
+
+  auto one_step = [&](const float4 n, float z0, float z1, int& q0, int& q1, int row) {
+    q0 = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(z0, qscale, kLeanMagic)));
+    q1 = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(z1, qscale, kLeanMagic)));
+    const float s0 = __saturatef(fmaf(lc.k0, z0, n.x));
+    const float s1 = __saturatef(fmaf(lc.k1, z1, n.y));
+    float ah, g;
+    lean_controls<MODEL>(lc, s0, s1, ah, g, th);
+    float sa, ca;
+    sincos_tiny(ah, sa, ca);
+    if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {
+      dx = fmaf(g, cth, dx);
+      dy = fmaf(g, sth, dy);
+      const float cn = fmaf(cth, ca, -(sth * sa));
+      sth = fmaf(sth, ca, cth * sa);
+      cth = cn;
+    } else {
+      const float c2 = fmaf(cth, ca, -(sth * sa)), s2 = fmaf(sth, ca, cth * sa);
+      const float h = g * fmaf(2.0f, ca, 4.0f);
+      dx = fmaf(h, c2, dx);
+      dy = fmaf(h, s2, dy);
+      cth = fmaf(c2, ca, -(s2 * sa));
+      sth = fmaf(s2, ca, c2 * sa);
+    }
+    float c = n.w * z1;
+    c = fmaf(n.z, z0, c);
+    c = fmaf(dx, dx + lc.ax2, c);
+    c = fmaf(dy, dy + lc.ay2, c);
+    if (HAS_GRID) c += lean_grid_cost(cc, cells, dx, dy);
+    acc += c;
+    prow[row * PS] = acc;
+  };
+  int t4 = t_begin;
+  for (; t4 + 4 <= t_end; t4 += 4) {
+    const float4 z0 = za, z1 = zb;
+    za = lean_normal4(a.lean, kglobal, (unsigned)(t4 >> 1) + 2u, step);   // one iteration ahead
+    zb = lean_normal4(a.lean, kglobal, (unsigned)(t4 >> 1) + 3u, step);
+    const float4* nl = nomL + t4;
+    int4 qa, qb;
+    one_step(nl[0], z0.x, z0.y, qa.x, qa.y, 0);
+    one_step(nl[1], z0.z, z0.w, qa.z, qa.w, 1);
+    one_step(nl[2], z1.x, z1.y, qb.x, qb.y, 2);
+    one_step(nl[3], z1.z, z1.w, qb.z, qb.w, 3);
+    if (lane == 0) {
+      *reinterpret_cast<int4*>(ezrow + 2 * t4) = qa;
+      *reinterpret_cast<int4*>(ezrow + 2 * t4 + 4) = qb;
+    }
+    prow += 4 * PS;
+    const float f = fmaf(fmaf(cth, cth, sth * sth), -0.5f, 1.5f);
+    cth *= f;
+    sth *= f;
+  }
+  if (role == 1) {   // hand the state to warps 14, 15 and leave
+    hand[0 * BLOCK + col] = dx;
+    hand[1 * BLOCK + col] = dy;
+    hand[2 * BLOCK + col] = cth;
+    hand[3 * BLOCK + col] = sth;
+    hand[4 * BLOCK + col] = acc;
+    hand[5 * BLOCK + col] = th;
+    __threadfence_block();
+    named_bar_arrive(1, 128);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    return;
+  }
+  if (t4 < T) {   // T = 4n + 2: one more pair
+    const float4* nl = nomL + t4;
+    int4 qa;
+    one_step(nl[0], za.x, za.y, qa.x, qa.y, 0);
+    one_step(nl[1], za.z, za.w, qa.z, qa.w, 1);
+    if (lane == 0) *reinterpret_cast<int4*>(ezrow + 2 * t4) = qa;
+  }
+  RTS2(3);
+  if (MODEL != MPPI_MODEL_UNICYCLE_EULER) th = atan2f(sth, cth);
+  cc.gth2 = post[0];
+  acc += terminal_cost<R>(cc, dx, dy, th);
+  if (!valid) acc = Math<R>::inf();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  RTS2(4);
+  prow[(T - 1 - t4) * PS] = acc;                             // row T: the rollout total
+  named_bar_sync(2 + sub, BLOCK);                            // the tile's two finishing warps
+  RTS2(5);
+
+  // ---- transposed pass of this tile: lane l of the tile's warp w owns row t = 32 w + l (+ 64 i) ----
+  constexpr double kToGeneric = kZFixScale / (double)kLeanFixScale;
+  const R neg_inv_lam = post[1];
+  for (int tb = wslot * 32; tb < T; tb += BLOCK) {
+    const int t = tb + lane;
+    if (t < T) {
+      const long long f0 = (long long)(int)((unsigned)ezw[2 * t] - kLeanBias32) + (long long)(int)((unsigned)ezw[2 * T + 2 * t] - kLeanBias32);
+      const long long f1 = (long long)(int)((unsigned)ezw[2 * t + 1] - kLeanBias32) + (long long)(int)((unsigned)ezw[2 * T + 2 * t + 1] - kLeanBias32);
+      transposed_row<R, MODE, BLOCK>(a, t, vtile, vtile, nvt, P, run, ccount, nullptr, cost_to_go, neg_inv_lam, margin, lc.std0, lc.std1,
+                                     step, true, (double)f0 * kToGeneric, (double)f1 * kToGeneric);
+    }
+  }
+  RTS2(6);
+}
+
+inline size_t rollout_lean_sm_smem_bytes(int T, int grid_bytes_padded_in_smem) {
+  size_t off = 16 + (size_t)T * sizeof(float4) + (size_t)6 * 64 * sizeof(float);
+  off += (size_t)kSmTiles * rollout_lean_sm_tile_bytes(T);
+  off += (size_t)grid_bytes_padded_in_smem;
+  return off + 128;
+}
+
 inline size_t rollout_lean_smem_bytes(int T, int block, int grid_bytes_padded_in_smem) {
   size_t off = 16 + (size_t)T * sizeof(float4);
   off += (size_t)T * sizeof(float4);               // run

@@ -66,6 +66,33 @@ class ShardedMPPI(object):
         k_local, k_offset = shard_plan(samples_total, self.world, self.rank)
         backend = dist.get_backend(group)
         self.exchange = exchange or ("p2p" if backend == "nccl" and self.world > 1 else "host")
+        self.horizon = horizon
+        self._engine_opts = dict(engine)
+        self._create_engine(k_local, k_offset)
+        if self.exchange == "p2p":
+            # every rank must end up on the same transport: agree on whether the peer mappings succeeded
+            ok = 1
+            try:
+                self._connect_p2p(backend)
+            except (_capi.MppiError, RuntimeError) as ex:
+                ok, self.p2p_error = 0, str(ex)
+            flag = torch.tensor([ok], dtype=torch.int32)
+            if backend == "nccl":
+                flag = flag.cuda()
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                # no peer access between some pair of GPUs (or IPC unavailable): fall back to the collective
+                self.mppi.close()
+                self.exchange = "nccl" if backend == "nccl" else "host"
+                self._create_engine(k_local, k_offset)
+            dist.barrier(group=group)
+        if self.exchange == "nccl":
+            self._rec_t = torch.as_tensor(_DevBuf(self._rec_ptr, self._n_rec), device="cuda")
+            self._gat_t = torch.as_tensor(_DevBuf(self._gat_ptr, self._n_rec * self.world), device="cuda")
+
+    def _create_engine(self, k_local, k_offset):
+        torch = self._torch
+        engine = dict(self._engine_opts)
         self.stream = None
         if self.exchange == "nccl":
             # a dedicated non-default stream: the engine launches its kernels on it and the NCCL collective
@@ -74,29 +101,32 @@ class ShardedMPPI(object):
             # "engine-owned stream")
             self.stream = torch.cuda.Stream()
             engine.setdefault("stream", self.stream.cuda_stream)
-        self.mppi = MPPI(horizon=horizon, samples=k_local, k_offset=k_offset, k_total=samples_total,
+        self.mppi = MPPI(horizon=self.horizon, samples=k_local, k_offset=k_offset, k_total=self.samples_total,
                          world_size=self.world, rank=self.rank, **engine)
-        self.horizon = horizon
         lib, h = self.mppi._lib, self.mppi._h
         rec, gat = C.c_void_p(), C.c_void_p()
         rb, gb = C.c_size_t(), C.c_size_t()
         _capi.check(lib.mppi_exchange_buffers(h, C.byref(rec), C.byref(rb), C.byref(gat), C.byref(gb)), "mppi_exchange_buffers")
         self._n_rec = rb.value // 8
-        if self.exchange == "p2p":
-            mine = (C.c_ubyte * 64)()
-            _capi.check(lib.mppi_p2p_export(h, C.cast(mine, C.c_void_p)), "mppi_p2p_export")
-            t = torch.tensor(list(bytes(mine)), dtype=torch.uint8)
-            if backend == "nccl":
-                t = t.cuda()
-            out = [torch.empty_like(t) for _ in range(self.world)]
-            dist.all_gather(out, t, group=group)
-            allh = bytes(torch.cat([o.cpu() for o in out]).tolist())
-            buf = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
-            _capi.check(lib.mppi_p2p_connect(h, C.cast(buf, C.c_void_p)), "mppi_p2p_connect")
-            dist.barrier(group=group)
-        if self.exchange == "nccl":
-            self._rec_t = torch.as_tensor(_DevBuf(rec.value, self._n_rec), device="cuda")
-            self._gat_t = torch.as_tensor(_DevBuf(gat.value, self._n_rec * self.world), device="cuda")
+        self._rec_ptr, self._gat_ptr = rec.value, gat.value
+
+    def _connect_p2p(self, backend):
+        """Map every peer's exchange buffer (CUDA IPC) so that the reduce kernel can store its record there."""
+        torch, dist, group = self._torch, self._dist, self.group
+        lib, h = self.mppi._lib, self.mppi._h
+        mine = (C.c_ubyte * 64)()
+        st = lib.mppi_p2p_export(h, C.cast(mine, C.c_void_p))
+        t = torch.tensor(list(bytes(mine)) + [0 if st == 0 else 1], dtype=torch.uint8)
+        if backend == "nccl":
+            t = t.cuda()
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t, group=group)         # every rank takes part, also one whose export failed
+        allb = torch.stack([o.cpu() for o in out])
+        if int(allb[:, 64].max()) != 0:
+            raise RuntimeError("mppi_p2p_export failed on a rank")
+        allh = bytes(allb[:, :64].reshape(-1).tolist())
+        buf = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
+        _capi.check(lib.mppi_p2p_connect(h, C.cast(buf, C.c_void_p)), "mppi_p2p_connect")
 
     def get_path(self, state, goal, sig=np.array([[.9, 0.0], [0.0, .9]]), lam=.001):
         """MPPI.get_path (control/src/mppi:85-102) with K sharded over the group."""

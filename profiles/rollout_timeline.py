@@ -18,7 +18,8 @@ T = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 m = mp.MPPI(horizon=T, samples=K, precision=prec, seed=0)
 goal = np.array([0.0, -1.0, 0.0])
 lib, h = m._lib, m._h
-n = m.launch_info()["grid"]
+li = m.launch_info()
+n = (K + 63) // 64 if li["block"] == 512 else li["grid"]   # stamps per partial record (tile)
 _capi.check(lib.mppi_debug_rollout_timestamps(h, None, 0), "arm rollout")
 _capi.check(lib.mppi_debug_reduce_timestamps(h, None), "arm reduce")
 s = np.zeros(3)
@@ -42,7 +43,11 @@ for flush in (False, True):
     ru, du = (r[:, :7] - t0) / 1e3, (d[:, :7] - t0) / 1e3
     smid = r[:, 7]
     q = lambda a: "min %.2f  p50 %.2f  p90 %.2f  max %.2f" % (a.min(), np.percentile(a, 50), np.percentile(a, 90), a.max())  # noqa: E731
-    print("%s K=%d T=%d grid=%d L2 %s; host-side mppi_step %.1f us" % (prec, K, T, n, "flushed" if flush else "warm", host_us))
+    print("%s K=%d T=%d block=%d records=%d L2 %s; host-side mppi_step %.1f us" % (prec, K, T, li["block"], n, "flushed" if flush else "warm", host_us))
+    if li["block"] == 512:
+        shared = np.arange(n) % 7 == 6
+        print("  shared (time-cut) tiles: loop end %s" % q(ru[shared, 3]))
+        print("  full tiles:              loop end %s" % q(ru[~shared, 3]))
     print("  CTA entry (after first)          ", q(ru[:, 0]))
     print("  prologue: entry -> loads issued  ", q(ru[:, 1] - ru[:, 0]))
     print("  prologue: loads -> barrier passed", q(ru[:, 2] - ru[:, 1]))
