@@ -230,7 +230,10 @@ def run_single(args):
     ms = r["step_ms"]
     value = K / (ms * 1e-3)
     achieved = F_ALG * K * T / (r["rollout_ms"] * 1e-3) / 1e12
-    hbm_alg_bytes = 16 * T * r["launch"]["grid"] * 3 + 16 * T     # per-CTA partials (m,S,N0,N1 + E) out, nominal in
+    nrec = r["launch"].get("records_per_step") or r["launch"]["grid"]
+    hbm_alg_bytes = 16 * T * nrec * 3 + 16 * T     # per-tile partial records (meta + floor sums + candidates) out, nominal in
+    kname = "rollout_lean_sm_kernel" if (r["launch"].get("variant") == "lean" and r["launch"]["block"] == 512) else \
+        "rollout_%s_kernel" % r["launch"].get("variant", "?")
     cpu = cpu_baseline_port() if not args.no_cpu else None
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
@@ -267,8 +270,9 @@ def run_single(args):
         "kernels_ms": {"rollout": r["rollout_ms"], "reduce": r["reduce_ms"], "finalize": r["finalize_ms"]},
         "roofline": {"bound": "fp32_alu", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
                      "frac": achieved / tf.value if tf.value else None, "traffic": traffic,
-                     "traffic_note": "DRAM bytes per launch from profiles/r01_ncu_summary.json (ncu --set full); the ~2 MB of per-CTA partials stay in L2",
-                     "kernel": "rollout_%s_kernel" % r["launch"].get("variant", "?"), "flop_per_state_step": F_ALG,
+                     "traffic_note": "DRAM bytes per launch from profiles/r01_ncu_summary.json (ncu --set full, caches flushed by ncu before the launch); "
+                                     "most of the ~3 MB of per-tile partial records stay in L2",
+                     "kernel": kname, "flop_per_state_step": F_ALG,
                      "peak_source": "FFMA chain measured in this run (mppi_measure_fp32_peak); MEASURED_PEAKS.json has no fp32 entry",
                      "hbm_view": {"algorithmic_bytes": hbm_alg_bytes,
                                   "achieved_GBps": hbm_alg_bytes / (r["rollout_ms"] * 1e-3) / 1e9,
@@ -292,8 +296,11 @@ def run_multi(args):
     from motion_planning_b200.distributed import ShardedMPPI
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    # rank 0 prints ONE JSON line on stdout: everything the libraries write there (NCCL's version banner is printed at
+    # every NCCL_DEBUG level but NONE) goes to stderr instead; the JSON line is written to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K_total, T = K_PER_GPU * world, T_HORIZON
@@ -375,7 +382,8 @@ def run_multi(args):
                     "d2h_bytes_per_step": io[1] * world, "ms_per_step": e2e_ms},
             "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     dist.barrier()
     dist.destroy_process_group()
 

@@ -405,6 +405,7 @@ class MPPI(object):
         _capi.check(self._lib.mppi_launch_info(self._h, info), "mppi_launch_info")
         d = dict(zip(["block", "grid", "tiles", "smem_bytes", "ctas_per_sm", "regs"], list(info)[:6]))
         d["variant"] = ("general", "fast", "lean")[info[6]]
+        d["records_per_step"] = info[7]     # partial records per time step (== grid, or one per 64-rollout tile of the SM-wide kernel)
         return d
 
     def bench(self, x0, steps=20, warmup=3, flush_l2=True, per_kernel=True):
