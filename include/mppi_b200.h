@@ -222,6 +222,11 @@ MPPI_API mppi_status mppi_debug_reduce_timestamps(mppi_handle h, unsigned long l
  * stored, barrier passed, tile done, SM id.  The first call (out may be NULL) arms the stamps. */
 MPPI_API mppi_status mppi_debug_rollout_timestamps(mppi_handle h, unsigned long long* out, size_t n_ctas);
 
+/* Profiling aid: mean host-side duration (us) of the phases of mppi_step since the previous call of this function:
+ * out[0] entry -> rollout kernel launched, [1] -> reduce kernel launched, [2] -> result seen in mapped host memory,
+ * [3] -> return. */
+MPPI_API mppi_status mppi_debug_host_timing(mppi_handle h, double out[4]);
+
 MPPI_API const char* mppi_last_error(void);
 MPPI_API const char* mppi_version(void);
 MPPI_API int32_t mppi_device_count(void);

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "mppi_debug_flush_l2": [_H],
     "mppi_debug_reduce_timestamps": [_H, C.POINTER(C.c_uint64)],
     "mppi_debug_rollout_timestamps": [_H, C.POINTER(C.c_uint64), C.c_size_t],
+    "mppi_debug_host_timing": [_H, _dp],
     "mppi_last_error": [],
     "mppi_version": [],
     "mppi_device_count": [],

@@ -8,6 +8,7 @@
 
 #include <atomic>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -78,6 +79,16 @@ struct mppi_engine {
   float4* d_cand_meta = nullptr;
   uint2* d_cand = nullptr;
   size_t part_capacity_ctas = 0;
+  // host-side phases of mppi_step (profiling aid, mppi_debug_host_timing): entry -> rollout launched -> reduce launched
+  // -> result seen -> return, accumulated in nanoseconds
+  double host_ns[4] = {0, 0, 0, 0};
+  long long host_calls = 0;
+  std::chrono::steady_clock::time_point tp_launch1, tp_launch2;
+  // MIXED back-off: after a candidate-list overflow (the soft-min support has grown beyond what the fp32 screen lists,
+  // typically within centimetres of the goal) the next `f64_holdoff` steps go straight to the fp64 pipeline instead of
+  // paying for a doomed mixed attempt plus its redo; the hold-off doubles (8 .. 64 steps) while overflows persist
+  int f64_holdoff = 0, f64_backoff = 8;
+  bool attempted_mixed = false;
   int lean_split = 0;   // MPPI_B200_SPLIT: first step of the second pair of warps of the SM-wide kernel's shared tile (0 = default)
   signed char* d_grid = nullptr;
   double* d_eps_ext = nullptr;
@@ -512,13 +523,18 @@ extern "C" mppi_status mppi_destroy(mppi_handle e) {
     set_err("null handle");                       \
     return MPPI_ERR_INVALID;                      \
   }                                               \
-  CK(cudaSetDevice((e)->dev))
+  {                                               \
+    int cur_ = -1;                                \
+    if (cudaGetDevice(&cur_) != cudaSuccess || cur_ != (e)->dev) CK(cudaSetDevice((e)->dev)); \
+  }
 
 extern "C" mppi_status mppi_reset(mppi_handle e) {
   ENTER(e);
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaMemsetAsync(e->d_Umaster, 0, 2 * e->sp.T * sizeof(double), e->stream));   // control/src/mppi:81
   e->local_pending = false;
+  e->f64_holdoff = 0;
+  e->f64_backoff = 8;
   return prep_nominal(e);
 }
 
@@ -777,6 +793,7 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   }
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[0], st));
   CK(rollout_launch(kind, e->sp.model, e->sp.has_grid != 0, c.block, c.variant, c.grid, c.smem, st, ra));
+  e->tp_launch1 = std::chrono::steady_clock::now();
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[1], st));
   ReduceArgs rd;
   memset(&rd, 0, sizeof(rd));
@@ -812,6 +829,7 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
     CK(reduce_screen_launch(e->sp.model, e->sp.has_grid != 0, e->sp.T, st, rd));
   else
     CK(reduce_softmin_launch(kind == ROLLOUT_F64_SOFTMIN, e->sp.T, st, rd));
+  e->tp_launch2 = std::chrono::steady_clock::now();
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[2], st));
   e->last_capture_kind = kind;
   return MPPI_OK;
@@ -908,6 +926,10 @@ static mppi_status finish_outputs(mppi_engine* e, double u_out[2], double x_next
     CKS(launch_local(e, e->stream, MPPI_PRECISION_F64, FUSE_STEP, nullptr, &in));
     CKS(wait_result(e));
     e->last.refine_overflow += 1;
+    e->f64_holdoff = e->f64_backoff;
+    e->f64_backoff = e->f64_backoff * 2 > 64 ? 64 : e->f64_backoff * 2;
+  } else if (e->attempted_mixed) {
+    e->f64_backoff = 8;   // a mixed step went through: the next overflow starts from the short hold-off again
   }
   e->last.refine_candidates = o->candidates;
   e->last.refine_max_dev = o->max_dev;
@@ -959,13 +981,43 @@ extern "C" mppi_status mppi_step(mppi_handle e, const double x0[3], double u_out
     set_err("world_size > 1: connect the peer-to-peer exchange (mppi_p2p_connect) or use mppi_step_local / mppi_step_finish");
     return MPPI_ERR_STATE;
   }
+  const auto tp0 = std::chrono::steady_clock::now();
   CKS(pre_step(e, x0));
   // two launches, no copies: x0 / goal ride in the kernel arguments, the result comes back through mapped host memory
   const StepInput in = step_input(e);
   e->seq += 1;
-  CKS(launch_local(e, e->stream, e->p.precision, FUSE_STEP, nullptr, &in));
+  int precision = e->p.precision;
+  if (precision == MPPI_PRECISION_MIXED) {
+    if (e->f64_holdoff > 0) {
+      precision = MPPI_PRECISION_F64;   // same result (mixed == f64 to rounding), without the screen that would overflow
+      e->f64_holdoff -= 1;
+    }
+  }
+  e->attempted_mixed = precision == MPPI_PRECISION_MIXED;
+  CKS(launch_local(e, e->stream, precision, FUSE_STEP, nullptr, &in));
   CKS(wait_result(e));
-  return finish_outputs(e, u_out, x_next);
+  const auto tp3 = std::chrono::steady_clock::now();
+  const mppi_status st = finish_outputs(e, u_out, x_next);
+  const auto tp4 = std::chrono::steady_clock::now();
+  typedef std::chrono::duration<double, std::nano> ns;
+  e->host_ns[0] += ns(e->tp_launch1 - tp0).count();
+  e->host_ns[1] += ns(e->tp_launch2 - e->tp_launch1).count();
+  e->host_ns[2] += ns(tp3 - e->tp_launch2).count();
+  e->host_ns[3] += ns(tp4 - tp3).count();
+  e->host_calls += 1;
+  return st;
+}
+
+// profiling aid: mean host-side duration (us) of the phases of mppi_step since the last call of this function:
+// out[0] entry -> rollout kernel launched, [1] -> reduce kernel launched, [2] -> result seen in mapped memory, [3] -> return
+extern "C" mppi_status mppi_debug_host_timing(mppi_handle e, double out[4]) {
+  ENTER(e);
+  for (int i = 0; i < 4; ++i) {
+    if (out) out[i] = e->host_calls ? e->host_ns[i] / (double)e->host_calls * 1e-3 : 0.0;
+    e->host_ns[i] = 0;
+  }
+  e->host_calls = 0;
+  return MPPI_OK;
 }
 
 extern "C" mppi_status mppi_step_local(mppi_handle e, const double x0[3]) {
@@ -1269,7 +1321,7 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
   std::vector<cudaEvent_t> ev((size_t)2 * steps);
   for (auto& v : ev) CK(cudaEventCreate(&v));
   for (int i = 0; i < steps; ++i) {
-    if (flush_l2) CK(cudaMemsetAsync(e->d_flush, i & 0xff, e->flush_bytes, e->stream));
+    if (flush_l2) CK(flush_l2_launch(e->stream, e->d_flush, e->flush_bytes, (unsigned)(i & 0xff)));
     CK(cudaEventRecord(ev[2 * i], e->stream));
     CK(cudaGraphLaunch(e->g_loop, e->stream));
     CK(cudaEventRecord(ev[2 * i + 1], e->stream));
@@ -1292,7 +1344,7 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
     for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&kev.ev[i]));
     double acc[3] = {0, 0, 0};
     for (int i = 0; i < steps; ++i) {
-      if (flush_l2) CK(cudaMemsetAsync(e->d_flush, i & 0xff, e->flush_bytes, e->stream));
+      if (flush_l2) CK(flush_l2_launch(e->stream, e->d_flush, e->flush_bytes, (unsigned)(i & 0xff)));
       CKS(launch_local(e, e->stream, e->p.precision, FUSE_LOOP, &kev));
       CK(cudaEventRecord(kev.ev[3], e->stream));
       CK(cudaStreamSynchronize(e->stream));
@@ -1364,7 +1416,7 @@ extern "C" mppi_status mppi_debug_flush_l2(mppi_handle e) {
     e->flush_bytes = (size_t)256 << 20;   // > 126 MB L2
     CK(cudaMalloc(&e->d_flush, e->flush_bytes));
   }
-  CK(cudaMemsetAsync(e->d_flush, (int)(e->seq & 0xff), e->flush_bytes, e->stream));
+  CK(flush_l2_launch(e->stream, e->d_flush, e->flush_bytes, (unsigned)(e->seq & 0xff)));
   CK(cudaStreamSynchronize(e->stream));
   return MPPI_OK;
 }

@@ -13,6 +13,18 @@ namespace mppi {
 // stream is still draining; it synchronises on-device with griddepcontrol.wait
 template <typename Fn>
 static cudaError_t launch_pdl(Fn f, int grid, int block, size_t smem, cudaStream_t st, const ReduceArgs& a) {
+  // same L1 / shared-memory split as the rollout kernels (rollout_tu.inc): no SM reconfiguration inside a step
+  static thread_local const void* carved[16] = {};
+  bool seen = false;
+  for (const void* p : carved) seen |= (p == (const void*)f);
+  if (!seen) {
+    cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    for (auto& p : carved)
+      if (!p) {
+        p = (const void*)f;
+        break;
+      }
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -90,6 +102,22 @@ cudaError_t reduce_screen_launch(int model, bool has_grid, int T, cudaStream_t s
 cudaError_t finalize_launch(cudaStream_t st, const FinalizeArgs& a) {
   const size_t smem = (size_t)4 * a.sp.T * sizeof(double);
   finalize_kernel<<<1, 256, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+// measurement aid: overwrite a buffer larger than L2.  A kernel of ours (not cudaMemsetAsync) so that it runs with the
+// same L1 / shared-memory split as the step's kernels: the timed step after it starts without an SM reconfiguration.
+__global__ void __launch_bounds__(256) flush_l2_kernel(uint4* p, size_t n16, unsigned int v) {
+  const uint4 val = make_uint4(v, v, v, v);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = val;
+}
+cudaError_t flush_l2_launch(cudaStream_t st, void* buf, size_t bytes, unsigned int value) {
+  static thread_local bool carved = false;
+  if (!carved) {
+    cudaFuncSetAttribute(flush_l2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    carved = true;
+  }
+  flush_l2_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<uint4*>(buf), bytes / 16, value * 0x01010101u);
   return cudaGetLastError();
 }
 

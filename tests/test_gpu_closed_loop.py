@@ -78,3 +78,26 @@ def test_cpp_facade_closed_loop():
     r = subprocess.run([exe, "2048", "32", "1500"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "WAYPOINT REACHED" in r.stdout
+
+
+def test_mixed_overflow_backs_off_to_fp64_and_stays_exact():
+    """A candidate-list overflow of the mixed mode (here forced by an absurd screening margin; in the field: within
+    centimetres of the goal, where hundreds of rollouts carry weight) redoes the step in fp64 and sends the next 8, 16,
+    32 ... steps straight to the fp64 pipeline.  The controls must equal those of an fp64 engine, and the number of
+    doomed mixed attempts must follow the back-off schedule (steps 1, 10, 27 of 40)."""
+    K, T = 4096, 32
+    a = mp().MPPI(horizon=T, samples=K, seed=6, precision="mixed", refine_margin=50.0)
+    b = mp().MPPI(horizon=T, samples=K, seed=6, precision="f64")
+    sa = sb = np.array([0.0, 0.0, 0.2])
+    for _ in range(40):
+        sa = a.get_path(sa, PARK)
+        sb = b.get_path(sb, PARK)
+        np.testing.assert_allclose(a.latest_uvec, b.latest_uvec, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(sa, sb, rtol=1e-12, atol=1e-14)
+    assert a.stats()["refine_overflow"] == 3
+    a.initialize()                      # initialize() re-arms the short hold-off
+    a.get_path(np.zeros(3), PARK)
+    a.get_path(np.zeros(3), PARK)
+    assert a.stats()["refine_overflow"] == 4
+    a.close()
+    b.close()
