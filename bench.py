@@ -256,7 +256,7 @@ def run_single(args):
         "dtype": {"mixed": "f32 rollouts + f64 re-evaluation of the softmin support", "f32": "f32", "f64": "f64"}[args.precision],
         "data": "synthetic",
         "config": {"workload": "diff-drive parallel-park K=%d T=%d (BASELINE.json configs[1])" % (K, T), "K": K, "T": T,
-                   "precision": args.precision, "weighting": "cost_to_go (reference)", "noise": "Philox4x32-10 in registers",
+                   "precision": args.precision, "weighting": "cost_to_go (reference)", "noise": "Philox4x32-10 in registers, 6 normals (3 steps x 2 channels) per call",
                    "l2": "flushed between timed steps (256 MiB overwritten by a store kernel outside the timed intervals)",
                    "loop": "closed loop on the model, state resident in HBM", "launch": r["launch"]},
         "state_steps_per_s": value * T,

@@ -240,8 +240,8 @@ __device__ __forceinline__ R clamp_(R v, R lim) {
   return Math<R>::max_(-lim, Math<R>::min_(v, lim));
 }
 
-// ---- Philox4x32-10 (Salmon et al., SC'11), counter-based: the noise of rollout k at step pair
-// t2 of engine step `step` is a pure function of (seed, k_global, t2, step) -- independent of how
+// ---- Philox4x32-10 (Salmon et al., SC'11), counter-based: the noise of rollout k at the step triple
+// `call` of engine step `step` is a pure function of (seed, k_global, call, step) -- independent of how
 // K is sharded over GPUs and regenerable anywhere (reduction kernels, noise export).
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -267,31 +267,38 @@ __device__ __forceinline__ float lg2_approx(float x) {
   return r;
 }
 
-// 4 standard normals (fp32) = the z of (t=2*t2: ch0, ch1), (t=2*t2+1: ch0, ch1).  Box-Muller on the
-// SFU pipe (lg2, rsqrt/sqrt, sin, cos).  Bit-identical wherever it is called from (intrinsics only,
+// 6 standard normals (fp32) per Philox call = the z of the three time steps 3c, 3c+1, 3c+2 (channel 0, channel 1 each),
+// c = the call index (counter word z).  The 128 random bits make THREE Box-Muller pairs: pair j takes the 22 high bits
+// of word j as the radius uniform (tail to 5.6 sigma, 4 M levels) and 20 angle bits (the 10 low bits of word j over 10 bits
+// of word 3) -- fp32 normals carry 24 bits, so nothing an fp32 rollout can see is lost against 32 + 32 bits per pair, and
+// the generator (43 % of the rollout loop's issue time at two steps per call) is called a third less often.
+// Box-Muller on the SFU pipe (lg2, sqrt, sin, cos).  Bit-identical wherever it is called from (intrinsics only,
 // nothing for the compiler to contract).
-__device__ __forceinline__ float4 normal4_from_bits(uint4 r);
-__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long kglobal,
-                                                 unsigned int t2, unsigned int step) {
-  uint4 ctr = make_uint4((uint32_t)kglobal, (uint32_t)(kglobal >> 32), t2, step);
-  uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-  return normal4_from_bits(philox4x32_10(ctr, key));
+struct Normal6 {
+  float v[6];
+};
+__device__ __forceinline__ Normal6 normal6_from_bits(uint4 r) {
+  Normal6 o;
+  const uint32_t w[3] = {r.x, r.y, r.z};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const uint32_t rb = w[j] >> 10;                                                       // 22 bits
+    const uint32_t ab = ((w[j] & 0x3FFu) << 10) | ((r.w >> (22 - 10 * j)) & 0x3FFu);      // 20 bits
+    const float u = __fmaf_rn((float)rb, 2.384185791015625e-07f, 1.1920928955078125e-07f);   // (rb + 1/2) 2^-22 in (0, 1)
+    // sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u): MUFU.LG2 + FMUL + MUFU.SQRT
+    const float ra = sqrt_approx(__fmul_rn(-1.38629436111989062f, lg2_approx(u)));
+    float sn, cs;
+    __sincosf(__fmul_rn((float)ab, 5.992112452678286e-06f), &sn, &cs);                    // 2 pi 2^-20
+    o.v[2 * j] = __fmul_rn(ra, cs);
+    o.v[2 * j + 1] = __fmul_rn(ra, sn);
+  }
+  return o;
 }
-__device__ __forceinline__ float4 normal4_from_bits(uint4 r) {
-#ifdef MPPI_EXP_NOMUFU   // measurement only (profiles/variants.py): uniform noise without the SFU pipe -- NOT a product path
-  return make_float4(fmaf((float)r.x, 8e-10f, -1.7f), fmaf((float)r.y, 8e-10f, -1.7f), fmaf((float)r.z, 8e-10f, -1.7f), fmaf((float)r.w, 8e-10f, -1.7f));
-#endif
-  const float S = 2.3283064365386963e-10f;   // 2^-32
-  float u0 = __fmaf_rn((float)r.x, S, 1.1641532182693481e-10f);   // (0,1]
-  float u2 = __fmaf_rn((float)r.z, S, 1.1641532182693481e-10f);
-  // sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u): MUFU.LG2 + FMUL + MUFU.SQRT
-  float ra = sqrt_approx(__fmul_rn(-1.38629436111989062f, lg2_approx(u0)));
-  float rb = sqrt_approx(__fmul_rn(-1.38629436111989062f, lg2_approx(u2)));
-  float sa, ca, sb, cb;
-  const float TWO_PI_2M32 = 1.46291807926715968e-09f;   // 2 pi * 2^-32
-  __sincosf(__fmul_rn((float)r.y, TWO_PI_2M32), &sa, &ca);
-  __sincosf(__fmul_rn((float)r.w, TWO_PI_2M32), &sb, &cb);
-  return make_float4(__fmul_rn(ra, ca), __fmul_rn(ra, sa), __fmul_rn(rb, cb), __fmul_rn(rb, sb));
+__device__ __forceinline__ Normal6 philox_normal6(unsigned long long seed, unsigned long long kglobal, unsigned int call,
+                                                  unsigned int step) {
+  uint4 ctr = make_uint4((uint32_t)kglobal, (uint32_t)(kglobal >> 32), call, step);
+  uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  return normal6_from_bits(philox4x32_10(ctr, key));
 }
 
 // eps = noise_std * z, rounded once in fp32: THE sample value (what mppi_get_noise exports)
@@ -300,9 +307,10 @@ __device__ __forceinline__ float eps_from_z(float std_, float z) { return __fmul
 // eps of (rollout kglobal, time t, channel pair) regenerated from counters
 __device__ __forceinline__ void philox_eps(unsigned long long seed, unsigned long long kglobal, int t,
                                            unsigned int step, float std0, float std1, float& e0, float& e1) {
-  float4 z = philox_normal4(seed, kglobal, (unsigned)t >> 1, step);
-  e0 = eps_from_z(std0, (t & 1) ? z.z : z.x);
-  e1 = eps_from_z(std1, (t & 1) ? z.w : z.y);
+  const unsigned int call = (unsigned)t / 3u, j = (unsigned)t - 3u * call;
+  const Normal6 z = philox_normal6(seed, kglobal, call, step);
+  e0 = eps_from_z(std0, j == 0 ? z.v[0] : (j == 1 ? z.v[2] : z.v[4]));
+  e1 = eps_from_z(std1, j == 0 ? z.v[1] : (j == 1 ? z.v[3] : z.v[5]));
 }
 
 // ---- vehicle models: every supported model has a state-independent yaw rate, so one step is

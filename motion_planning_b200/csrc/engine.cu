@@ -240,7 +240,7 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
       const bool sm_wide = block == 512;   // rollout_lean_sm_kernel: 7 tiles of 64 per CTA, at most one CTA per SM
       const int rollouts = sm_wide ? 64 * 7 : block;
       c.ntiles = (sp.K + rollouts - 1) / rollouts;
-      if (sm_wide && c.ntiles > e->num_sms) continue;
+      if (sm_wide && (c.ntiles > e->num_sms || sp.T < 12)) continue;
       c.smem = rollout_smem(kind, sp.T, block, variant, gin);
       if (c.smem > 227 * 1024) continue;
       cudaError_t ce = rollout_prepare(kind, sp.model, has_grid, block, variant, c.smem, &c.ctas_per_sm, &c.regs);
@@ -785,7 +785,7 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
     ls.g_inv_res = (float)(sp.g_inv_res / sq);
     ls.w_obs_100 = (float)(sp.w_obs / 100.0);
     ls.margin = (float)sp.margin;
-    ls.split = e->lean_split > 0 ? e->lean_split : ((sp.T * 9 / 16 + 3) & ~3);
+    ls.split = e->lean_split > 0 ? e->lean_split : ((sp.T * 9 / 16 + 5) / 6) * 6;
     for (int i = 0; i < MPPI_PHILOX_ROUNDS; ++i) {
       ls.pkx[i] = (uint32_t)sp.seed + (uint32_t)i * 0x9E3779B9u;
       ls.pky[i] = (uint32_t)(sp.seed >> 32) + (uint32_t)i * 0xBB67AE85u;

@@ -774,13 +774,17 @@ __global__ void noise_export_kernel(StaticParams sp, const DynState* dyn, unsign
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= sp.K) return;
   const float std0 = (float)dyn->noise_std[0], std1 = (float)dyn->noise_std[1];
-  for (int t2 = 0; t2 < (sp.T >> 1); ++t2) {
-    const float4 z = philox_normal4(sp.seed, (unsigned long long)(sp.k_offset + k), (unsigned)t2, step);
-    const size_t b = (size_t)(2 * t2) * 2 * sp.K + k;
-    eps[b] = (double)eps_from_z(std0, z.x);
-    eps[b + sp.K] = (double)eps_from_z(std1, z.y);
-    eps[b + 2 * (size_t)sp.K] = (double)eps_from_z(std0, z.z);
-    eps[b + 3 * (size_t)sp.K] = (double)eps_from_z(std1, z.w);
+  for (int call = 0; 3 * call < sp.T; ++call) {
+    const Normal6 z = philox_normal6(sp.seed, (unsigned long long)(sp.k_offset + k), (unsigned)call, step);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int t = 3 * call + j;
+      if (t < sp.T) {
+        const size_t b = (size_t)t * 2 * sp.K + k;
+        eps[b] = (double)eps_from_z(std0, z.v[2 * j]);
+        eps[b + sp.K] = (double)eps_from_z(std1, z.v[2 * j + 1]);
+      }
+    }
   }
 }
 

@@ -313,19 +313,20 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
     R dx = R(0), dy = R(0), th = cc.th0, acc = R(0);
     R cth, sth;
     Math<R>::sincos_(th, sth, cth);
-    int eown0 = 0, eown1 = 0;   // fixed-point floor sums of the step this lane owns in the current 32-step chunk
+    int eown0 = 0, eown1 = 0;   // fixed-point floor sums of the step this lane owns in the current 30-step chunk
 
     // ---- the T-step rollout (hot loop 1, control/src/mppi:136-163) ----------------------------
-    // one model step + running cost + prefix store; `zq` = the two standard normals of the step (FAST)
-    auto one_step = [&](int t, R e0, R e1, float z0, float z1) {
-      if (FAST || !sp.noise_external) {
+    // one model step + running cost + prefix store; z0, z1 = the two standard normals of the step (Philox noise);
+    // `own` = the step's position in the current 30-step chunk of floor sums
+    auto one_step = [&](int t, int own, R e0, R e1, float z0, float z1) {
+      if (!sp.noise_external) {
         // floor-term sums: exact fixed point (2^-20, |z| < 8 so 32 lanes fit an int), one warp integer
-        // add (REDUX) per channel; the lane with lane == t mod 32 keeps the warp sums of step t
+        // add (REDUX) per channel; lane `own` keeps the warp sums of step t until the chunk is flushed
         int q0 = valid ? __float2int_rn(z0 * (float)kZFixScale) : 0;
         int q1 = valid ? __float2int_rn(z1 * (float)kZFixScale) : 0;
         q0 = __reduce_add_sync(0xffffffffu, q0);
         q1 = __reduce_add_sync(0xffffffffu, q1);
-        if (lane == (t & 31)) {
+        if (lane == own) {
           eown0 = q0;
           eown1 = q1;
         }
@@ -339,61 +340,62 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
       acc += c;
       P[(t + 1) * PS + tid] = acc;
     };
-    // every lane flushes the step it owns in the 32-step chunk starting at `base`
+    // every lane flushes the step it owns in the chunk of (at most 30) steps starting at `base`
     auto flush_chunk = [&](int base) {
       const int town = base + lane;
-      if (town < T) {
+      if (lane < 30 && town < T) {
         atomicAdd(&ez32[2 * town], eown0);
         atomicAdd(&ez32[2 * town + 1], eown1);
       }
+      eown0 = 0;
+      eown1 = 0;
     };
-    if (FAST) {
-      // FAST path: Philox noise, four steps per iteration in ONE basic block (no branch inside a step), the
-      // Philox + Box-Muller chains of the NEXT four steps issued alongside so that the integer/SFU work
+    if (!sp.noise_external) {
+      // Philox noise: SIX steps per iteration from two generator calls (three steps each), no branch inside a step
+      // (FAST), the Philox + Box-Muller chains of the NEXT six steps issued alongside so that the integer / SFU work
       // overlaps the FP chain; (cos, sin) re-synchronised from theta at the end of every iteration.
-      float4 za = philox_normal4(sp.seed, kglobal, 0u, step);
-      float4 zb = philox_normal4(sp.seed, kglobal, 1u, step);
-      int t4 = 0;
-      for (; t4 + 4 <= T; t4 += 4) {
-        const float4 z0 = za, z1 = zb;
-        za = philox_normal4(sp.seed, kglobal, (unsigned)(t4 >> 1) + 2u, step);   // one iteration ahead
-        zb = philox_normal4(sp.seed, kglobal, (unsigned)(t4 >> 1) + 3u, step);
-        one_step(t4 + 0, R(eps_from_z(std0, z0.x)), R(eps_from_z(std1, z0.y)), z0.x, z0.y);
-        one_step(t4 + 1, R(eps_from_z(std0, z0.z)), R(eps_from_z(std1, z0.w)), z0.z, z0.w);
-        one_step(t4 + 2, R(eps_from_z(std0, z1.x)), R(eps_from_z(std1, z1.y)), z1.x, z1.y);
-        one_step(t4 + 3, R(eps_from_z(std0, z1.z)), R(eps_from_z(std1, z1.w)), z1.z, z1.w);
-        Math<R>::sincos_(th, sth, cth);
-        if ((t4 & 31) == 28) flush_chunk(t4 & ~31);
-      }
-      if (t4 < T) {   // T = 4n + 2: one more pair
-        one_step(t4 + 0, R(eps_from_z(std0, za.x)), R(eps_from_z(std1, za.y)), za.x, za.y);
-        one_step(t4 + 1, R(eps_from_z(std0, za.z)), R(eps_from_z(std1, za.w)), za.z, za.w);
-      }
-      if (T & 31) flush_chunk(T & ~31);
-    } else {
-      // GENERAL path: replayed noise from HBM and/or large yaw increments (full-range trig, multi-turn wrap)
-      for (int t2 = 0; t2 < (T >> 1); ++t2) {
-        float zf[4] = {0.f, 0.f, 0.f, 0.f};
-        R ev[4];
-        if (sp.noise_external) {
-          const int kk = valid ? k_local : 0;
+      Normal6 za = philox_normal6(sp.seed, kglobal, 0u, step);
+      Normal6 zb = philox_normal6(sp.seed, kglobal, 1u, step);
+      int t6 = 0, own = 0, chunk = 0;
+      unsigned int call = 0u;
+      for (; t6 + 6 <= T; t6 += 6) {
+        const Normal6 z0 = za, z1 = zb;
+        call += 2u;
+        za = philox_normal6(sp.seed, kglobal, call, step);        // one iteration ahead
+        zb = philox_normal6(sp.seed, kglobal, call + 1u, step);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) ev[i] = load_eps_ext<R>(a.eps_ext, 2 * t2 + (i >> 1), i & 1, sp.K, kk);
-        } else {
-          const float4 z = philox_normal4(sp.seed, kglobal, (unsigned)t2, step);
-          zf[0] = z.x;
-          zf[1] = z.y;
-          zf[2] = z.z;
-          zf[3] = z.w;
-          ev[0] = R(eps_from_z(std0, z.x));
-          ev[1] = R(eps_from_z(std1, z.y));
-          ev[2] = R(eps_from_z(std0, z.z));
-          ev[3] = R(eps_from_z(std1, z.w));
+        for (int j = 0; j < 3; ++j)
+          one_step(t6 + j, own + j, R(eps_from_z(std0, z0.v[2 * j])), R(eps_from_z(std1, z0.v[2 * j + 1])), z0.v[2 * j], z0.v[2 * j + 1]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          one_step(t6 + 3 + j, own + 3 + j, R(eps_from_z(std0, z1.v[2 * j])), R(eps_from_z(std1, z1.v[2 * j + 1])), z1.v[2 * j],
+                   z1.v[2 * j + 1]);
+        Math<R>::sincos_(th, sth, cth);
+        own += 6;
+        if (own == 30) {
+          flush_chunk(chunk);
+          chunk += 30;
+          own = 0;
         }
-        one_step(2 * t2, ev[0], ev[1], zf[0], zf[1]);
-        one_step(2 * t2 + 1, ev[2], ev[3], zf[2], zf[3]);
-        if ((t2 & 1) == 1) Math<R>::sincos_(th, sth, cth);
-        if (!sp.noise_external && ((t2 & 15) == 15 || t2 == (T >> 1) - 1)) flush_chunk((2 * t2 + 1) & ~31);
+      }
+      // the last T mod 6 steps: za / zb already hold their normals
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        if (t6 + j < T) {
+          const Normal6& zz = (j < 3) ? za : zb;
+          const int jj = (j < 3) ? j : j - 3;
+          one_step(t6 + j, own + j, R(eps_from_z(std0, zz.v[2 * jj])), R(eps_from_z(std1, zz.v[2 * jj + 1])), zz.v[2 * jj], zz.v[2 * jj + 1]);
+        }
+      }
+      if (chunk < T) flush_chunk(chunk);
+    } else {
+      // replayed noise from HBM (mppi_set_noise): eps arrives in f64, the floor sums are formed in the transposed pass
+      for (int t = 0; t < T; ++t) {
+        const int kk = valid ? k_local : 0;
+        const R e0 = load_eps_ext<R>(a.eps_ext, t, 0, sp.K, kk);
+        const R e1 = load_eps_ext<R>(a.eps_ext, t, 1, sp.K, kk);
+        one_step(t, 0, e0, e1, 0.f, 0.f);
+        if ((t & 3) == 3) Math<R>::sincos_(th, sth, cth);
       }
     }
     acc += terminal_cost<R>(cc, dx, dy, th);                                 // :165-171

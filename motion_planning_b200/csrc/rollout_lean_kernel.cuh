@@ -80,8 +80,8 @@ __device__ __forceinline__ uint4 philox4x32_sched(uint4 c, const LeanStatic& ls)
   }
   return c;
 }
-__device__ __forceinline__ float4 lean_normal4(const LeanStatic& ls, unsigned long long kglobal, unsigned int t2, unsigned int step) {
-  return normal4_from_bits(philox4x32_sched(make_uint4((uint32_t)kglobal, (uint32_t)(kglobal >> 32), t2, step), ls));
+__device__ __forceinline__ Normal6 lean_normal6(const LeanStatic& ls, unsigned long long kglobal, unsigned int call, unsigned int step) {
+  return normal6_from_bits(philox4x32_sched(make_uint4((uint32_t)kglobal, (uint32_t)(kglobal >> 32), call, step), ls));
 }
 
 // NEW occupancy-grid term, same cell as grid_cost<float> in common.cuh (floor, outside = 100) with the
@@ -293,35 +293,45 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
       acc += c;
       prow[row * PS] = acc;
     };
-    float4 za = lean_normal4(a.lean, kglobal, 0u, step);
-    float4 zb = lean_normal4(a.lean, kglobal, 1u, step);
-    int t4 = 0;
-    for (; t4 + 4 <= T; t4 += 4) {
-      const float4 z0 = za, z1 = zb;
-      za = lean_normal4(a.lean, kglobal, (unsigned)(t4 >> 1) + 2u, step);   // one iteration ahead
-      zb = lean_normal4(a.lean, kglobal, (unsigned)(t4 >> 1) + 3u, step);
-      const float4* nl = nomL + t4;
-      int4 qa, qb;
-      one_step(nl[0], z0.x, z0.y, qa.x, qa.y, 0);
-      one_step(nl[1], z0.z, z0.w, qa.z, qa.w, 1);
-      one_step(nl[2], z1.x, z1.y, qb.x, qb.y, 2);
-      one_step(nl[3], z1.z, z1.w, qb.z, qb.w, 3);
-      if (lane == 0) {   // the warp sums of the four steps: two 16-byte stores by one lane
-        *reinterpret_cast<int4*>(ezrow + 2 * t4) = qa;
-        *reinterpret_cast<int4*>(ezrow + 2 * t4 + 4) = qb;
+    Normal6 za = lean_normal6(a.lean, kglobal, 0u, step);
+    Normal6 zb = lean_normal6(a.lean, kglobal, 1u, step);
+    int t6 = 0;
+    unsigned int call = 0u;
+    for (; t6 + 6 <= T; t6 += 6) {   // six steps per iteration: two generator calls of three steps each
+      const Normal6 z0 = za, z1 = zb;
+      call += 2u;
+      za = lean_normal6(a.lean, kglobal, call, step);   // one iteration ahead
+      zb = lean_normal6(a.lean, kglobal, call + 1u, step);
+      const float4* nl = nomL + t6;
+      int4 qa, qb, qc;
+      one_step(nl[0], z0.v[0], z0.v[1], qa.x, qa.y, 0);
+      one_step(nl[1], z0.v[2], z0.v[3], qa.z, qa.w, 1);
+      one_step(nl[2], z0.v[4], z0.v[5], qb.x, qb.y, 2);
+      one_step(nl[3], z1.v[0], z1.v[1], qb.z, qb.w, 3);
+      one_step(nl[4], z1.v[2], z1.v[3], qc.x, qc.y, 4);
+      one_step(nl[5], z1.v[4], z1.v[5], qc.z, qc.w, 5);
+      if (lane == 0) {   // the warp sums of the six steps: three 16-byte stores by one lane
+        int4* ez4 = reinterpret_cast<int4*>(ezrow + 2 * t6);
+        ez4[0] = qa;
+        ez4[1] = qb;
+        ez4[2] = qc;
       }
-      prow += 4 * PS;
+      prow += 6 * PS;
       // keep (cos, sin) on the unit circle
       const float f = fmaf(fmaf(cth, cth, sth * sth), -0.5f, 1.5f);
       cth *= f;
       sth *= f;
     }
-    if (t4 < T) {   // T = 4n + 2: one more pair
-      const float4* nl = nomL + t4;
-      int4 qa;
-      one_step(nl[0], za.x, za.y, qa.x, qa.y, 0);
-      one_step(nl[1], za.z, za.w, qa.z, qa.w, 1);
-      if (lane == 0) *reinterpret_cast<int4*>(ezrow + 2 * t4) = qa;
+    // the last T mod 6 steps: za / zb already hold their normals
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      if (t6 + j < T) {
+        const Normal6& zz = (j < 3) ? za : zb;
+        const int jj = (j < 3) ? j : j - 3;
+        int2 q;
+        one_step(nomL[t6 + j], zz.v[2 * jj], zz.v[2 * jj + 1], q.x, q.y, j);
+        if (lane == 0) *reinterpret_cast<int2*>(ezrow + 2 * (t6 + j)) = q;
+      }
     }
     RTS(3);
     // rk4 wraps theta into (-pi, pi] after every step (:52-53): theta_T is the angle of the carried pair
@@ -332,7 +342,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
     // PDL: the reduce kernel may start getting resident now (it still waits for this grid to complete)
     if (tile + nCTA >= a.ntiles) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     RTS(4);
-    prow[(T - 1 - t4) * PS] = acc;   // row T holds the rollout total Tot[k] (addressed from the running row pointer: the
+    prow[(T - 1 - t6) * PS] = acc;   // row T holds the rollout total Tot[k] (addressed from the running row pointer: the
                                      // tile-invariant form P + T*PS + tid gets hoisted and spilled)
     __syncthreads();
     RTS(5);
@@ -519,8 +529,8 @@ __global__ void __launch_bounds__(kSmThreads, 1) rollout_lean_sm_kernel(const __
   const R margin = a.lean.margin;
   const signed char* cells = grid_smem ? gcells : a.grid;
   const bool cost_to_go = sp.weighting == MPPI_WEIGHT_COST_TO_GO;
-  int split = a.lean.split & ~3;                           // first step of the second part (a multiple of 4)
-  split = max(4, min(split, (T - 1) & ~3));
+  int split = (a.lean.split / 6) * 6;                      // first step of the second part (a multiple of 6: whole iterations)
+  split = max(6, min(split, ((T - 1) / 6) * 6));
   const int t_begin = (role == 2) ? split : 0;
   const int t_end = (role == 1) ? split : T;
   const int k_local = vtile * BLOCK + col;
@@ -528,8 +538,9 @@ __global__ void __launch_bounds__(kSmThreads, 1) rollout_lean_sm_kernel(const __
   const unsigned long long kglobal = (unsigned long long)(sp.k_offset + k_local);
   const float qscale = valid ? kLeanFixScale : 0.f;
   // the first normals of this warp's range, drawn before anything is waited for
-  float4 za = lean_normal4(a.lean, kglobal, (unsigned)(t_begin >> 1), step);
-  float4 zb = lean_normal4(a.lean, kglobal, (unsigned)(t_begin >> 1) + 1u, step);
+  unsigned int call = (unsigned)t_begin / 3u;
+  Normal6 za = lean_normal6(a.lean, kglobal, call, step);
+  Normal6 zb = lean_normal6(a.lean, kglobal, call + 1u, step);
   R dx = 0.f, dy = 0.f, th = lc.th0, acc = 0.f, cth, sth;
   Math<R>::sincos_(lc.th0, sth, cth);
   int* ezrow = ezw + (size_t)wslot * T * 2;
@@ -583,22 +594,27 @@ __global__ void __launch_bounds__(kSmThreads, 1) rollout_lean_sm_kernel(const __
     acc += c;
     prow[row * PS] = acc;
   };
-  int t4 = t_begin;
-  for (; t4 + 4 <= t_end; t4 += 4) {
-    const float4 z0 = za, z1 = zb;
-    za = lean_normal4(a.lean, kglobal, (unsigned)(t4 >> 1) + 2u, step);   // one iteration ahead
-    zb = lean_normal4(a.lean, kglobal, (unsigned)(t4 >> 1) + 3u, step);
-    const float4* nl = nomL + t4;
-    int4 qa, qb;
-    one_step(nl[0], z0.x, z0.y, qa.x, qa.y, 0);
-    one_step(nl[1], z0.z, z0.w, qa.z, qa.w, 1);
-    one_step(nl[2], z1.x, z1.y, qb.x, qb.y, 2);
-    one_step(nl[3], z1.z, z1.w, qb.z, qb.w, 3);
+  int t6 = t_begin;
+  for (; t6 + 6 <= t_end; t6 += 6) {
+    const Normal6 z0 = za, z1 = zb;
+    call += 2u;
+    za = lean_normal6(a.lean, kglobal, call, step);   // one iteration ahead
+    zb = lean_normal6(a.lean, kglobal, call + 1u, step);
+    const float4* nl = nomL + t6;
+    int4 qa, qb, qc;
+    one_step(nl[0], z0.v[0], z0.v[1], qa.x, qa.y, 0);
+    one_step(nl[1], z0.v[2], z0.v[3], qa.z, qa.w, 1);
+    one_step(nl[2], z0.v[4], z0.v[5], qb.x, qb.y, 2);
+    one_step(nl[3], z1.v[0], z1.v[1], qb.z, qb.w, 3);
+    one_step(nl[4], z1.v[2], z1.v[3], qc.x, qc.y, 4);
+    one_step(nl[5], z1.v[4], z1.v[5], qc.z, qc.w, 5);
     if (lane == 0) {
-      *reinterpret_cast<int4*>(ezrow + 2 * t4) = qa;
-      *reinterpret_cast<int4*>(ezrow + 2 * t4 + 4) = qb;
+      int4* ez4 = reinterpret_cast<int4*>(ezrow + 2 * t6);
+      ez4[0] = qa;
+      ez4[1] = qb;
+      ez4[2] = qc;
     }
-    prow += 4 * PS;
+    prow += 6 * PS;
     const float f = fmaf(fmaf(cth, cth, sth * sth), -0.5f, 1.5f);
     cth *= f;
     sth *= f;
@@ -615,12 +631,16 @@ __global__ void __launch_bounds__(kSmThreads, 1) rollout_lean_sm_kernel(const __
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     return;
   }
-  if (t4 < T) {   // T = 4n + 2: one more pair
-    const float4* nl = nomL + t4;
-    int4 qa;
-    one_step(nl[0], za.x, za.y, qa.x, qa.y, 0);
-    one_step(nl[1], za.z, za.w, qa.z, qa.w, 1);
-    if (lane == 0) *reinterpret_cast<int4*>(ezrow + 2 * t4) = qa;
+  // the last T mod 6 steps: za / zb already hold their normals
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    if (t6 + j < T) {
+      const Normal6& zz = (j < 3) ? za : zb;
+      const int jj = (j < 3) ? j : j - 3;
+      int2 q;
+      one_step(nomL[t6 + j], zz.v[2 * jj], zz.v[2 * jj + 1], q.x, q.y, j);
+      if (lane == 0) *reinterpret_cast<int2*>(ezrow + 2 * (t6 + j)) = q;
+    }
   }
   RTS2(3);
   if (MODEL != MPPI_MODEL_UNICYCLE_EULER) th = atan2f(sth, cth);
@@ -629,7 +649,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) rollout_lean_sm_kernel(const __
   if (!valid) acc = Math<R>::inf();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   RTS2(4);
-  prow[(T - 1 - t4) * PS] = acc;                             // row T: the rollout total
+  prow[(T - 1 - t6) * PS] = acc;                             // row T: the rollout total
   named_bar_sync(2 + sub, BLOCK);                            // the tile's two finishing warps
   RTS2(5);
 
