@@ -277,21 +277,23 @@ __device__ __forceinline__ float lg2_approx(float x) {
 struct Normal6 {
   float v[6];
 };
+// one Box-Muller pair from the 32 bits of its own word and its 10 bits of word 3 (already shifted down and masked)
+__device__ __forceinline__ void normal_pair_from_bits(uint32_t wj, uint32_t w10, float& z0, float& z1) {
+  const uint32_t rb = wj >> 10;                                                            // 22 bits
+  const uint32_t ab = ((wj & 0x3FFu) << 10) | w10;                                         // 20 bits
+  const float u = __fmaf_rn((float)rb, 2.384185791015625e-07f, 1.1920928955078125e-07f);   // (rb + 1/2) 2^-22 in (0, 1)
+  // sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u): MUFU.LG2 + FMUL + MUFU.SQRT
+  const float ra = sqrt_approx(__fmul_rn(-1.38629436111989062f, lg2_approx(u)));
+  float sn, cs;
+  __sincosf(__fmul_rn((float)ab, 5.992112452678286e-06f), &sn, &cs);                       // 2 pi 2^-20
+  z0 = __fmul_rn(ra, cs);
+  z1 = __fmul_rn(ra, sn);
+}
 __device__ __forceinline__ Normal6 normal6_from_bits(uint4 r) {
   Normal6 o;
-  const uint32_t w[3] = {r.x, r.y, r.z};
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const uint32_t rb = w[j] >> 10;                                                       // 22 bits
-    const uint32_t ab = ((w[j] & 0x3FFu) << 10) | ((r.w >> (22 - 10 * j)) & 0x3FFu);      // 20 bits
-    const float u = __fmaf_rn((float)rb, 2.384185791015625e-07f, 1.1920928955078125e-07f);   // (rb + 1/2) 2^-22 in (0, 1)
-    // sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u): MUFU.LG2 + FMUL + MUFU.SQRT
-    const float ra = sqrt_approx(__fmul_rn(-1.38629436111989062f, lg2_approx(u)));
-    float sn, cs;
-    __sincosf(__fmul_rn((float)ab, 5.992112452678286e-06f), &sn, &cs);                    // 2 pi 2^-20
-    o.v[2 * j] = __fmul_rn(ra, cs);
-    o.v[2 * j + 1] = __fmul_rn(ra, sn);
-  }
+  normal_pair_from_bits(r.x, r.w >> 22, o.v[0], o.v[1]);
+  normal_pair_from_bits(r.y, (r.w >> 12) & 0x3FFu, o.v[2], o.v[3]);
+  normal_pair_from_bits(r.z, (r.w >> 2) & 0x3FFu, o.v[4], o.v[5]);
   return o;
 }
 __device__ __forceinline__ Normal6 philox_normal6(unsigned long long seed, unsigned long long kglobal, unsigned int call,
@@ -304,13 +306,17 @@ __device__ __forceinline__ Normal6 philox_normal6(unsigned long long seed, unsig
 // eps = noise_std * z, rounded once in fp32: THE sample value (what mppi_get_noise exports)
 __device__ __forceinline__ float eps_from_z(float std_, float z) { return __fmul_rn(std_, z); }
 
-// eps of (rollout kglobal, time t, channel pair) regenerated from counters
+// eps of (rollout kglobal, time t, channel pair) regenerated from counters: only the pair of step t is expanded
 __device__ __forceinline__ void philox_eps(unsigned long long seed, unsigned long long kglobal, int t,
                                            unsigned int step, float std0, float std1, float& e0, float& e1) {
   const unsigned int call = (unsigned)t / 3u, j = (unsigned)t - 3u * call;
-  const Normal6 z = philox_normal6(seed, kglobal, call, step);
-  e0 = eps_from_z(std0, j == 0 ? z.v[0] : (j == 1 ? z.v[2] : z.v[4]));
-  e1 = eps_from_z(std1, j == 0 ? z.v[1] : (j == 1 ? z.v[3] : z.v[5]));
+  const uint4 ctr = make_uint4((uint32_t)kglobal, (uint32_t)(kglobal >> 32), call, step);
+  const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t wj = (j == 0u) ? r.x : ((j == 1u) ? r.y : r.z);
+  float z0, z1;
+  normal_pair_from_bits(wj, (r.w >> (22u - 10u * j)) & 0x3FFu, z0, z1);
+  e0 = eps_from_z(std0, z0);
+  e1 = eps_from_z(std1, z1);
 }
 
 // ---- vehicle models: every supported model has a state-independent yaw rate, so one step is
