@@ -16,6 +16,7 @@
 #define MPPI_HPP_
 
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -168,6 +169,105 @@ class MPPI {
   mppi_handle h_ = nullptr;
   int T_ = 0;
   State x_next_{{0, 0, 0}};
+};
+
+// ---- the caller: Controller (control/src/mppi:296-389) for a C++ node -------------------------------------
+// Same state machine as the reference's rospy node and as motion_planning_b200.Controller (the Python mirror that is
+// tested against the unmodified reference): one odometry sample in, one MPPI step, one Twist out; waypoint list
+// (cyclic) or parallel park.  `Engine` needs setGoal(State), reset(), step(State) -> Control; it defaults to
+// mppi::MPPI and is a template parameter so that the host logic can be exercised without a GPU.
+struct Twist {
+  double vx = 0.0, wz = 0.0;   // geometry_msgs/Twist linear.x, angular.z (control/src/mppi:383-385)
+};
+
+// yaw of tf.transformations.euler_from_quaternion(q)[2] (call site control/src/mppi:333-334): the two matrix entries of
+// tf's quaternion_matrix the yaw needs, the quaternion scaled by sqrt(2 / |q|^2)
+inline double yawFromQuaternion(double x, double y, double z, double w) {
+  const double nq = x * x + y * y + z * z + w * w;
+  if (nq < 8.881784197001252e-16) return 0.0;
+  const double s = std::sqrt(2.0 / nq);
+  x *= s;
+  y *= s;
+  z *= s;
+  w *= s;
+  return std::atan2(x * y + z * w, 1.0 - y * y - z * z);
+}
+
+template <typename Engine = MPPI>
+class Controller {
+ public:
+  using Waypoints = std::vector<std::array<double, 2>>;
+  // waypoints empty = parallel park (control/src/mppi:305-309); thresh = MPPI.thresh (:62,74)
+  explicit Controller(Engine& engine, Waypoints waypoints = {}, double thresh = 0.05, double wheel_radius = 0.033,
+                      double wheel_base = 0.16)
+      : mppi_(engine), waypoints_(std::move(waypoints)), thresh_(thresh), r_(wheel_radius), L_(wheel_base) {
+    parallel_park_ = waypoints_.empty();
+  }
+
+  // planner hand-off: a new vertex list (e.g. the path of global_planner's trace_path); re-initialises towards its head
+  void setWaypoints(Waypoints waypoints) {
+    waypoints_ = std::move(waypoints);
+    parallel_park_ = waypoints_.empty();
+    idx_ = 0;
+    init_ = true;
+    done_ = false;
+  }
+
+  // Controller.pos_cb, control/src/mppi:328-386
+  Twist posCb(double x, double y, double theta) {
+    start_ = State{{x, y, theta}};                                        // :335
+    stepped_ = false;
+    if (parallel_park_) goal_ = State{{0.0, -1.0, 0.0}};                  // :337
+    if (std::hypot(start_[0] - goal_[0], start_[1] - goal_[1]) > thresh_ && !init_) {
+      mppi_.setGoal(goal_);
+      last_u_ = mppi_.step(start_);                                       // :341 -- the hot path
+      stepped_ = true;
+      done_ = false;
+    } else if (init_) {                                                   // :344-354
+      initialize();
+      if (!parallel_park_) goal_ = goalTowards(waypoints_[idx_]);
+      init_ = false;
+    } else {
+      if (!parallel_park_) {                                              // :357-373: next waypoint, cyclic
+        idx_ = (idx_ + 1 >= waypoints_.size()) ? 0 : idx_ + 1;
+        initialize();
+        goal_ = goalTowards(waypoints_[idx_]);
+      } else {
+        done_ = true;                                                     // :375
+      }
+    }
+    const Control u = done_ ? Control{{0.0, 0.0}} : last_u_;              // :378-381
+    Twist tw;                                                             // wheelsToTwist, :320-326
+    tw.vx = r_ * (u[0] + u[1]) / 2.0;
+    tw.wz = r_ * (-u[0] + u[1]) / L_;
+    return tw;
+  }
+  Twist posCb(double x, double y, double qx, double qy, double qz, double qw) {   // nav_msgs/Odometry pose
+    return posCb(x, y, yawFromQuaternion(qx, qy, qz, qw));
+  }
+
+  size_t idx() const { return idx_; }
+  bool init() const { return init_; }
+  bool done() const { return done_; }
+  bool stepped() const { return stepped_; }   // did the last posCb run an MPPI step (or only (re)initialise / stop)?
+  bool parallelPark() const { return parallel_park_; }
+  const State& goal() const { return goal_; }
+
+ private:
+  void initialize() {            // MPPI.initialize (:79-83): uvec = [[0, 0]]
+    mppi_.reset();
+    last_u_ = Control{{0.0, 0.0}};
+  }
+  State goalTowards(const std::array<double, 2>& w) const {   // :347-352
+    return State{{w[0], w[1], std::atan2(w[1] - start_[1], w[0] - start_[0])}};
+  }
+  Engine& mppi_;
+  Waypoints waypoints_;
+  double thresh_, r_, L_;
+  bool parallel_park_ = true, init_ = true, done_ = false, stepped_ = false;
+  size_t idx_ = 0;
+  State start_{{0, 0, 0}}, goal_{{0, 0, 0}};
+  Control last_u_{{0, 0}};
 };
 
 }  // namespace mppi
