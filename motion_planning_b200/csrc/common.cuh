@@ -12,13 +12,9 @@
 #ifndef MPPI_PHILOX_ROUNDS
 #define MPPI_PHILOX_ROUNDS 10   // Philox4x32-10 (the cuRAND default); 7 is the smallest Crush-resistant count
 #endif
-#ifndef MPPI_UNROLL_T2
-#define MPPI_UNROLL_T2 1
-#endif
 
 namespace mppi {
 
-constexpr int kUnrollT2 = MPPI_UNROLL_T2;   // step pairs per iteration of the rollout loop
 constexpr int kMaxCand = 16;        // SCREEN: candidate slots per (CTA, t)
 constexpr int kMaxRefine = 256;     // SCREEN: fp64 re-evaluations per t after the global filter
 constexpr int kRecordStride = 6;    // doubles per t in an exchange record: m, S, N0, N1, E0, E1

@@ -6,8 +6,7 @@
 // so this variant is written to minimise executed instructions per state-step under the conditions the host
 // has checked for it (engine.cu: try_configure):
 //   * Q[2] == 0 (the reference's Q = diag(1e3, 1e3, 0), control/src/mppi:69): theta enters the running cost
-//     nowhere, so it is carried as a plain sum of yaw increments, wrapped once per four steps (branch-free,
-//     round-to-nearest turn count) and used only by the terminal cost (:165-171);
+//     nowhere and is needed by the terminal cost only (:165-171);
 //   * |dt * yaw rate| <= 1/8 for every admissible control: sin/cos of the HALF increment (|a| <= 1/16) are short
 //     polynomials (sin: a (1 - a^2/6), phase error 0.008 a^5 < 8e-9 rad per rotation; cos: next term a^6/720 < 1e-10).
 // Differences from the generic FAST step:
@@ -23,12 +22,14 @@
 //     the carried pair, once per rollout); the Euler model (no wrap, :57-58) keeps a plain sum;
 //   * Simpson weights through the mid-point rotation only: c1 + 4 c2 + c4 = c2 (4 + 2 cos a) because
 //     c1 + c4 = 2 c2 cos a -- one rotation feeds the position update, a second one advances (cos, sin);
-//   * (cos, sin) is never re-derived from theta: one first-order renormalisation per four steps keeps the
+//   * (cos, sin) is never re-derived from theta: one first-order renormalisation per iteration (six steps) keeps the
 //     pair on the unit circle, the phase error stays at rounding level (~1e-6 rad over 128 steps);
 //   * floor-term sums: round(z * 2^18) by the magic-number trick (FFMA, no F2I on the SFU-class pipe), the
-//     rollout-valid mask folded into the scale; the warp REDUX results (uniform registers) of four steps leave
-//     through two 16-byte shared-memory stores of one lane into per-warp slots -- no selects, no atomics; the
-//     32 lanes' bias is removed when the slots are summed.
+//     rollout-valid mask folded into the scale; the warp REDUX results (uniform registers) of six steps leave
+//     through three 16-byte shared-memory stores of one lane into per-warp slots -- no selects, no atomics; the
+//     32 lanes' bias is removed when the slots are summed;
+//   * six steps per loop iteration from two Philox calls (three steps = three Box-Muller pairs per call, common.cuh),
+//     the calls of the next iteration issued one iteration ahead.
 //   (bicycle: additionally |delta| <= u_max[1] <= pi/4, so tan(delta) needs no range reduction.)
 // Anything outside those conditions (Q[2] != 0, large yaw increments, replayed noise, fp64) runs rollout_kernel.
 #pragma once

@@ -8,7 +8,7 @@ import sys
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 K = sys.argv[1] if len(sys.argv) > 1 else "65536"
 T = sys.argv[2] if len(sys.argv) > 2 else "64"
-tags = sys.argv[3:] or ["", "u2", "p7", "u2p7"]
+tags = sys.argv[3:] or ["", "block64", "p7"]
 code = r'''
 import sys, os, json
 sys.path.insert(0, %r)
