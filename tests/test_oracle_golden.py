@@ -89,3 +89,41 @@ def test_oracle_matches_live_reference_with_replayed_noise():
     np.testing.assert_allclose(out["u0"], m.uvec[-1], rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(out["x_next"], x1, rtol=1e-8, atol=1e-12)
     np.testing.assert_allclose(out["U_shift"], m.latest_uvec, rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.skipif(ref_loader.available() is None, reason="reference not loadable here")
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_matches_live_reference_on_varied_parameters(seed):
+    """The reference's tunables are public attributes / arguments (Q, R, P1 at control/src/mppi:69-73; sig, lam at :85):
+    random diagonal Q / P1, a full R, non-default sig (whose [0,0] entry is ALSO the noise std, :144-146) and lam, random
+    start / goal / nominal -- two consecutive get_path calls of the live reference against the restatement."""
+    rng = np.random.RandomState(1000 + seed)
+    K, T = int(rng.choice([7, 32, 65])), int(rng.choice([6, 16, 30]))
+    Q = np.array([rng.uniform(1, 2e3), rng.uniform(1, 2e3), rng.choice([0.0, rng.uniform(0, 50)])])
+    P1 = rng.uniform(1, 2e3, size=3)
+    R = np.array([[rng.uniform(0.5, 2), 0.1], [0.1, rng.uniform(0.5, 2)]])
+    sig = np.array([[rng.uniform(0.3, 1.2), 0.05], [0.02, rng.uniform(0.3, 1.2)]])
+    lam = float(rng.choice([1e-3, 1e-2, 0.1]))
+    x0, goal = rng.uniform(-1, 1, size=3) * [1, 1, 3], rng.uniform(-1, 1, size=3) * [1, 1, 3]
+    ref = ref_loader.load_reference()
+    m = ref.MPPI(horizon=T, samples=K)
+    m.Q, m.R, m.P1 = np.diag(Q), R.copy(), np.diag(P1)
+    m.latest_uvec = rng.normal(size=(2, T)) * 2
+    p = orc.Params(K=K, T=T, Q=Q, R=R, P1=P1, sig=sig, lam=lam, noise_std=np.array([sig[0, 0], sig[0, 0]]))
+    U, s = m.latest_uvec.copy(), x0.copy()
+    sref = x0.copy()
+    orig = np.random.normal
+    for _ in range(2):
+        eps = rng.standard_normal((T, 2, K)) * sig[0, 0]
+        feed = iter(eps)
+        np.random.normal = lambda *a, **k: next(feed).copy()
+        try:
+            sref = m.get_path(sref, goal, sig=sig, lam=lam)
+        finally:
+            np.random.normal = orig
+        out = orc.step(p, s, goal, U, eps)
+        np.testing.assert_allclose(out["u0"], m.uvec[-1], rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(out["x_next"], sref, rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(out["U_shift"], m.latest_uvec, rtol=1e-7, atol=1e-8)
+        # continue from the reference's own state so that the second step is compared from identical inputs
+        s, U = sref.copy(), m.latest_uvec.copy()
