@@ -6,7 +6,6 @@ import sys
 import time
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import numpy as np, motion_planning_b200 as mp
-from motion_planning_b200 import _capi
 K, T = 65536, 64
 prec = sys.argv[1] if len(sys.argv) > 1 else "mixed"
 m = mp.MPPI(horizon=T, samples=K, precision=prec, seed=0)

@@ -1,6 +1,5 @@
 """Compare experimental kernel builds (motion_planning_b200/lib/libmppi_b200_<tag>.so) on one config.
    python profiles/variants.py [K] [T] [tags...]"""
-import json
 import os
 import subprocess
 import sys

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from motion_planning_b200.controller import Controller, FakeDiffDrive
+from motion_planning_b200.controller import Controller
 from oracle import ref_controller
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
