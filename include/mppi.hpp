@@ -121,10 +121,15 @@ class MPPI {
     dyn.apply(p);
     cost.apply(p);
     check(mppi_create(&p, &h_), "mppi_create");
-    if (cost.grid.weight != 0.0 && !cost.grid.cells.empty())
-      check(mppi_set_grid(h_, cost.grid.cells.data(), cost.grid.width, cost.grid.height, cost.grid.resolution,
-                          cost.grid.origin_x, cost.grid.origin_y, cost.grid.weight),
-            "mppi_set_grid");
+    if (cost.grid.weight != 0.0 && !cost.grid.cells.empty()) {
+      const mppi_status st = mppi_set_grid(h_, cost.grid.cells.data(), cost.grid.width, cost.grid.height, cost.grid.resolution,
+                                           cost.grid.origin_x, cost.grid.origin_y, cost.grid.weight);
+      if (st != MPPI_OK) {   // the destructor does not run for a constructor that throws: release the engine here
+        mppi_destroy(h_);
+        h_ = nullptr;
+        check(st, "mppi_set_grid");
+      }
+    }
   }
   MPPI(const MPPI&) = delete;
   MPPI& operator=(const MPPI&) = delete;
@@ -152,6 +157,14 @@ class MPPI {
   void setNominal(const std::vector<double>& U) {
     if (static_cast<int>(U.size()) != 2 * T_) throw std::invalid_argument("nominal must have 2*T entries");
     check(mppi_set_nominal(h_, U.data()), "mppi_set_nominal");
+  }
+
+  // incremental map update (Grid::update_grid, map/src/map/grid.cpp:155-199): overwrite rows y0.., columns x0.. of the
+  // resident occupancy grid with the row-major (height, width) patch; asynchronous, ordered before the next step
+  void updateGrid(const std::vector<int8_t>& patch, int x0, int y0, int width, int height) {
+    if (static_cast<long long>(patch.size()) != static_cast<long long>(width) * height)
+      throw std::invalid_argument("patch must have width*height cells");
+    check(mppi_update_grid(h_, patch.data(), x0, y0, width, height), "mppi_update_grid");
   }
 
   // twist for cmd_vel, Controller.wheelsToTwist (control/src/mppi:319-325)

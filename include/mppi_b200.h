@@ -44,7 +44,10 @@ typedef enum {
   MPPI_ERR_NO_DEVICE = 3,    /* no usable CUDA device (no CPU fallback exists) */
   MPPI_ERR_UNSUPPORTED = 4,  /* valid request this build cannot serve */
   MPPI_ERR_STATE = 5,        /* call sequence error (e.g. step_finish without step_local) */
-  MPPI_ERR_NONFINITE = 6     /* NaN/Inf reached the control output */
+  MPPI_ERR_NONFINITE = 6,    /* NaN/Inf reached the control output */
+  MPPI_ERR_RETRY = 7         /* split-phase sharded step only: the fp32 screen of precision MIXED overflowed on some rank;
+                                nothing was applied on ANY rank -- call mppi_step_local again with the same x0 (it now runs
+                                the fp64 pipeline), exchange, mppi_step_finish.  Every rank gets this status for the same step. */
 } mppi_status;
 
 /* model = integrator-step functor of the reference ctor `MPPI(model=rk4, ...)`, control/src/mppi:62,66 */
@@ -92,7 +95,8 @@ typedef struct {
   int32_t world_size;        /* <=0 -> 1 */
   int32_t rank;
   void* stream;              /* optional cudaStream_t to launch on (NULL -> engine-owned stream + CUDA graph) */
-  double refine_margin;      /* MIXED: cost window re-evaluated in fp64; <=0 -> default */
+  double refine_margin;      /* MIXED: cost window re-evaluated in fp64; <=0 -> default = 40 lambda + a head-room for the
+                                fp32 error of the screen that scales with the step's cost magnitude */
 } mppi_params;
 
 /* Fill *p with the reference's hard-coded constants (control/src/mppi:18-20,62-73,88-89): K=10, T=100. */
@@ -129,6 +133,12 @@ MPPI_API mppi_status mppi_get_last_update(mppi_handle h, double* U);
  * running cost += w_obs * value/100, outside the map counts as 100. */
 MPPI_API mppi_status mppi_set_grid(mppi_handle h, const int8_t* cells, int32_t W, int32_t H, double res,
                           double x_min, double y_min, double w_obs);
+/* Patch a rectangle of the resident grid without reallocation or reconfiguration: rows y0..y0+h-1, columns x0..x0+w-1,
+ * `cells` row-major (h, w).  This is how the incrementally revealed map of the reference's simulated sensor
+ * (Grid::update_grid / fake_occupancy_grid, map/src/map/grid.cpp:155-199: the (2v+1)^2 neighbourhood of the robot's cell per
+ * tick, global_planner/src/dsl.cpp:325-327) reaches the controller.  Asynchronous: staged in pinned memory and copied on the
+ * engine's stream, i.e. ordered before the next step; the call does not wait for the device. */
+MPPI_API mppi_status mppi_update_grid(mppi_handle h, const int8_t* cells, int32_t x0, int32_t y0, int32_t w, int32_t hgt);
 MPPI_API mppi_status mppi_clear_grid(mppi_handle h);
 
 /* ---- noise record / replay ("identical RNG seeds" protocol) ----------------------- */
@@ -193,6 +203,8 @@ typedef struct {
   int32_t refine_candidates;  /* MIXED: fp64 re-evaluations in the last step */
   int32_t refine_overflow;    /* MIXED: candidate-list overflows seen (forces a full-fp64 redo) */
   double refine_max_dev;      /* MIXED: max |V_fp32 - V_fp64| over re-evaluated rollouts, last step */
+  double refine_head_room;    /* MIXED: head-room of the screening window of the last step; a step whose refine_max_dev exceeds
+                                 half of it is redone in fp64 (counted in refine_overflow) */
 } mppi_timing;
 
 /* Device-resident closed loop on the model (x0 <- x_next on the device, as solve_path does,

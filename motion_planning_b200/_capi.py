@@ -13,7 +13,8 @@ LIB_PATH = os.environ.get("MPPI_B200_LIB") or os.path.join(_HERE, "lib", "libmpp
 
 MPPI_OK = 0
 STATUS_NAMES = {0: "MPPI_OK", 1: "MPPI_ERR_INVALID", 2: "MPPI_ERR_CUDA", 3: "MPPI_ERR_NO_DEVICE",
-                4: "MPPI_ERR_UNSUPPORTED", 5: "MPPI_ERR_STATE", 6: "MPPI_ERR_NONFINITE"}
+                4: "MPPI_ERR_UNSUPPORTED", 5: "MPPI_ERR_STATE", 6: "MPPI_ERR_NONFINITE", 7: "MPPI_ERR_RETRY"}
+MPPI_ERR_RETRY = 7
 
 MODEL_DIFF_DRIVE, MODEL_UNICYCLE_EULER, MODEL_BICYCLE = 0, 1, 2
 WEIGHT_COST_TO_GO, WEIGHT_TOTAL_COST = 0, 1
@@ -41,7 +42,7 @@ class MppiTiming(C.Structure):
     _fields_ = [
         ("step_ms", C.c_float), ("rollout_ms", C.c_float), ("reduce_ms", C.c_float), ("finalize_ms", C.c_float),
         ("launches", C.c_int32), ("steps", C.c_int32), ("refine_candidates", C.c_int32),
-        ("refine_overflow", C.c_int32), ("refine_max_dev", C.c_double),
+        ("refine_overflow", C.c_int32), ("refine_max_dev", C.c_double), ("refine_head_room", C.c_double),
     ]
 
 
@@ -68,6 +69,7 @@ _SIGNATURES = {
     "mppi_set_nominal": [_H, _dp],
     "mppi_get_last_update": [_H, _dp],
     "mppi_set_grid": [_H, C.POINTER(C.c_int8), C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double],
+    "mppi_update_grid": [_H, C.POINTER(C.c_int8), C.c_int32, C.c_int32, C.c_int32, C.c_int32],
     "mppi_clear_grid": [_H],
     "mppi_set_noise": [_H, _dp],
     "mppi_use_philox": [_H, C.c_uint64],

@@ -45,9 +45,29 @@ struct StaticParams {
   double wheel_r, wheel_L;
   double eps_floor;
   double g_inv_res, g_x0, g_y0, w_obs;
-  double margin;         // SCREEN window (cost units)
+  double margin;         // SCREEN window (cost units): the soft-min SUPPORT part, 40 lam (or the caller's whole window)
+  // head-room of the window for the fp32 error of the screened cost-to-go, scaled with the cost magnitude of the step:
+  //   head = max(head_min, head_scale * 2^-23 * Vmax),  Vmax = vm_c0 + vm_ca * |pos(x0) - pos(goal)| + vm_cth * |th0 - th_goal|
+  // (Vmax bounds |V| in delta form over the horizon; head_scale == 0: static window = margin, the caller's refine_margin)
+  double head_scale, head_min, vm_c0, vm_ca, vm_cth;
   unsigned long long seed;
 };
+
+// the SCREEN window of a step and its head-room part.  Evaluated with explicitly rounded operations so that the rollout
+// kernel (which lists candidates against it) and the reduce kernel (which filters them against the global minimum) get the
+// bit-identical value from the same (x0, goal).
+__device__ __forceinline__ double screen_window(const StaticParams& sp, const double x0[3], const double g[3], double* head_out = nullptr) {
+  if (sp.head_scale == 0.0) {
+    if (head_out) *head_out = 0.5 * sp.margin;
+    return sp.margin;
+  }
+  const double ax = __dsub_rn(x0[0], g[0]), ay = __dsub_rn(x0[1], g[1]), at = fabs(__dsub_rn(x0[2], g[2]));
+  const double a = __dsqrt_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
+  const double v = __dadd_rn(__dadd_rn(sp.vm_c0, __dmul_rn(sp.vm_ca, a)), __dmul_rn(sp.vm_cth, at));
+  const double head = fmax(sp.head_min, __dmul_rn(sp.head_scale * 1.1920928955078125e-07, v));
+  if (head_out) *head_out = head;
+  return __dadd_rn(sp.margin, head);
+}
 
 // ---- dynamic state living in HBM (changes every step; lets the CUDA graph stay static) ---------
 struct DynState {
@@ -68,6 +88,7 @@ struct DynState {
   int last_candidates;   // statistics of the last finished step (finalize_kernel)
   double refine_max_dev;
   double last_max_dev;
+  double last_head;      // head-room of the screening window of the last finished step
   int overflow_total;    // steps that hit a candidate-list overflow since creation
   unsigned int xchg;     // p2p exchange epoch: +1 per step, never rewound (arrival flags carry xchg+1)
   // fp32 mirrors of lam / noise_std kept by the host (LEAN rollout prologue: no fp64 division, no conversions)
@@ -81,6 +102,7 @@ struct HostResult {
   double out_u[2];
   double out_x[3];
   double max_dev;
+  double head;           // head-room of the screening window of this step (max_dev is checked against half of it)
   int status;
   int candidates;
   int overflow_total;

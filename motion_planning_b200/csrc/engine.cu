@@ -1,9 +1,10 @@
 // engine.cu -- host side of libmppi_b200.so: the C ABI declared in include/mppi_b200.h.
 //
-// One engine = one CUDA device.  A step (= MPPI.get_path, control/src/mppi:85-102) is three kernels
-//   rollout_kernel -> reduce_{softmin,screen}_kernel -> finalize_kernel
-// captured once into a CUDA graph together with the 48-byte H2D copy of (x0, goal) and the D2H copy
-// of the result block; all controller state (nominal U, Philox step counter) stays resident in HBM.
+// One engine = one CUDA device.  A step (= MPPI.get_path, control/src/mppi:85-102) is TWO kernel launches and no copy:
+//   rollout_{lean,lean_sm,}_kernel --PDL--> reduce_{softmin,screen}_kernel (+ exchange and finalize in its last block)
+// x0 / goal ride in the kernels' argument buffers, the result block is stored by the finalize phase into mapped pinned
+// host memory; all controller state (nominal U, noise step counter) stays resident in HBM.  mppi_bench replays the same
+// two launches from a CUDA graph with x0 resident on the device (closed loop on the model).
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -43,6 +44,18 @@ static void set_err(const char* fmt, ...) {
     mppi_status _s = (call);            \
     if (_s != MPPI_OK) return _s;       \
   } while (0)
+
+// Host <-> device copies of the set-up / debug entry points run ON the engine's stream and are waited for there: a
+// synchronous cudaMemcpy from pageable memory goes through the legacy stream, which a cudaStreamNonBlocking stream is not
+// ordered with (the copy may return before its DMA has landed while a kernel of ours is already being launched).
+#define COPY_SYNC(e, dst, src, bytes, kind)                                             \
+  do {                                                                                  \
+    CK(cudaMemcpyAsync((dst), (src), (bytes), (kind), (e)->stream));                    \
+    CK(cudaStreamSynchronize((e)->stream));                                             \
+  } while (0)
+
+struct mppi_engine;
+static cudaError_t memcpy_on(mppi_engine* e, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
 
 struct KindCfg {
   int variant = ROLLOUT_GENERAL;
@@ -91,6 +104,9 @@ struct mppi_engine {
   bool attempted_mixed = false;
   int lean_split = 0;   // MPPI_B200_SPLIT: first step of the second pair of warps of the SM-wide kernel's shared tile (0 = default)
   signed char* d_grid = nullptr;
+  signed char* h_grid_stage = nullptr;   // pinned staging of mppi_update_grid patches
+  size_t grid_stage_cap = 0;
+  cudaEvent_t grid_stage_ev = nullptr;
   double* d_eps_ext = nullptr;
   void* d_vcap = nullptr;
   void* d_flush = nullptr;
@@ -115,6 +131,12 @@ struct mppi_engine {
   bool local_pending = false;
   mppi_timing last{};
 };
+
+static cudaError_t memcpy_on(mppi_engine* e, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+  cudaError_t ce = cudaMemcpyAsync(dst, src, bytes, kind, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  return ce;
+}
 
 static int kind_of(int precision) {
   return precision == MPPI_PRECISION_F32 ? ROLLOUT_F32_SOFTMIN
@@ -162,11 +184,39 @@ extern "C" mppi_status mppi_default_params(mppi_params* p) {
   return MPPI_OK;
 }
 
-static double default_margin(const mppi_engine* e, double lam) {
-  if (e->p.refine_margin > 0) return e->p.refine_margin;
-  // e^-40 ~ 4e-18 relative weight is far below the 1e-8 floor; 0.04 covers the fp32 screening error
-  // of the cost-to-go (measured max |V32 - V64| <= 2.9e-3 over all BASELINE configs incl. K=2M,T=128, see profiles/) 14x over.
-  return 40.0 * lam + 0.04;
+// The SCREEN window = support + head-room (common.cuh: screen_window).  Support: e^-40 ~ 4e-18 relative weight is far
+// below the 1e-8 floor.  Head-room: the fp32 error of the screened cost-to-go grows with the magnitude of the costs being
+// summed, so it is scaled with a bound Vmax of |V| in delta form over the horizon (distance to the goal enters through
+// d (d + 2a)): head = max(2e-3, 4 * 2^-23 * Vmax) -- 5..8x the measured max |V32 - V64| of all BASELINE configs (profiles/),
+// and the reduce kernel redoes the step in fp64 when the deviation it can observe exceeds half of it.
+static void set_window(mppi_engine* e, double lam) {
+  StaticParams& sp = e->sp;
+  if (e->p.refine_margin > 0) {   // caller's static window
+    sp.margin = e->p.refine_margin;
+    sp.head_scale = sp.head_min = sp.vm_c0 = sp.vm_ca = sp.vm_cth = 0.0;
+    return;
+  }
+  sp.margin = 40.0 * lam;
+  sp.head_scale = 4.0;
+  sp.head_min = 2e-3;
+  const double horizon = sp.T * sp.dt;
+  double v, w;   // largest forward speed / yaw rate of a clipped control
+  if (sp.model == MPPI_MODEL_DIFF_DRIVE) {
+    v = 0.5 * sp.wheel_r * (sp.u_max[0] + sp.u_max[1]);
+    w = sp.wheel_r / sp.wheel_L * (sp.u_max[0] + sp.u_max[1]);
+  } else if (sp.model == MPPI_MODEL_UNICYCLE_EULER) {
+    v = sp.u_max[0];
+    w = sp.u_max[1];
+  } else {
+    v = sp.u_max[0];
+    w = sp.u_max[0] * std::tan(std::fmin(sp.u_max[1], 1.55)) / sp.wheel_L;
+  }
+  const double D = v * horizon, Th = w * horizon;
+  const double cA = sp.T * 0.5 * std::fmax(sp.q[0], sp.q[1]) + std::fmax(sp.p1[0], sp.p1[1]);
+  const double cTh = sp.T * 0.5 * sp.q[2] + sp.p1[2];
+  sp.vm_c0 = cA * D * D + cTh * Th * Th + std::fabs(sp.w_obs) * sp.T;
+  sp.vm_ca = 2.0 * cA * D;
+  sp.vm_cth = 2.0 * cTh * Th;
 }
 
 static void free_partials(mppi_engine* e) {
@@ -267,7 +317,9 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
     e->cfg[kind] = best;
     if (best.ready && (size_t)best.nparts > *max_ctas) *max_ctas = best.nparts;
   }
-  return e->cfg[kind_of(e->p.precision)].ready && e->cfg[ROLLOUT_F64_SOFTMIN].ready;
+  // the fp64 family is needed by precision F64 itself and by MIXED (redo of an overflowing step); an F32 engine only needs
+  // it for the debug entry point mppi_cost_to_go, which then reports MPPI_ERR_UNSUPPORTED by itself
+  return e->cfg[kind_of(e->p.precision)].ready && (e->p.precision == MPPI_PRECISION_F32 || e->cfg[ROLLOUT_F64_SOFTMIN].ready);
 }
 
 static mppi_status configure(mppi_engine* e) {
@@ -280,7 +332,9 @@ static mppi_status configure(mppi_engine* e) {
     ok = try_configure(e, 0, &max_ctas);
   }
   if (!ok) {
-    set_err("no launch configuration fits (T=%d needs too much shared memory)", sp.T);
+    set_err("no launch configuration fits: the cost tile of T=%d steps needs too much shared memory for precision %s "
+            "(fp64 rollouts: T <= ~400; fp32 rollouts: T <= ~800)", sp.T,
+            e->p.precision == MPPI_PRECISION_F32 ? "F32" : (e->p.precision == MPPI_PRECISION_F64 ? "F64" : "MIXED"));
     return MPPI_ERR_UNSUPPORTED;
   }
   sp.grid_in_smem = gin > 0 ? 1 : 0;
@@ -320,7 +374,7 @@ static void savgol_basis(int T, double& a, double& b, double inv_norm[4]) {
 
 static mppi_status upload_dyn_sampling(mppi_engine* e, const double sig[4], double lam, const double nstd[2]) {
   DynState tmp;
-  CK(cudaMemcpy(&tmp, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost));
+  COPY_SYNC(e, &tmp, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost);
   for (int i = 0; i < 4; ++i) tmp.sig[i] = sig[i];
   tmp.lam = lam;
   tmp.noise_std[0] = nstd[0];
@@ -328,7 +382,7 @@ static mppi_status upload_dyn_sampling(mppi_engine* e, const double sig[4], doub
   tmp.neg_inv_lam_f = (float)(-1.0 / lam);
   tmp.noise_std_f[0] = (float)nstd[0];
   tmp.noise_std_f[1] = (float)nstd[1];
-  CK(cudaMemcpy(e->d_dyn, &tmp, sizeof(DynState), cudaMemcpyHostToDevice));
+  COPY_SYNC(e, e->d_dyn, &tmp, sizeof(DynState), cudaMemcpyHostToDevice);
   return MPPI_OK;
 }
 
@@ -422,8 +476,8 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
   sp.wheel_L = p.wheel_base;
   sp.eps_floor = p.eps_floor;
   sp.seed = p.seed;
-  sp.margin = default_margin(e, p.lambda);
   sp.g_inv_res = 1.0;
+  set_window(e, p.lambda);
 
   const int T = p.T;
   auto fail = [&](mppi_status s) {
@@ -474,7 +528,7 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
     d.neg_inv_lam_f = (float)(-1.0 / p.lambda);
     d.noise_std_f[0] = (float)p.noise_std[0];
     d.noise_std_f[1] = (float)p.noise_std[1];
-    CKF(cudaMemcpy(e->d_dyn, &d, sizeof(d), cudaMemcpyHostToDevice));
+    CKF(memcpy_on(e, e->d_dyn, &d, sizeof(d), cudaMemcpyHostToDevice));
   }
   e->U_prev.assign(2 * T, 0.0);
   mppi_status s = configure(e);
@@ -507,6 +561,8 @@ extern "C" mppi_status mppi_destroy(mppi_handle e) {
   cudaFree(e->d_p2p_peers);
   cudaFree(e->d_p2p);
   cudaFree(e->d_grid);
+  if (e->h_grid_stage) cudaFreeHost(e->h_grid_stage);
+  if (e->grid_stage_ev) cudaEventDestroy(e->grid_stage_ev);
   cudaFree(e->d_eps_ext);
   cudaFree(e->d_vcap);
   cudaFree(e->d_flush);
@@ -557,11 +613,9 @@ extern "C" mppi_status mppi_set_sampling(mppi_handle e, const double sig[4], dou
   for (int i = 0; i < 4; ++i) e->p.sig[i] = sig[i];
   e->p.lambda = lambda;
   e->p.noise_std[0] = e->p.noise_std[1] = sig[0];
-  const double m = default_margin(e, lambda);
-  if (m != e->sp.margin) {
-    e->sp.margin = m;
-    drop_graphs(e);
-  }
+  const double m = e->sp.margin;
+  set_window(e, lambda);
+  if (m != e->sp.margin) drop_graphs(e);
   return prep_nominal(e);
 }
 
@@ -578,24 +632,21 @@ extern "C" mppi_status mppi_set_noise_std(mppi_handle e, const double nstd[2]) {
 extern "C" mppi_status mppi_get_nominal(mppi_handle e, double* U) {
   ENTER(e);
   if (!U) return MPPI_ERR_INVALID;
-  CK(cudaStreamSynchronize(e->stream));
-  CK(cudaMemcpy(U, e->d_Umaster, 2 * e->sp.T * sizeof(double), cudaMemcpyDeviceToHost));
+  COPY_SYNC(e, U, e->d_Umaster, 2 * e->sp.T * sizeof(double), cudaMemcpyDeviceToHost);
   return MPPI_OK;
 }
 
 extern "C" mppi_status mppi_set_nominal(mppi_handle e, const double* U) {
   ENTER(e);
   if (!U) return MPPI_ERR_INVALID;
-  CK(cudaStreamSynchronize(e->stream));
-  CK(cudaMemcpy(e->d_Umaster, U, 2 * e->sp.T * sizeof(double), cudaMemcpyHostToDevice));
+  COPY_SYNC(e, e->d_Umaster, U, 2 * e->sp.T * sizeof(double), cudaMemcpyHostToDevice);
   return prep_nominal(e);
 }
 
 extern "C" mppi_status mppi_get_last_update(mppi_handle e, double* U) {
   ENTER(e);
   if (!U) return MPPI_ERR_INVALID;
-  CK(cudaStreamSynchronize(e->stream));
-  CK(cudaMemcpy(U, e->d_Ulast, 2 * e->sp.T * sizeof(double), cudaMemcpyDeviceToHost));
+  COPY_SYNC(e, U, e->d_Ulast, 2 * e->sp.T * sizeof(double), cudaMemcpyDeviceToHost);
   return MPPI_OK;
 }
 
@@ -608,11 +659,18 @@ extern "C" mppi_status mppi_set_grid(mppi_handle e, const int8_t* cells, int32_t
   }
   CK(cudaStreamSynchronize(e->stream));
   const size_t n = (size_t)W * H, padded = (n + 15) & ~(size_t)15;
+  // the new grid is complete on the device before the old one is released: a failure leaves the engine as it was
+  signed char* fresh = nullptr;
+  CK(cudaMalloc(&fresh, padded));
+  cudaError_t ce = cudaMemsetAsync(fresh, 100, padded, e->stream);
+  if (ce == cudaSuccess) ce = memcpy_on(e, fresh, cells, n, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) {
+    cudaFree(fresh);
+    set_err("mppi_set_grid: upload failed: %s", cudaGetErrorString(ce));
+    return MPPI_ERR_CUDA;
+  }
   cudaFree(e->d_grid);
-  e->d_grid = nullptr;
-  CK(cudaMalloc(&e->d_grid, padded));
-  CK(cudaMemset(e->d_grid, 100, padded));
-  CK(cudaMemcpy(e->d_grid, cells, n, cudaMemcpyHostToDevice));
+  e->d_grid = fresh;
   StaticParams& sp = e->sp;
   sp.has_grid = 1;
   sp.gW = W;
@@ -622,7 +680,42 @@ extern "C" mppi_status mppi_set_grid(mppi_handle e, const int8_t* cells, int32_t
   sp.g_x0 = x_min;
   sp.g_y0 = y_min;
   sp.w_obs = w_obs;
+  set_window(e, e->p.lambda);
   return configure(e);
+}
+
+// Patch a rectangle of the resident grid (the incrementally revealed map of the planners' simulated sensor,
+// map/src/map/grid.cpp:155-199: Grid::update_grid / fake_occupancy_grid; or any nav_msgs/OccupancyGrid update): rows
+// y0 .. y0+h-1, columns x0 .. x0+w-1, `cells` row-major (h, w).  Asynchronous: the patch is staged in pinned host memory and
+// copied on the engine's stream, so it is ordered before the next step's kernels and the call does not wait for the device;
+// no reallocation, no reconfiguration (the rollout kernel re-reads the grid from HBM -- through TMA into shared memory when
+// it fits -- at every launch).
+extern "C" mppi_status mppi_update_grid(mppi_handle e, const int8_t* cells, int32_t x0, int32_t y0, int32_t w, int32_t h) {
+  ENTER(e);
+  const StaticParams& sp = e->sp;
+  if (!sp.has_grid || !e->d_grid) {
+    set_err("mppi_update_grid: no grid is resident (call mppi_set_grid first)");
+    return MPPI_ERR_STATE;
+  }
+  if (!cells || w < 1 || h < 1 || x0 < 0 || y0 < 0 || (long long)x0 + w > sp.gW || (long long)y0 + h > sp.gH) {
+    set_err("mppi_update_grid: patch [%d,%d)+(%d x %d) outside the %d x %d grid", x0, y0, w, h, sp.gW, sp.gH);
+    return MPPI_ERR_INVALID;
+  }
+  const size_t bytes = (size_t)w * h;
+  if (e->grid_stage_ev) CK(cudaEventSynchronize(e->grid_stage_ev));   // the previous patch has left the staging buffer
+  if (bytes > e->grid_stage_cap) {
+    if (e->h_grid_stage) cudaFreeHost(e->h_grid_stage);
+    e->h_grid_stage = nullptr;
+    e->grid_stage_cap = 0;
+    CK(cudaMallocHost(&e->h_grid_stage, bytes < 4096 ? 4096 : bytes));
+    e->grid_stage_cap = bytes < 4096 ? 4096 : bytes;
+  }
+  if (!e->grid_stage_ev) CK(cudaEventCreateWithFlags(&e->grid_stage_ev, cudaEventDisableTiming));
+  memcpy(e->h_grid_stage, cells, bytes);
+  CK(cudaMemcpy2DAsync(e->d_grid + (size_t)y0 * sp.gW + x0, (size_t)sp.gW, e->h_grid_stage, (size_t)w, (size_t)w, (size_t)h,
+                       cudaMemcpyHostToDevice, e->stream));
+  CK(cudaEventRecord(e->grid_stage_ev, e->stream));
+  return MPPI_OK;
 }
 
 extern "C" mppi_status mppi_clear_grid(mppi_handle e) {
@@ -631,6 +724,7 @@ extern "C" mppi_status mppi_clear_grid(mppi_handle e) {
   e->sp.has_grid = 0;
   e->sp.grid_in_smem = 0;
   e->sp.w_obs = 0;
+  set_window(e, e->p.lambda);
   return configure(e);
 }
 
@@ -640,7 +734,7 @@ extern "C" mppi_status mppi_set_noise(mppi_handle e, const double* eps) {
   CK(cudaStreamSynchronize(e->stream));
   const size_t n = (size_t)e->sp.T * 2 * e->sp.K;
   if (!e->d_eps_ext) CK(cudaMalloc(&e->d_eps_ext, n * sizeof(double)));
-  CK(cudaMemcpy(e->d_eps_ext, eps, n * sizeof(double), cudaMemcpyHostToDevice));
+  COPY_SYNC(e, e->d_eps_ext, eps, n * sizeof(double), cudaMemcpyHostToDevice);
   if (!e->sp.noise_external) {
     e->sp.noise_external = 1;
     return configure(e);     // replayed noise runs on the GENERAL kernels
@@ -654,7 +748,7 @@ extern "C" mppi_status mppi_use_philox(mppi_handle e, uint64_t seed) {
   e->sp.noise_external = 0;
   e->sp.seed = seed;
   unsigned int zero = 0;
-  CK(cudaMemcpy(&e->d_dyn->step, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+  COPY_SYNC(e, &e->d_dyn->step, &zero, sizeof(zero), cudaMemcpyHostToDevice);
   return configure(e);
 }
 
@@ -664,11 +758,11 @@ extern "C" mppi_status mppi_get_noise(mppi_handle e, double* eps) {
   CK(cudaStreamSynchronize(e->stream));
   const size_t n = (size_t)e->sp.T * 2 * e->sp.K;
   if (e->sp.noise_external) {
-    CK(cudaMemcpy(eps, e->d_eps_ext, n * sizeof(double), cudaMemcpyDeviceToHost));
+    COPY_SYNC(e, eps, e->d_eps_ext, n * sizeof(double), cudaMemcpyDeviceToHost);
     return MPPI_OK;
   }
   unsigned int step = 0;
-  CK(cudaMemcpy(&step, &e->d_dyn->step, sizeof(step), cudaMemcpyDeviceToHost));
+  COPY_SYNC(e, &step, &e->d_dyn->step, sizeof(step), cudaMemcpyDeviceToHost);
   if (step == 0) {
     set_err("mppi_get_noise: no step has been run since the noise stream was (re)seeded");
     return MPPI_ERR_STATE;
@@ -676,8 +770,8 @@ extern "C" mppi_status mppi_get_noise(mppi_handle e, double* eps) {
   double* tmp = nullptr;
   CK(cudaMalloc(&tmp, n * sizeof(double)));
   cudaError_t ce = noise_export_launch(e->stream, e->sp, e->d_dyn, step - 1, tmp);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(eps, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-  if (ce == cudaSuccess) ce = cudaMemcpy(eps, tmp, n * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(tmp);
   CK(ce);
   return MPPI_OK;
@@ -784,7 +878,6 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
     ls.p1th = (float)sp.p1[2];
     ls.g_inv_res = (float)(sp.g_inv_res / sq);
     ls.w_obs_100 = (float)(sp.w_obs / 100.0);
-    ls.margin = (float)sp.margin;
     ls.split = e->lean_split > 0 ? e->lean_split : ((sp.T * 9 / 16 + 5) / 6) * 6;
     for (int i = 0; i < MPPI_PHILOX_ROUNDS; ++i) {
       ls.pkx[i] = (uint32_t)sp.seed + (uint32_t)i * 0x9E3779B9u;
@@ -918,8 +1011,14 @@ static mppi_status finish_outputs(mppi_engine* e, double u_out[2], double x_next
     // MIXED: a candidate list overflowed; redo this step entirely in fp64 (same noise: the step
     // counter was not advanced, U and x0 are untouched).
     if (e->sp.world > 1 && !e->p2p_on) {
-      set_err("MIXED overflow in a sharded step with an external exchange: rerun with precision F64");
-      return MPPI_ERR_UNSUPPORTED;
+      // split-phase step with an external exchange: the host owns the exchange, so the redo is a second round trip of
+      // mppi_step_local (now fp64: the hold-off is armed) / exchange / mppi_step_finish.  Every rank merged the same
+      // records, so every rank lands here for the same step and keeps the same hold-off schedule.
+      e->last.refine_overflow += 1;
+      e->f64_holdoff = e->f64_backoff + 1;   // + 1: the redo itself consumes one
+      e->f64_backoff = e->f64_backoff * 2 > 64 ? 64 : e->f64_backoff * 2;
+      set_err("the fp32 screen overflowed on some rank: repeat mppi_step_local / exchange / mppi_step_finish for this step (it runs in fp64)");
+      return MPPI_ERR_RETRY;
     }
     const StepInput in = step_input(e);
     e->seq += 1;
@@ -933,6 +1032,7 @@ static mppi_status finish_outputs(mppi_engine* e, double u_out[2], double x_next
   }
   e->last.refine_candidates = o->candidates;
   e->last.refine_max_dev = o->max_dev;
+  e->last.refine_head_room = o->head;
   if (u_out) {
     u_out[0] = o->out_u[0];
     u_out[1] = o->out_u[1];
@@ -965,8 +1065,7 @@ static mppi_status pre_step(mppi_engine* e, const double x0[3]) {
     e->last_goal[i] = e->goal[i];
   }
   if (e->sp.capture) {   // debug: remember the nominal this step starts from (offset of get_cost_to_go)
-    CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy(e->U_prev.data(), e->d_Umaster, 2 * e->sp.T * sizeof(double), cudaMemcpyDeviceToHost));
+    COPY_SYNC(e, e->U_prev.data(), e->d_Umaster, 2 * e->sp.T * sizeof(double), cudaMemcpyDeviceToHost);
   }
   return MPPI_OK;
 }
@@ -1028,7 +1127,13 @@ extern "C" mppi_status mppi_step_local(mppi_handle e, const double x0[3]) {
   }
   CKS(pre_step(e, x0));
   CK(cudaMemcpyAsync(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-  CKS(launch_local(e, e->stream, e->p.precision, FUSE_NONE, nullptr));
+  int precision = e->p.precision;
+  if (precision == MPPI_PRECISION_MIXED && e->f64_holdoff > 0) {   // same back-off as mppi_step (identical on every rank)
+    precision = MPPI_PRECISION_F64;
+    e->f64_holdoff -= 1;
+  }
+  e->attempted_mixed = precision == MPPI_PRECISION_MIXED;
+  CKS(launch_local(e, e->stream, precision, FUSE_NONE, nullptr));
   e->local_pending = true;
   return MPPI_OK;
 }
@@ -1048,7 +1153,7 @@ extern "C" mppi_status mppi_read_record(mppi_handle e, double* record) {
   ENTER(e);
   if (!record) return MPPI_ERR_INVALID;
   CK(cudaStreamSynchronize(e->stream));
-  CK(cudaMemcpy(record, e->d_record, (size_t)e->sp.T * kRecordStride * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(memcpy_on(e, record, e->d_record, (size_t)e->sp.T * kRecordStride * sizeof(double), cudaMemcpyDeviceToHost));
   return MPPI_OK;
 }
 
@@ -1098,7 +1203,7 @@ extern "C" mppi_status mppi_p2p_connect(mppi_handle e, const void* handles) {
     peers[g] = (double*)ptr;
   }
   if (!e->d_p2p_peers) CK(cudaMalloc(&e->d_p2p_peers, world * sizeof(double*)));
-  CK(cudaMemcpy(e->d_p2p_peers, peers.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
+  CK(memcpy_on(e, e->d_p2p_peers, peers.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
   e->p2p_on = true;
   return drop_graphs(e);
 }
@@ -1140,10 +1245,10 @@ static mppi_status read_vcap(mppi_engine* e, int kind, const std::vector<double>
   const int T = e->sp.T, K = e->sp.K;
   const size_t n = (size_t)T * K;
   if (kind == ROLLOUT_F64_SOFTMIN) {
-    CK(cudaMemcpy(V, e->d_vcap, n * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(memcpy_on(e, V, e->d_vcap, n * sizeof(double), cudaMemcpyDeviceToHost));
   } else {
     std::vector<float> tmp(n);
-    CK(cudaMemcpy(tmp.data(), e->d_vcap, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(memcpy_on(e, tmp.data(), e->d_vcap, n * sizeof(float), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n; ++i) V[i] = (double)tmp[i];
   }
   for (int t = 0; t < T; ++t)
@@ -1176,8 +1281,8 @@ extern "C" mppi_status mppi_cost_to_go(mppi_handle e, const double x0[3], const 
   StaticParams sp_save = e->sp;
   double* eps_save = e->d_eps_ext;
   DynState dyn_save;
-  CK(cudaMemcpy(&dyn_save, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(e->d_Utmp, e->d_Umaster, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice));
+  CK(memcpy_on(e, &dyn_save, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost));
+  CK(memcpy_on(e, e->d_Utmp, e->d_Umaster, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice));
   double* eps_tmp = nullptr;
   CK(cudaMalloc(&eps_tmp, ne * sizeof(double)));
   mppi_status s = MPPI_OK;
@@ -1186,18 +1291,28 @@ extern "C" mppi_status mppi_cost_to_go(mppi_handle e, const double x0[3], const 
       s = MPPI_ERR_CUDA;
       break;
     }
-    cudaMemcpy(eps_tmp, eps, ne * sizeof(double), cudaMemcpyHostToDevice);
-    cudaMemcpy(e->d_Umaster, U, 2 * T * sizeof(double), cudaMemcpyHostToDevice);
     DynState d = dyn_save;
     for (int i = 0; i < 3; ++i) {
       d.x0[i] = x0[i];
       d.goal[i] = goal[i];
     }
-    cudaMemcpy(e->d_dyn, &d, sizeof(d), cudaMemcpyHostToDevice);
+    cudaError_t ce = memcpy_on(e, eps_tmp, eps, ne * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = memcpy_on(e, e->d_Umaster, U, 2 * T * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = memcpy_on(e, e->d_dyn, &d, sizeof(d), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+      set_err("mppi_cost_to_go: staging copy failed: %s", cudaGetErrorString(ce));
+      s = MPPI_ERR_CUDA;
+      break;
+    }
     e->d_eps_ext = eps_tmp;
     e->sp.noise_external = 1;
     e->sp.capture = 1;
     if ((s = configure(e)) != MPPI_OK) break;
+    if (!e->cfg[ROLLOUT_F64_SOFTMIN].ready) {
+      set_err("mppi_cost_to_go: the fp64 rollout kernel has no launch configuration for T=%d (its cost tile needs too much shared memory)", T);
+      s = MPPI_ERR_UNSUPPORTED;
+      break;
+    }
     if ((s = prep_nominal(e)) != MPPI_OK) break;
     if ((s = launch_local(e, e->stream, MPPI_PRECISION_F64, FUSE_NONE, nullptr)) != MPPI_OK) break;
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
@@ -1214,8 +1329,8 @@ extern "C" mppi_status mppi_cost_to_go(mppi_handle e, const double x0[3], const 
   e->d_eps_ext = eps_save;
   e->last_capture_kind = -1;
   configure(e);
-  cudaMemcpy(e->d_dyn, &dyn_save, sizeof(DynState), cudaMemcpyHostToDevice);
-  cudaMemcpy(e->d_Umaster, e->d_Utmp, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
+  memcpy_on(e, e->d_dyn, &dyn_save, sizeof(DynState), cudaMemcpyHostToDevice);
+  memcpy_on(e, e->d_Umaster, e->d_Utmp, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
   cudaFree(eps_tmp);
   mppi_status s2 = prep_nominal(e);
   return s != MPPI_OK ? s : s2;
@@ -1235,12 +1350,12 @@ extern "C" mppi_status mppi_update_action(mppi_handle e, const double* U_in, con
     return MPPI_ERR_CUDA;
   }
   mppi_status s = MPPI_OK;
-  cudaMemcpy(dV, V, (size_t)T * K * sizeof(double), cudaMemcpyHostToDevice);
-  cudaMemcpy(deps, eps, (size_t)T * 2 * K * sizeof(double), cudaMemcpyHostToDevice);
-  cudaMemcpy(e->d_Utmp, e->d_Umaster, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
-  cudaMemcpy(e->d_Utmp + 2 * T, e->d_Ulast, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
-  cudaMemcpy(e->d_Umaster, U_in, 2 * T * sizeof(double), cudaMemcpyHostToDevice);
-  cudaError_t ce = weights_from_v_launch(e->stream, e->sp, e->d_dyn, dV, deps, e->d_record_tmp);
+  cudaError_t ce = memcpy_on(e, dV, V, (size_t)T * K * sizeof(double), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = memcpy_on(e, deps, eps, (size_t)T * 2 * K * sizeof(double), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = memcpy_on(e, e->d_Utmp, e->d_Umaster, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
+  if (ce == cudaSuccess) ce = memcpy_on(e, e->d_Utmp + 2 * T, e->d_Ulast, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
+  if (ce == cudaSuccess) ce = memcpy_on(e, e->d_Umaster, U_in, 2 * T * sizeof(double), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = weights_from_v_launch(e->stream, e->sp, e->d_dyn, dV, deps, e->d_record_tmp);
   if (ce == cudaSuccess) {
     FinalizeArgs fa;
     memset(&fa, 0, sizeof(fa));
@@ -1260,13 +1375,13 @@ extern "C" mppi_status mppi_update_action(mppi_handle e, const double* U_in, con
     ce = finalize_launch(e->stream, fa);
   }
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-  if (ce == cudaSuccess) ce = cudaMemcpy(U_out, e->d_Ulast, 2 * T * sizeof(double), cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess) ce = memcpy_on(e, U_out, e->d_Ulast, 2 * T * sizeof(double), cudaMemcpyDeviceToHost);
   if (ce != cudaSuccess) {
     set_err("mppi_update_action: %s", cudaGetErrorString(ce));
     s = MPPI_ERR_CUDA;
   }
-  cudaMemcpy(e->d_Umaster, e->d_Utmp, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
-  cudaMemcpy(e->d_Ulast, e->d_Utmp + 2 * T, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
+  memcpy_on(e, e->d_Umaster, e->d_Utmp, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
+  memcpy_on(e, e->d_Ulast, e->d_Utmp + 2 * T, 2 * T * sizeof(double), cudaMemcpyDeviceToDevice);
   cudaFree(dV);
   cudaFree(deps);
   return s;
@@ -1277,11 +1392,11 @@ extern "C" mppi_status mppi_model_step(mppi_handle e, const double* x, const dou
   if (!x || !u || !x_out || n < 1) return MPPI_ERR_INVALID;
   double* d = nullptr;
   CK(cudaMalloc(&d, (size_t)8 * n * sizeof(double)));
-  cudaError_t ce = cudaMemcpy(d, x, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice);
-  if (ce == cudaSuccess) ce = cudaMemcpy(d + 3 * (size_t)n, u, (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice);
+  cudaError_t ce = memcpy_on(e, d, x, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = memcpy_on(e, d + 3 * (size_t)n, u, (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice);
   if (ce == cudaSuccess) ce = model_step_launch(e->stream, e->sp, d, d + 3 * (size_t)n, n, d + 5 * (size_t)n);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-  if (ce == cudaSuccess) ce = cudaMemcpy(x_out, d + 5 * (size_t)n, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess) ce = memcpy_on(e, x_out, d + 5 * (size_t)n, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(d);
   CK(ce);
   return MPPI_OK;
@@ -1311,7 +1426,9 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
   }
   CKS(pre_step(e, x0));
   CKS(build_graphs(e));
-  CK(cudaMemcpy(e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice));
+  CK(memcpy_on(e, e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice));
+  int ovf_before = 0;
+  CK(memcpy_on(e, &ovf_before, &e->d_dyn->overflow_total, sizeof(int), cudaMemcpyDeviceToHost));
   if (flush_l2 && !e->d_flush) {
     e->flush_bytes = (size_t)256 << 20;   // > 126 MB L2
     CK(cudaMalloc(&e->d_flush, e->flush_bytes));
@@ -1359,12 +1476,20 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
     t.reduce_ms = (float)(acc[1] / steps);
     t.finalize_ms = (float)(acc[2] / steps);
   }
-  CK(cudaMemcpy(e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost));
+  CK(memcpy_on(e, e->h_out, e->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost));
   t.refine_candidates = e->h_out->last_candidates;
   t.refine_overflow = e->h_out->overflow_total;
   t.refine_max_dev = e->h_out->last_max_dev;
+  t.refine_head_room = e->h_out->last_head;
   e->last = t;
   *out = t;
+  if (e->h_out->overflow_total != ovf_before) {
+    // the device-resident loop has no host in it to redo an overflowing MIXED step in fp64: such a step leaves U, x0 and the
+    // noise counter untouched and every later graph launch would replay it -- the timing would be of a loop that stands still
+    set_err("mppi_bench: the fp32 screen of precision MIXED overflowed inside the device-resident loop (%d step(s)); the timed "
+            "region is invalid -- start further from the goal, or bench precision F64 / F32", e->h_out->overflow_total - ovf_before);
+    return MPPI_ERR_STATE;
+  }
   return MPPI_OK;
 }
 
@@ -1379,7 +1504,7 @@ extern "C" mppi_status mppi_debug_reduce_timestamps(mppi_handle e, unsigned long
     CK(cudaMemset(e->d_debug_ts, 0, n * sizeof(unsigned long long)));
     drop_graphs(e);
   }
-  if (out) CK(cudaMemcpy(out, e->d_debug_ts, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (out) CK(memcpy_on(e, out, e->d_debug_ts, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return MPPI_OK;
 }
 
@@ -1396,7 +1521,7 @@ extern "C" mppi_status mppi_debug_rollout_timestamps(mppi_handle e, unsigned lon
   }
   if (out) {
     if (n_ctas > e->debug_rts_ctas) n_ctas = e->debug_rts_ctas;
-    CK(cudaMemcpy(out, e->d_debug_rts, n_ctas * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(memcpy_on(e, out, e->d_debug_rts, n_ctas * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   }
   return MPPI_OK;
 }

@@ -80,7 +80,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us);
 
 // one thread: store the step's result block into mapped host memory and publish it (seq last, system-scope fences)
 __device__ __forceinline__ void publish_result(const FinalizeArgs& a, int status, const double* u, const double* xn, int cand,
-                                               double dev, int overflow_total) {
+                                               double dev, int overflow_total, double head = 0.0) {
   if (!a.host_res) return;
   __threadfence();                       // DynState / nominal updates of this step are ordered before the hand-over
   volatile HostResult* r = a.host_res;
@@ -94,6 +94,7 @@ __device__ __forceinline__ void publish_result(const FinalizeArgs& a, int status
     r->out_x[2] = xn[2];
   }
   r->max_dev = dev;
+  r->head = head;
   r->status = status;
   r->candidates = cand;
   r->overflow_total = overflow_total;
@@ -398,6 +399,9 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   const double neg_inv_lam = -1.0 / a.fin.dyn->lam;
   const float std0 = (float)a.fin.dyn->noise_std[0], std1 = (float)a.fin.dyn->noise_std[1];
   const unsigned int philox_step = a.fin.dyn->step;
+  double xs_[3], gs_[3], head;
+  load_step_input(a.fin.in, a.fin.dyn, xs_, gs_);
+  const float window = (float)screen_window(sp, xs_, gs_, &head);   // the same value the rollout kernel listed against
   for (int i = tid; i < 4 * T; i += nth) nomS[i] = a.nomD[i];
   griddep_wait();   // PDL: the block is resident, with its constants loaded, before the rollout kernel has drained
   TS(0);
@@ -446,7 +450,7 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   TS(1);
   // phase B: compact the candidates inside the window of the GLOBAL minimum; a CTA whose list does
   // not cover that window (it had to tighten its own window) is an overflow
-  const float lim = m32 + (float)sp.margin;
+  const float lim = m32 + window;
   for (int base = 0; base < a.nCTA; base += 4 * nth) {
     float4 md[4];
 #pragma unroll
@@ -496,6 +500,10 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     }
     m64 = warp_min<double>(m64);
     dev = -warp_min<double>(-dev);
+    // the safety net of the screen: the window's head-room assumes |V32 - V64| stays well inside it.  The deviation is
+    // observable on the re-evaluated rollouts; more than half the head-room there means a rollout of the support may have
+    // been screened out -> treat like a list overflow (the step is redone in fp64)
+    if (dev > 0.5 * head) overflow = 1;
     double S = 0, N0 = 0, N1 = 0;
     for (int c = lane; c < n; c += 32) {
       const double e = exp((sel_v64[c] - m64) * neg_inv_lam);
@@ -602,7 +610,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
   double x0r[3] = {0.0, 0.0, 0.0};
   unsigned int step_r = 0, xchg_r = 0;
   int cand_r = 0;
-  double dev_r = 0.0;
+  double dev_r = 0.0, head_r = 0.0;
   if (owner) {
     bad = 0;
     any_ovf = 0;
@@ -612,6 +620,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
     dev_r = __ldcg(&a.dyn->refine_max_dev);
     double goalr[3];
     load_step_input(a.in, a.dyn, x0r, goalr);
+    screen_window(sp, x0r, goalr, &head_r);
     for (int i = 0; i < 3; ++i) {
       if (a.mode == 0 && (!isfinite(x0r[i]) || !isfinite(goalr[i]))) bad = 1;
       if (a.mode == 0 && a.in.from_args) {   // keep DynState the single record of "the last step's input"
@@ -678,7 +687,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       d->refine_candidates = 0;
       d->refine_overflow = 0;
       d->refine_max_dev = 0.0;
-      publish_result(a, kStatusRedoF64, nullptr, nullptr, cand_r, dev_r, d->overflow_total);
+      publish_result(a, kStatusRedoF64, nullptr, nullptr, cand_r, dev_r, d->overflow_total, head_r);
     }
     return;
   }
@@ -740,10 +749,11 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
     }
     d->last_candidates = cand_r;
     d->last_max_dev = dev_r;
+    d->last_head = head_r;
     d->refine_candidates = 0;
     d->refine_overflow = 0;
     d->refine_max_dev = 0.0;
-    publish_result(a, status, uo, xn, cand_r, dev_r, ovf_total);
+    publish_result(a, status, uo, xn, cand_r, dev_r, ovf_total, head_r);
   }
   // -- update_action result, receding-horizon shift (:100-101), next nominal block: one pass, no further barrier
   for (int t = tid; t < T; t += blockDim.x) {

@@ -13,7 +13,6 @@ struct LeanStatic {
   float sq;                  // sqrt(Q[0] / 2) (== sqrt(Q[1] / 2): admission condition)
   float p1x, p1y, p1th;      // P1 / (Q/2) for x, y (terminal cost on cost-unit positions); P1[2]
   float g_inv_res, w_obs_100;   // cells per cost unit
-  float margin;
   int split;                 // SM-wide balanced kernel: first step rolled by the second pair of warps of the shared tile
   uint32_t pkx[MPPI_PHILOX_ROUNDS], pky[MPPI_PHILOX_ROUNDS];   // Philox key schedule key + i * Weyl, per round
 };

@@ -300,7 +300,9 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
   const float std0 = (float)a.dyn->noise_std[0], std1 = (float)a.dyn->noise_std[1];
   const unsigned int step = a.dyn->step;
   const R neg_inv_lam = R(-1.0 / a.dyn->lam);
-  const R margin = R(sp.margin);
+  double xs_[3], gs_[3];
+  load_step_input(a.in, a.dyn, xs_, gs_);
+  const R margin = R((float)screen_window(sp, xs_, gs_));   // SCREEN window of this step (common.cuh)
   const signed char* cells = grid_smem ? gcells : a.grid;
   const bool cost_to_go = sp.weighting == MPPI_WEIGHT_COST_TO_GO;
   mbar_wait(bar, 0);

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
     cc.gW = sp.gW;
     cc.gH = sp.gH;
   }
-  const R margin = a.lean.margin;
+  const R margin = (float)screen_window(sp, xs, gs);   // SCREEN window of this step (common.cuh)
   const signed char* cells = grid_smem ? gcells : a.grid;
   const bool cost_to_go = sp.weighting == MPPI_WEIGHT_COST_TO_GO;
   float sth0, cth0;
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) rollout_lean_sm_kernel(const __
     cc.gW = sp.gW;
     cc.gH = sp.gH;
   }
-  const R margin = a.lean.margin;
+  const R margin = (float)screen_window(sp, xs, gs);   // SCREEN window of this step (common.cuh)
   const signed char* cells = grid_smem ? gcells : a.grid;
   const bool cost_to_go = sp.weighting == MPPI_WEIGHT_COST_TO_GO;
   int split = (a.lean.split / 6) * 6;                      // first step of the second part (a multiple of 6: whole iterations)

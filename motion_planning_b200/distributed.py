@@ -136,17 +136,24 @@ class ShardedMPPI(object):
             return m.get_path(state, goal, sig, lam)      # plain mppi_step: the exchange is inside the graph
         _capi.check(lib.mppi_set_goal(h, _capi.dptr(_capi.f64(goal, (3,)))), "mppi_set_goal")
         m._goal_bytes = None
-        _capi.check(lib.mppi_step_local(h, _capi.dptr(_capi.f64(state, (3,)))), "mppi_step_local")
-        if self.exchange == "nccl":
-            with self._torch.cuda.stream(self.stream):
-                self._dist.all_gather_into_tensor(self._gat_t, self._rec_t, group=self.group)
-        else:
-            rec = np.empty(self._n_rec)
-            _capi.check(lib.mppi_read_record(h, _capi.dptr(rec)), "mppi_read_record")
-            allrec = exchange_host(self._torch, self._dist, rec, self.world, self.group)
-            _capi.check(lib.mppi_write_gather(h, _capi.dptr(allrec)), "mppi_write_gather")
         u, x = np.empty(2), np.empty(3)
-        _capi.check(lib.mppi_step_finish(h, _capi.dptr(u), _capi.dptr(x)), "mppi_step_finish")
+        for attempt in range(3):
+            _capi.check(lib.mppi_step_local(h, _capi.dptr(_capi.f64(state, (3,)))), "mppi_step_local")
+            if self.exchange == "nccl":
+                with self._torch.cuda.stream(self.stream):
+                    self._dist.all_gather_into_tensor(self._gat_t, self._rec_t, group=self.group)
+            else:
+                rec = np.empty(self._n_rec)
+                _capi.check(lib.mppi_read_record(h, _capi.dptr(rec)), "mppi_read_record")
+                allrec = exchange_host(self._torch, self._dist, rec, self.world, self.group)
+                _capi.check(lib.mppi_write_gather(h, _capi.dptr(allrec)), "mppi_write_gather")
+            st = lib.mppi_step_finish(h, _capi.dptr(u), _capi.dptr(x))
+            # MPPI_ERR_RETRY: the fp32 screen of precision 'mixed' overflowed on some rank (systematic within centimetres of
+            # the goal).  Every rank merged the same records, so every rank is here for the same step: nothing was applied,
+            # the second round runs the fp64 pipeline on the same noise.
+            if st != _capi.MPPI_ERR_RETRY:
+                break
+        _capi.check(st, "mppi_step_finish")
         m._path_log.append(x)
         m._uvec_log.append(u)
         m.fin_time.append(m.fin_time[-1] + m.dt)

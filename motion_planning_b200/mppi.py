@@ -387,6 +387,14 @@ class MPPI(object):
         _capi.check(self._lib.mppi_set_grid(self._h, cells.ctypes.data_as(C.POINTER(C.c_int8)), W, H, float(res),
                                             float(origin[0]), float(origin[1]), float(w_obs)), "mppi_set_grid")
 
+    def update_grid(self, patch, x0, y0):
+        """NEW: overwrite the rectangle [y0:y0+h, x0:x0+w] of the resident grid with `patch` (h, w) int8 -- the incremental map
+        updates of map/src/map/grid.cpp:155-199 -- asynchronously, without re-creating anything."""
+        patch = np.ascontiguousarray(np.asarray(patch, dtype=np.int8))
+        h, w = patch.shape
+        _capi.check(self._lib.mppi_update_grid(self._h, patch.ctypes.data_as(C.POINTER(C.c_int8)), int(x0), int(y0), w, h),
+                    "mppi_update_grid")
+
     def clear_grid(self):
         _capi.check(self._lib.mppi_clear_grid(self._h), "mppi_clear_grid")
 

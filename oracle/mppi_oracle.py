@@ -20,8 +20,6 @@ Extensions that have NO reference counterpart (bicycle model, occupancy-grid
 cost, total-cost weighting) are marked "NEW"; their parity is unpinned by the
 reference and they are pinned only by this oracle.
 """
-import math
-
 import numpy as np
 
 # control/src/mppi:18-20
@@ -255,62 +253,5 @@ def softmin_gaps(V):
     return s[:, 1] - s[:, 0]
 
 
-# --------------------------------------------------------------------------- map rasteriser (NEW input format)
-
-def _point_in_convex_ccw_or_cw(px, py, poly):
-    sign = 0
-    n = len(poly)
-    for i in range(n):
-        x0, y0 = poly[i]
-        x1, y1 = poly[(i + 1) % n]
-        cr = (x1 - x0) * (py - y0) - (y1 - y0) * (px - x0)
-        if cr != 0:
-            s = 1 if cr > 0 else -1
-            if sign == 0:
-                sign = s
-            elif s != sign:
-                return False
-    return True
-
-
-def _dist_point_segment(px, py, x0, y0, x1, y1):
-    dx, dy = x1 - x0, y1 - y0
-    L2 = dx * dx + dy * dy
-    t = 0.0 if L2 == 0 else max(0.0, min(1.0, ((px - x0) * dx + (py - y0) * dy) / L2))
-    return math.hypot(px - (x0 + t * dx), py - (y0 + t * dy))
-
-
-def rasterise_map(obstacles, bounds, scale, res, inflate):
-    """NEW input-format helper: an int8 occupancy grid with the map package's conventions.
-
-    Cell (j, i) has centre (x_min + (j+.5) res, y_min + (i+.5) res); 100 if the centre lies
-    inside an obstacle polygon, 50 if within ``inflate`` of one, else 0; row-major idx = j + i*W
-    (map/src/map/grid.cpp:17-69,126-144).  Obstacles are convex polygons in "cell" units times
-    ``scale`` (map/config/map.yaml:1-18, map/launch/viz_map.launch:52-57).  This is a simplified
-    geometric restatement (exact inside test + distance-to-edge inflation) of
-    map/src/map/prm.cpp:267-394; it is a test-input generator, not a parity target.
-    """
-    polys = [[(vx / scale, vy / scale) for vx, vy in ob] for ob in obstacles]
-    xs = [b[0] / scale for b in bounds]
-    ys = [b[1] / scale for b in bounds]
-    x_min, x_max, y_min, y_max = min(xs), max(xs), min(ys), max(ys)
-    W = int(math.ceil((x_max - x_min) / res - 1e-9))
-    H = int(math.ceil((y_max - y_min) / res - 1e-9))
-    g = np.zeros((H, W), dtype=np.int8)
-    for i in range(H):
-        cy = y_min + (i + 0.5) * res
-        for j in range(W):
-            cx = x_min + (j + 0.5) * res
-            v = 0
-            for poly in polys:
-                if len(poly) >= 3 and _point_in_convex_ccw_or_cw(cx, cy, poly):
-                    v = 100
-                    break
-                n = len(poly)
-                for e in range(n if n > 2 else 1):
-                    x0, y0 = poly[e]
-                    x1, y1 = poly[(e + 1) % n]
-                    if _dist_point_segment(cx, cy, x0, y0, x1, y1) < inflate:
-                        v = max(v, 50)
-            g[i, j] = v
-    return g, res, np.array([x_min, y_min])
+# The occupancy-grid INPUT FORMAT (Grid::build_map / occupancy_grid of the map package) is restated in oracle/map_grid.py,
+# pinned cell by cell against the reference's own map sources compiled by oracle/build_map_ref.py.

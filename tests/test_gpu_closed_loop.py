@@ -101,3 +101,54 @@ def test_mixed_overflow_backs_off_to_fp64_and_stays_exact():
     assert a.stats()["refine_overflow"] == 4
     a.close()
     b.close()
+
+
+def test_sharded_external_exchange_survives_the_overflow_regime():
+    """a sharded engine with an EXTERNAL exchange (mppi_step_local / exchange / mppi_step_finish, the 'nccl' and
+    'host' transports of ShardedMPPI) must drive all the way into the goal: within centimetres of it the fp32 screen's
+    candidate lists overflow systematically; the split-phase API then answers MPPI_ERR_RETRY on every rank and the repeated
+    round runs in fp64 on the same noise.  Two shards on one device, host-staged exchange; the single-engine loop is the
+    reference trajectory (mixed == f64 to rounding)."""
+    import motion_planning_b200 as mp
+    from motion_planning_b200 import _capi
+    from motion_planning_b200.distributed import shard_plan
+    K, T, G = 4096, 32, 2
+    goal = np.array([0.0, -0.06, 0.0])
+    one = mp.MPPI(horizon=T, samples=K, precision="f64", seed=0)
+    eng = []
+    for r in range(G):
+        kl, ko = shard_plan(K, G, r)
+        eng.append(mp.MPPI(horizon=T, samples=kl, precision="mixed", seed=0, k_offset=ko, k_total=K, world_size=G, rank=r))
+    s, retries, steps = np.zeros(3), 0, 0
+    for it in range(400):
+        s1 = one.get_path(s, goal)
+        for attempt in range(3):
+            recs = []
+            for e in eng:
+                _capi.check(e._lib.mppi_set_goal(e._h, _capi.dptr(goal)), "goal")
+                _capi.check(e._lib.mppi_step_local(e._h, _capi.dptr(_capi.f64(s))), "local")
+                rec = np.empty(T * 6)
+                _capi.check(e._lib.mppi_read_record(e._h, _capi.dptr(rec)), "read")
+                recs.append(rec)
+            allrec = np.concatenate(recs)
+            sts = []
+            for e in eng:
+                _capi.check(e._lib.mppi_write_gather(e._h, _capi.dptr(allrec)), "write")
+                u, x = np.empty(2), np.empty(3)
+                sts.append(e._lib.mppi_step_finish(e._h, _capi.dptr(u), _capi.dptr(x)))
+            assert len(set(sts)) == 1, sts                       # every rank takes the same decision
+            if sts[0] != _capi.MPPI_ERR_RETRY:
+                break
+            retries += 1
+        _capi.check(sts[0], "mppi_step_finish")
+        np.testing.assert_allclose(x, s1, rtol=0, atol=1e-10)
+        for e in eng:
+            assert np.max(np.abs(e.latest_uvec - one.latest_uvec)) < 1e-7 * max(1.0, np.max(np.abs(one.latest_uvec)))
+        s = s1
+        steps += 1
+        if np.linalg.norm(s[:2] - goal[:2]) < 0.002 and retries >= 2:
+            break
+    print("sharded external exchange: %d steps, %d retried in fp64, final distance %.4f" % (steps, retries, np.linalg.norm(s[:2] - goal[:2])))
+    assert retries >= 1, "the loop never reached the overflow regime"
+    for o in [one] + eng:
+        o.close()

@@ -1,16 +1,13 @@
-"""GPU (opt-in until it has been run on a B200 once: set MPPI_B200_EXTRA_TESTS=1): the engine against the oracle over
+"""GPU: the engine against the oracle over
 the reference's tunables -- diagonal Q / P1, a full R, a non-diagonal sig (whose [0,0] entry is also the noise std,
 control/src/mppi:144-146) and lam -- the CUDA twin of
 tests/test_oracle_golden.py::test_oracle_matches_live_reference_on_varied_parameters (which pins the oracle itself)."""
-import os
-
 import numpy as np
 import pytest
 
 from oracle import mppi_oracle as orc
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MPPI_B200_EXTRA_TESTS") != "1", reason="opt-in: not yet run on a GPU box")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("precision", ["f64", "mixed"])

@@ -422,3 +422,129 @@ def test_full_size_c2_mixed_equals_f64_and_shards_merge():
         s = s1
     for o in [a, b, c, one] + eng:
         o.close()
+
+
+@pytest.mark.parametrize("precision", ["mixed", "f32"])
+def test_total_cost_weighting_screened_and_fp32(precision):
+    """north_star's wording (one soft-min over the K total rollout costs) through the fp32 pipelines: 'mixed' is held to the
+    fp64 tolerance, 'f32' to 1e-5 when the single soft-min is well conditioned (gap best / 2nd best > 50 lam)."""
+    K, T = 4096, 32
+    p = orc.Params(K=K, T=T, weighting=orc.WEIGHT_TOTAL_COST)
+    m = mp().MPPI(horizon=T, samples=K, precision=precision, weighting="total_cost", seed=1)
+    s, U = np.array([0.0, 0.0, 0.5]), np.zeros((2, T))
+    for it in range(3):
+        s_in = s.copy()
+        s = m.get_path(s_in, PARK)
+        eps = m.get_noise()
+        out = orc.step(p, s_in, PARK, U, eps)
+        gap = orc.softmin_gaps(out["V"][:1]).min()
+        if precision == "mixed":
+            np.testing.assert_allclose(m.latest_uvec, out["U_shift"], rtol=1e-8, atol=1e-9)
+        else:
+            err = rel_err(m.latest_uvec, out["U_shift"])
+            print("total_cost f32 step %d: gap %.3g rel err %.3g" % (it, gap, err))
+            assert err < (1e-5 if gap > 0.05 else 5e-2)
+            m.latest_uvec = out["U_shift"]
+            s = out["x_next"]
+        U = out["U_shift"]
+    m.close()
+
+
+# ------------------------------------------------------------------ quality of the in-register noise
+def _z_of_one_step(K=65536, T=66, seed=123):
+    m = mp().MPPI(horizon=T, samples=K, precision="f32", seed=seed)
+    m.get_path(np.zeros(3), PARK)
+    z = m.get_noise() / np.float64(np.float32(0.9))
+    m.close()
+    return z            # (T, 2, K)
+
+
+def test_noise_distribution_tails_and_ks():
+    """The generator feeds Box-Muller with 22 radius + 20 angle bits per pair on the SFU approximations: check the shape of
+    the distribution it really produces -- Kolmogorov-Smirnov against N(0,1), tail counts beyond 3 / 4 / 4.5 sigma against their
+    binomial expectation, and the hard tail cut sqrt(-2 ln 2^-23) = 5.65."""
+    import scipy.stats
+    z = _z_of_one_step().reshape(-1)
+    n = z.size                                            # 8.65 M
+    d, _ = scipy.stats.kstest(z[:: 8], "norm")
+    assert d < 1.95 / np.sqrt(n / 8), d                   # 0.1 % critical value
+    for lim in (3.0, 4.0, 4.5):
+        pexp = 2 * scipy.stats.norm.sf(lim)
+        cnt = int((np.abs(z) > lim).sum())
+        assert abs(cnt - n * pexp) < 5 * np.sqrt(n * pexp) + 2, (lim, cnt, n * pexp)
+    assert np.abs(z).max() < 5.66
+    # symmetric, and the two channels of a step (cos / sin branch of one pair) have the same law
+    assert abs((z > 0).mean() - 0.5) < 4 * 0.5 / np.sqrt(n)
+    zz = z.reshape(-1, 2, 65536)
+    assert abs(zz[:, 0].std() - zz[:, 1].std()) < 2e-3
+
+
+def test_noise_pairs_of_one_call_are_uncorrelated():
+    """One generator call yields 6 normals = 3 steps x 2 channels (common.cuh: normal6_from_bits): the three Box-Muller pairs
+    share the low bits of word 3 for their angles.  No linear correlation, no correlation of magnitudes (radius / angle
+    coupling), none between neighbouring rollouts or consecutive calls."""
+    z = _z_of_one_step()                                   # (66, 2, K): 22 calls
+    T, _, K = z.shape
+    six = z.reshape(T // 3, 6, K).transpose(1, 0, 2).reshape(6, -1)        # rows: (step in call, channel)
+    n = six.shape[1]
+    tol = 5.0 / np.sqrt(n)
+    for name, v in (("linear", six), ("magnitude", np.abs(six) - np.abs(six).mean(axis=1, keepdims=True)), ("square", six ** 2 - 1.0)):
+        c = np.corrcoef(v)
+        off = np.abs(c - np.eye(6)).max()
+        assert off < tol, (name, off, tol)
+    flat = z[:, 0, :]
+    assert abs(np.corrcoef(flat[:, :-1].reshape(-1), flat[:, 1:].reshape(-1))[0, 1]) < 5.0 / np.sqrt(flat.size)     # rollout k vs k+1
+    assert abs(np.corrcoef(z[:-3].reshape(-1), z[3:].reshape(-1))[0, 1]) < 5.0 / np.sqrt(z[3:].size)               # call c vs c+1
+    # steps of different engine steps are different draws
+    m = mp().MPPI(horizon=12, samples=4096, precision="f32", seed=5)
+    m.get_path(np.zeros(3), PARK)
+    e0 = m.get_noise()
+    m.get_path(np.zeros(3), PARK)
+    e1 = m.get_noise()
+    assert abs(np.corrcoef(e0.reshape(-1), e1.reshape(-1))[0, 1]) < 5.0 / np.sqrt(e0.size)
+    m.close()
+
+
+def test_incremental_grid_updates_equal_a_fresh_upload():
+    """mppi_update_grid (the map package's incremental reveal, map/src/map/grid.cpp:155-199): start from an all-free grid of
+    the planner demo's size, reveal the true map patch by patch along the robot's cells (FakeGrid restates
+    Grid::update_grid), and step after every patch: each step equals the oracle on the grid as revealed so far, and the final
+    resident grid behaves exactly like a fresh mppi_set_grid upload of the same cells."""
+    from oracle import map_grid
+    K, T = 2048, 32
+    true, res, origin = map_grid.build_map(map_grid.scale_obstacles(map_grid.MAP_YAML_OBSTACLES, 10.0), 0.1, 0.1)
+    fg = map_grid.FakeGrid(true)
+    w = 300.0
+    m = mp().MPPI(horizon=T, samples=K, precision="mixed", seed=21)
+    m.set_grid(fg.occupancy(), res, origin, w)
+    s = np.array([0.55, 0.35, 0.4])                       # free cell south-west of obstacle A
+    goal = np.array([2.0, 1.0, 0.0])
+    U = np.full((2, T), 4.0)
+    m.latest_uvec = U
+    changed = 0
+    for it in range(6):
+        ix, iy = int((s[0] - origin[0]) / res), int((s[1] - origin[1]) / res)
+        before = fg.occupancy()
+        x0, y0, pw, ph, patch = fg.update(ix, iy, 6)      # the simulated sensor sees 6 cells around the robot
+        changed += int((fg.occupancy() != before).sum())
+        m.update_grid(patch, x0, y0)
+        s_in = s.copy()
+        s = m.get_path(s_in, goal)
+        p = orc.Params(K=K, T=T, grid=fg.occupancy(), grid_res=res, grid_origin=origin, w_obs=w)
+        out = orc.step(p, s_in, goal, U, m.get_noise())
+        np.testing.assert_allclose(m.latest_uvec, out["U_shift"], rtol=1e-8, atol=1e-9)
+        np.testing.assert_allclose(s, out["x_next"], rtol=1e-9, atol=1e-12)
+        U = out["U_shift"]
+    assert changed > 0, "the revealed patches never contained an obstacle cell"
+    fresh = mp().MPPI(horizon=T, samples=K, precision="mixed", seed=21)
+    fresh.set_grid(fg.occupancy(), res, origin, w)
+    for e in (m, fresh):
+        e.use_philox(99)
+        e.latest_uvec = U
+    a, b = m.get_path(s, goal), fresh.get_path(s, goal)
+    assert np.array_equal(a, b) and np.array_equal(m.latest_uvec, fresh.latest_uvec)
+    M = mp()
+    with pytest.raises(M.MppiError):
+        m.update_grid(np.zeros((3, 3), dtype=np.int8), true.shape[1] - 2, 0)      # sticks out of the grid
+    m.close()
+    fresh.close()

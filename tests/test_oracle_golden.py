@@ -127,3 +127,33 @@ def test_oracle_matches_live_reference_on_varied_parameters(seed):
         np.testing.assert_allclose(out["U_shift"], m.latest_uvec, rtol=1e-7, atol=1e-8)
         # continue from the reference's own state so that the second step is compared from identical inputs
         s, U = sref.copy(), m.latest_uvec.copy()
+
+
+@pytest.mark.skipif(ref_loader.available() is None, reason="reference not loadable here")
+@pytest.mark.parametrize("seed", range(3))
+def test_oracle_euler_model_matches_live_reference(seed):
+    """The reference's second integrator-step functor, `euler` over `unicycle_dynamics` (control/src/mppi:33-36,57-58),
+    plugged into the UNMODIFIED class through its own `model=` hook (:62,66,154): pins the oracle's
+    MODEL_UNICYCLE_EULER path (no theta wrap, explicit Euler) to the reference itself."""
+    ref = ref_loader.load_reference()
+    rng = np.random.RandomState(300 + seed)
+    K, T = int(rng.choice([16, 48])), int(rng.choice([8, 16, 30]))
+    m = ref.MPPI(model=ref.euler, horizon=T, samples=K)
+    m.latest_uvec = rng.normal(size=(2, T))
+    p = orc.Params(K=K, T=T, model=orc.MODEL_UNICYCLE_EULER)
+    x0, goal = rng.uniform(-1, 1, size=3) * [1, 1, 3], rng.uniform(-1, 1, size=3) * [1, 1, 3]
+    U, s = m.latest_uvec.copy(), x0.copy()
+    orig = np.random.normal
+    for _ in range(3):
+        eps = rng.standard_normal((T, 2, K)) * 0.9
+        feed = iter(eps)
+        np.random.normal = lambda *a, **k: next(feed).copy()
+        try:
+            sref = m.get_path(s, goal)
+        finally:
+            np.random.normal = orig
+        out = orc.step(p, s, goal, U, eps)
+        np.testing.assert_allclose(out["u0"], m.uvec[-1], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(out["x_next"], sref, rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(out["U_shift"], m.latest_uvec, rtol=1e-8, atol=1e-9)
+        s, U = sref.copy(), m.latest_uvec.copy()
