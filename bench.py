@@ -9,7 +9,10 @@ costs -> per-t soft-min weights -> control update -> clip / Savitzky-Golay / cli
 
 Workload (N=1): BASELINE.json configs[1] = diff-drive parallel-park, K=65536, T=64, 1 x B200.  For
 N > 1 the rollouts are sharded over ranks with per-GPU K fixed (weak scaling, K_total = N * 65536)
-and one 3 KB all-gather per step.
+and one 3 KB record exchanged per step; that line's `value` is comparable with N=1.  EVERY line
+(N = 1 too) additionally carries a `config5` block: BASELINE.json configs[4], K_total = 2097152,
+T = 128 sharded over the N GPUs of the run (strong scaling), and for N > 1 a `parity` record: the
+sharded engines against ONE engine at K_total on rank 0, same noise, two closed-loop steps.
 
 value   = rollouts/s with the controller state resident in HBM (closed loop on the model entirely on
           the device), CUDA events on the launch stream, L2 flushed between timed steps.
@@ -33,6 +36,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 K_PER_GPU, T_HORIZON = 65536, 64
+K5_TOTAL, T5 = 2097152, 128                # BASELINE.json configs[4]: sharded over the GPUs of the run
 GOAL = np.array([0.0, -1.0, 0.0])          # parallel park, control/src/mppi:337
 X0 = np.array([0.0, 0.0, 0.0])
 F_ALG = 133.0                              # algorithmic FLOP per (rollout, step), SURVEY.md 8(d)
@@ -150,12 +154,30 @@ def run_reference_arm(args):
         s = stepper(s)
     dt = (time.perf_counter() - t0) / steps
     val = Ks / dt
+    # the reference's get_path is a Python loop over the K samples (control/src/mppi:158-161): linear in K.  One step at the
+    # FULL K of the workload is timed as well, so the sampled figure is checked against the real configuration in this run
+    # (--ref-full times every step at full K instead; ~15-40 s per step)
+    full = None
+    if ref_loader.available() and (args.ref_full or args.ref_full_step):
+        mf = ref.MPPI(horizon=T_HORIZON, samples=K_PER_GPU)
+        nfull = steps if args.ref_full else 1
+        tf0 = time.perf_counter()
+        sf = X0.copy()
+        for _ in range(nfull):
+            sf = mf.get_path(sf, GOAL)
+        tfull = (time.perf_counter() - tf0) / nfull
+        full = {"K": K_PER_GPU, "T": T_HORIZON, "steps": nfull, "s_per_step": tfull, "rollouts_per_s": K_PER_GPU / tfull,
+                "sampled_over_full": val / (K_PER_GPU / tfull)}
+        if args.ref_full:
+            val, dt, Ks = K_PER_GPU / tfull, tfull, K_PER_GPU
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "rollouts/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "diff-drive parallel-park K=%d T=%d (BASELINE.json configs[1])" % (K_PER_GPU, T_HORIZON),
-                   "sample_K": Ks, "T": T_HORIZON},
+                   "K": K_PER_GPU, "T": T_HORIZON, "sample_K": Ks, "full_K_step": full,
+                   "note": "value = rollouts/s of get_path; every timed step rolls sample_K of the K samples at the full horizon "
+                           "(the reference is linear in K); full_K_step = one get_path at the full K timed in this run"},
         "cpu_baseline": {"value": val, "unit": "rollouts/s", "cores": cores, "kind": kind,
                          "sample": "%s; %d of the %d rollouts per step at T=%d, %d timed steps" % (what, Ks, K_PER_GPU, T_HORIZON, steps)},
         "e2e": {"value": val, "unit": "rollouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -225,6 +247,22 @@ def run_single(args):
         r["stats"] = m.stats()
         results[prec] = r
         m.close()
+    # BASELINE.json configs[4] on this one GPU (the N=1 point of its strong-scaling curve; also where the fixed costs of the
+    # rollout kernel vanish and its roofline fraction is best read)
+    c5 = None
+    if not args.no_config5:
+        m5 = mp.MPPI(horizon=T5, samples=K5_TOTAL, precision=args.precision, seed=0)
+        m5.goal = GOAL
+        r5 = m5.bench(X0, steps=max(3, min(args.steps, 30)), warmup=3, flush_l2=True, per_kernel=True)
+        ach5 = F_ALG * K5_TOTAL * T5 / (r5["rollout_ms"] * 1e-3) / 1e12
+        c5 = {"workload": "diff-drive parallel-park K_total=%d T=%d (BASELINE.json configs[4]) on %d GPU" % (K5_TOTAL, T5, 1),
+              "n_gpus": 1, "scaling": "strong", "ms_per_step": r5["step_ms"], "value": K5_TOTAL / (r5["step_ms"] * 1e-3),
+              "unit": "rollouts/s", "state_steps_per_s": K5_TOTAL * T5 / (r5["step_ms"] * 1e-3), "steps": r5["steps"],
+              "rollout_ms": r5["rollout_ms"], "roofline_frac_rollout_kernel": ach5 / tf.value if tf.value else None,
+              "achieved_TFLOPs": ach5, "launch": m5.launch_info(),
+              "refine": {"candidates_last_step": r5["refine_candidates"], "overflow_steps": r5["refine_overflow"],
+                         "max_abs_dev_fp32_vs_fp64": r5["refine_max_dev"], "head_room": r5["refine_head_room"]}}
+        m5.close()
     clocks = sampler.stop()
     r = results[args.precision]
     ms = r["step_ms"]
@@ -235,9 +273,11 @@ def run_single(args):
     kname = "rollout_lean_sm_kernel" if (r["launch"].get("variant") == "lean" and r["launch"]["block"] == 512) else \
         "rollout_%s_kernel" % r["launch"].get("variant", "?")
     cpu = cpu_baseline_port() if not args.no_cpu else None
-    traffic = None
+    traffic, traffic_file = None, None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
+        cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_ncu_summary.json"))
+        traffic_file = "profiles/" + cands[-1]
+        ncu = json.load(open(os.path.join(ROOT, traffic_file)))
         key = [k for k in ncu if k.startswith("rollout") and ("precision %s" % args.precision) in k]
         if key:
             m_ = ncu[key[0]]
@@ -270,15 +310,17 @@ def run_single(args):
         "kernels_ms": {"rollout": r["rollout_ms"], "reduce": r["reduce_ms"], "finalize": r["finalize_ms"]},
         "roofline": {"bound": "fp32_alu", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
                      "frac": achieved / tf.value if tf.value else None, "traffic": traffic,
-                     "traffic_note": "DRAM bytes per launch from profiles/r01_ncu_summary.json (ncu --set full, caches flushed by ncu before the launch); "
-                                     "most of the ~3 MB of per-tile partial records stay in L2",
+                     "traffic_source": "from profile, NOT measured in this run: %s (dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                       "ncu --set full capture of this kernel at this configuration, caches flushed by ncu before the launch); "
+                                       "most of the ~3 MB of per-tile partial records stay in L2" % traffic_file,
                      "kernel": kname, "flop_per_state_step": F_ALG,
                      "peak_source": "FFMA chain measured in this run (mppi_measure_fp32_peak); MEASURED_PEAKS.json has no fp32 entry",
                      "hbm_view": {"algorithmic_bytes": hbm_alg_bytes,
                                   "achieved_GBps": hbm_alg_bytes / (r["rollout_ms"] * 1e-3) / 1e9,
                                   "peak_GBps": peaks.get("hbm_gbs"), "note": "not HBM bound: nothing of size K*T leaves the SM"}},
         "refine": {"candidates_last_step": r["refine_candidates"], "overflow_steps": r["refine_overflow"],
-                   "max_abs_dev_fp32_vs_fp64": r["refine_max_dev"]},
+                   "max_abs_dev_fp32_vs_fp64": r["refine_max_dev"], "head_room": r["refine_head_room"]},
+        "config5": c5,
         "other_precisions": {p: {"value": K / (v["step_ms"] * 1e-3), "ms_per_step": v["step_ms"], "rollout_ms": v["rollout_ms"],
                                  "e2e_ms": v["e2e_ms"]} for p, v in results.items() if p != args.precision},
         "clocks": clocks,
@@ -288,10 +330,66 @@ def run_single(args):
     print(json.dumps(line))
 
 
+def _sharded_parity(mp, dist, torch, m, rank, local, K_total, T, precision, steps=2):
+    """Sharded == single, checked INSIDE the benchmark run: every rank steps its shard `steps` times from X0 (fresh noise
+    counters), then rank 0 alone builds ONE engine at K_total with the same seed and steps it from the same state; the two
+    nominal sequences (latest_uvec after the shift) and predicted states must agree to summation order."""
+    s = X0.copy()
+    for _ in range(steps):
+        s = m.get_path(s, GOAL)
+    U_sh = m.latest_uvec
+    rec = None
+    if rank == 0:
+        one = mp.MPPI(horizon=T, samples=K_total, precision=precision, seed=0, device=local)
+        s1 = X0.copy()
+        for _ in range(steps):
+            s1 = one.get_path(s1, GOAL)
+        U1 = one.latest_uvec
+        one.close()
+        errU = float(np.max(np.abs(U_sh - U1)) / max(np.max(np.abs(U1)), 1e-300))
+        errx = float(np.max(np.abs(s - s1)))
+        rec = {"against": "one engine at K_total=%d on rank 0, same seed / noise counters, %d closed-loop steps" % (K_total, steps),
+               "max_rel_err_U": errU, "max_abs_err_x_next": errx, "tol_rel_U": 1e-9, "pass": bool(errU < 1e-9 and errx < 1e-11)}
+    dist.barrier()
+    # back to step 0 of the noise stream and a zero nominal on every rank
+    m.mppi.use_philox(0)
+    m.initialize()
+    return rec
+
+
+def _bench_sharded(args, dist, torch, m, steps):
+    """device-timed closed loop of a sharded engine (max over ranks is taken by the caller)"""
+    if m.exchange == "p2p":
+        # the exchange lives inside the per-rank CUDA graph: time the device-resident closed loop with CUDA
+        # events on the engine's launch stream (ranks run in lockstep through the arrival flags)
+        m.mppi.goal = GOAL
+        dist.barrier()
+        torch.cuda.synchronize()
+        r = m.mppi.bench(X0, steps=steps, warmup=args.warmup, flush_l2=True, per_kernel=False)
+        return r["step_ms"], r["launches"], "CUDA events on the engine's launch stream around each graph launch, max over ranks", r
+    s = X0.copy()
+    for _ in range(args.warmup):
+        s = m.get_path(s, GOAL)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    st = m.stream if m.stream is not None else torch.cuda.current_stream()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    dist.barrier()
+    torch.cuda.synchronize()
+    for i in range(steps):
+        with torch.cuda.stream(st):
+            flush.fill_(i & 0xff)
+            ev[i][0].record(st)
+        s = m.get_path(s, GOAL)
+        ev[i][1].record(st)
+    torch.cuda.synchronize()
+    return (sum(a.elapsed_time(b) for a, b in ev) / steps, 3 * steps,
+            "CUDA events on the stream shared by the engine kernels and the NCCL all-gather, max over ranks", None)
+
+
 def run_multi(args):
-    import ctypes as C
     import torch
     import torch.distributed as dist
+    import motion_planning_b200 as mp
     from motion_planning_b200 import _capi
     from motion_planning_b200.distributed import ShardedMPPI
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -306,35 +404,11 @@ def run_multi(args):
     K_total, T = K_PER_GPU * world, T_HORIZON
     m = ShardedMPPI(T, K_total, precision=args.precision, seed=0, device=local, exchange=args.exchange)
     lib, h = m.mppi._lib, m.mppi._h
+    parity = _sharded_parity(mp, dist, torch, m, rank, local, K_total, T, args.precision)
     sampler = ClockSampler(local) if rank == 0 else None
-    if m.exchange == "p2p":
-        # the exchange lives inside the per-rank CUDA graph: time the device-resident closed loop with CUDA
-        # events on the engine's launch stream (ranks run in lockstep through the arrival flags)
-        m.mppi.goal = GOAL
-        dist.barrier()
-        torch.cuda.synchronize()
-        r = m.mppi.bench(X0, steps=args.steps, warmup=args.warmup, flush_l2=True, per_kernel=False)
-        dev_ms, launches = r["step_ms"], r["launches"]
-        timing = "CUDA events on the engine's launch stream around each graph launch, max over ranks"
-    else:
-        s = X0.copy()
-        for _ in range(args.warmup):
-            s = m.get_path(s, GOAL)
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-        st = m.stream if m.stream is not None else torch.cuda.current_stream()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        dist.barrier()
-        torch.cuda.synchronize()
-        for i in range(args.steps):
-            with torch.cuda.stream(st):
-                flush.fill_(i & 0xff)
-                ev[i][0].record(st)
-            s = m.get_path(s, GOAL)
-            ev[i][1].record(st)
-        torch.cuda.synchronize()
-        dev_ms, launches = sum(a.elapsed_time(b) for a, b in ev) / args.steps, 3 * args.steps
-        timing = "CUDA events on the stream shared by the engine kernels and the NCCL all-gather, max over ranks"
-    # e2e: host x0 in, (u, x_next) out every step through the C ABI, closed loop on the host
+    dev_ms, launches, timing, _ = _bench_sharded(args, dist, torch, m, args.steps)
+    # e2e: host x0 in, (u, x_next) out every step through the C ABI, closed loop on the host; every timed call starts from a
+    # flushed L2 on every rank (as at N=1), the flush outside the timed intervals
     m.initialize()
     x, u, xn = X0.copy(), np.empty(2), np.empty(3)
     if m.exchange == "p2p":
@@ -343,7 +417,7 @@ def run_multi(args):
 
         def one():
             if lib.mppi_step(h, px, pu, pn) != 0:
-                raise RuntimeError("mppi_step failed")
+                raise RuntimeError("mppi_step failed: " + lib.mppi_last_error().decode())
             x[:] = xn
     else:
         def one():
@@ -352,17 +426,48 @@ def run_multi(args):
         one()
     dist.barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    acc = 0.0
     for _ in range(args.steps):
+        _capi.check(lib.mppi_debug_flush_l2(h), "mppi_debug_flush_l2")
+        t0 = time.perf_counter()
         one()
+        acc += time.perf_counter() - t0
     torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    e2e_ms = acc / args.steps * 1e3
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
+    launch_info = m.mppi.launch_info()
+    io = m.mppi.io_bytes()
+    exchange = m.exchange
+    m.mppi.close()
+
+    # ---- BASELINE.json configs[4]: K_total = 2097152, T = 128 sharded over the ranks of this run (strong scaling) ----
+    c5 = None
+    if not args.no_config5:
+        m5 = ShardedMPPI(T5, K5_TOTAL, precision=args.precision, seed=0, device=local, exchange=args.exchange)
+        parity5 = _sharded_parity(mp, dist, torch, m5, rank, local, K5_TOTAL, T5, args.precision)
+        steps5 = max(3, min(args.steps, 30))
+        ms5, launches5, _, _ = _bench_sharded(args, dist, torch, m5, steps5)
+        t5 = torch.tensor([ms5], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        ms5 = float(t5[0])
+        info5 = m5.mppi.launch_info()
+        m5.mppi.close()
+        n1_ms = None
+        if rank == 0:     # the same workload on ONE GPU, timed in this run: the base of the strong-scaling curve
+            one5 = mp.MPPI(horizon=T5, samples=K5_TOTAL, precision=args.precision, seed=0, device=local)
+            one5.goal = GOAL
+            n1_ms = one5.bench(X0, steps=max(3, min(steps5, 10)), warmup=3, flush_l2=True, per_kernel=False)["step_ms"]
+            one5.close()
+        dist.barrier()
+        c5 = {"workload": "diff-drive parallel-park K_total=%d T=%d (BASELINE.json configs[4]) sharded over %d GPUs, %d rollouts "
+                          "per GPU, one %d-byte record exchanged per step" % (K5_TOTAL, T5, world, K5_TOTAL // world, T5 * 48),
+              "n_gpus": world, "scaling": "strong", "ms_per_step": ms5, "value": K5_TOTAL / (ms5 * 1e-3), "unit": "rollouts/s",
+              "state_steps_per_s": K5_TOTAL * T5 / (ms5 * 1e-3), "steps": steps5, "gpu_launches": launches5,
+              "one_gpu_same_run_ms_per_step": n1_ms, "launch": info5, "parity": parity5}
     clocks = sampler.stop() if sampler else {}
     if rank == 0:
-        io = m.mppi.io_bytes()
         xbytes = T * 48
         line = {
             "metric": METRIC, "value": K_total / (dev_ms * 1e-3), "unit": "rollouts/s", "n_gpus": world, "steps": args.steps,
@@ -372,15 +477,16 @@ def run_multi(args):
             "config": {"workload": "diff-drive parallel-park K=%d per GPU (K_total=%d) T=%d, rollouts sharded over ranks, "
                                    "one %d-byte record exchanged all-to-all per step" % (K_PER_GPU, K_total, T, xbytes),
                        "K_total": K_total, "T": T, "precision": args.precision,
-                       "exchange": {"p2p": "fused: reduce kernel stores its record into every peer's memory over NVLink "
-                                           "(CUDA IPC), finalize kernel spins on arrival flags; one CUDA graph per rank",
+                       "exchange": {"p2p": "fused: every reduce block stores its row of the record into every peer's memory over NVLink "
+                                           "(CUDA IPC) and raises a per-row flag; the finalize phase waits on the rows; one CUDA graph per rank",
                                     "nccl": "ncclAllGather of the device-resident records (torch.distributed)",
-                                    "host": "host-staged all-gather"}[m.exchange],
-                       "l2": "flushed between timed steps", "timing": timing, "launch": m.mppi.launch_info()},
+                                    "host": "host-staged all-gather"}[exchange],
+                       "l2": "flushed between timed steps", "timing": timing, "launch": launch_info},
             "state_steps_per_s": K_total / (dev_ms * 1e-3) * T,
             "e2e": {"value": K_total / (e2e_ms * 1e-3), "unit": "rollouts/s", "h2d_bytes_per_step": io[0] * world,
-                    "d2h_bytes_per_step": io[1] * world, "ms_per_step": e2e_ms},
-            "gpu_launches": launches, "clocks": clocks,
+                    "d2h_bytes_per_step": io[1] * world, "ms_per_step": e2e_ms,
+                    "l2": "flushed on every rank before every timed call (outside the timed interval)"},
+            "gpu_launches": launches, "clocks": clocks, "parity": parity, "config5": c5,
         }
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -396,6 +502,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="mixed", choices=["mixed", "f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-config5", action="store_true", help="skip the K=2097152 T=128 block (BASELINE.json configs[4])")
+    ap.add_argument("--ref-full", action="store_true", help="--impl reference: time EVERY step at the full K=65536 (15-40 s per step)")
+    ap.add_argument("--no-ref-full-step", dest="ref_full_step", action="store_false",
+                    help="--impl reference: skip the single full-K step that checks the sampled figure")
     ap.add_argument("--exchange", default=None, choices=["p2p", "nccl", "host"], help="multi-GPU record exchange (default p2p)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
