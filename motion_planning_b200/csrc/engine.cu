@@ -77,14 +77,14 @@ struct mppi_engine {
   float* d_nomF = nullptr;
   double sg_a = 0, sg_b = 0, sg_inv_norm[4] = {0, 0, 0, 0};
   double *d_record = nullptr, *d_gather = nullptr, *d_record_tmp = nullptr;
-  unsigned int* d_done = nullptr;
   unsigned long long* d_debug_ts = nullptr;
   unsigned long long* d_debug_rts = nullptr;   // rollout kernel stamps (MPPI_EXP_TIMELINE builds)
   size_t debug_rts_ctas = 0;
-  // peer-to-peer exchange
-  double* d_p2p = nullptr;          // local buffer (exported through CUDA IPC)
-  size_t p2p_bytes = 0;
-  double** d_p2p_peers = nullptr;   // device array of peer base pointers
+  // row exchange of the fused step (reduce_kernels.cuh): this rank's flag-in-data buffer (exported through CUDA IPC when
+  // world > 1) and the device array of all ranks' buffer pointers (own buffer + IPC mappings of the peers')
+  uint2* d_ll = nullptr;
+  size_t ll_bytes = 0;
+  uint2** d_ll_peers = nullptr;
   std::vector<void*> p2p_opened;    // IPC mappings to close
   bool p2p_on = false;
   void* d_part = nullptr;
@@ -501,8 +501,11 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
   CKF(cudaMalloc(&e->d_record, (size_t)T * kRecordStride * sizeof(double)));
   CKF(cudaMalloc(&e->d_record_tmp, (size_t)T * kRecordStride * sizeof(double)));
   CKF(cudaMalloc(&e->d_gather, (size_t)p.world_size * T * kRecordStride * sizeof(double)));
-  CKF(cudaMalloc(&e->d_done, sizeof(unsigned int)));
-  CKF(cudaMemset(e->d_done, 0, sizeof(unsigned int)));
+  e->ll_bytes = (size_t)2 * p.world_size * T * kRowWords * sizeof(uint2);
+  CKF(cudaMalloc(&e->d_ll, e->ll_bytes));
+  CKF(cudaMemset(e->d_ll, 0, e->ll_bytes));       // flag 0 never matches an epoch + 1
+  CKF(cudaMalloc(&e->d_ll_peers, p.world_size * sizeof(uint2*)));
+  if (p.world_size == 1) CKF(cudaMemcpy(e->d_ll_peers, &e->d_ll, sizeof(uint2*), cudaMemcpyHostToDevice));
   CKF(cudaMallocHost(&e->h_in, 6 * sizeof(double)));
   CKF(cudaMallocHost(&e->h_out, sizeof(DynState)));
   CKF(cudaHostAlloc(&e->h_res, sizeof(HostResult), cudaHostAllocMapped));
@@ -554,12 +557,11 @@ extern "C" mppi_status mppi_destroy(mppi_handle e) {
   cudaFree(e->d_record);
   cudaFree(e->d_record_tmp);
   cudaFree(e->d_gather);
-  cudaFree(e->d_done);
   cudaFree(e->d_debug_ts);
   cudaFree(e->d_debug_rts);
   for (void* q : e->p2p_opened) cudaIpcCloseMemHandle(q);
-  cudaFree(e->d_p2p_peers);
-  cudaFree(e->d_p2p);
+  cudaFree(e->d_ll_peers);
+  cudaFree(e->d_ll);
   cudaFree(e->d_grid);
   if (e->h_grid_stage) cudaFreeHost(e->h_grid_stage);
   if (e->grid_stage_ev) cudaEventDestroy(e->grid_stage_ev);
@@ -800,8 +802,7 @@ static FinalizeArgs make_fin(mppi_engine* e, bool closed_loop) {
   fa.sp = e->sp;
   fa.dyn = e->d_dyn;
   fa.gather = (e->sp.world > 1) ? e->d_gather : e->d_record;
-  fa.p2p = 0;
-  fa.p2p_local = e->d_p2p;
+  fa.ll_local = nullptr;
   fa.Umaster = e->d_Umaster;
   fa.Ulast = e->d_Ulast;
   fa.nomF = e->d_nomF;
@@ -899,15 +900,14 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
       rd.fin.seq = e->seq;
     }
   }
-  if (fuse != FUSE_NONE && e->p2p_on) {   // sharded + p2p: the last block also exchanges and finalizes
-    rd.fin.p2p = 1;
+  rd.fused = fuse != FUSE_NONE ? 1 : 0;   // (callers have checked: world == 1, or the peers' row buffers are mapped)
+  if (rd.fused) {
+    rd.fin.ll_local = e->d_ll;
     rd.fin.gather = nullptr;
+    rd.fin.debug_ts = e->d_debug_ts ? e->d_debug_ts + (size_t)e->sp.T * 8 : nullptr;
   }
-  rd.fuse_finalize = (fuse != FUSE_NONE && e->sp.world == 1) ? 1 : 0;
-  rd.done_counter = e->d_done;
   rd.rank = e->p.rank;
-  rd.p2p_push = (fuse != FUSE_NONE && e->p2p_on) ? 1 : 0;
-  rd.p2p_peers = e->d_p2p_peers;
+  rd.ll_peers = e->d_ll_peers;
   rd.debug_ts = e->d_debug_ts;
   rd.part = e->d_part;
   rd.epart = e->d_epart;
@@ -929,16 +929,11 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
 }
 
 // stand-alone finalize (sharded steps: after the exchange)
-static mppi_status launch_finalize(mppi_engine* e, cudaStream_t st, bool closed_loop, KernelEvents* kev, bool p2p = false,
-                                   bool publish = false) {
+static mppi_status launch_finalize(mppi_engine* e, cudaStream_t st, bool closed_loop, KernelEvents* kev, bool publish = false) {
   FinalizeArgs fa = make_fin(e, closed_loop);
   if (publish) {
     fa.host_res = e->d_res;
     fa.seq = e->seq;
-  }
-  if (p2p) {   // records arrive in the local IPC buffer; parity is resolved on the device from dyn->xchg
-    fa.p2p = 1;
-    fa.gather = nullptr;
   }
   CK(finalize_launch(st, fa));
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[3], st));
@@ -1170,29 +1165,23 @@ extern "C" mppi_status mppi_p2p_export(mppi_handle e, void* handle64) {
   ENTER(e);
   if (!handle64) return MPPI_ERR_INVALID;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  if (!e->d_p2p) {
-    const size_t nrec = (size_t)2 * e->sp.world * e->sp.T * kRecordStride * sizeof(double);
-    e->p2p_bytes = nrec + (size_t)2 * e->sp.world * sizeof(unsigned int) + 64;
-    CK(cudaMalloc(&e->d_p2p, e->p2p_bytes));
-    CK(cudaMemset(e->d_p2p, 0, e->p2p_bytes));
-  }
   cudaIpcMemHandle_t hnd;
-  CK(cudaIpcGetMemHandle(&hnd, e->d_p2p));
+  CK(cudaIpcGetMemHandle(&hnd, e->d_ll));
   memcpy(handle64, &hnd, 64);
   return MPPI_OK;
 }
 
 extern "C" mppi_status mppi_p2p_connect(mppi_handle e, const void* handles) {
   ENTER(e);
-  if (!handles || !e->d_p2p) {
+  if (!handles) {
     set_err("mppi_p2p_connect: call mppi_p2p_export on every rank first and pass all world_size handles");
     return MPPI_ERR_STATE;
   }
   const int world = e->sp.world;
-  std::vector<double*> peers(world, nullptr);
+  std::vector<uint2*> peers(world, nullptr);
   for (int g = 0; g < world; ++g) {
     if (g == e->p.rank) {
-      peers[g] = e->d_p2p;
+      peers[g] = e->d_ll;
       continue;
     }
     cudaIpcMemHandle_t hnd;
@@ -1200,10 +1189,9 @@ extern "C" mppi_status mppi_p2p_connect(mppi_handle e, const void* handles) {
     void* ptr = nullptr;
     CK(cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
     e->p2p_opened.push_back(ptr);
-    peers[g] = (double*)ptr;
+    peers[g] = (uint2*)ptr;
   }
-  if (!e->d_p2p_peers) CK(cudaMalloc(&e->d_p2p_peers, world * sizeof(double*)));
-  CK(memcpy_on(e, e->d_p2p_peers, peers.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
+  CK(memcpy_on(e, e->d_ll_peers, peers.data(), world * sizeof(uint2*), cudaMemcpyHostToDevice));
   e->p2p_on = true;
   return drop_graphs(e);
 }
@@ -1216,7 +1204,7 @@ extern "C" mppi_status mppi_step_finish(mppi_handle e, double u_out[2], double x
   }
   e->local_pending = false;
   e->seq += 1;
-  CKS(launch_finalize(e, e->stream, false, nullptr, false, true));
+  CKS(launch_finalize(e, e->stream, false, nullptr, true));
   CKS(wait_result(e));
   return finish_outputs(e, u_out, x_next);
 }
@@ -1498,7 +1486,7 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
 extern "C" mppi_status mppi_debug_reduce_timestamps(mppi_handle e, unsigned long long* out) {
   ENTER(e);
   CK(cudaStreamSynchronize(e->stream));
-  const size_t n = (size_t)e->sp.T * 8;
+  const size_t n = (size_t)(e->sp.T + 1) * 8;   // row T: the finalizer block
   if (!e->d_debug_ts) {
     CK(cudaMalloc(&e->d_debug_ts, n * sizeof(unsigned long long)));
     CK(cudaMemset(e->d_debug_ts, 0, n * sizeof(unsigned long long)));

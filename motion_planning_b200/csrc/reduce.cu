@@ -72,10 +72,25 @@ size_t rollout_smem(int kind, int T, int block, int variant, int grid_bytes_in_s
                                      : rollout_smem_bytes<float>(T, block, grid_bytes_in_smem);
 }
 
+// shared memory of the finalize phase: the 4*T doubles of the update + (fused step) the rows of all ranks
+static size_t finalize_smem(const StaticParams& sp, bool fused) {
+  return ((size_t)4 * sp.T + (fused ? (size_t)sp.world * sp.T * kRowDoubles : 0)) * sizeof(double);
+}
+
+template <typename Fn>
+static cudaError_t opt_in_smem(Fn f, size_t smem) {
+  if (smem <= 32 * 1024) return cudaSuccess;   // static + dynamic shared memory beyond 48 KB needs the opt-in
+  return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+// grid: one block per time step (+ the finalizer block of a fused step)
 cudaError_t reduce_softmin_launch(bool f64, int T, cudaStream_t st, const ReduceArgs& a) {
-  const size_t smem = (size_t)4 * T * sizeof(double);
-  if (f64) return launch_pdl(reduce_softmin_kernel<double>, T, 256, smem, st, a);
-  return launch_pdl(reduce_softmin_kernel<float>, T, 256, smem, st, a);
+  const size_t smem = finalize_smem(a.sp, a.fused != 0);
+  const int grid = T + (a.fused ? 1 : 0);
+  cudaError_t e = f64 ? opt_in_smem(reduce_softmin_kernel<double>, smem) : opt_in_smem(reduce_softmin_kernel<float>, smem);
+  if (e != cudaSuccess) return e;
+  if (f64) return launch_pdl(reduce_softmin_kernel<double>, grid, 256, smem, st, a);
+  return launch_pdl(reduce_softmin_kernel<float>, grid, 256, smem, st, a);
 }
 
 typedef void (*ScreenFn)(const ReduceArgs);
@@ -91,12 +106,11 @@ cudaError_t reduce_screen_launch(int model, bool has_grid, int T, cudaStream_t s
       break;
     default: f = has_grid ? sfn_<MPPI_MODEL_BICYCLE, true>() : sfn_<MPPI_MODEL_BICYCLE, false>(); break;
   }
-  const size_t smem = (size_t)(8 * 7 + 4) * T * sizeof(double);   // scan scratch of 8 warps + nominal block
-  if (smem > 32 * 1024) {   // static + dynamic shared memory beyond 48 KB needs the opt-in
-    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  return launch_pdl(f, T, 256, smem, st, a);
+  size_t smem = (size_t)(8 * 7 + 4) * T * sizeof(double);   // scan scratch of 8 warps + nominal block
+  if (finalize_smem(a.sp, a.fused != 0) > smem) smem = finalize_smem(a.sp, a.fused != 0);   // the finalizer block's needs
+  cudaError_t e = opt_in_smem(f, smem);
+  if (e != cudaSuccess) return e;
+  return launch_pdl(f, T + (a.fused ? 1 : 0), 256, smem, st, a);
 }
 
 cudaError_t finalize_launch(cudaStream_t st, const FinalizeArgs& a) {

@@ -102,88 +102,48 @@ __device__ __forceinline__ void publish_result(const FinalizeArgs& a, int status
   r->seq = a.seq;
 }
 
-// "last block done": the block that finishes the last record runs the finalize phase, saving one
-// kernel boundary on the serial tail of the step (world_size 1 only; sharded steps exchange first)
-__device__ __forceinline__ bool last_block_done(unsigned int* counter, unsigned int nblocks) {
-  // precondition: the block's global results (its record, statistics) were written by THREAD 0 only, so one
-  // fence + one atomic by that thread order them before the ticket; the others just learn the outcome
-  __shared__ unsigned int ticket;
-  if (threadIdx.x == 0) {
-    __threadfence();
-    ticket = atomicAdd(counter, 1u);
-  }
-  __syncthreads();
-  const bool last = (ticket == nblocks - 1);
-  if (last) {
-    if (threadIdx.x == 0) *counter = 0u;
-    __threadfence();   // acquire side: the other blocks' records are visible to every thread of the last block
-  }
-  return last;
+// ---- row exchange of the fused step: flag-in-data rows (any world size; over NVLink for world > 1) -------------------
+// Every reduce block owns one time step t and ends with one ROW: the record (m, S, N0, N1, E0, E1) plus the block's
+// statistics (max |V32 - V64|, candidates).  The row leaves as kRowWords 8-byte stores, each carrying 4 bytes of payload and
+// the 4-byte flag `epoch + 1` -- an aligned 8-byte store is single-copy atomic, so a word whose flag matches IS valid and
+// neither a fence nor a separate arrival flag is needed (the scheme of NCCL's low-latency protocol).  The block stores its row
+// into the buffer of EVERY rank, its own included (plain stores into CUDA-IPC mappings for the peers): buffer layout
+// uint2 [2 parity][world][T][kRowWords], parity = epoch & 1 (a rank can be at most one step ahead of its slowest peer).
+// Block T of the grid (the FINALIZER) does no row work: it loads everything the finalize phase needs while the rows are
+// still being computed, then polls the rows of all ranks and finishes the step -- no ticket, no last-block election, no
+// system-scope fence on the serial tail; the exchange costs one NVLink store latency after a rank's last row.
+__device__ __forceinline__ void st_ll(uint2* p, unsigned int w, unsigned int flag) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(w), "r"(flag) : "memory");
 }
-
-// ---- peer-to-peer exchange over NVLink (world > 1) ------------------------------------------------------
-// Buffer of every rank: doubles [2 parity][world][T*6], then uint32 flags [2][world].  Rank r stores its
-// record into slot r of EVERY rank's buffer (plain stores to CUDA-IPC-mapped peer memory), fences at
-// system scope and raises flag[parity][r] = epoch+1 there; the finalize kernel of each rank spins on its
-// own flags.  Two parities suffice: a rank can be at most one step ahead of its slowest peer.
-__device__ __forceinline__ unsigned int* p2p_flags(double* base, int world, int T) {
-  return reinterpret_cast<unsigned int*>(base + (size_t)2 * world * T * kRecordStride);
+__device__ __forceinline__ uint4 ld_ll2(const uint2* p) {   // two consecutive words (16 bytes; each half is atomic by itself)
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
 }
-__device__ inline void p2p_push_record(const ReduceArgs& a) {
-  const int T = a.sp.T, world = a.sp.world, rank = a.rank;
-  const unsigned int epoch = a.fin.dyn->xchg;
-  const int par = (int)(epoch & 1u);
-  const int n = T * kRecordStride;
-  for (int g = 0; g < world; ++g) {
-    double* dst = a.p2p_peers[g] + ((size_t)par * world + rank) * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcg(a.record + i);
-  }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < world) {
-    unsigned int* f = p2p_flags(a.p2p_peers[threadIdx.x], world, T) + (size_t)par * world + rank;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch + 1u) : "memory");
+// called by ALL lanes of warp 0 of a row block; `row` = kRowDoubles doubles in shared memory, complete and visible to the warp
+__device__ __forceinline__ void ll_push_row(const ReduceArgs& a, int t, const double* row, unsigned int flag) {
+  const int lane = threadIdx.x & 31, world = a.sp.world, T = a.sp.T;
+  const size_t slot = ((size_t)((flag - 1u) & 1u) * world + a.rank) * T + t;
+  const unsigned int* w32 = reinterpret_cast<const unsigned int*>(row);
+  for (int idx = lane; idx < world * kRowWords; idx += 32) {
+    const int g = idx / kRowWords, j = idx - g * kRowWords;
+    st_ll(a.ll_peers[g] + slot * kRowWords + j, w32[j], flag);
   }
 }
-__device__ inline bool p2p_wait_all(const FinalizeArgs& a) {
-  __shared__ int timed_out;
-  const int T = a.sp.T, world = a.sp.world;
-  if (threadIdx.x == 0) timed_out = 0;
-  __syncthreads();
-  const unsigned int epoch = a.dyn->xchg;
-  const int par = (int)(epoch & 1u);
-  if ((int)threadIdx.x < world) {
-    const unsigned int* f = p2p_flags(a.p2p_local, world, T) + (size_t)par * world + threadIdx.x;
-    const long long t0 = clock64();
-    unsigned int v;
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if (clock64() - t0 > (1LL << 33)) {   // ~4 s: a peer died
-        timed_out = 1;
-        break;
-      }
-    } while (v != epoch + 1u);
-  }
-  __syncthreads();
-  return timed_out == 0;
-}
-
-// What the last block of a reduce kernel does once every record of this rank is complete:
-//   world == 1 : finalize in place;
-//   world  > 1 : store the record into every peer (NVLink), wait for all peers' records, finalize --
-//                the whole sharded step stays at TWO kernels per rank.
-__device__ inline void last_block_epilogue(const ReduceArgs& a, double* scratch4T) {
-  if (a.p2p_push) {
-    p2p_push_record(a);
-    if (!p2p_wait_all(a.fin)) {
-      if (threadIdx.x == 0) {   // exchange timed out (a peer died)
-        a.fin.dyn->status = (int)MPPI_ERR_STATE;
-        publish_result(a.fin, (int)MPPI_ERR_STATE, nullptr, nullptr, 0, 0.0, 0);
-      }
-      return;
+// poll row (g, t) until all its words carry `flag`; false on time-out (a peer died)
+__device__ __forceinline__ bool ll_read_row(const uint2* ll, int world, int T, unsigned int flag, int g, int t, double out[kRowDoubles]) {
+  const uint2* src = ll + (((size_t)((flag - 1u) & 1u) * world + g) * T + t) * kRowWords;
+  const long long t0 = clock64();
+#pragma unroll
+  for (int d = 0; d < kRowDoubles; ++d) {
+    uint4 v = ld_ll2(src + 2 * d);
+    while (v.y != flag || v.w != flag) {
+      if (clock64() - t0 > (1LL << 33)) return false;   // ~4 s
+      v = ld_ll2(src + 2 * d);
     }
+    out[d] = __hiloint2double((int)v.z, (int)v.x);
   }
-  finalize_body(a.fin, scratch4T);
+  return true;
 }
 
 // ---- kernel 2a: SOFTMIN merge.  grid = T blocks of 256 threads --------------------------------------
@@ -195,6 +155,12 @@ __global__ void __launch_bounds__(256) reduce_softmin_kernel(const __grid_consta
   extern __shared__ __align__(16) unsigned char smem_fin[];
   __shared__ double scratch[8];
   __shared__ double scratch5[40];
+  __shared__ double rowbuf[kRowDoubles];
+  if (a.fused && blockIdx.x == (unsigned)a.sp.T) {   // the finalizer block (see the row exchange above)
+    finalize_body(a.fin, reinterpret_cast<double*>(smem_fin));
+    return;
+  }
+  const unsigned int row_flag = a.fin.dyn->xchg + 1u;   // exchange epoch of this step
   griddep_wait();   // PDL: everything above overlapped the rollout kernel's tail
   const int t = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const Vec4* part = reinterpret_cast<const Vec4*>(a.part) + (size_t)t * a.nCTA;
@@ -250,9 +216,19 @@ __global__ void __launch_bounds__(256) reduce_softmin_kernel(const __grid_consta
     r[3] = v5[2];
     r[4] = v5[3] * s0;
     r[5] = v5[4] * s1;
+    rowbuf[0] = m;
+    rowbuf[1] = v5[0];
+    rowbuf[2] = v5[1];
+    rowbuf[3] = v5[2];
+    rowbuf[4] = v5[3] * s0;
+    rowbuf[5] = v5[4] * s1;
+    rowbuf[6] = 0.0;
+    rowbuf[7] = 0.0;
   }
-  if ((a.fuse_finalize || a.p2p_push) && last_block_done(a.done_counter, gridDim.x))
-    last_block_epilogue(a, reinterpret_cast<double*>(smem_fin));
+  if (a.fused && tid < 32) {
+    __syncwarp();
+    ll_push_row(a, t, rowbuf, row_flag);
+  }
 }
 
 // ---- fp64 re-evaluation of ONE rollout by ONE warp, parallel in time ------------------------------
@@ -383,8 +359,15 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   __shared__ double sel_v64[kMaxRefine];
   __shared__ double sel_eps[kMaxRefine][2];
   __shared__ int nsel, overflow;
+  __shared__ double rowbuf[kRowDoubles];
   const StaticParams& sp = a.sp;
   const int T = sp.T;
+  if (a.fused && blockIdx.x == (unsigned)T) {   // the finalizer block (see the row exchange above)
+    TS(0);
+    finalize_body(a.fin, warp_scratch);
+    TS(2);
+    return;
+  }
   double* nomS = warp_scratch + (size_t)8 * 7 * T;   // [4][T] copy of the fp64 nominal block
   const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nth = blockDim.x;
@@ -399,6 +382,7 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   const double neg_inv_lam = -1.0 / a.fin.dyn->lam;
   const float std0 = (float)a.fin.dyn->noise_std[0], std1 = (float)a.fin.dyn->noise_std[1];
   const unsigned int philox_step = a.fin.dyn->step;
+  const unsigned int row_flag = a.fin.dyn->xchg + 1u;   // exchange epoch of this step
   double xs_[3], gs_[3], head;
   load_step_input(a.fin.in, a.fin.dyn, xs_, gs_);
   const float window = (float)screen_window(sp, xs_, gs_, &head);   // the same value the rollout kernel listed against
@@ -525,18 +509,24 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
       r[3] = N1;
       r[4] = E0 * s0;
       r[5] = E1 * s1;
-      atomicAdd(&a.fin.dyn->refine_candidates, n);
-      if (overflow) atomicOr(&a.fin.dyn->refine_overflow, 1);
-      // max of non-negative doubles == max of their bit patterns
-      atomicMax(reinterpret_cast<unsigned long long*>(&a.fin.dyn->refine_max_dev), (unsigned long long)__double_as_longlong(dev));
+      if (a.fused) {   // statistics travel with the row
+#pragma unroll
+        for (int i = 0; i < 6; ++i) rowbuf[i] = r[i];
+        rowbuf[6] = dev;
+        rowbuf[7] = (double)n;
+      } else {
+        atomicAdd(&a.fin.dyn->refine_candidates, n);
+        if (overflow) atomicOr(&a.fin.dyn->refine_overflow, 1);
+        // max of non-negative doubles == max of their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long*>(&a.fin.dyn->refine_max_dev), (unsigned long long)__double_as_longlong(dev));
+      }
+    }
+    if (a.fused) {
+      __syncwarp();
+      ll_push_row(a, t, rowbuf, row_flag);
     }
   }
   TS(4);
-  if ((a.fuse_finalize || a.p2p_push) && last_block_done(a.done_counter, gridDim.x)) {
-    TS(5);
-    last_block_epilogue(a, warp_scratch);
-    TS(6);
-  }
 }
 
 // ---- kernel 3: finalize.  one block of 256 threads ------------------------------------------------
@@ -616,8 +606,8 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
     any_ovf = 0;
     step_r = a.dyn->step;
     xchg_r = a.dyn->xchg;
-    cand_r = __ldcg(&a.dyn->refine_candidates);
-    dev_r = __ldcg(&a.dyn->refine_max_dev);
+    cand_r = a.dyn->refine_candidates;      // (split-phase step: accumulated by the row blocks of the previous kernel)
+    dev_r = a.dyn->refine_max_dev;
     double goalr[3];
     load_step_input(a.in, a.dyn, x0r, goalr);
     screen_window(sp, x0r, goalr, &head_r);
@@ -629,50 +619,81 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       }
     }
   }
-  const double* gather = a.p2p ? a.p2p_local + (size_t)(a.dyn->xchg & 1u) * sp.world * T * kRecordStride : a.gather;
+  // -- the records of all ranks.  Fused step: poll the flag-in-data rows (this rank's own blocks and, over NVLink, the peers'),
+  //    one row per thread with its eight 16-byte loads in flight together, into shared memory; otherwise the gathered records
+  //    of a previous kernel / copy
+  __shared__ int timed_out, s_cand;
+  __shared__ unsigned long long s_dev;
+  const double* recs = a.gather;
+  int stride = kRecordStride;
+  if (tid == 0) {
+    timed_out = 0;
+    s_cand = 0;
+    s_dev = 0ull;
+  }
+  // nominal controls of this thread's (c, t): loaded before the wait
+  double u_nom[2] = {0.0, 0.0};
+  {
+    int q = 0;
+    for (int idx = tid; idx < 2 * T && q < 2; idx += blockDim.x, ++q) u_nom[q] = a.Umaster[idx];
+  }
   __syncthreads();
+  if (a.ll_local) {
+    double* rows = Us + 4 * T;                       // [world][T][kRowDoubles]
+    const unsigned int flag = a.dyn->xchg + 1u;      // (only this block ever advances xchg, at the very end)
+    for (int i = tid; i < sp.world * T; i += blockDim.x) {
+      const int g = i / T, t = i - g * T;
+      double r[kRowDoubles];
+      if (!ll_read_row(a.ll_local, sp.world, T, flag, g, t, r)) timed_out = 1;
+#pragma unroll
+      for (int d = 0; d < kRowDoubles; ++d) rows[(size_t)i * kRowDoubles + d] = r[d];
+      if (r[7] != 0.0) atomicAdd(&s_cand, (int)r[7]);
+      if (r[6] > 0.0) atomicMax(&s_dev, (unsigned long long)__double_as_longlong(r[6]));   // non-negative doubles order like their bits
+    }
+    recs = rows;
+    stride = kRowDoubles;
+    __syncthreads();
+    if (timed_out) {   // a peer never delivered (it died): report, leave the controller state untouched
+      if (owner && a.mode == 0) {
+        a.dyn->status = (int)MPPI_ERR_STATE;
+        publish_result(a, (int)MPPI_ERR_STATE, nullptr, nullptr, 0, 0.0, 0);
+      }
+      return;
+    }
+    if (owner) {
+      cand_r = s_cand;
+      dev_r = __longlong_as_double((long long)s_dev);
+      if (a.debug_ts) a.debug_ts[1] = gtime();
+    }
+  }
   // -- merge the records of all ranks and apply the weighted noise (control/src/mppi:189-199) ----
   const double neg_inv_lam = -1.0 / lam;
-  for (int idx = tid; idx < 2 * T; idx += blockDim.x) {
-    const int c = idx / T, t = idx - c * T;
-    double rec[4];   // world == 1 fast path keeps the record in registers (one batch of loads)
-    double m = Math<double>::inf();
-    if (sp.world == 1) {
-      const double* r = gather + (size_t)t * kRecordStride;
-      rec[0] = __ldcg(r);
-      rec[1] = __ldcg(r + 1);
-      rec[2] = __ldcg(r + 2 + c);
-      rec[3] = __ldcg(r + 4 + c);
-      m = rec[0];
-    } else {
-      for (int g = 0; g < sp.world; ++g) m = fmin(m, __ldcg(&gather[((size_t)g * T + t) * kRecordStride]));
-    }
-    double S = 0, N = 0, E = 0;
-    bool ovf = false;
-    if (sp.world == 1) {
-      S = rec[1];
-      N = rec[2];
-      E = rec[3];
-      ovf = rec[1] < 0.0;
-    } else {
+  {
+    int q = 0;
+    for (int idx = tid; idx < 2 * T; idx += blockDim.x, ++q) {
+      const int c = idx / T, t = idx - c * T;
+      double m = Math<double>::inf();
+      for (int g = 0; g < sp.world; ++g) m = fmin(m, recs[((size_t)g * T + t) * stride]);
+      double S = 0, N = 0, E = 0;
+      bool ovf = false;
       for (int g = 0; g < sp.world; ++g) {
-        const double* r = gather + ((size_t)g * T + t) * kRecordStride;
-        const double rm = __ldcg(r), rs = __ldcg(r + 1);
+        const double* r = recs + ((size_t)g * T + t) * stride;
+        const double rm = r[0], rs = r[1];
         const double sc = (rm == m) ? 1.0 : exp((rm - m) * neg_inv_lam);
         ovf |= rs < 0.0;
         S += rs * sc;
-        N += __ldcg(r + 2 + c) * sc;
-        E += __ldcg(r + 4 + c);
+        N += r[2 + c] * sc;
+        E += r[4 + c];
       }
+      // MIXED: a record with S < 0 means some rank's fp32 screen overflowed a candidate list (see below)
+      if (ovf) any_ovf = 1;
+      const double dU = (N + sp.eps_floor * E) / (S + sp.eps_floor * (double)sp.k_total);
+      const double u = (q < 2 ? u_nom[q] : a.Umaster[idx]) + dU;
+      // the reference lets NaN propagate silently; here a non-finite input or an empty
+      // softmin support (S == 0 can only come from NaN costs) is reported as MPPI_ERR_NONFINITE
+      if (!isfinite(u) || !(S > 0.0)) atomicOr(&bad, 1);
+      Us[c * T + t] = clamp_<double>(u, sp.u_max[c]);                          // :198-199
     }
-    // MIXED: a record with S < 0 means some rank's fp32 screen overflowed a candidate list (see below)
-    if (ovf) any_ovf = 1;
-    const double dU = (N + sp.eps_floor * E) / (S + sp.eps_floor * (double)sp.k_total);
-    const double u = a.Umaster[c * T + t] + dU;
-    // the reference lets NaN propagate silently; here a non-finite input or an empty
-    // softmin support (S == 0 can only come from NaN costs) is reported as MPPI_ERR_NONFINITE
-    if (!isfinite(u) || !(S > 0.0)) atomicOr(&bad, 1);
-    Us[c * T + t] = clamp_<double>(u, sp.u_max[c]);                          // :198-199
   }
   __syncthreads();
   if (a.mode == 0 && any_ovf) {
@@ -718,6 +739,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
     }
   }
   __syncthreads();
+  if (owner && a.debug_ts) a.debug_ts[3] = gtime();
   // filtered and clipped U[c][t] (:202-206): evaluate fit A (t <= h) or fit B at its abscissa
   auto sg_eval = [&](int c, int t) -> double {
     const int fit = (t <= h) ? 0 : 1;
@@ -754,6 +776,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
     d->refine_overflow = 0;
     d->refine_max_dev = 0.0;
     publish_result(a, status, uo, xn, cand_r, dev_r, ovf_total, head_r);
+    if (a.debug_ts) a.debug_ts[4] = gtime();
   }
   // -- update_action result, receding-horizon shift (:100-101), next nominal block: one pass, no further barrier
   for (int t = tid; t < T; t += blockDim.x) {
@@ -771,10 +794,6 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
 
 __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw3[];
-  if (a.p2p && !p2p_wait_all(a)) {
-    if (threadIdx.x == 0) a.dyn->status = (int)MPPI_ERR_STATE;   // exchange timed out
-    return;
-  }
   finalize_body(a, reinterpret_cast<double*>(smem_raw3));
 }
 

@@ -46,9 +46,12 @@ struct FinalizeArgs {
   double sg_inv_norm[4];     // 1 / sum_j p_i(z_j)^2
   int mode;                  // 0: full step, 1: update only (mppi_update_action)
   int closed_loop;           // 1: dyn->x0 <- x_next (device-resident loop of mppi_bench)
-  // peer-to-peer exchange (world > 1, NVLink): wait for every rank's record to land in p2p_local
-  int p2p;
-  double* p2p_local;         // this rank's buffer: [2 parity][world][T*6] doubles, then flags [2][world] uint32
+  // row exchange of the fused step (any world size): the finalizer block reads the rows of ALL ranks (its own included)
+  // from this rank's flag-in-data buffer, uint2 [2 parity][world][T][kRowWords] (see reduce_kernels.cuh); nullptr: the
+  // records are taken from `gather` (split-phase step with an external exchange, mppi_update_action)
+  const uint2* ll_local;
+  unsigned long long* debug_ts;   // optional 8 globaltimer stamps of the finalize phase (profiling aid): [1] all rows seen,
+                                  // [3] filter coefficients done, [4] result published
   StepInput in;              // x0 / goal of this step (also used by the reduce kernel's fp64 re-evaluation)
   HostResult* host_res;      // mapped pinned host memory (nullptr: results are fetched from DynState)
   unsigned long long seq;    // value that publishes host_res
@@ -57,11 +60,11 @@ struct FinalizeArgs {
 struct ReduceArgs {
   StaticParams sp;
   FinalizeArgs fin;          // fin.dyn is THE DynState; the rest is used when fuse_finalize != 0
-  int fuse_finalize;         // 1: the last block to finish also runs the finalize phase (world_size 1)
-  unsigned int* done_counter;
+  int fused;                 // 1: rows leave through the flag-in-data buffers and block T of the grid (the finalizer) runs the
+                             //    finalize phase as soon as the rows of all ranks have arrived; 0: rows go to `record` only
   int rank;
-  int p2p_push;              // 1: the last block stores this rank's record into every peer's buffer
-  double* const* p2p_peers;  // device array [world] of peer buffer base pointers (CUDA IPC mappings)
+  uint2* const* ll_peers;    // device array [world] of row-buffer base pointers: this rank's own buffer and, for world > 1,
+                             // the CUDA IPC mappings of the peers' buffers (stores travel over NVLink)
   unsigned long long* debug_ts;   // optional [T][8] globaltimer stamps of the reduce phases (profiling aid)
   const void* part;          // SOFTMIN partials Vec4[T][nCTA]
   const double* epart;       // [T][nCTA][2]

@@ -18,15 +18,18 @@ _capi.check(m._lib.mppi_debug_reduce_timestamps(m._h, None), "arm")
 s = np.zeros(3)
 for _ in range(5):
     s = m.get_path(s, goal)
-ts = np.zeros((T, 8), dtype=np.uint64)
+ts = np.zeros((T + 1, 8), dtype=np.uint64)          # row T: the finalizer block
 _capi.check(m._lib.mppi_debug_reduce_timestamps(m._h, ts.ctypes.data_as(C.POINTER(C.c_uint64))), "read")
 ts = ts.astype(np.int64)
-t0 = ts[:, 0].min()
-rel = (ts - t0) / 1e3
-names = ["start", "A:min+E", "B:compact", "C:resim", "D:softmin", "ticket", "finalize_end"]
-print(prec, K, T, "block start spread %.2f us" % (rel[:, 0].max()))
+rows, fin = ts[:T], ts[T]
+t0 = rows[:, 0].min()
+rel = (rows - t0) / 1e3
+names = ["start", "A:min+E", "B:compact", "C:resim", "D:softmin+push"]
+print(prec, K, T, "row blocks pass the PDL wait within %.2f us of each other" % (rel[:, 0].max()))
 for j in range(1, 5):
     d = rel[:, j] - rel[:, j - 1]
-    print("  phase %-10s mean %.2f  max %.2f us (block %d)" % (names[j], d.mean(), d.max(), d.argmax()))
-print("  all blocks done at %.2f us; last block: ticket %.2f, finalize end %.2f us" % (
-    rel[:, 4].max(), rel[:, 5].max(), rel[:, 6].max()))
+    print("  phase %-14s mean %.2f  max %.2f us (block %d)" % (names[j], d.mean(), d.max(), d.argmax()))
+f = (fin - t0) / 1e3
+print("  last row pushed at %.2f us" % rel[:, 4].max())
+print("  finalizer block: resident at %.2f, all rows seen %.2f, filter coefficients %.2f, result published %.2f, end %.2f us" % (
+    f[0], f[1], f[3], f[4], f[2]))

@@ -16,16 +16,21 @@ def main():
     K, T = int(sys.argv[1]), int(sys.argv[2])
     precision = sys.argv[3] if len(sys.argv) > 3 else "mixed"
     exchange = sys.argv[4] if len(sys.argv) > 4 else "nccl"
+    to_goal = len(sys.argv) > 5 and sys.argv[5] == "togoal"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    goal = np.array([0.0, -1.0, 0.0])
+    goal = np.array([0.0, -0.06, 0.0]) if to_goal else np.array([0.0, -1.0, 0.0])
     sh = ShardedMPPI(T, K, precision=precision, seed=0, device=local, exchange=exchange)
     one = mp.MPPI(horizon=T, samples=K, precision=precision, seed=0, device=local) if rank == 0 else None
     s = np.zeros(3)
     worst = 0.0
-    for it in range(4):
+    for it in range(400 if to_goal else 4):
+        # to_goal: drive INTO the goal -- within centimetres of it the fp32 screen overflows systematically and the step is
+        # redone in fp64 (p2p: inside mppi_step; nccl / host: MPPI_ERR_RETRY round trip of ShardedMPPI.get_path)
+        if to_goal and np.linalg.norm(s[:2] - goal[:2]) < 0.002:
+            break
         s1 = sh.get_path(s, goal)
         if one is not None:
             s2 = one.get_path(s, goal)
@@ -39,7 +44,11 @@ def main():
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     spread = float((hi - lo).abs().max())
     if rank == 0:
-        ok = worst < 1e-9 and spread == 0.0
+        ok = worst < (1e-7 if to_goal else 1e-9) and spread == 0.0
+        if to_goal:
+            ovf = sh.mppi.stats()["refine_overflow"]
+            ok = ok and np.linalg.norm(s[:2] - goal[:2]) < 0.01 and (precision != "mixed" or ovf >= 1)
+            print("to goal: %d steps, final distance %.4f, steps redone in fp64 %d" % (it, np.linalg.norm(s[:2] - goal[:2]), ovf))
         print("DIST %s world=%d K=%d T=%d %s/%s: max rel err vs 1 GPU %.3e, rank spread %.1e" % (
             "OK" if ok else "FAIL", world, K, T, precision, exchange, worst, spread))
     dist.barrier()

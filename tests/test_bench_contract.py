@@ -17,7 +17,7 @@ def _run(args, env=None):
 
 
 def test_reference_arm_prints_one_contract_line():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "3"])
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "3", "--no-ref-full-step"])    # (the full-K step takes ~40 s here)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -26,6 +26,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["metric"].startswith("MPPI rollouts/sec") and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 3
     assert d["value"] > 0 and d["gpu_launches"] == 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert "workload" in d["config"] and "K=65536 T=64" in d["config"]["workload"]
+    assert d["config"]["K"] == 65536 and d["config"]["T"] == 64 and d["config"]["sample_K"] <= 65536
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "rollouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

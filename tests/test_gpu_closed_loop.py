@@ -119,7 +119,7 @@ def test_sharded_external_exchange_survives_the_overflow_regime():
     for r in range(G):
         kl, ko = shard_plan(K, G, r)
         eng.append(mp.MPPI(horizon=T, samples=kl, precision="mixed", seed=0, k_offset=ko, k_total=K, world_size=G, rank=r))
-    s, retries, steps = np.zeros(3), 0, 0
+    s, retries, steps, worst = np.zeros(3), 0, 0, 0.0
     for it in range(400):
         s1 = one.get_path(s, goal)
         for attempt in range(3):
@@ -141,14 +141,19 @@ def test_sharded_external_exchange_survives_the_overflow_regime():
                 break
             retries += 1
         _capi.check(sts[0], "mppi_step_finish")
-        np.testing.assert_allclose(x, s1, rtol=0, atol=1e-10)
-        for e in eng:
-            assert np.max(np.abs(e.latest_uvec - one.latest_uvec)) < 1e-7 * max(1.0, np.max(np.abs(one.latest_uvec)))
+        errU = max(np.max(np.abs(e.latest_uvec - one.latest_uvec)) for e in eng) / max(1.0, np.max(np.abs(one.latest_uvec)))
+        worst = max(worst, errU)
+        if errU > 1e-7:
+            print("step %d: errU %.3g dist %.4f attempt %d stats %s" % (it, errU, np.linalg.norm(s[:2] - goal[:2]), attempt, eng[0].stats()))
+        assert errU < 1e-7, (it, errU)
+        np.testing.assert_allclose(x, s1, rtol=0, atol=1e-9)
+        assert np.array_equal(eng[0].latest_uvec, eng[1].latest_uvec)      # every rank holds the identical nominal
         s = s1
         steps += 1
         if np.linalg.norm(s[:2] - goal[:2]) < 0.002 and retries >= 2:
             break
-    print("sharded external exchange: %d steps, %d retried in fp64, final distance %.4f" % (steps, retries, np.linalg.norm(s[:2] - goal[:2])))
+    print("sharded external exchange: %d steps, %d retried in fp64, final distance %.4f, worst rel err U %.3g" % (
+        steps, retries, np.linalg.norm(s[:2] - goal[:2]), worst))
     assert retries >= 1, "the loop never reached the overflow regime"
     for o in [one] + eng:
         o.close()

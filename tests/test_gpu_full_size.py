@@ -31,11 +31,6 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
-def head_room(lam=1e-3):
-    """the part of the default screening window that is there to absorb the fp32 error of V (engine.cu: default_margin)."""
-    return 0.04
-
-
 def run_full_size(K, T, make, oracle_params, x0, goal, U0=None, steps=3, check_v=True):
     a, b, c = make("f64"), make("mixed"), make("f32")
     if U0 is not None:
@@ -57,7 +52,9 @@ def run_full_size(K, T, make, oracle_params, x0, goal, U0=None, steps=3, check_v
         st = b.stats()
         assert st["refine_overflow"] == 0                                                        # (c)
         assert st["refine_candidates"] >= T
-        assert st["refine_max_dev"] < head_room() / 4, st
+        # head-room = the part of the screening window that absorbs the fp32 error of V (engine.cu: set_window); the engine
+        # itself redoes a step in fp64 beyond HALF of it -- here the margin to that trigger is asserted to be 2x
+        assert 0 < st["refine_head_room"] < 0.1 and st["refine_max_dev"] < st["refine_head_room"] / 4, st
         if it == 0 and check_v:                                                                  # (b)
             eps = a.get_noise()
             V = orc.get_cost2go(oracle_params, s_in, U, goal, eps)
@@ -108,11 +105,11 @@ def test_full_size_c4_grid():
     g, res, origin = map_grid.reference_demo_grid()
     assert g.shape == (160, 114) or g.shape == (161, 114)
     w = 250.0
-    x0 = np.array([1.0, 1.5, 0.0])                       # global_planner/config/path.yaml:4 start / 5
-    goal = np.array([1.9, 1.2, 0.0])                     # ~1 m away in free space, an obstacle corner (A) on the way
+    x0 = np.array([1.0, 1.5, np.pi])                     # global_planner/config/path.yaml:4 start / 5, facing obstacle D
+    goal = np.array([1.0, 0.5, -np.pi / 2])              # 1 m away in free space
     assert g[int((x0[1] - origin[1]) / res), int((x0[0] - origin[0]) / res)] == 0
     assert g[int((goal[1] - origin[1]) / res), int((goal[0] - origin[0]) / res)] == 0
-    U0 = np.full((2, T), 5.0)                            # already driving: the rollouts reach the obstacle in the horizon
+    U0 = np.full((2, T), 5.0)                            # already driving: the rollouts reach D's inflation band in the horizon
 
     def make(prec):
         m = mp().MPPI(horizon=T, samples=K, precision=prec, seed=5)

@@ -30,3 +30,21 @@ def test_sharded_equals_single_gpu(precision, exchange):
            "32768", "32", precision, exchange]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "DIST OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_sharded_closed_loop_into_the_goal(exchange):
+    """the default multi-GPU controller (precision 'mixed') must survive the overflow regime near the goal on every
+    transport -- p2p redoes the step inside mppi_step, nccl / host through the MPPI_ERR_RETRY round trip."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
+           "4096", "32", "mixed", exchange, "togoal"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "DIST OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
