@@ -15,6 +15,7 @@
 #ifndef MPPI_HPP_
 #define MPPI_HPP_
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -220,14 +221,62 @@ class Controller {
   // planner hand-off: a new vertex list (e.g. the path of global_planner's trace_path); re-initialises towards its head
   void setWaypoints(Waypoints waypoints) {
     waypoints_ = std::move(waypoints);
+    tracking_ = false;
     parallel_park_ = waypoints_.empty();
     idx_ = 0;
     init_ = true;
     done_ = false;
   }
 
+  // planner hand-off, tracking variant (NEW; same semantics as motion_planning_b200.Controller.track_path): follow the
+  // polyline with a moving look-ahead goal -- the point `lookahead` metres of arc length beyond the robot's projection onto
+  // the path, heading along the path -- instead of stopping at every vertex; the nominal sequence is kept between samples
+  void trackPath(Waypoints path, double lookahead = 0.3) {
+    track_ = std::move(path);
+    lookahead_ = lookahead;
+    progress_ = 0.0;
+    tracking_ = !track_.empty();
+    parallel_park_ = false;
+    idx_ = 0;
+    init_ = true;
+    done_ = false;
+  }
+
+  // look-ahead point of a polyline: (x, y, heading of the path there); s_proj in/out = arc length of the projection (monotone)
+  static State lookaheadGoal(const Waypoints& p, double px, double py, double lookahead, double& s_proj) {
+    const size_t n = p.size();
+    if (n == 1) return State{{p[0][0], p[0][1], 0.0}};
+    std::vector<double> len(n - 1), cum(n, 0.0);
+    for (size_t i = 0; i + 1 < n; ++i) {
+      len[i] = std::hypot(p[i + 1][0] - p[i][0], p[i + 1][1] - p[i][1]);
+      cum[i + 1] = cum[i] + len[i];
+    }
+    const double s_min = s_proj;
+    double best = 1e300, sp = s_min;
+    for (size_t i = 0; i + 1 < n; ++i) {
+      if (len[i] == 0.0 || cum[i + 1] < s_min) continue;
+      const double ex = p[i + 1][0] - p[i][0], ey = p[i + 1][1] - p[i][1];
+      double u = ((px - p[i][0]) * ex + (py - p[i][1]) * ey) / (len[i] * len[i]);
+      u = std::min(1.0, std::max(u, std::max(0.0, (s_min - cum[i]) / len[i])));
+      const double d = std::hypot(px - (p[i][0] + u * ex), py - (p[i][1] + u * ey));
+      if (d < best - 1e-12) {
+        best = d;
+        sp = cum[i] + u * len[i];
+      }
+    }
+    s_proj = sp;
+    const double s_goal = std::min(sp + lookahead, cum[n - 1]);
+    size_t i = 0;
+    while (i + 2 < n && cum[i + 1] <= s_goal) ++i;       // last segment whose start is <= s_goal
+    while (len[i] == 0.0 && i > 0) --i;
+    const double u = len[i] > 0.0 ? (s_goal - cum[i]) / len[i] : 0.0;
+    const double ex = p[i + 1][0] - p[i][0], ey = p[i + 1][1] - p[i][1];
+    return State{{p[i][0] + u * ex, p[i][1] + u * ey, std::atan2(ey, ex)}};
+  }
+
   // Controller.pos_cb, control/src/mppi:328-386
   Twist posCb(double x, double y, double theta) {
+    if (tracking_) return trackCb(x, y, theta);
     start_ = State{{x, y, theta}};                                        // :335
     stepped_ = false;
     if (parallel_park_) goal_ = State{{0.0, -1.0, 0.0}};                  // :337
@@ -267,6 +316,28 @@ class Controller {
   const State& goal() const { return goal_; }
 
  private:
+  Twist trackCb(double x, double y, double theta) {
+    start_ = State{{x, y, theta}};
+    stepped_ = false;
+    goal_ = lookaheadGoal(track_, x, y, lookahead_, progress_);
+    const std::array<double, 2>& end = track_.back();
+    if (init_) {
+      initialize();
+      init_ = false;
+    } else if (std::hypot(x - end[0], y - end[1]) > thresh_) {
+      mppi_.setGoal(goal_);
+      last_u_ = mppi_.step(start_);
+      stepped_ = true;
+      done_ = false;
+    } else {
+      done_ = true;
+    }
+    const Control u = done_ ? Control{{0.0, 0.0}} : last_u_;
+    Twist tw;
+    tw.vx = r_ * (u[0] + u[1]) / 2.0;
+    tw.wz = r_ * (-u[0] + u[1]) / L_;
+    return tw;
+  }
   void initialize() {            // MPPI.initialize (:79-83): uvec = [[0, 0]]
     mppi_.reset();
     last_u_ = Control{{0.0, 0.0}};
@@ -275,7 +346,9 @@ class Controller {
     return State{{w[0], w[1], std::atan2(w[1] - start_[1], w[0] - start_[0])}};
   }
   Engine& mppi_;
-  Waypoints waypoints_;
+  Waypoints waypoints_, track_;
+  double lookahead_ = 0.3, progress_ = 0.0;
+  bool tracking_ = false;
   double thresh_, r_, L_;
   bool parallel_park_ = true, init_ = true, done_ = false, stepped_ = false;
   size_t idx_ = 0;

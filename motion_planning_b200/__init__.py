@@ -6,7 +6,7 @@ reference interface.  There is no CPU implementation in this package.
 """
 from .mppi import MPPI, rk4, euler, bicycle_rk4, WHEEL_VEL_MAX, WHEEL_RADIUS, WHEEL_BASE  # noqa: F401
 from ._capi import MppiError  # noqa: F401
-from .controller import Controller, FakeDiffDrive, waypoints_from_path  # noqa: F401
+from .controller import Controller, FakeDiffDrive, waypoints_from_path, lookahead_goal  # noqa: F401
 
 __all__ = ["MPPI", "rk4", "euler", "bicycle_rk4", "MppiError", "WHEEL_VEL_MAX", "WHEEL_RADIUS", "WHEEL_BASE",
-           "Controller", "FakeDiffDrive", "waypoints_from_path"]
+           "Controller", "FakeDiffDrive", "waypoints_from_path", "lookahead_goal"]

@@ -20,6 +20,12 @@ Planner hand-off: the reference reads its waypoints from a 
 `waypoints_from_path` accept what the planners produce -- the vertex list of `trace_path`
 (global_planner/src/global_planner/heuristic.cpp:199-223) or the cell path of D* Lite
 (incremental.cpp:291-336) -- and feed it to the same state machine.
+
+Path tracking (the "tracking-cost variant"): with `track_path(path, lookahead)` the goal handed to
+`MPPI.get_path` on every odometry sample is the LOOK-AHEAD point of the planner's polyline -- the point `lookahead` metres
+of arc length beyond the robot's projection onto the path, heading along the path there -- so the quadratic goal cost of
+control/src/mppi:165-171,180-184 becomes a path-tracking cost; the nominal control sequence is kept from step to step (the
+goal moves continuously; no `initialize()` between samples as at a waypoint switch).  NEW: no reference counterpart.
 """
 import math
 
@@ -76,6 +82,38 @@ def waypoints_from_path(path, min_spacing=0.0, origin=(0.0, 0.0), resolution=Non
     return [[float(v[0]), float(v[1])] for v in keep]
 
 
+def lookahead_goal(path, pos, lookahead, s_min=0.0):
+    """Look-ahead point of a polyline.  path (n,2) vertices in driving order, pos (2,), lookahead in metres, s_min = arc
+    length already covered (progress never moves backwards, so a path that crosses itself is followed in order).
+    Returns (goal (3,) = (x, y, heading of the path at that point), s_proj = arc length of the robot's projection)."""
+    p = np.asarray(path, dtype=np.float64).reshape(-1, 2)
+    pos = np.asarray(pos, dtype=np.float64)[:2]
+    if len(p) == 1:
+        return np.array([p[0, 0], p[0, 1], 0.0]), 0.0
+    seg = p[1:] - p[:-1]
+    seglen = np.hypot(seg[:, 0], seg[:, 1])
+    cum = np.concatenate([[0.0], np.cumsum(seglen)])
+    # projection onto every segment, clamped to the segment and to the progress made so far
+    best_d, s_proj = np.inf, s_min
+    for i in range(len(seg)):
+        if seglen[i] == 0.0 or cum[i + 1] < s_min:
+            continue
+        u = float(np.dot(pos - p[i], seg[i]) / (seglen[i] * seglen[i]))
+        u = min(1.0, max(u, max(0.0, (s_min - cum[i]) / seglen[i])))
+        q = p[i] + u * seg[i]
+        d = float(np.hypot(pos[0] - q[0], pos[1] - q[1]))
+        if d < best_d - 1e-12:
+            best_d, s_proj = d, cum[i] + u * seglen[i]
+    s_goal = min(s_proj + lookahead, cum[-1])
+    i = int(np.searchsorted(cum, s_goal, side="right") - 1)
+    i = min(max(i, 0), len(seg) - 1)
+    while seglen[i] == 0.0 and i > 0:
+        i -= 1
+    u = (s_goal - cum[i]) / seglen[i] if seglen[i] > 0 else 0.0
+    g = p[i] + u * seg[i]
+    return np.array([g[0], g[1], math.atan2(seg[i, 1], seg[i, 0])]), s_proj
+
+
 class Controller(object):
     def __init__(self, mppi=None, waypoints=None, publish=None, log=None):
         """control/src/mppi:297-319.  `mppi` defaults to `MPPI()` (K=10, T=100: what the node runs, :298)."""
@@ -90,6 +128,7 @@ class Controller(object):
             self.waypoints = [list(w) for w in waypoints]
         self.idx = 0
         self.init = True
+        self._track = None
         self.state = self.mppi.start
         self.cmd = (0.0, 0.0)
         self._emit(0.0, 0.0)                                # :313-316: a zero Twist at start-up
@@ -114,6 +153,40 @@ class Controller(object):
         self.idx = 0
         self.init = True
         self.done = False
+        self._track = None
+
+    def track_path(self, path, lookahead=0.3):
+        """Planner hand-off, tracking variant: follow the polyline `path` (trace_path vertices, metres) with a moving
+        look-ahead goal instead of stopping at every vertex.  `pos_cb` then runs `_track_cb`."""
+        self._track = np.asarray(path, dtype=np.float64).reshape(-1, 2).copy()
+        self._lookahead = float(lookahead)
+        self._progress = 0.0
+        self.parallel_park = False
+        self.waypoints = [list(self._track[-1])]
+        self.idx = 0
+        self.init = True
+        self.done = False
+
+    def _track_cb(self, x, y, theta):
+        m = self.mppi
+        m.start = np.array([x, y, theta])
+        goal, self._progress = lookahead_goal(self._track, m.start, self._lookahead, self._progress)
+        m.goal = goal
+        end = self._track[-1]
+        if self.init:                                       # first sample: zero nominal, like :344-354
+            m.initialize()
+            self.state = m.start
+            self.init = False
+            self._info("TRACKING {} vertices, look-ahead {} m".format(len(self._track), self._lookahead))
+        elif np.linalg.norm(m.start[:2] - end) > m.thresh:
+            self.state = m.get_path(m.start, m.goal)        # the hot path, goal = look-ahead point
+            self.done = False
+        else:
+            self.done = True                                # end of the path reached: zero Twist, like :375
+        u = m.uvec[-1, :] if not self.done else np.array([0.0, 0.0])
+        vx, wz = self.wheelsToTwist(u)
+        self._emit(vx, wz)
+        return vx, wz
 
     # ---- reference methods ----------------------------------------------------------------------
     def wheelsToTwist(self, wheel_vels):
@@ -133,6 +206,8 @@ class Controller(object):
         """control/src/mppi:328-386: one odometry message -> one MPPI step -> one Twist (returned as (vx, wz))."""
         m = self.mppi
         x, y, theta = _pose_of(odom)
+        if getattr(self, "_track", None) is not None:
+            return self._track_cb(x, y, theta)
         m.start = np.array([x, y, theta])                   # :335
         if self.parallel_park:
             m.goal = np.array([0.0, -1.0, 0.0])             # :337

@@ -19,6 +19,7 @@ constexpr int kMaxCand = 16;        // SCREEN: candidate slots per (CTA, t)
 constexpr int kMaxRefine = 256;     // SCREEN: fp64 re-evaluations per t after the global filter
 constexpr int kRecordStride = 6;    // doubles per t in an exchange record: m, S, N0, N1, E0, E1
 constexpr int kRowDoubles = 8;      // fused step: a row = the record + (max |V32 - V64|, candidates) of that row
+constexpr int kMaxFusedWorld = 16;  // ranks of a fused (peer-to-peer) exchange; larger groups use the split-phase step
 constexpr int kRowWords = 2 * kRowDoubles;   // 32-bit payload words per row, each travelling with its own flag (8-byte stores)
 constexpr double kZFixScale = 1048576.0;   // 2^20: fixed-point scale of the floor-term noise sums
 constexpr double kLeanMaxYawInc = 0.125;   // LEAN rollout kernel: admission bound on |dt * yaw rate| (half of it for Euler)

@@ -84,7 +84,7 @@ struct mppi_engine {
   // world > 1) and the device array of all ranks' buffer pointers (own buffer + IPC mappings of the peers')
   uint2* d_ll = nullptr;
   size_t ll_bytes = 0;
-  uint2** d_ll_peers = nullptr;
+  uint2* ll_peers[kMaxFusedWorld] = {};   // host copy of the ranks' buffer pointers: they travel in the kernel arguments
   std::vector<void*> p2p_opened;    // IPC mappings to close
   bool p2p_on = false;
   void* d_part = nullptr;
@@ -504,8 +504,7 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
   e->ll_bytes = (size_t)2 * p.world_size * T * kRowWords * sizeof(uint2);
   CKF(cudaMalloc(&e->d_ll, e->ll_bytes));
   CKF(cudaMemset(e->d_ll, 0, e->ll_bytes));       // flag 0 never matches an epoch + 1
-  CKF(cudaMalloc(&e->d_ll_peers, p.world_size * sizeof(uint2*)));
-  if (p.world_size == 1) CKF(cudaMemcpy(e->d_ll_peers, &e->d_ll, sizeof(uint2*), cudaMemcpyHostToDevice));
+  if (p.world_size == 1) e->ll_peers[0] = e->d_ll;
   CKF(cudaMallocHost(&e->h_in, 6 * sizeof(double)));
   CKF(cudaMallocHost(&e->h_out, sizeof(DynState)));
   CKF(cudaHostAlloc(&e->h_res, sizeof(HostResult), cudaHostAllocMapped));
@@ -560,7 +559,6 @@ extern "C" mppi_status mppi_destroy(mppi_handle e) {
   cudaFree(e->d_debug_ts);
   cudaFree(e->d_debug_rts);
   for (void* q : e->p2p_opened) cudaIpcCloseMemHandle(q);
-  cudaFree(e->d_ll_peers);
   cudaFree(e->d_ll);
   cudaFree(e->d_grid);
   if (e->h_grid_stage) cudaFreeHost(e->h_grid_stage);
@@ -907,7 +905,7 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
     rd.fin.debug_ts = e->d_debug_ts ? e->d_debug_ts + (size_t)e->sp.T * 8 : nullptr;
   }
   rd.rank = e->p.rank;
-  rd.ll_peers = e->d_ll_peers;
+  for (int g = 0; g < kMaxFusedWorld; ++g) rd.ll_peers[g] = e->ll_peers[g];
   rd.debug_ts = e->d_debug_ts;
   rd.part = e->d_part;
   rd.epart = e->d_epart;
@@ -1178,10 +1176,13 @@ extern "C" mppi_status mppi_p2p_connect(mppi_handle e, const void* handles) {
     return MPPI_ERR_STATE;
   }
   const int world = e->sp.world;
-  std::vector<uint2*> peers(world, nullptr);
+  if (world > kMaxFusedWorld) {
+    set_err("the fused peer-to-peer exchange supports up to %d ranks; use mppi_step_local / mppi_step_finish", kMaxFusedWorld);
+    return MPPI_ERR_UNSUPPORTED;
+  }
   for (int g = 0; g < world; ++g) {
     if (g == e->p.rank) {
-      peers[g] = e->d_ll;
+      e->ll_peers[g] = e->d_ll;
       continue;
     }
     cudaIpcMemHandle_t hnd;
@@ -1189,9 +1190,8 @@ extern "C" mppi_status mppi_p2p_connect(mppi_handle e, const void* handles) {
     void* ptr = nullptr;
     CK(cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
     e->p2p_opened.push_back(ptr);
-    peers[g] = (uint2*)ptr;
+    e->ll_peers[g] = (uint2*)ptr;
   }
-  CK(memcpy_on(e, e->d_ll_peers, peers.data(), world * sizeof(uint2*), cudaMemcpyHostToDevice));
   e->p2p_on = true;
   return drop_graphs(e);
 }

@@ -134,15 +134,18 @@ __device__ __forceinline__ void ll_push_row(const ReduceArgs& a, int t, const do
 __device__ __forceinline__ bool ll_read_row(const uint2* ll, int world, int T, unsigned int flag, int g, int t, double out[kRowDoubles]) {
   const uint2* src = ll + (((size_t)((flag - 1u) & 1u) * world + g) * T + t) * kRowWords;
   const long long t0 = clock64();
+  uint4 v[kRowDoubles];
+  for (;;) {   // all loads of the row in flight together: one round trip per attempt
+    bool ok = true;
 #pragma unroll
-  for (int d = 0; d < kRowDoubles; ++d) {
-    uint4 v = ld_ll2(src + 2 * d);
-    while (v.y != flag || v.w != flag) {
-      if (clock64() - t0 > (1LL << 33)) return false;   // ~4 s
-      v = ld_ll2(src + 2 * d);
-    }
-    out[d] = __hiloint2double((int)v.z, (int)v.x);
+    for (int d = 0; d < kRowDoubles; ++d) v[d] = ld_ll2(src + 2 * d);
+#pragma unroll
+    for (int d = 0; d < kRowDoubles; ++d) ok &= (v[d].y == flag) & (v[d].w == flag);
+    if (ok) break;
+    if (clock64() - t0 > (1LL << 33)) return false;   // ~4 s
   }
+#pragma unroll
+  for (int d = 0; d < kRowDoubles; ++d) out[d] = __hiloint2double((int)v[d].z, (int)v[d].x);
   return true;
 }
 

@@ -63,8 +63,9 @@ struct ReduceArgs {
   int fused;                 // 1: rows leave through the flag-in-data buffers and block T of the grid (the finalizer) runs the
                              //    finalize phase as soon as the rows of all ranks have arrived; 0: rows go to `record` only
   int rank;
-  uint2* const* ll_peers;    // device array [world] of row-buffer base pointers: this rank's own buffer and, for world > 1,
-                             // the CUDA IPC mappings of the peers' buffers (stores travel over NVLink)
+  uint2* ll_peers[kMaxFusedWorld];   // row-buffer base pointers of all ranks, IN the argument block (no dependent load on the
+                             // serial tail): this rank's own buffer and, for world > 1, the CUDA IPC mappings of the peers'
+                             // buffers (stores travel over NVLink)
   unsigned long long* debug_ts;   // optional [T][8] globaltimer stamps of the reduce phases (profiling aid)
   const void* part;          // SOFTMIN partials Vec4[T][nCTA]
   const double* epart;       // [T][nCTA][2]

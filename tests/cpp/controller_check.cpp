@@ -22,10 +22,14 @@ struct StubEngine {   // setGoal / reset / step, like mppi::MPPI
 };
 
 int main(int argc, char** argv) {
+  // usage: controller_check [x y]...            waypoint list (none = parallel park)
+  //        controller_check track L [x y]...    follow the polyline with look-ahead L
   mppi::Controller<StubEngine>::Waypoints wps;
-  for (int i = 1; i + 1 < argc; i += 2) wps.push_back({std::atof(argv[i]), std::atof(argv[i + 1])});
+  const bool track = argc > 2 && std::string(argv[1]) == "track";
+  for (int i = track ? 3 : 1; i + 1 < argc; i += 2) wps.push_back({std::atof(argv[i]), std::atof(argv[i + 1])});
   StubEngine eng;
-  mppi::Controller<StubEngine> node(eng, wps);
+  mppi::Controller<StubEngine> node(eng, track ? mppi::Controller<StubEngine>::Waypoints{} : wps);
+  if (track) node.trackPath(wps, std::atof(argv[2]));
   std::string line;
   while (std::getline(std::cin, line)) {
     std::istringstream is(line);

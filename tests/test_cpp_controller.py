@@ -85,3 +85,36 @@ def test_cpp_controller_matches_python_mirror(exe, waypoints):
     assert stub.steps >= 3 and stub.resets >= (3 if waypoints else 1)
     if not waypoints:
         assert any(e[2] == 1 for e in expect)                   # parallel park reaches `done`
+
+
+def test_cpp_path_tracking_matches_python_mirror(exe):
+    """the look-ahead tracking variant (Controller.track_path / mppi::Controller::trackPath): same goals, same decisions."""
+    path = [[0.0, 0.0], [0.5, 0.0], [0.5, 0.4], [0.9, 0.4], [0.9, 0.4], [1.0, 0.7]]       # with a repeated vertex
+    L = 0.25
+    rng = np.random.RandomState(3)
+    stub = StubMPPI()
+    node = Controller(mppi=stub)
+    node.track_path(path, lookahead=L)
+    # poses wandering along the polyline with some cross-track noise, then sitting at its end
+    dense = []
+    for a, b in zip(path[:-1], path[1:]):
+        for u in np.linspace(0.0, 1.0, 6, endpoint=False):
+            dense.append((1 - u) * np.array(a) + u * np.array(b))
+    dense += [np.array(path[-1])] * 3
+    lines, expect = [], []
+    for q in dense:
+        x, y, th = q[0] + 0.02 * rng.normal(), q[1] + 0.02 * rng.normal(), rng.uniform(-3, 3)
+        lines.append("%.17g %.17g %.17g" % (x, y, th))
+        vx, wz = node.pos_cb((x, y, th))
+        g = node.mppi.goal
+        expect.append((int(node.init), int(node.done), vx, wz, g[0], g[1], g[2], stub.steps, stub.resets))
+    args = ["track", str(L)] + [str(v) for w in path for v in w]
+    r = subprocess.run([exe] + args, input="\n".join(lines) + "\n", capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = [l.split() for l in r.stdout.splitlines()]
+    assert len(got) == len(expect)
+    for gline, e in zip(got, expect):
+        assert (int(gline[1]), int(gline[2])) == e[:2]
+        np.testing.assert_allclose([float(v) for v in gline[3:8]], e[2:7], rtol=0, atol=1e-12)
+        assert (int(gline[8]), int(gline[9])) == e[7:]
+    assert expect[-1][1] == 1 and stub.steps > 10 and stub.resets == 1      # reached the end, one initialise only

@@ -145,9 +145,13 @@ def test_sharded_external_exchange_survives_the_overflow_regime():
         worst = max(worst, errU)
         if errU > 1e-7:
             print("step %d: errU %.3g dist %.4f attempt %d stats %s" % (it, errU, np.linalg.norm(s[:2] - goal[:2]), attempt, eng[0].stats()))
-        assert errU < 1e-7, (it, errU)
-        np.testing.assert_allclose(x, s1, rtol=0, atol=1e-9)
+        assert errU < 1e-8, (it, errU)
+        np.testing.assert_allclose(x, s1, rtol=0, atol=1e-10)
         assert np.array_equal(eng[0].latest_uvec, eng[1].latest_uvec)      # every rank holds the identical nominal
+        # every step is compared from IDENTICAL inputs: the map U -> U' amplifies a 1e-10 difference of the nominal by up to
+        # 1/lam per step (the soft-min is nearly an arg-min), so two free-running loops drift apart chaotically
+        for e in eng:
+            e.latest_uvec = one.latest_uvec
         s = s1
         steps += 1
         if np.linalg.norm(s[:2] - goal[:2]) < 0.002 and retries >= 2:

@@ -26,3 +26,37 @@ def test_log_from_array_and_row_copy():
     log.append(row)
     row[:] = 0.0                      # the log must hold a copy, not a reference to the caller's buffer
     assert np.array_equal(log.array[-1], [1.0, 2.0])
+
+
+def test_lookahead_goal_against_brute_force():
+    """Controller.track_path's goal: the point `lookahead` metres of arc length past the robot's projection onto the planner's
+    polyline -- checked against a dense sampling of the polyline."""
+    import numpy as np
+    from motion_planning_b200.controller import lookahead_goal
+    rng = np.random.RandomState(0)
+    for trial in range(20):
+        n = rng.randint(2, 7)
+        path = np.cumsum(rng.uniform(-0.2, 0.6, size=(n, 2)), axis=0)
+        seg = np.diff(path, axis=0)
+        seglen = np.hypot(seg[:, 0], seg[:, 1])
+        cum = np.concatenate([[0], np.cumsum(seglen)])
+        s = np.linspace(0, cum[-1], 20001)
+        idx = np.minimum(np.searchsorted(cum, s, side="right") - 1, n - 2)
+        pts = path[idx] + ((s - cum[idx]) / seglen[idx])[:, None] * seg[idx]
+        for _ in range(10):
+            pos = path[rng.randint(n)] + rng.normal(size=2) * 0.15
+            L = rng.uniform(0.05, 0.5)
+            goal, s_proj = lookahead_goal(path, pos, L)
+            d = np.hypot(pts[:, 0] - pos[0], pts[:, 1] - pos[1])
+            j = int(np.argmin(d))
+            assert abs(d[j] - np.hypot(*(pts[np.argmin(np.abs(s - s_proj))] - pos))) < 1e-3      # projection is a nearest point
+            want = pts[np.argmin(np.abs(s - min(s_proj + L, cum[-1])))]
+            assert np.hypot(goal[0] - want[0], goal[1] - want[1]) < 2e-4
+            k = min(np.searchsorted(cum, min(s_proj + L, cum[-1]), side="right") - 1, n - 2)
+            assert abs(goal[2] - np.arctan2(seg[k, 1], seg[k, 0])) < 1e-12
+    # progress is monotone: a path that returns to its start is followed in order
+    loop = [[0, 0], [1, 0], [1, 1], [0, 1], [0, 0.05]]
+    g1, s1 = lookahead_goal(loop, (0.02, 0.02), 0.3, s_min=0.0)
+    assert s1 < 0.1 and abs(g1[1]) < 1e-12
+    g2, s2 = lookahead_goal(loop, (0.02, 0.3), 0.3, s_min=3.0)
+    assert s2 > 3.0 and abs(g2[0]) < 1e-12
