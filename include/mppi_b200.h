@@ -20,8 +20,16 @@
 #ifndef MPPI_B200_H_
 #define MPPI_B200_H_
 
+#ifdef __CUDACC_RTC__   /* run-time compilation of a user model (mppi_create_user): no host headers */
+typedef signed char int8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -54,7 +62,8 @@ typedef enum {
 typedef enum {
   MPPI_MODEL_DIFF_DRIVE = 0,     /* rk4 + dd_dynamics        control/src/mppi:23-30,39-54 */
   MPPI_MODEL_UNICYCLE_EULER = 1, /* euler + unicycle_dynamics control/src/mppi:33-36,57-58 */
-  MPPI_MODEL_BICYCLE = 2         /* NEW (BASELINE.json config 3): u=(v,delta), RK4 + wrap */
+  MPPI_MODEL_BICYCLE = 2,        /* NEW (BASELINE.json config 3): u=(v,delta), RK4 + wrap */
+  MPPI_MODEL_USER = 3            /* caller-supplied ODE (and optionally cost), compiled at run time: mppi_create_user */
 } mppi_model;
 
 typedef enum {
@@ -99,12 +108,42 @@ typedef struct {
                                 fp32 error of the screen that scales with the step's cost magnitude */
 } mppi_params;
 
+#ifndef __CUDACC_RTC__   /* (device-side run-time compilation only needs the enums and structs above) */
 /* Fill *p with the reference's hard-coded constants (control/src/mppi:18-20,62-73,88-89): K=10, T=100. */
 MPPI_API mppi_status mppi_default_params(mppi_params* p);
 
 /* MPPI.__init__ (control/src/mppi:62-77): allocate device state, U := zeros(2,T). */
 MPPI_API mppi_status mppi_create(const mppi_params* p, mppi_handle* out);
 MPPI_API mppi_status mppi_destroy(mppi_handle h);
+
+/* ---- user-defined dynamics / cost functors -----------------------------------------
+ * The reference takes its model as a constructor argument, `MPPI(model=rk4)` (control/src/mppi:62,66), called as
+ * model(states, u, dt) (:154,213); its C++ library registers an ODE functor `ode(x, u, xdot_out)` with a generic RK4
+ * (control/include/control/rk4.hpp:32,58).  Here the functor is CUDA source text, compiled for sm_100a at run time (NVRTC)
+ * into its own instantiation of the rollout / reduce / finalize kernels:
+ *
+ *   required   template <typename R> __device__ void mppi_user_ode(const R x[3], const R u[2], R xdot[3]);
+ *   optional   (has_cost != 0)
+ *              template <typename R> __device__ R mppi_user_running_cost(const R x[3], const R goal[3], const R u_nom[2],
+ *                                                                       const R eps[2], int t);
+ *              template <typename R> __device__ R mppi_user_terminal_cost(const R x[3], const R goal[3]);
+ *
+ * x = (x, y, theta) AFTER the step for the running cost (control/src/mppi:160-161), u_nom = the nominal control of step t,
+ * eps = the sample's noise.  R is float or double (both are instantiated).  Without a cost functor the reference's quadratic
+ * cost (Q, R, P1 of mppi_params, control/src/mppi:165-171,180-184) applies.  integrator: 0 = classic RK4 with the control
+ * held over the step (control/src/mppi:39-50), 1 = explicit Euler (:57-58); wrap_theta != 0 wraps theta into (-pi, pi] after
+ * every step (:52-53).  Precision F64 or F32 (the fp32 screen of MIXED relies on properties of the built-in models).
+ * params->model is ignored (set to MPPI_MODEL_USER).  Compilation errors: MPPI_ERR_INVALID, text in mppi_last_error(). */
+typedef struct {
+  const char* source;        /* CUDA C++ text defining the functions above */
+  int32_t integrator;        /* 0 RK4, 1 explicit Euler */
+  int32_t wrap_theta;
+  int32_t has_cost;
+} mppi_user_model;
+MPPI_API mppi_status mppi_create_user(const mppi_params* p, const mppi_user_model* um, mppi_handle* out);
+/* Compile a functor text without creating an engine (needs no GPU): MPPI_OK, or MPPI_ERR_INVALID with the compiler's log in
+ * mppi_last_error(). */
+MPPI_API mppi_status mppi_check_user_model(const mppi_user_model* um);
 
 /* MPPI.initialize (control/src/mppi:79-83): latest_uvec := zeros(2,T). Noise stream is NOT rewound. */
 MPPI_API mppi_status mppi_reset(mppi_handle h);
@@ -242,6 +281,7 @@ MPPI_API mppi_status mppi_debug_host_timing(mppi_handle h, double out[4]);
 MPPI_API const char* mppi_last_error(void);
 MPPI_API const char* mppi_version(void);
 MPPI_API int32_t mppi_device_count(void);
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

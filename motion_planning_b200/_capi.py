@@ -16,7 +16,7 @@ STATUS_NAMES = {0: "MPPI_OK", 1: "MPPI_ERR_INVALID", 2: "MPPI_ERR_CUDA", 3: "MPP
                 4: "MPPI_ERR_UNSUPPORTED", 5: "MPPI_ERR_STATE", 6: "MPPI_ERR_NONFINITE", 7: "MPPI_ERR_RETRY"}
 MPPI_ERR_RETRY = 7
 
-MODEL_DIFF_DRIVE, MODEL_UNICYCLE_EULER, MODEL_BICYCLE = 0, 1, 2
+MODEL_DIFF_DRIVE, MODEL_UNICYCLE_EULER, MODEL_BICYCLE, MODEL_USER = 0, 1, 2, 3
 WEIGHT_COST_TO_GO, WEIGHT_TOTAL_COST = 0, 1
 PRECISION_F32, PRECISION_F64, PRECISION_MIXED = 0, 1, 2
 ABI_VERSION = 1
@@ -35,6 +35,11 @@ class MppiParams(C.Structure):
         ("k_offset", C.c_int64), ("k_total", C.c_int64), ("world_size", C.c_int32), ("rank", C.c_int32),
         ("stream", C.c_void_p), ("refine_margin", C.c_double),
     ]
+
+
+class MppiUserModel(C.Structure):
+    """mirror of `mppi_user_model`."""
+    _fields_ = [("source", C.c_char_p), ("integrator", C.c_int32), ("wrap_theta", C.c_int32), ("has_cost", C.c_int32)]
 
 
 class MppiTiming(C.Structure):
@@ -59,6 +64,8 @@ _H = C.c_void_p
 _SIGNATURES = {
     "mppi_default_params": [C.POINTER(MppiParams)],
     "mppi_create": [C.POINTER(MppiParams), C.POINTER(_H)],
+    "mppi_create_user": [C.POINTER(MppiParams), C.POINTER(MppiUserModel), C.POINTER(_H)],
+    "mppi_check_user_model": [C.POINTER(MppiUserModel)],
     "mppi_destroy": [_H],
     "mppi_reset": [_H],
     "mppi_set_goal": [_H, _dp],

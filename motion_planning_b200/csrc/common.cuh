@@ -4,8 +4,10 @@
 // get_cost2go (:127-178) -> update_action (:186-208) -> perform_action (:210-213) -> shift.
 // Everything here is new code written for sm_100a; reference lines are cited for semantics only.
 #pragma once
+#ifndef __CUDACC_RTC__   // (run-time compilation of a user model gets the CUDA built-ins without host headers)
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 #include "../../include/mppi_b200.h"
 
@@ -345,7 +347,43 @@ __device__ __forceinline__ void philox_eps(unsigned long long seed, unsigned lon
 template <typename R>
 struct ModelConsts {
   R dt, half_r, r_over_L, inv_L;
+  R x0, y0;     // start position of the step: a user ODE (MPPI_MODEL_USER) sees absolute coordinates
 };
+
+#ifdef MPPI_USER_MODEL
+// ---- caller-supplied functors (mppi_create_user; the text is compiled together with these headers by NVRTC) ----------
+//   template <typename R> __device__ void mppi_user_ode(const R x[3], const R u[2], R xdot[3]);
+//   (MPPI_USER_COST)  mppi_user_running_cost<R>(x, goal, u_nom, eps, t),  mppi_user_terminal_cost<R>(x, goal)
+// One integrator step of the user's ODE on the absolute state, as the reference's integrator functors do it:
+// MPPI_USER_INTEGRATOR 0 = rk4 with the control held (control/src/mppi:39-50; generic RK4 of control/src/rk4.cpp),
+// 1 = explicit Euler (:57-58); MPPI_USER_WRAP = the theta wrap of :52-53.
+template <typename R>
+__device__ __forceinline__ void user_integrate(R dt, const R x[3], const R u[2], R xn[3]) {
+#if MPPI_USER_INTEGRATOR == 1
+  R k1[3];
+  mppi_user_ode<R>(x, u, k1);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) xn[i] = x[i] + dt * k1[i];
+#else
+  R k1[3], k2[3], k3[3], k4[3], xt[3];
+  mppi_user_ode<R>(x, u, k1);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { k1[i] *= dt; xt[i] = x[i] + k1[i] / R(2); }
+  mppi_user_ode<R>(xt, u, k2);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { k2[i] *= dt; xt[i] = x[i] + k2[i] / R(2); }
+  mppi_user_ode<R>(xt, u, k3);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { k3[i] *= dt; xt[i] = x[i] + k3[i]; }
+  mppi_user_ode<R>(xt, u, k4);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) xn[i] = x[i] + (R(1.0) / R(6.0)) * (k1[i] + R(2) * k2[i] + R(2) * k3[i] + dt * k4[i]);
+#endif
+#if MPPI_USER_WRAP
+  xn[2] = Math<R>::wrap_(xn[2]);
+#endif
+}
+#endif
 
 template <typename R, int MODEL>
 __device__ __forceinline__ void speed_yaw(const ModelConsts<R>& mc, R u0, R u1, R& s, R& w) {
@@ -373,6 +411,17 @@ __device__ __forceinline__ void speed_yaw(const ModelConsts<R>& mc, R u0, R u1, 
 // the increment's sin/cos are plain polynomials and one wrap turn suffices: no branch in the step.
 template <typename R, int MODEL, bool FAST = false>
 __device__ __forceinline__ void model_step(const ModelConsts<R>& mc, R u0, R u1, R& dx, R& dy, R& th, R& c, R& s) {
+#ifdef MPPI_USER_MODEL
+  if (MODEL == MPPI_MODEL_USER) {   // the caller's ODE through the generic integrator; (c, s) are not carried
+    const R x[3] = {mc.x0 + dx, mc.y0 + dy, th}, u[2] = {u0, u1};
+    R xn[3];
+    user_integrate<R>(mc.dt, x, u, xn);
+    dx = xn[0] - mc.x0;
+    dy = xn[1] - mc.y0;
+    th = xn[2];
+    return;
+  }
+#endif
   R spd, w;
   speed_yaw<R, MODEL>(mc, u0, u1, spd, w);
   const R kth = mc.dt * w;
@@ -419,6 +468,7 @@ struct CostConsts {
   R p1x, p1y, p1th;
   R ax2, ay2;            // 2*(x0 - goal)
   R th0, gth2;           // theta0, 2*goal_theta
+  R gx, gy, x0, y0;      // goal / start position (absolute; a user cost functor sees absolute coordinates)
   // grid
   R g_inv_res, g_ox, g_oy, w_obs_100;   // (x0 - origin) folded into g_ox/g_oy
   int gW, gH;
@@ -471,6 +521,12 @@ __device__ __forceinline__ void make_consts(const StaticParams& sp, const StepIn
   cc.p1x = R(sp.p1[0]);
   cc.p1y = R(sp.p1[1]);
   cc.p1th = R(sp.p1[2]);
+  mc.x0 = R(x0);
+  mc.y0 = R(y0);
+  cc.gx = R(gx);
+  cc.gy = R(gy);
+  cc.x0 = R(x0);
+  cc.y0 = R(y0);
   cc.ax2 = R(2.0 * (x0 - gx));
   cc.ay2 = R(2.0 * (y0 - gy));
   cc.th0 = R(th0);

@@ -112,6 +112,8 @@ struct mppi_engine {
   void* d_flush = nullptr;
   size_t flush_bytes = 0;
   KindCfg cfg[3];
+  bool user_has_cost = false;
+  UserKernels* user = nullptr;   // MPPI_MODEL_USER: the step's kernels instantiated at run time for the caller's functors
   // pinned host staging
   double* h_in = nullptr;      // x0[3], goal[3]
   DynState* h_out = nullptr;
@@ -207,9 +209,11 @@ static void set_window(mppi_engine* e, double lam) {
   } else if (sp.model == MPPI_MODEL_UNICYCLE_EULER) {
     v = sp.u_max[0];
     w = sp.u_max[1];
-  } else {
+  } else if (sp.model == MPPI_MODEL_BICYCLE) {
     v = sp.u_max[0];
     w = sp.u_max[0] * std::tan(std::fmin(sp.u_max[1], 1.55)) / sp.wheel_L;
+  } else {
+    v = w = 0.0;   // MPPI_MODEL_USER: no fp32 screen (precision MIXED is refused), the window is not used
   }
   const double D = v * horizon, Th = w * horizon;
   const double cA = sp.T * 0.5 * std::fmax(sp.q[0], sp.q[1]) + std::fmax(sp.p1[0], sp.p1[1]);
@@ -242,6 +246,7 @@ static mppi_status drop_graphs(mppi_engine* e) {
 // largest |dt * yaw rate| any admissible (clipped) control can produce
 static double max_yaw_increment(const StaticParams& sp) {
   double w;
+  if (sp.model == MPPI_MODEL_USER) return 1e9;   // unknown: only the general code path applies
   if (sp.model == MPPI_MODEL_DIFF_DRIVE)
     w = sp.wheel_r / sp.wheel_L * (sp.u_max[0] + sp.u_max[1]);
   else if (sp.model == MPPI_MODEL_UNICYCLE_EULER)
@@ -271,6 +276,29 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
   for (int kind = 0; kind < 3; ++kind) {
     KindCfg best;
     double best_cost = 1e300;
+    if (e->user) {   // run-time instantiation: general code path, tiles of 64, soft-min families only
+      if (kind != ROLLOUT_F32_SCREEN) {
+        KindCfg c;
+        c.variant = ROLLOUT_GENERAL;
+        c.block = 64;
+        c.ntiles = (sp.K + 63) / 64;
+        c.smem = rollout_smem(kind, sp.T, 64, ROLLOUT_GENERAL, gin);
+        if (c.smem <= 227 * 1024 &&
+            user_rollout_prepare(e->user, kind == ROLLOUT_F64_SOFTMIN, has_grid, c.smem, &c.ctas_per_sm, &c.regs) == cudaSuccess &&
+            c.ctas_per_sm >= 1) {
+          const long long resident = (long long)e->num_sms * c.ctas_per_sm;
+          c.grid = (int)((c.ntiles < resident) ? c.ntiles : resident);
+          c.nparts = c.grid;
+          c.ready = true;
+          best = c;
+        } else {
+          cudaGetLastError();
+        }
+      }
+      e->cfg[kind] = best;
+      if (best.ready && (size_t)best.nparts > *max_ctas) *max_ctas = best.nparts;
+      continue;
+    }
     const int variant = !fast ? ROLLOUT_GENERAL : ((lean && kind != ROLLOUT_F64_SOFTMIN) ? ROLLOUT_LEAN : ROLLOUT_FAST);
     int shapes[3], nshapes = 0;
     if (variant == ROLLOUT_GENERAL) {
@@ -392,7 +420,36 @@ static mppi_status prep_nominal(mppi_engine* e) {
   return MPPI_OK;
 }
 
+static mppi_status create_impl(const mppi_params* pin, const mppi_user_model* um, mppi_handle* out);
+
 extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
+  if (pin && pin->model == MPPI_MODEL_USER) {
+    set_err("model MPPI_MODEL_USER needs its functor source: use mppi_create_user");
+    return MPPI_ERR_INVALID;
+  }
+  return create_impl(pin, nullptr, out);
+}
+
+extern "C" mppi_status mppi_create_user(const mppi_params* pin, const mppi_user_model* um, mppi_handle* out) {
+  if (!um) {
+    set_err("null mppi_user_model");
+    return MPPI_ERR_INVALID;
+  }
+  return create_impl(pin, um, out);
+}
+
+extern "C" mppi_status mppi_check_user_model(const mppi_user_model* um) {
+  std::string log;
+  size_t bytes = 0;
+  const mppi_status s = user_model_check(um, &log, &bytes);
+  if (s != MPPI_OK)
+    set_err("%s", log.c_str());
+  else
+    set_err("user model compiled for sm_100a: %zu bytes of cubin", bytes);
+  return s;
+}
+
+static mppi_status create_impl(const mppi_params* pin, const mppi_user_model* um, mppi_handle* out) {
   if (!pin || !out) {
     set_err("null argument");
     return MPPI_ERR_INVALID;
@@ -404,13 +461,19 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
     return MPPI_ERR_INVALID;
   }
   mppi_params p = *pin;
+  if (um) p.model = MPPI_MODEL_USER;
   if (p.K < 1 || p.T < 6 || (p.T & 1) || p.T > 1024) {
     set_err("need K >= 1 and even 6 <= T <= 1024 (savgol window T-1 must be odd, control/src/mppi:202); got K=%d T=%d", p.K, p.T);
     return MPPI_ERR_INVALID;
   }
-  if (p.model < 0 || p.model > 2 || p.weighting < 0 || p.weighting > 1 || p.precision < 0 || p.precision > 2) {
+  if (p.model < 0 || p.model > 3 || p.weighting < 0 || p.weighting > 1 || p.precision < 0 || p.precision > 2) {
     set_err("bad model/weighting/precision enum");
     return MPPI_ERR_INVALID;
+  }
+  if (um && p.precision == MPPI_PRECISION_MIXED) {
+    set_err("a user-defined model runs with precision F64 or F32: the fp32 screen of MIXED (delta-form cost, time-parallel fp64 "
+            "re-evaluation) relies on properties of the built-in models");
+    return MPPI_ERR_UNSUPPORTED;
   }
   if (p.precision == MPPI_PRECISION_MIXED && p.T > 400) {
     set_err("precision MIXED supports T <= 400 (fp64 refinement scratch is 56*T bytes per warp); use F64 or F32");
@@ -533,6 +596,15 @@ extern "C" mppi_status mppi_create(const mppi_params* pin, mppi_handle* out) {
     CKF(memcpy_on(e, e->d_dyn, &d, sizeof(d), cudaMemcpyHostToDevice));
   }
   e->U_prev.assign(2 * T, 0.0);
+  if (um) {   // compile the caller's functors into their own instantiation of the step's kernels
+    std::string log;
+    const mppi_status us = user_kernels_build(um, &e->user, &log);
+    if (us != MPPI_OK) {
+      set_err("%s", log.c_str());
+      return fail(us);
+    }
+    e->user_has_cost = um->has_cost != 0;
+  }
   mppi_status s = configure(e);
   if (s != MPPI_OK) return fail(s);
   s = prep_nominal(e);
@@ -547,6 +619,7 @@ extern "C" mppi_status mppi_destroy(mppi_handle e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   drop_graphs(e);
   free_partials(e);
+  user_kernels_free(e->user);
   cudaFree(e->d_dyn);
   cudaFree(e->d_Umaster);
   cudaFree(e->d_Ulast);
@@ -884,7 +957,10 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
     }
   }
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[0], st));
-  CK(rollout_launch(kind, e->sp.model, e->sp.has_grid != 0, c.block, c.variant, c.grid, c.smem, st, ra));
+  if (e->user)
+    CK(user_rollout_launch(e->user, kind == ROLLOUT_F64_SOFTMIN, e->sp.has_grid != 0, c.grid, c.smem, st, ra));
+  else
+    CK(rollout_launch(kind, e->sp.model, e->sp.has_grid != 0, c.block, c.variant, c.grid, c.smem, st, ra));
   e->tp_launch1 = std::chrono::steady_clock::now();
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[1], st));
   ReduceArgs rd;
@@ -916,7 +992,9 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   rd.eps_ext = e->d_eps_ext;
   rd.record = e->d_record;
   rd.nCTA = c.nparts;
-  if (kind == ROLLOUT_F32_SCREEN)
+  if (e->user)
+    CK(user_reduce_softmin_launch(e->user, kind == ROLLOUT_F64_SOFTMIN, e->sp.T, st, rd));
+  else if (kind == ROLLOUT_F32_SCREEN)
     CK(reduce_screen_launch(e->sp.model, e->sp.has_grid != 0, e->sp.T, st, rd));
   else
     CK(reduce_softmin_launch(kind == ROLLOUT_F64_SOFTMIN, e->sp.T, st, rd));
@@ -933,7 +1011,7 @@ static mppi_status launch_finalize(mppi_engine* e, cudaStream_t st, bool closed_
     fa.host_res = e->d_res;
     fa.seq = e->seq;
   }
-  CK(finalize_launch(st, fa));
+  CK(e->user ? user_finalize_launch(e->user, st, fa) : finalize_launch(st, fa));
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[3], st));
   return MPPI_OK;
 }
@@ -1213,6 +1291,10 @@ extern "C" mppi_status mppi_step_finish(mppi_handle e, double u_out[2], double x
 static void cost_offsets(const mppi_engine* e, const double* U, const double x0[3], const double goal[3],
                          std::vector<double>& off) {
   const int T = e->sp.T;
+  if (e->user_has_cost) {   // a user cost functor is evaluated on the absolute state: nothing was dropped
+    off.assign(T, 0.0);
+    return;
+  }
   const double a[3] = {x0[0] - goal[0], x0[1] - goal[1], x0[2] - goal[2]};
   const double still = 0.5 * (e->sp.q[0] * a[0] * a[0] + e->sp.q[1] * a[1] * a[1] + e->sp.q[2] * a[2] * a[2]);
   const double term = e->sp.p1[0] * a[0] * a[0] + e->sp.p1[1] * a[1] * a[1] + e->sp.p1[2] * a[2] * a[2];
@@ -1360,7 +1442,7 @@ extern "C" mppi_status mppi_update_action(mppi_handle e, const double* U_in, con
     fa.sg_b = e->sg_b;
     for (int i = 0; i < 4; ++i) fa.sg_inv_norm[i] = e->sg_inv_norm[i];
     fa.mode = 1;
-    ce = finalize_launch(e->stream, fa);
+    ce = e->user ? user_finalize_launch(e->user, e->stream, fa) : finalize_launch(e->stream, fa);
   }
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
   if (ce == cudaSuccess) ce = memcpy_on(e, U_out, e->d_Ulast, 2 * T * sizeof(double), cudaMemcpyDeviceToHost);
@@ -1382,7 +1464,9 @@ extern "C" mppi_status mppi_model_step(mppi_handle e, const double* x, const dou
   CK(cudaMalloc(&d, (size_t)8 * n * sizeof(double)));
   cudaError_t ce = memcpy_on(e, d, x, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice);
   if (ce == cudaSuccess) ce = memcpy_on(e, d + 3 * (size_t)n, u, (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice);
-  if (ce == cudaSuccess) ce = model_step_launch(e->stream, e->sp, d, d + 3 * (size_t)n, n, d + 5 * (size_t)n);
+  if (ce == cudaSuccess)
+    ce = e->user ? user_model_step_launch(e->user, e->stream, e->sp, d, d + 3 * (size_t)n, n, d + 5 * (size_t)n)
+                 : model_step_launch(e->stream, e->sp, d, d + 3 * (size_t)n, n, d + 5 * (size_t)n);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
   if (ce == cudaSuccess) ce = memcpy_on(e, x_out, d + 5 * (size_t)n, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(d);

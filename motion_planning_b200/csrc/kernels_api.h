@@ -1,5 +1,7 @@
 // kernels_api.h -- host-side launch interface between engine.cu and the kernel translation units.
 #pragma once
+#include <string>
+
 #include "common.cuh"
 #include "reduce_kernels_args.h"
 
@@ -30,5 +32,17 @@ cudaError_t weights_from_v_launch(cudaStream_t st, const StaticParams& sp, const
                                   const double* eps, double* record);
 cudaError_t model_step_launch(cudaStream_t st, const StaticParams& sp, const double* x, const double* u, int n, double* out);
 cudaError_t fp32_peak_launch(cudaStream_t st, int blocks, int threads, float* out, int iters);
+
+// ---- caller-supplied dynamics / cost functor: the step's kernels instantiated at run time (user_model.cu) ----------------
+struct UserKernels;
+mppi_status user_kernels_build(const mppi_user_model* um, UserKernels** out, std::string* err);
+void user_kernels_free(UserKernels* uk);
+mppi_status user_model_check(const mppi_user_model* um, std::string* err, size_t* cubin_bytes);
+cudaError_t user_rollout_prepare(const UserKernels* uk, bool f64, bool has_grid, size_t smem, int* ctas_per_sm, int* regs);
+cudaError_t user_rollout_launch(const UserKernels* uk, bool f64, bool has_grid, int grid, size_t smem, cudaStream_t st, const RolloutArgs& a);
+cudaError_t user_reduce_softmin_launch(const UserKernels* uk, bool f64, int T, cudaStream_t st, const ReduceArgs& a);
+cudaError_t user_finalize_launch(const UserKernels* uk, cudaStream_t st, const FinalizeArgs& a);
+cudaError_t user_model_step_launch(const UserKernels* uk, cudaStream_t st, const StaticParams& sp, const double* x, const double* u, int n,
+                                   double* out);
 
 }  // namespace mppi

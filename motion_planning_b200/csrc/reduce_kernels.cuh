@@ -577,6 +577,13 @@ __device__ void model_step_abs_f64(const StaticParams& sp, const double x[3], do
 }
 
 __device__ inline void model_step_dispatch_f64(const StaticParams& sp, const double x[3], double u0, double u1, double out[3]) {
+#ifdef MPPI_USER_MODEL
+  if (sp.model == MPPI_MODEL_USER) {   // perform_action / the `model` functor with the caller's ODE
+    const double u[2] = {u0, u1};
+    user_integrate<double>(sp.dt, x, u, out);
+    return;
+  }
+#endif
   if (sp.model == MPPI_MODEL_DIFF_DRIVE)
     model_step_abs_f64<MPPI_MODEL_DIFF_DRIVE>(sp, x, u0, u1, out);
   else if (sp.model == MPPI_MODEL_UNICYCLE_EULER)

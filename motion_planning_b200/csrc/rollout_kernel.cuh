@@ -22,8 +22,6 @@
 // accumulated exactly in fixed point (2^-20) with one REDUX (warp integer add) per channel and step;
 // integer sums make the term independent of the summation order / sharding.
 #pragma once
-#include <type_traits>
-
 #include "common.cuh"
 #include "reduce_kernels_args.h"
 
@@ -82,6 +80,8 @@ template <> struct Vec16<double> {
   static constexpr int N = 2;
   static __device__ __forceinline__ double min_diff(const double2& a, const double2& b) { return fmin(a.x - b.x, a.y - b.y); }
 };
+template <bool SMALL> struct MaskOf { typedef unsigned int type; };
+template <> struct MaskOf<false> { typedef unsigned long long type; };
 template <typename R, int BLOCK>
 struct CostTile {
   static constexpr int PS = BLOCK + 16 / (int)sizeof(R);          // row stride in Reals
@@ -105,7 +105,7 @@ __device__ __forceinline__ void transposed_row(const RolloutArgs& a, int t, int 
   constexpr int PS = CostTile<R, BLOCK>::PS;
   constexpr int N = Vec16<R>::N;
   constexpr int NG = BLOCK / N;                                   // 16-byte groups per row
-  typedef typename std::conditional<(NG <= 32), unsigned int, unsigned long long>::type Mask;
+  typedef typename MaskOf<(NG <= 32)>::type Mask;
   const StaticParams& sp = a.sp;
   const int T = sp.T;
   const R* tot = P + (size_t)T * PS;                              // row T: rollout totals
@@ -337,7 +337,13 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
       const R u0 = clamp_<R>(nomU0[t] + e0, um0);
       const R u1 = clamp_<R>(nomU1[t] + e1, um1);
       model_step<R, MODEL, FAST>(mc, u0, u1, dx, dy, th, cth, sth);          // :154
+#if defined(MPPI_USER_MODEL) && defined(MPPI_USER_COST)
+      const R xa_[3] = {cc.x0 + dx, cc.y0 + dy, th}, ga_[3] = {cc.gx, cc.gy, cc.gth2 * R(0.5)};
+      const R un_[2] = {nomU0[t], nomU1[t]}, ep_[2] = {e0, e1};
+      R c = mppi_user_running_cost<R>(xa_, ga_, un_, ep_, t);               // the caller's cost functor (absolute state)
+#else
       R c = running_cost<R>(cc, dx, dy, th, nomG0[t], nomG1[t], e0, e1);     // :160-161,180-184
+#endif
       if (HAS_GRID) c += grid_cost<R>(cc, cells, dx, dy);
       acc += c;
       P[(t + 1) * PS + tid] = acc;
@@ -400,7 +406,14 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
         if ((t & 3) == 3) Math<R>::sincos_(th, sth, cth);
       }
     }
+#if defined(MPPI_USER_MODEL) && defined(MPPI_USER_COST)
+    {
+      const R xa_[3] = {cc.x0 + dx, cc.y0 + dy, th}, ga_[3] = {cc.gx, cc.gy, cc.gth2 * R(0.5)};
+      acc += mppi_user_terminal_cost<R>(xa_, ga_);
+    }
+#else
     acc += terminal_cost<R>(cc, dx, dy, th);                                 // :165-171
+#endif
     if (!valid) acc = Math<R>::inf();
     P[T * PS + tid] = acc;   // row T holds the rollout total Tot[k]
     __syncthreads();
@@ -437,7 +450,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(const __grid_constant__ 
 
 // shared memory needed by one CTA of rollout_kernel
 template <typename R>
-inline size_t rollout_smem_bytes(int T, int block, int grid_bytes_padded_in_smem) {
+__host__ __device__ inline size_t rollout_smem_bytes(int T, int block, int grid_bytes_padded_in_smem) {
   size_t off = 16 + (size_t)4 * T * sizeof(R);
   off = (off + 15) & ~(size_t)15;
   off += (size_t)T * 4 * sizeof(R);              // run
