@@ -21,6 +21,8 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "mppi_b200.h"
@@ -72,6 +74,27 @@ struct UnicycleEuler {   // unicycle_dynamics + euler, control/src/mppi:33-36,57
   }
 };
 
+// A caller-supplied model: the ODE functor `ode(x, u, xdot_out)` of the reference's C++ library (control/include/control/
+// rk4.hpp:32,58; registerODE) -- on the device a functor is a template argument, so it is handed over as CUDA text and
+// compiled for sm_100a at run time (mppi_create_user):
+//   template <typename R> __device__ void mppi_user_ode(const R x[3], const R u[2], R xdot[3]) { ... }
+struct UserDynamics {
+  std::string ode_source;
+  int integrator = 0;          // 0: RK4 with the control held (control/src/mppi:39-50), 1: explicit Euler (:57-58)
+  bool wrap_theta = true;      // control/src/mppi:52-53
+  double u_max0 = 6.35492, u_max1 = 6.35492;
+  double noise_std0 = 0.9, noise_std1 = 0.9;
+  UserDynamics() = default;
+  explicit UserDynamics(std::string src) : ode_source(std::move(src)) {}
+  void apply(mppi_params& p) const {
+    p.model = MPPI_MODEL_USER;
+    p.u_max[0] = u_max0;
+    p.u_max[1] = u_max1;
+    p.noise_std[0] = noise_std0;
+    p.noise_std[1] = noise_std1;
+  }
+};
+
 // ---- cost functor ------------------------------------------------------------------------------------
 struct OccupancyGrid {   // nav_msgs/OccupancyGrid layout as published by map/src/viz_grid.cpp:109-137
   std::vector<int8_t> cells;   // row-major, idx = ix + iy * width, values 0 / 50 / 100
@@ -92,6 +115,18 @@ struct QuadraticCost {   // get_cost + terminal cost, control/src/mppi:69-73,165
     }
     for (int i = 0; i < 4; ++i) p.r[i] = R[i];
   }
+};
+
+// A caller-supplied cost functor (with UserDynamics): CUDA text defining
+//   template <typename R> __device__ R mppi_user_running_cost(const R x[3], const R goal[3], const R u_nom[2], const R eps[2], int t);
+//   template <typename R> __device__ R mppi_user_terminal_cost(const R x[3], const R goal[3]);
+// in place of get_cost (control/src/mppi:180-184) and the terminal cost (:165-171)
+struct UserCost {
+  std::string source;
+  OccupancyGrid grid;    // the occupancy-grid term stays available on top of a user cost
+  UserCost() = default;
+  explicit UserCost(std::string src) : source(std::move(src)) {}
+  void apply(mppi_params&) const {}
 };
 
 struct Options {
@@ -121,7 +156,21 @@ class MPPI {
     p.device = opt.device;
     dyn.apply(p);
     cost.apply(p);
-    check(mppi_create(&p, &h_), "mppi_create");
+    constexpr bool user_dyn = std::is_same<Dynamics, UserDynamics>::value, user_cost = std::is_same<Cost, UserCost>::value;
+    static_assert(user_dyn || !user_cost, "a UserCost functor needs UserDynamics (the kernels are instantiated for the pair)");
+    if constexpr (user_dyn) {
+      std::string text = dyn.ode_source;
+      if constexpr (user_cost) text += "\n" + cost.source;
+      mppi_user_model um;
+      um.source = text.c_str();
+      um.integrator = dyn.integrator;
+      um.wrap_theta = dyn.wrap_theta ? 1 : 0;
+      um.has_cost = user_cost ? 1 : 0;
+      if (p.precision == MPPI_PRECISION_MIXED) p.precision = MPPI_PRECISION_F64;   // user models: F64 (default) or F32
+      check(mppi_create_user(&p, &um, &h_), "mppi_create_user");
+    } else {
+      check(mppi_create(&p, &h_), "mppi_create");
+    }
     if (cost.grid.weight != 0.0 && !cost.grid.cells.empty()) {
       const mppi_status st = mppi_set_grid(h_, cost.grid.cells.data(), cost.grid.width, cost.grid.height, cost.grid.resolution,
                                            cost.grid.origin_x, cost.grid.origin_y, cost.grid.weight);

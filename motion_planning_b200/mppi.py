@@ -41,6 +41,9 @@ class _Model(object):
         self.__name__ = name
         self.model_id = model_id
 
+    def _create_engine(self, lib, p, h):
+        _capi.check(lib.mppi_create(C.byref(p), C.byref(h)), "mppi_create")
+
     def __call__(self, x0, u, dt):
         x0 = _capi.f64(x0)
         u = _capi.f64(u)
@@ -49,8 +52,9 @@ class _Model(object):
         lib = _capi.load()
         _capi.check(lib.mppi_default_params(C.byref(p)), "mppi_default_params")
         p.K, p.T, p.model, p.dt = 1, 6, self.model_id, float(dt)
+        p.precision = _capi.PRECISION_F64
         h = C.c_void_p()
-        _capi.check(lib.mppi_create(C.byref(p), C.byref(h)), "mppi_create")
+        self._create_engine(lib, p, h)
         try:
             out = np.empty((3, n))
             _capi.check(lib.mppi_model_step(h, _capi.dptr(x0), _capi.dptr(u), n, _capi.dptr(out)), "mppi_model_step")
@@ -60,6 +64,40 @@ class _Model(object):
 
     def __repr__(self):
         return "<mppi model %s>" % self.__name__
+
+
+class UserModel(_Model):
+    """A caller-supplied model: the integrator-step functor the reference takes as `MPPI(model=...)` (control/src/mppi:62,66),
+    given as CUDA text and compiled for sm_100a at run time (mppi_create_user, include/mppi_b200.h).
+
+        ode_source    template <typename R> __device__ void mppi_user_ode(const R x[3], const R u[2], R xdot[3]) {...}
+                      -- the signature of the reference C++ library's ODE functor, control/include/control/rk4.hpp:32,58
+        integrator    "rk4" (control held over the step, control/src/mppi:39-50) or "euler" (:57-58)
+        wrap_theta    wrap theta into (-pi, pi] after every step (:52-53)
+        cost_source   optional: mppi_user_running_cost<R>(x, goal, u_nom, eps, t) and mppi_user_terminal_cost<R>(x, goal)
+                      replacing get_cost (:180-184) and the terminal cost (:165-171)
+
+    Engines with a user model run with precision 'f64' (default) or 'f32'."""
+
+    def __init__(self, ode_source, name="user_model", integrator="rk4", wrap_theta=True, cost_source=None):
+        _Model.__init__(self, name, _capi.MODEL_USER)
+        self.source = ode_source + ("\n" + cost_source if cost_source else "")
+        self.integrator = {"rk4": 0, "euler": 1}[integrator]
+        self.wrap_theta = bool(wrap_theta)
+        self.has_cost = cost_source is not None
+
+    def _spec(self):
+        self._src_bytes = self.source.encode("utf-8")       # kept alive for the duration of the call
+        return _capi.MppiUserModel(self._src_bytes, self.integrator, int(self.wrap_theta), int(self.has_cost))
+
+    def check(self):
+        """compile only (no GPU needed); raises MppiError with the compiler's log"""
+        um = self._spec()
+        _capi.check(_capi.load().mppi_check_user_model(C.byref(um)), "mppi_check_user_model")
+
+    def _create_engine(self, lib, p, h):
+        um = self._spec()
+        _capi.check(lib.mppi_create_user(C.byref(p), C.byref(um), C.byref(h)), "mppi_create_user")
 
 
 rk4 = _Model("rk4", _capi.MODEL_DIFF_DRIVE)                 # control/src/mppi:39-54 (+ dd_dynamics :23-30)
@@ -122,8 +160,8 @@ class MPPI(object):
             name = getattr(model, "__name__", "")
             model = {"rk4": rk4, "euler": euler}.get(name)
             if model is None:
-                raise TypeError("model must be one of rk4 / euler / bicycle_rk4 (device functors); arbitrary "
-                                "Python callables cannot run inside the rollout kernel")
+                raise TypeError("model must be one of rk4 / euler / bicycle_rk4 or a UserModel (CUDA text compiled at run time); "
+                                "arbitrary Python callables cannot run inside the rollout kernel")
         self.horizon = int(horizon)                                             # :63
         self.samples = int(samples)                                             # :64
         self.uvec_init = np.zeros((2, self.horizon))                            # :65
@@ -152,7 +190,7 @@ class MPPI(object):
         p.K, p.T = self.samples, self.horizon
         p.model = self.model.model_id
         p.dt = self.dt
-        p.precision = _PRECISIONS[o.pop("precision", "mixed")]
+        p.precision = _PRECISIONS[o.pop("precision", "f64" if isinstance(self.model, UserModel) else "mixed")]
         p.weighting = _WEIGHTINGS[o.pop("weighting", "cost_to_go")]
         p.seed = int(o.pop("seed", 0))
         p.device = int(o.pop("device", 0))
@@ -176,7 +214,7 @@ class MPPI(object):
         if o:
             raise TypeError("unknown engine options: %s" % sorted(o))
         h = C.c_void_p()
-        _capi.check(self._lib.mppi_create(C.byref(p), C.byref(h)), "mppi_create")
+        self.model._create_engine(self._lib, p, h)
         self._h = h
         self._cost_key = (tuple(q), tuple(p1), tuple(np.asarray(self.R, dtype=np.float64).reshape(4)))
         self._cost_bytes = self._cost_fingerprint()

@@ -30,6 +30,7 @@ WHEEL_BASE = 0.16
 MODEL_DIFF_DRIVE = 0      # rk4 + dd_dynamics            control/src/mppi:23-30,39-54
 MODEL_UNICYCLE_EULER = 1  # euler + unicycle_dynamics    control/src/mppi:33-36,57-58
 MODEL_BICYCLE = 2         # NEW: kinematic bicycle, RK4 + wrap (no reference lines)
+MODEL_USER = 3            # a caller's ODE through the reference's `model=` hook (control/src/mppi:62,66,154)
 
 WEIGHT_COST_TO_GO = 0     # reference: per-t softmin on cost-to-go   control/src/mppi:175,187-196
 WEIGHT_TOTAL_COST = 1     # NEW (north_star wording): one softmin on the total rollout cost
@@ -59,6 +60,15 @@ class Params(object):
         self.grid_res = 1.0
         self.grid_origin = np.array([0.0, 0.0])           # map_min           map/src/viz_grid.cpp:112-129
         self.w_obs = 0.0
+        # MODEL_USER: the integrator-step functor the reference takes as MPPI(model=...) (control/src/mppi:62,66), built from
+        # an ODE right-hand side f(x (3,N), u (2,N)) -> (3,N) like the reference's own rk4 / euler are (:39-58)
+        self.user_ode = None
+        self.user_integrator = "rk4"      # "rk4" (:39-50) | "euler" (:57-58)
+        self.user_wrap = True             # theta wrap of :52-53
+        # optional cost functors replacing get_cost (:180-184) and the terminal cost (:165-171):
+        #   user_running_cost(st (3,N), goal (3,), u_nom (2,), eps_t (2,N), t) -> (N,);  user_terminal_cost(st, goal) -> (N,)
+        self.user_running_cost = None
+        self.user_terminal_cost = None
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)
@@ -114,7 +124,28 @@ def model_step(p, x, u):
         return euler(x, u, p.dt)
     if p.model == MODEL_BICYCLE:
         return rk4(x, u, p.dt, lambda a, b: bicycle_dynamics(a, b, p.wheel_base))
+    if p.model == MODEL_USER:
+        return user_model_step(p.user_ode, p.user_integrator, p.user_wrap)(x, u, p.dt)
     raise ValueError("model")
+
+
+def user_model_step(f, integrator="rk4", wrap=True):
+    """An integrator-step functor `model(states, u, dt)` for the reference's `MPPI(model=...)` hook (control/src/mppi:62,66,
+    154), built from an ODE right-hand side exactly as the reference builds its own: rk4 (:39-50) or euler (:57-58), with or
+    without the theta wrap (:52-53)."""
+    def model(x0, u, dt):
+        if integrator == "euler":
+            xnew = x0 + dt * f(x0, u)
+        else:
+            k1 = dt * f(x0, u)
+            k2 = dt * f(x0 + k1 / 2, u)
+            k3 = dt * f(x0 + k2 / 2, u)
+            k4 = dt * f(x0 + k3, u)
+            xnew = x0 + (1.0 / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+        if wrap:
+            xnew[2, :] = _wrap(xnew[2, :])
+        return xnew
+    return model
 
 
 # --------------------------------------------------------------------------- grid (NEW)
@@ -159,11 +190,17 @@ def get_cost2go(p, state, uvec, goal, eps):
         d = st - goal[:, None]
         u = uvec[:, t]
         # get_cost, control/src/mppi:180-184 -- x is the post-step state, u the NOMINAL control
-        q = p.Q[0] * d[0] * d[0] + p.Q[1] * d[1] * d[1] + p.Q[2] * d[2] * d[2]
-        cost2go[t] = 0.5 * (q + u.dot(p.R).dot(u)) + p.lam * (u.dot(p.sig)).dot(eps[t])
+        if p.user_running_cost is not None:
+            cost2go[t] = p.user_running_cost(st, goal, u, eps[t], t)
+        else:
+            q = p.Q[0] * d[0] * d[0] + p.Q[1] * d[1] * d[1] + p.Q[2] * d[2] * d[2]
+            cost2go[t] = 0.5 * (q + u.dot(p.R).dot(u)) + p.lam * (u.dot(p.sig)).dot(eps[t])
         cost2go[t] += grid_cost(p, st)
     d = st - goal[:, None]                                                      # :165-171 (theta NOT wrapped)
-    cost2go[-1] += p.P1[0] * d[0] * d[0] + p.P1[1] * d[1] * d[1] + p.P1[2] * d[2] * d[2]
+    if p.user_terminal_cost is not None:
+        cost2go[-1] += p.user_terminal_cost(st, goal)
+    else:
+        cost2go[-1] += p.P1[0] * d[0] * d[0] + p.P1[1] * d[1] * d[1] + p.P1[2] * d[2] * d[2]
     V = np.flip(np.cumsum(np.flip(cost2go, 0), axis=0), 0)                      # :175
     if p.weighting == WEIGHT_TOTAL_COST:
         V = np.tile(V[0], (T, 1))

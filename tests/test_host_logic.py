@@ -60,3 +60,15 @@ def test_lookahead_goal_against_brute_force():
     assert s1 < 0.1 and abs(g1[1]) < 1e-12
     g2, s2 = lookahead_goal(loop, (0.02, 0.3), 0.3, s_min=3.0)
     assert s2 > 3.0 and abs(g2[0]) < 1e-12
+
+
+def test_user_model_text_is_compiled_without_a_gpu():
+    """mppi_check_user_model: NVRTC compiles the caller's functor text together with the embedded kernel headers for sm_100a
+    (cross-compilation, no device needed); a broken text comes back with the compiler's log."""
+    import motion_planning_b200 as mp
+    import user_models as um
+    import pytest
+    mp.UserModel(um.SKID_CUDA, cost_source=um.COST_CUDA, integrator="euler", wrap_theta=False).check()
+    with pytest.raises(mp.MppiError) as ei:
+        mp.UserModel("template <typename R> __device__ void mppi_user_ode(const R x[3], const R u[2], R xdot[3]) { xdot[0] = nope; }").check()
+    assert ei.value.status == 1 and "nope" in str(ei.value)

@@ -157,3 +157,43 @@ def test_oracle_euler_model_matches_live_reference(seed):
         np.testing.assert_allclose(out["x_next"], sref, rtol=1e-8, atol=1e-12)
         np.testing.assert_allclose(out["U_shift"], m.latest_uvec, rtol=1e-8, atol=1e-9)
         s, U = sref.copy(), m.latest_uvec.copy()
+
+
+@pytest.mark.skipif(ref_loader.available() is None, reason="reference not loadable here")
+@pytest.mark.parametrize("integrator,wrap", [("rk4", True), ("euler", False)])
+def test_oracle_user_model_matches_live_reference_through_its_model_hook(integrator, wrap):
+    """an arbitrary ODE plugged into the UNMODIFIED reference class through its own `model=` constructor
+    argument (control/src/mppi:62,66,154,213) -- here one whose speed and yaw rate depend on the state -- and, for the cost
+    functor, a subclass overriding get_cost (:180-184).  Pins the oracle's MODEL_USER path and its cost hooks."""
+    import user_models as um
+    ref = ref_loader.load_reference()
+    rng = np.random.RandomState(77)
+    K, T = 24, 12
+    model = orc.user_model_step(um.skid_numpy, integrator, wrap)
+
+    class CostMPPI(ref.MPPI):
+        def get_cost(self, state, goal, u, lam, sig, eps):
+            return float(um.running_cost_numpy(state.reshape(3, 1), goal, u, eps.reshape(2, 1), 0)[0])
+
+    for cls, cost in ((ref.MPPI, False), (CostMPPI, True)):
+        m = cls(model=model, horizon=T, samples=K)
+        m.latest_uvec = rng.normal(size=(2, T)) * 2
+        p = orc.Params(K=K, T=T, model=orc.MODEL_USER, user_ode=um.skid_numpy, user_integrator=integrator, user_wrap=wrap)
+        if cost:
+            p.user_running_cost, p.user_terminal_cost = um.running_cost_numpy, um.terminal_cost_numpy
+        x0, goal = np.array([0.2, -0.1, 0.7]), np.array([0.6, -0.5, -0.3])
+        U, s = m.latest_uvec.copy(), x0.copy()
+        orig = np.random.normal
+        for _ in range(2):
+            eps = rng.standard_normal((T, 2, K)) * 0.9
+            feed = iter(eps)
+            np.random.normal = lambda *a, **k: next(feed).copy()
+            try:
+                sref = m.get_path(s, goal)
+            finally:
+                np.random.normal = orig
+            out = orc.step(p, s, goal, U, eps)
+            np.testing.assert_allclose(out["u0"], m.uvec[-1], rtol=1e-8, atol=1e-10)
+            np.testing.assert_allclose(out["x_next"], sref, rtol=1e-8, atol=1e-12)
+            np.testing.assert_allclose(out["U_shift"], m.latest_uvec, rtol=1e-8, atol=1e-9)
+            s, U = sref.copy(), m.latest_uvec.copy()
