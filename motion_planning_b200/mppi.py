@@ -8,7 +8,7 @@ the ROS `Controller` (control/src/mppi:296-389) can do `self.mppi = MPPI()` unch
     MPPI(model=rk4, horizon=100, samples=10,       same + keyword-only engine options
          thresh=0.05)                 :62-77
     initialize()                      :79-83       mppi_reset
-    get_path(state, goal, sig, lam)   :85-102      mppi_step  (3 kernels in one CUDA graph)
+    get_path(state, goal, sig, lam)   :85-102      mppi_step  (2 kernel launches, no copy: engine.cu)
     solve_path(start, goal, sig, lam) :104-125     loop over get_path
     get_cost2go(state,uvec,goal,lam,sig) :127-178  mppi_cost_to_go (Philox noise drawn on device)
     update_action(uvec,eps,V,sig,lam) :186-208     mppi_update_action

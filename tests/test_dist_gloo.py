@@ -113,3 +113,93 @@ def test_merge_is_invariant_to_the_number_of_shards():
             recs.append(shard_record(p, V, eps, ko, ko + kl))
         dU = merge_records(np.stack(recs), p.lam, p.eps_floor, K)
         np.testing.assert_allclose(dU, want, rtol=1e-12, atol=1e-14)
+
+
+# ---- the split-phase step's retry round trip (MPPI_ERR_RETRY) through ShardedMPPI.get_path, without a GPU ----------------
+class _StubLib(object):
+    """Stands in for libmppi_b200.so behind ShardedMPPI.get_path (exchange='host'): every rank's record carries its rank and
+    the attempt number; mppi_step_finish answers MPPI_ERR_RETRY for the first attempt of step 1 -- on EVERY rank, because the
+    decision is a function of the gathered records only (as in finalize_body, csrc/reduce_kernels.cuh)."""
+
+    def __init__(self, rank, world, T):
+        self.rank, self.world, self.T = rank, world, T
+        self.step, self.attempt, self.gathered, self.log = 0, 0, None, []
+
+    def mppi_set_goal(self, h, g):
+        return 0
+
+    def mppi_step_local(self, h, x):
+        self.log.append(("local", self.step, self.attempt))
+        return 0
+
+    def mppi_read_record(self, h, rec):
+        a = np.ctypeslib.as_array(rec, shape=(self.T * 6,))
+        a[:] = 100.0 * self.rank + 10.0 * self.step + self.attempt
+        if self.step == 1 and self.attempt == 0 and self.rank == 1:
+            a[1] = -1.0                                     # rank 1's screen overflowed: S < 0 marks it for everybody
+        return 0
+
+    def mppi_write_gather(self, h, allrec):
+        self.gathered = np.ctypeslib.as_array(allrec, shape=(self.world, self.T * 6)).copy()
+        return 0
+
+    def mppi_step_finish(self, h, u, x):
+        overflow = bool((self.gathered[:, 1] < 0).any())
+        self.log.append(("finish", self.step, self.attempt, overflow))
+        if overflow:
+            self.attempt += 1
+            return 7                                        # MPPI_ERR_RETRY
+        np.ctypeslib.as_array(x, shape=(3,))[:] = self.gathered[:, 0].sum()
+        np.ctypeslib.as_array(u, shape=(2,))[:] = self.step
+        self.step, self.attempt = self.step + 1, 0
+        return 0
+
+    def mppi_last_error(self):
+        return b"stub"
+
+
+def _retry_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from motion_planning_b200 import distributed as D
+        T = 8
+        sh = object.__new__(D.ShardedMPPI)
+        sh._torch, sh._dist, sh.group, sh.world, sh.rank, sh.exchange, sh._n_rec = torch, dist, None, world, rank, "host", T * 6
+        lib = _StubLib(rank, world, T)
+
+        class _M(object):
+            _lib, _h, dt, fin_time = lib, None, 1.0 / T, [0]
+            _path_log, _uvec_log = [], []
+
+            def _sync_sampling(self, sig, lam):
+                pass
+        sh.mppi = _M()
+        outs = [sh.get_path(np.zeros(3), np.zeros(3)) for _ in range(3)]
+        q.put((rank, [float(o[0]) for o in outs], lib.log))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_get_path_repeats_the_round_trip_on_retry():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = tmp.get_context("fork")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_retry_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    (r0, out0, log0), (r1, out1, log1) = res
+    assert out0 == out1                                      # every rank ends every step with the same result
+    assert out0 == [100.0, 100.0 + 20.0 + 2.0, 100.0 + 40.0]  # step 1 was finished by its SECOND attempt (attempt digit 1 per rank)
+    for log in (log0, log1):                                  # both ranks: local/finish, local/finish(retry)/local/finish, local/finish
+        assert [e[0] for e in log] == ["local", "finish", "local", "finish", "local", "finish", "local", "finish"]
+        assert [e[3] for e in log if e[0] == "finish"] == [False, True, False, False]
