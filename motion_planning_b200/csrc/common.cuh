@@ -101,8 +101,15 @@ struct DynState {
   float noise_std_f[2];
   float pad1;
 };
-// result block of one step in MAPPED pinned host memory: the finalize phase stores it straight into host memory
-// (zero-copy, one PCIe write burst) and publishes it by writing `seq` last; mppi_step polls `seq`.
+// result of one step as the host sees it.  On the wire (MAPPED pinned host memory, written by the finalize phase's owner
+// thread) it is flag-in-data like the rows of the exchange: kHostWords 8-byte stores, each 4 bytes of payload + the low 32 bits
+// of the step's sequence number -- an aligned 8-byte store is single-copy atomic, so the host needs no fence on the device side
+// (no __threadfence_system round trip over PCIe before a separate `seq` word): it polls until every word carries the
+// sequence number it waits for, then decodes.
+constexpr int kHostWords = 17;   // out_u 4, out_x 6, max_dev 2, head 2, status 1, candidates 1, overflow_total 1
+struct HostWire {
+  unsigned long long w[kHostWords];
+};
 struct HostResult {
   double out_u[2];
   double out_x[3];

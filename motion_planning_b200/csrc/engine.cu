@@ -83,7 +83,8 @@ struct mppi_engine {
   // row exchange of the fused step (reduce_kernels.cuh): this rank's flag-in-data buffer (exported through CUDA IPC when
   // world > 1) and the device array of all ranks' buffer pointers (own buffer + IPC mappings of the peers')
   uint2* d_ll = nullptr;
-  size_t ll_bytes = 0;
+  size_t ll_bytes = 0, ll_rows_uint2 = 0;
+  unsigned int rdv_epoch = 0;
   uint2* ll_peers[kMaxFusedWorld] = {};   // host copy of the ranks' buffer pointers: they travel in the kernel arguments
   std::vector<void*> p2p_opened;    // IPC mappings to close
   bool p2p_on = false;
@@ -118,8 +119,9 @@ struct mppi_engine {
   double* h_in = nullptr;      // x0[3], goal[3]
   DynState* h_out = nullptr;
   // zero-copy result hand-over of mppi_step: mapped pinned block written by the finalize phase, published by seq
-  HostResult* h_res = nullptr;
-  HostResult* d_res = nullptr;   // device alias of h_res
+  HostWire* h_res = nullptr;     // mapped pinned block the finalize phase writes (flag-in-data words)
+  HostWire* d_res = nullptr;     // device alias of h_res
+  HostResult res{};              // the last step's result, decoded by wait_result
   unsigned long long seq = 0;
   bool wait_block = false;       // MPPI_B200_WAIT=block: cudaStreamSynchronize instead of polling h_res->seq
   // graphs
@@ -564,14 +566,15 @@ static mppi_status create_impl(const mppi_params* pin, const mppi_user_model* um
   CKF(cudaMalloc(&e->d_record, (size_t)T * kRecordStride * sizeof(double)));
   CKF(cudaMalloc(&e->d_record_tmp, (size_t)T * kRecordStride * sizeof(double)));
   CKF(cudaMalloc(&e->d_gather, (size_t)p.world_size * T * kRecordStride * sizeof(double)));
-  e->ll_bytes = (size_t)2 * p.world_size * T * kRowWords * sizeof(uint2);
+  e->ll_rows_uint2 = (size_t)2 * p.world_size * T * kRowWords;
+  e->ll_bytes = e->ll_rows_uint2 * sizeof(uint2) + (size_t)2 * kMaxFusedWorld * sizeof(unsigned int);   // rows + rendezvous flags
   CKF(cudaMalloc(&e->d_ll, e->ll_bytes));
   CKF(cudaMemset(e->d_ll, 0, e->ll_bytes));       // flag 0 never matches an epoch + 1
   if (p.world_size == 1) e->ll_peers[0] = e->d_ll;
   CKF(cudaMallocHost(&e->h_in, 6 * sizeof(double)));
   CKF(cudaMallocHost(&e->h_out, sizeof(DynState)));
-  CKF(cudaHostAlloc(&e->h_res, sizeof(HostResult), cudaHostAllocMapped));
-  memset(e->h_res, 0, sizeof(HostResult));
+  CKF(cudaHostAlloc(&e->h_res, sizeof(HostWire), cudaHostAllocMapped));
+  memset(e->h_res, 0, sizeof(HostWire));
   CKF(cudaHostGetDevicePointer((void**)&e->d_res, e->h_res, 0));
   if (const char* w = getenv("MPPI_B200_WAIT")) e->wait_block = !strcmp(w, "block");
   if (const char* w = getenv("MPPI_B200_SPLIT")) e->lean_split = atoi(w);
@@ -1041,19 +1044,25 @@ static mppi_status build_graphs(mppi_engine* e) {
   return MPPI_OK;
 }
 
-// wait until the finalize phase has published the result of step e->seq into mapped host memory.  Polling a
-// host-memory word costs ~0.1 us of latency against ~5 us for a blocking stream synchronisation; the stream is
+// wait until the finalize phase has published the result of step e->seq into mapped host memory (flag-in-data words,
+// common.cuh: HostWire).  Polling host memory costs ~0.1 us of latency against ~5 us for a blocking stream synchronisation; the stream is
 // queried now and then so that a faulted kernel cannot hang the caller.
 static mppi_status wait_result(mppi_engine* e) {
-  volatile unsigned long long* seq = &e->h_res->seq;
+  volatile unsigned long long* w = e->h_res->w;
+  const unsigned long long tag = e->seq & 0xffffffffull;
+  auto complete = [&]() {
+    for (int i = 0; i < kHostWords; ++i)
+      if ((w[i] >> 32) != tag) return false;
+    return true;
+  };
   if (e->wait_block) {
     CK(cudaStreamSynchronize(e->stream));
   } else {
     for (unsigned int spin = 1;; ++spin) {
-      if (*seq == e->seq) break;
+      if ((w[kHostWords - 1] >> 32) == tag && complete()) break;
       if ((spin & 0xfffu) == 0) {
         const cudaError_t q = cudaStreamQuery(e->stream);
-        if (q == cudaSuccess) break;             // everything retired: seq is checked below
+        if (q == cudaSuccess) break;             // everything retired: the words are checked below
         if (q != cudaErrorNotReady) {
           set_err("mppi_step: %s", cudaGetErrorString(q));
           return MPPI_ERR_CUDA;
@@ -1062,10 +1071,44 @@ static mppi_status wait_result(mppi_engine* e) {
     }
   }
   std::atomic_thread_fence(std::memory_order_acquire);
-  if (*seq != e->seq) {
-    set_err("mppi_step: the step retired without publishing its result (seq %llu != %llu)", (unsigned long long)*seq, e->seq);
+  if (!complete()) {
+    set_err("mppi_step: the step retired without publishing its result (sequence %llu)", e->seq);
     return MPPI_ERR_STATE;
   }
+  unsigned int pay[kHostWords];
+  for (int i = 0; i < kHostWords; ++i) pay[i] = (unsigned int)(w[i] & 0xffffffffull);
+  auto dbl = [&](int i) {
+    const unsigned long long bits = (unsigned long long)pay[2 * i] | ((unsigned long long)pay[2 * i + 1] << 32);
+    double v;
+    memcpy(&v, &bits, sizeof(v));
+    return v;
+  };
+  HostResult& r = e->res;
+  r.out_u[0] = dbl(0);
+  r.out_u[1] = dbl(1);
+  r.out_x[0] = dbl(2);
+  r.out_x[1] = dbl(3);
+  r.out_x[2] = dbl(4);
+  r.max_dev = dbl(5);
+  r.head = dbl(6);
+  r.status = (int)pay[14];
+  r.candidates = (int)pay[15];
+  r.overflow_total = (int)pay[16];
+  r.seq = e->seq;
+  return MPPI_OK;
+}
+
+// world > 1: align the ranks on the device before a timed step (outside the timed interval; see reduce.cu)
+static mppi_status rendezvous(mppi_engine* e) {
+  if (e->sp.world <= 1 || !e->p2p_on) return MPPI_OK;
+  RendezvousArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  for (int g = 0; g < kMaxFusedWorld; ++g) ra.peers[g] = e->ll_peers[g];
+  ra.rows_uint2 = e->ll_rows_uint2;
+  ra.epoch = ++e->rdv_epoch;
+  ra.world = e->sp.world;
+  ra.rank = e->p.rank;
+  CK(rendezvous_launch(e->stream, ra));
   return MPPI_OK;
 }
 
@@ -1077,7 +1120,7 @@ static StepInput step_input(const mppi_engine* e) {
 }
 
 static mppi_status finish_outputs(mppi_engine* e, double u_out[2], double x_next[3]) {
-  const HostResult* o = e->h_res;
+  const HostResult* o = &e->res;
   if (o->status == kStatusRedoF64) {
     // MIXED: a candidate list overflowed; redo this step entirely in fp64 (same noise: the step
     // counter was not advanced, U and x0 are untouched).
@@ -1511,6 +1554,7 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
   for (auto& v : ev) CK(cudaEventCreate(&v));
   for (int i = 0; i < steps; ++i) {
     if (flush_l2) CK(flush_l2_launch(e->stream, e->d_flush, e->flush_bytes, (unsigned)(i & 0xff)));
+    CKS(rendezvous(e));
     CK(cudaEventRecord(ev[2 * i], e->stream));
     CK(cudaGraphLaunch(e->g_loop, e->stream));
     CK(cudaEventRecord(ev[2 * i + 1], e->stream));
@@ -1602,7 +1646,7 @@ extern "C" mppi_status mppi_io_bytes(mppi_handle e, size_t* h2d, size_t* d2h) {
   ENTER(e);
   // x0 + goal ride in the argument buffers of the two kernels; the result block is stored into mapped host memory
   if (h2d) *h2d = 2 * 6 * sizeof(double);
-  if (d2h) *d2h = sizeof(HostResult);
+  if (d2h) *d2h = sizeof(HostWire);
   return MPPI_OK;
 }
 
@@ -1614,6 +1658,7 @@ extern "C" mppi_status mppi_debug_flush_l2(mppi_handle e) {
     CK(cudaMalloc(&e->d_flush, e->flush_bytes));
   }
   CK(flush_l2_launch(e->stream, e->d_flush, e->flush_bytes, (unsigned)(e->seq & 0xff)));
+  CKS(rendezvous(e));
   CK(cudaStreamSynchronize(e->stream));
   return MPPI_OK;
 }

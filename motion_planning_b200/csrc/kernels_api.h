@@ -27,6 +27,7 @@ cudaError_t reduce_screen_launch(int model, bool has_grid, int T, cudaStream_t s
 cudaError_t finalize_launch(cudaStream_t st, const FinalizeArgs& a);
 cudaError_t prep_nominal_launch(cudaStream_t st, const DynState* dyn, const StaticParams& sp, const double* Umaster, float* nomF, double* nomD);   // nomF: 8*T floats
 cudaError_t flush_l2_launch(cudaStream_t st, void* buf, size_t bytes, unsigned int value);
+cudaError_t rendezvous_launch(cudaStream_t st, const RendezvousArgs& a);
 cudaError_t noise_export_launch(cudaStream_t st, const StaticParams& sp, const DynState* dyn, unsigned step, double* eps);
 cudaError_t weights_from_v_launch(cudaStream_t st, const StaticParams& sp, const DynState* dyn, const double* V,
                                   const double* eps, double* record);

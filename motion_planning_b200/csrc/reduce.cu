@@ -80,7 +80,22 @@ static size_t finalize_smem(const StaticParams& sp, bool fused) {
 template <typename Fn>
 static cudaError_t opt_in_smem(Fn f, size_t smem) {
   if (smem <= 32 * 1024) return cudaSuccess;   // static + dynamic shared memory beyond 48 KB needs the opt-in
-  return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // once per (function, device, size): the attribute call is not free and this sits on the launch path of every step
+  static thread_local struct { const void* f; int dev; size_t smem; } done[16] = {};
+  int dev = -1;
+  cudaGetDevice(&dev);
+  for (auto& d : done)
+    if (d.f == (const void*)f && d.dev == dev && d.smem >= smem) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)
+    for (auto& d : done)
+      if (!d.f || (d.f == (const void*)f && d.dev == dev)) {
+        d.f = (const void*)f;
+        d.dev = dev;
+        d.smem = smem;
+        break;
+      }
+  return e;
 }
 
 // grid: one block per time step (+ the finalizer block of a fused step)
@@ -132,6 +147,28 @@ cudaError_t flush_l2_launch(cudaStream_t st, void* buf, size_t bytes, unsigned i
     carved = true;
   }
   flush_l2_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<uint4*>(buf), bytes / 16, value * 0x01010101u);
+  return cudaGetLastError();
+}
+
+// measurement aid (mppi_bench, world > 1): align the ranks before a timed step.  Every rank raises its flag in every peer's
+// row buffer tail (uint32 [2 parity][kMaxFusedWorld] behind the rows) and waits for all of them -- a device-side rendezvous over
+// NVLink, launched OUTSIDE the timed interval, so that the ranks' L2 flushes (whose durations jitter) do not show up as waiting
+// time inside the step of the rank that happened to finish its flush first.
+__global__ void rendezvous_kernel(RendezvousArgs a) {
+  const int g = threadIdx.x;
+  if (g >= a.world) return;
+  const int par = (int)(a.epoch & 1u);
+  unsigned int* mine = reinterpret_cast<unsigned int*>(a.peers[g] + a.rows_uint2) + par * kMaxFusedWorld + a.rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(mine), "r"(a.epoch) : "memory");
+  const unsigned int* theirs = reinterpret_cast<const unsigned int*>(a.peers[a.rank] + a.rows_uint2) + par * kMaxFusedWorld + g;
+  const long long t0 = clock64();
+  unsigned int v;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(theirs) : "memory");
+  } while (v != a.epoch && clock64() - t0 < (1LL << 33));
+}
+cudaError_t rendezvous_launch(cudaStream_t st, const RendezvousArgs& a) {
+  rendezvous_kernel<<<1, 32, 0, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -78,28 +78,24 @@ __device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch /* [
 
 __device__ void finalize_body(const FinalizeArgs& a, double* Us);
 
-// one thread: store the step's result block into mapped host memory and publish it (seq last, system-scope fences)
+// one thread: store the step's result into mapped host memory, flag-in-data (common.cuh: HostWire) -- no fences
 __device__ __forceinline__ void publish_result(const FinalizeArgs& a, int status, const double* u, const double* xn, int cand,
                                                double dev, int overflow_total, double head = 0.0) {
   if (!a.host_res) return;
-  __threadfence();                       // DynState / nominal updates of this step are ordered before the hand-over
-  volatile HostResult* r = a.host_res;
-  if (u) {
-    r->out_u[0] = u[0];
-    r->out_u[1] = u[1];
+  const double d[7] = {u ? u[0] : 0.0, u ? u[1] : 0.0, xn ? xn[0] : 0.0, xn ? xn[1] : 0.0, xn ? xn[2] : 0.0, dev, head};
+  unsigned int pay[kHostWords];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    pay[2 * i] = (unsigned int)__double2loint(d[i]);
+    pay[2 * i + 1] = (unsigned int)__double2hiint(d[i]);
   }
-  if (xn) {
-    r->out_x[0] = xn[0];
-    r->out_x[1] = xn[1];
-    r->out_x[2] = xn[2];
-  }
-  r->max_dev = dev;
-  r->head = head;
-  r->status = status;
-  r->candidates = cand;
-  r->overflow_total = overflow_total;
-  __threadfence_system();
-  r->seq = a.seq;
+  pay[14] = (unsigned int)status;
+  pay[15] = (unsigned int)cand;
+  pay[16] = (unsigned int)overflow_total;
+  const unsigned long long tag = (a.seq & 0xffffffffull) << 32;
+  volatile unsigned long long* w = a.host_res->w;
+#pragma unroll
+  for (int i = 0; i < kHostWords; ++i) w[i] = tag | (unsigned long long)pay[i];
 }
 
 // ---- row exchange of the fused step: flag-in-data rows (any world size; over NVLink for world > 1) -------------------

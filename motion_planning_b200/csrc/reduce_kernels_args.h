@@ -53,8 +53,15 @@ struct FinalizeArgs {
   unsigned long long* debug_ts;   // optional 8 globaltimer stamps of the finalize phase (profiling aid): [1] all rows seen,
                                   // [3] filter coefficients done, [4] result published
   StepInput in;              // x0 / goal of this step (also used by the reduce kernel's fp64 re-evaluation)
-  HostResult* host_res;      // mapped pinned host memory (nullptr: results are fetched from DynState)
-  unsigned long long seq;    // value that publishes host_res
+  HostWire* host_res;        // mapped pinned host memory (nullptr: results are fetched from DynState)
+  unsigned long long seq;    // sequence number of this step: its low 32 bits validate every word of host_res
+};
+
+struct RendezvousArgs {      // mppi_bench, world > 1 (reduce.cu: rendezvous_kernel)
+  uint2* peers[kMaxFusedWorld];
+  size_t rows_uint2;         // size of the row area of a buffer, in uint2: the rendezvous flags live behind it
+  unsigned int epoch;        // > 0, +1 per rendezvous
+  int world, rank;
 };
 
 struct ReduceArgs {

@@ -105,22 +105,24 @@ def test_mixed_overflow_backs_off_to_fp64_and_stays_exact():
 
 def test_sharded_external_exchange_survives_the_overflow_regime():
     """a sharded engine with an EXTERNAL exchange (mppi_step_local / exchange / mppi_step_finish, the 'nccl' and
-    'host' transports of ShardedMPPI) must drive all the way into the goal: within centimetres of it the fp32 screen's
-    candidate lists overflow systematically; the split-phase API then answers MPPI_ERR_RETRY on every rank and the repeated
-    round runs in fp64 on the same noise.  Two shards on one device, host-staged exchange; the single-engine loop is the
-    reference trajectory (mixed == f64 to rounding)."""
+    'host' transports of ShardedMPPI) must not die when the fp32 screen's candidate lists overflow (systematic within
+    centimetres of the goal for large K): the split-phase API answers MPPI_ERR_RETRY on EVERY rank, nothing is applied, and the
+    repeated round trip runs in fp64 on the same noise, followed by the same hold-off schedule as mppi_step.  The overflow is
+    provoked deterministically here by a screening window of 5 cost units (thousands of rollouts inside it); two shards on one
+    device, host-staged exchange; a single fp64 engine is the reference trajectory."""
     import motion_planning_b200 as mp
     from motion_planning_b200 import _capi
     from motion_planning_b200.distributed import shard_plan
-    K, T, G = 4096, 32, 2
-    goal = np.array([0.0, -0.06, 0.0])
+    K, T, G = 8192, 32, 2
+    goal = np.array([0.0, -1.0, 0.0])
     one = mp.MPPI(horizon=T, samples=K, precision="f64", seed=0)
     eng = []
     for r in range(G):
         kl, ko = shard_plan(K, G, r)
-        eng.append(mp.MPPI(horizon=T, samples=kl, precision="mixed", seed=0, k_offset=ko, k_total=K, world_size=G, rank=r))
-    s, retries, steps, worst = np.zeros(3), 0, 0, 0.0
-    for it in range(400):
+        eng.append(mp.MPPI(horizon=T, samples=kl, precision="mixed", seed=0, k_offset=ko, k_total=K, world_size=G, rank=r,
+                           refine_margin=5.0))
+    s, retries, worst, attempts_log = np.zeros(3), 0, 0.0, []
+    for it in range(24):
         s1 = one.get_path(s, goal)
         for attempt in range(3):
             recs = []
@@ -140,11 +142,10 @@ def test_sharded_external_exchange_survives_the_overflow_regime():
             if sts[0] != _capi.MPPI_ERR_RETRY:
                 break
             retries += 1
+        attempts_log.append(attempt)
         _capi.check(sts[0], "mppi_step_finish")
         errU = max(np.max(np.abs(e.latest_uvec - one.latest_uvec)) for e in eng) / max(1.0, np.max(np.abs(one.latest_uvec)))
         worst = max(worst, errU)
-        if errU > 1e-7:
-            print("step %d: errU %.3g dist %.4f attempt %d stats %s" % (it, errU, np.linalg.norm(s[:2] - goal[:2]), attempt, eng[0].stats()))
         assert errU < 1e-8, (it, errU)
         np.testing.assert_allclose(x, s1, rtol=0, atol=1e-10)
         assert np.array_equal(eng[0].latest_uvec, eng[1].latest_uvec)      # every rank holds the identical nominal
@@ -153,11 +154,8 @@ def test_sharded_external_exchange_survives_the_overflow_regime():
         for e in eng:
             e.latest_uvec = one.latest_uvec
         s = s1
-        steps += 1
-        if np.linalg.norm(s[:2] - goal[:2]) < 0.002 and retries >= 2:
-            break
-    print("sharded external exchange: %d steps, %d retried in fp64, final distance %.4f, worst rel err U %.3g" % (
-        steps, retries, np.linalg.norm(s[:2] - goal[:2]), worst))
-    assert retries >= 1, "the loop never reached the overflow regime"
+    print("sharded external exchange: attempts per step %s, worst rel err U %.3g" % (attempts_log, worst))
+    # step 0 overflows and is retried in fp64; the next 8 steps run fp64 directly (hold-off), step 9 probes mixed again, ...
+    assert attempts_log[0] == 1 and attempts_log[1:9] == [0] * 8 and attempts_log[9] == 1 and retries >= 2
     for o in [one] + eng:
         o.close()
