@@ -79,7 +79,7 @@ static size_t finalize_smem(const StaticParams& sp, bool fused) {
 
 template <typename Fn>
 static cudaError_t opt_in_smem(Fn f, size_t smem) {
-  if (smem <= 32 * 1024) return cudaSuccess;   // static + dynamic shared memory beyond 48 KB needs the opt-in
+  if (smem <= 24 * 1024) return cudaSuccess;   // static (up to ~13 KB) + dynamic shared memory beyond 48 KB needs the opt-in
   // once per (function, device, size): the attribute call is not free and this sits on the launch path of every step
   static thread_local struct { const void* f; int dev; size_t smem; } done[16] = {};
   int dev = -1;

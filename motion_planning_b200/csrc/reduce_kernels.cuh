@@ -230,63 +230,85 @@ __global__ void __launch_bounds__(256) reduce_softmin_kernel(const __grid_consta
   }
 }
 
-// ---- fp64 re-evaluation of ONE rollout by ONE warp, parallel in time ------------------------------
-// Every supported model has theta-dot independent of the state, so theta_t is a prefix sum of the
-// yaw increments and x_t, y_t are prefix sums of the position increments: three warp scans instead
-// of a T-long dependent chain (~2 us instead of ~50 us per rollout).  Per-step wrap and one final
-// wrap differ only by rounding.  `sm` = 7*T doubles of per-warp scratch.
+// ---- fp64 re-evaluation of ONE rollout, parallel in time, by a GROUP of warps -----------------------------------------
+// Every supported model has theta-dot independent of the state, so theta_t is a prefix sum of the yaw increments and
+// x_t, y_t are prefix sums of the position increments: prefix scans instead of a T-long dependent chain.  Per-step wrap
+// and one final wrap differ only by rounding.  The T steps are cut into chunks of 32 (one per lane); a group of `nwp`
+// warps (1, 2, 4 or 8: the chunks of T = 64 run on two warps at once, of T = 128 on four) takes the chunks round-robin,
+// scans each one locally and learns the carries of the chunks before it from their totals, exchanged through shared memory
+// under the group's named barrier -- three barrier-separated passes: controls + theta scan | positions scan | costs.
+// `sm` = 7*T doubles of scratch per group, `tot` = 4 x kMaxChunks doubles per group.  Returns V (valid in every lane of the
+// group's warp 0); the rollout's noise at step t_eps goes to eps_out.
+constexpr int kMaxChunks = 16;   // the screen (precision MIXED) serves T <= 400: 13 chunks
 template <int MODEL, bool HAS_GRID>
 __device__ double resim_cost_to_go_f64(const StaticParams& sp, const DynState* dyn, const double* __restrict__ nomD,
                                        const signed char* __restrict__ grid, const double* __restrict__ eps_ext,
                                        const ModelConsts<double>& mc, const CostConsts<double>& cc, float std0, float std1,
-                                       unsigned int step, int k_local, int t_target, double* sm, int t_eps = 0,
-                                       double* eps_out = nullptr) {
+                                       unsigned int step, int k_local, int t_target, double* sm, double* tot, int nwp, int sub,
+                                       int bar_id, int t_eps = 0, double* eps_out = nullptr) {
   const int T = sp.T, lane = threadIdx.x & 31;
-  double* s_kth = sm;          // yaw increment per step, then exclusive theta
+  const int nchunks = (T + 31) >> 5;
+  double* s_kth = sm;          // yaw increment per step
   double* s_spd = sm + T;      // forward speed
-  double* s_ix = sm + 2 * T;   // x increment -> inclusive dx
+  double* s_ix = sm + 2 * T;   // inclusive LOCAL scan of the x increments of the step's chunk
   double* s_iy = sm + 3 * T;
   double* s_e0 = sm + 4 * T;
   double* s_e1 = sm + 5 * T;
-  double* s_thn = sm + 6 * T;  // theta after the step (wrapped)
+  double* s_thn = sm + 6 * T;  // pass 1: inclusive local scan of the yaw increments; pass 2 on: theta after the step (wrapped)
+  double* tot_th = tot, *tot_x = tot + kMaxChunks, *tot_y = tot + 2 * kMaxChunks, *tot_v = tot + 3 * kMaxChunks;
   const unsigned long long kglobal = (unsigned long long)(sp.k_offset + k_local);
-  for (int t = lane; t < T; t += 32) {
-    double e0, e1;
-    if (sp.noise_external) {
-      e0 = eps_ext[((size_t)t * 2 + 0) * sp.K + k_local];
-      e1 = eps_ext[((size_t)t * 2 + 1) * sp.K + k_local];
-    } else {
-      float f0, f1;
-      philox_eps(sp.seed, kglobal, t, step, std0, std1, f0, f1);
-      e0 = (double)f0;
-      e1 = (double)f1;
+  auto group_sync = [&]() {
+    if (nwp == 1)
+      __syncwarp();
+    else
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * nwp) : "memory");
+  };
+  // pass 1: controls of every step, local scan of the yaw increments
+  for (int c = sub; c < nchunks; c += nwp) {
+    const int t = (c << 5) + lane;
+    double v = 0.0;
+    if (t < T) {
+      double e0, e1;
+      if (sp.noise_external) {
+        e0 = eps_ext[((size_t)t * 2 + 0) * sp.K + k_local];
+        e1 = eps_ext[((size_t)t * 2 + 1) * sp.K + k_local];
+      } else {
+        float f0, f1;
+        philox_eps(sp.seed, kglobal, t, step, std0, std1, f0, f1);
+        e0 = (double)f0;
+        e1 = (double)f1;
+      }
+      const double u0 = clamp_<double>(nomD[t] + e0, sp.u_max[0]);
+      const double u1 = clamp_<double>(nomD[T + t] + e1, sp.u_max[1]);
+      double s, w;
+      speed_yaw<double, MODEL>(mc, u0, u1, s, w);
+      v = mc.dt * w;
+      s_kth[t] = v;
+      s_spd[t] = s;
+      s_e0[t] = e0;
+      s_e1[t] = e1;
     }
-    const double u0 = clamp_<double>(nomD[t] + e0, sp.u_max[0]);
-    const double u1 = clamp_<double>(nomD[T + t] + e1, sp.u_max[1]);
-    double s, w;
-    speed_yaw<double, MODEL>(mc, u0, u1, s, w);
-    s_kth[t] = mc.dt * w;
-    s_spd[t] = s;
-    s_e0[t] = e0;
-    s_e1[t] = e1;
-  }
-  __syncwarp();
-  // scan 1: theta before each step
-  double carry = cc.th0;
-  for (int base = 0; base < T; base += 32) {
-    const int t = base + lane;
-    const double v = (t < T) ? s_kth[t] : 0.0;
     double inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const double n = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += n;
     }
-    const double th_pre = carry + (inc - v);
-    carry += __shfl_sync(0xffffffffu, inc, 31);
+    if (t < T) s_thn[t] = inc;
+    if (lane == 31) tot_th[c] = inc;
+  }
+  group_sync();
+  // pass 2: theta before each step -> position increments, their local scan
+  for (int c = sub; c < nchunks; c += nwp) {
+    const int t = (c << 5) + lane;
+    double carry = cc.th0;
+    for (int q = 0; q < c; ++q) carry += tot_th[q];
+    double ix = 0.0, iy = 0.0;
     if (t < T) {
+      const double v = s_kth[t];
+      const double th_pre = carry + (s_thn[t] - v);
       const double spd = s_spd[t];
-      double ix, iy, thn;
+      double thn;
       if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {
         double sn, cs;
         Math<double>::sincos_(th_pre, sn, cs);
@@ -305,17 +327,9 @@ __device__ double resim_cost_to_go_f64(const StaticParams& sp, const DynState* d
         iy = g * (s1 + 4.0 * s2 + s4);
         thn = Math<double>::wrap_(thw + v);
       }
-      s_ix[t] = ix;
-      s_iy[t] = iy;
       s_thn[t] = thn;
     }
-  }
-  __syncwarp();
-  // scan 2: positions after each step, then the costs
-  double cx = 0.0, cy = 0.0, vsum = 0.0;
-  for (int base = 0; base < T; base += 32) {
-    const int t = base + lane;
-    double ax = (t < T) ? s_ix[t] : 0.0, ay = (t < T) ? s_iy[t] : 0.0;
+    double ax = ix, ay = iy;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const double nx = __shfl_up_sync(0xffffffffu, ax, o);
@@ -325,23 +339,46 @@ __device__ double resim_cost_to_go_f64(const StaticParams& sp, const DynState* d
         ay += ny;
       }
     }
-    const double dx = cx + ax, dy = cy + ay;
-    cx += __shfl_sync(0xffffffffu, ax, 31);
-    cy += __shfl_sync(0xffffffffu, ay, 31);
-    if (t < T && t >= t_target) {
-      const double th = s_thn[t];
-      double c = running_cost<double>(cc, dx, dy, th, nomD[2 * T + t], nomD[3 * T + t], s_e0[t], s_e1[t]);
-      if (HAS_GRID) c += grid_cost<double>(cc, grid, dx, dy);
-      if (t == T - 1) c += terminal_cost<double>(cc, dx, dy, th);
-      vsum += c;
+    if (t < T) {
+      s_ix[t] = ax;
+      s_iy[t] = ay;
+    }
+    if (lane == 31) {
+      tot_x[c] = ax;
+      tot_y[c] = ay;
     }
   }
-  if (eps_out && lane == 0) {   // the rollout's noise at step t_eps (the softmin numerator needs exactly this sample)
-    eps_out[0] = s_e0[t_eps];
-    eps_out[1] = s_e1[t_eps];
+  group_sync();
+  // pass 3: positions after each step, the costs from t_target on
+  double vsum = 0.0;
+  for (int c = sub; c < nchunks; c += nwp) {
+    const int t = (c << 5) + lane;
+    double cx = 0.0, cy = 0.0;
+    for (int q = 0; q < c; ++q) {
+      cx += tot_x[q];
+      cy += tot_y[q];
+    }
+    if (t < T && t >= t_target) {
+      const double dx = cx + s_ix[t], dy = cy + s_iy[t];
+      const double th = s_thn[t];
+      double cst = running_cost<double>(cc, dx, dy, th, nomD[2 * T + t], nomD[3 * T + t], s_e0[t], s_e1[t]);
+      if (HAS_GRID) cst += grid_cost<double>(cc, grid, dx, dy);
+      if (t == T - 1) cst += terminal_cost<double>(cc, dx, dy, th);
+      vsum += cst;
+    }
+    if (eps_out && t == t_eps) {   // the rollout's noise at step t_eps (the softmin numerator needs exactly this sample)
+      eps_out[0] = s_e0[t];
+      eps_out[1] = s_e1[t];
+    }
   }
-  __syncwarp();
-  return warp_sum<double>(vsum);
+  vsum = warp_sum<double>(vsum);
+  if (nwp == 1) return vsum;
+  if (lane == 0) tot_v[sub] = vsum;
+  group_sync();
+  double v = 0.0;
+  for (int q = 0; q < nwp; ++q) v += tot_v[q];
+  group_sync();   // tot / sm are reused by the group's next candidate
+  return v;
 }
 
 // ---- kernel 2b: SCREEN -> fp64 refinement.  grid = T blocks of 256 threads ------------------------
@@ -359,6 +396,7 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   __shared__ double sel_eps[kMaxRefine][2];
   __shared__ int nsel, overflow;
   __shared__ double rowbuf[kRowDoubles];
+  __shared__ double chunk_tot[8][4 * kMaxChunks];   // per warp group: totals of the time chunks of a re-evaluation
   const StaticParams& sp = a.sp;
   const int T = sp.T;
   if (a.fused && blockIdx.x == (unsigned)T) {   // the finalizer block (see the row exchange above)
@@ -466,11 +504,16 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   __syncthreads();
   TS(2);
   const int n = min(nsel, kMaxRefine);
-  // phase C: fp64 re-evaluation, one warp per candidate
-  for (int c = warp; c < n; c += 8) {
+  // phase C: fp64 re-evaluation, one GROUP of warps per candidate: as many warps as there are 32-step chunks (up to 8),
+  // so a candidate's chunks are scanned at once; 8 / nwp candidates in flight
+  const int nchunks_ = (T + 31) >> 5;
+  const int nwp = nchunks_ >= 8 ? 8 : (nchunks_ >= 4 ? 4 : (nchunks_ >= 2 ? 2 : 1));
+  const int group = warp / nwp, sub = warp - group * nwp, ngroups = 8 / nwp;
+  for (int c = group; c < n; c += ngroups) {
     const double v64 = resim_cost_to_go_f64<MODEL, HAS_GRID>(sp, a.fin.dyn, nomS, a.grid, a.eps_ext, mc, cc, std0, std1, philox_step,
-                                                              sel_k[c], t_eval, warp_scratch + (size_t)warp * 7 * T, t, sel_eps[c]);
-    if (lane == 0) sel_v64[c] = v64;
+                                                              sel_k[c], t_eval, warp_scratch + (size_t)group * nwp * 7 * T,
+                                                              chunk_tot[group], nwp, sub, 1 + group, t, sel_eps[c]);
+    if (sub == 0 && lane == 0) sel_v64[c] = v64;
   }
   __syncthreads();
   TS(3);
