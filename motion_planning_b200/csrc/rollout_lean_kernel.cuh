@@ -103,6 +103,108 @@ __device__ __forceinline__ void sincos_tiny(float a, float& s, float& c) {
   c = fmaf(z, fmaf(z, 4.1666668e-2f, -0.5f), 1.0f);
 }
 
+// per-step constants of BOTH launch shapes (per-tile CTAs and the SM-wide kernel): LeanStatic (host-folded) + what depends on
+// x0 / goal / DynState.  Returns through `post` (two floats of shared memory, written by thread 0) the constants that are only
+// needed AFTER the T-step loop, so that they occupy neither registers nor a stack frame during it.
+__device__ __forceinline__ void lean_make_consts(const RolloutArgs& a, const double xs[3], const double gs[3], float std0_f, float std1_f,
+                                                 float neg_inv_lam_ld, float* post, LeanConsts& lc, CostConsts<float>& cc) {
+  const StaticParams& sp = a.sp;
+  const LeanStatic& ls = a.lean;
+  lc.A0 = ls.A0;
+  lc.A1 = ls.A1;
+  lc.Ac = ls.Ac;
+  lc.G0 = ls.G0;
+  lc.G1 = ls.G1;
+  lc.Gc = ls.Gc;
+  lc.um0 = ls.um0;
+  lc.um0x2 = 2.0f * ls.um0;
+  lc.um1 = ls.um1;
+  lc.um1x2 = 2.0f * ls.um1;
+  lc.bk = ls.bk;
+  lc.k0 = std0_f * ls.inv2um0;
+  lc.k1 = std1_f * ls.inv2um1;
+  lc.std0 = std0_f;
+  lc.std1 = std1_f;
+  lc.ax2 = (float)(2.0 * (xs[0] - gs[0]) * (double)ls.sq);
+  lc.ay2 = (float)(2.0 * (xs[1] - gs[1]) * (double)ls.sq);
+  lc.th0 = (float)xs[2];
+  cc.hqx = 1.f;
+  cc.hqy = 1.f;
+  cc.hqth = 0.f;
+  cc.p1x = ls.p1x;      // P1 / (Q/2): the terminal cost takes the positions in cost units too
+  cc.p1y = ls.p1y;
+  cc.p1th = ls.p1th;
+  cc.ax2 = lc.ax2;
+  cc.ay2 = lc.ay2;
+  cc.th0 = lc.th0;
+  cc.gth2 = 0.f;        // staged in shared memory (post[0]) until the terminal cost needs it
+  if (threadIdx.x == 0) {
+    post[0] = (float)(2.0 * gs[2]);
+    post[1] = neg_inv_lam_ld;
+  }
+  cc.g_inv_res = ls.g_inv_res;
+  cc.g_ox = (float)((xs[0] - sp.g_x0) * (double)ls.sq);
+  cc.g_oy = (float)((xs[1] - sp.g_y0) * (double)ls.sq);
+  cc.w_obs_100 = ls.w_obs_100;
+  cc.gW = sp.gW;
+  cc.gH = sp.gH;
+}
+
+// the state a LEAN rollout carries through the T-step loop
+struct LeanState {
+  float dx, dy, th, acc, cth, sth;
+};
+
+// one model step + running cost (control/src/mppi:147-161) of BOTH launch shapes; z0, z1 = the step's standard normals,
+// n = the step's nominal block (U0', U1', std0*g0, std1*g1); returns the running prefix cost to be stored in the cost tile
+template <int MODEL, bool HAS_GRID>
+__device__ __forceinline__ float lean_one_step(const LeanConsts& lc, const CostConsts<float>& cc, const signed char* __restrict__ cells,
+                                               float qscale, const float4 n, float z0, float z1, int& q0, int& q1, LeanState& st) {
+  // floor-term sums: exact fixed point (2^-18), one warp integer add (REDUX, warp-uniform result) per channel
+#ifdef MPPI_EXP_NOREDUX   // measurement only (profiles/variants.py): what the floor-term sums cost -- NOT a product path
+  q0 = q1 = 0;
+#else
+  q0 = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(z0, qscale, kLeanMagic)));
+  q1 = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(z1, qscale, kLeanMagic)));
+#endif
+  // u_samp = clip(U[:,t] + eps), eps = std * z, in clip units: one FFMA.SAT each (:147-152; eps itself stays unclipped)
+  const float s0 = __saturatef(fmaf(lc.k0, z0, n.x));
+  const float s1 = __saturatef(fmaf(lc.k1, z1, n.y));
+  float ah, g;
+  lean_controls<MODEL>(lc, s0, s1, ah, g, st.th);
+  float sa, ca;
+  sincos_tiny(ah, sa, ca);
+  if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {           // euler, :57-58: position with the OLD heading
+    st.dx = fmaf(g, st.cth, st.dx);
+    st.dy = fmaf(g, st.sth, st.dy);
+    const float cn = fmaf(st.cth, ca, -(st.sth * sa));
+    st.sth = fmaf(st.sth, ca, st.cth * sa);
+    st.cth = cn;
+  } else {                                            // rk4, :39-54 (Simpson in x, y; see header)
+    const float c2 = fmaf(st.cth, ca, -(st.sth * sa)), s2 = fmaf(st.sth, ca, st.cth * sa);
+    const float h = g * fmaf(2.0f, ca, 4.0f);
+    st.dx = fmaf(h, c2, st.dx);
+    st.dy = fmaf(h, s2, st.dy);
+    st.cth = fmaf(c2, ca, -(s2 * sa));
+    st.sth = fmaf(s2, ca, c2 * sa);
+  }
+  // get_cost in delta form and cost units (:180-184; common.cuh running_cost), increments summed before they meet acc
+  float c = n.w * z1;
+  c = fmaf(n.z, z0, c);
+  c = fmaf(st.dx, st.dx + lc.ax2, c);
+  c = fmaf(st.dy, st.dy + lc.ay2, c);
+  if (HAS_GRID) c += lean_grid_cost(cc, cells, st.dx, st.dy);
+  st.acc += c;
+  return st.acc;
+}
+
+// keep (cos, sin) on the unit circle: one first-order renormalisation per six steps
+__device__ __forceinline__ void lean_renormalise(LeanState& st) {
+  const float f = fmaf(fmaf(st.cth, st.cth, st.sth * st.sth), -0.5f, 1.5f);
+  st.cth *= f;
+  st.sth *= f;
+}
+
 #ifdef MPPI_EXP_TIMELINE   // measurement only (profiles/rollout_timeline.py) -- NOT compiled into the product library
 #define RTS(slot)                                                                  \
   do {                                                                             \
@@ -185,47 +287,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
   load_step_input(a.in, ds, xs, gs);
   LeanConsts lc;
   CostConsts<R> cc;     // grid / terminal constants in the layout lean_grid_cost / terminal_cost expect, in cost units
-  {
-    const LeanStatic& ls = a.lean;
-    lc.A0 = ls.A0;
-    lc.A1 = ls.A1;
-    lc.Ac = ls.Ac;
-    lc.G0 = ls.G0;
-    lc.G1 = ls.G1;
-    lc.Gc = ls.Gc;
-    lc.um0 = ls.um0;
-    lc.um0x2 = 2.0f * ls.um0;
-    lc.um1 = ls.um1;
-    lc.um1x2 = 2.0f * ls.um1;
-    lc.bk = ls.bk;
-    lc.k0 = std0_f * ls.inv2um0;
-    lc.k1 = std1_f * ls.inv2um1;
-    lc.std0 = std0_f;
-    lc.std1 = std1_f;
-    lc.ax2 = (float)(2.0 * (xs[0] - gs[0]) * (double)ls.sq);
-    lc.ay2 = (float)(2.0 * (xs[1] - gs[1]) * (double)ls.sq);
-    lc.th0 = (float)xs[2];
-    cc.hqx = 1.f;
-    cc.hqy = 1.f;
-    cc.hqth = 0.f;
-    cc.p1x = ls.p1x;      // P1 / (Q/2): the terminal cost takes the positions in cost units too
-    cc.p1y = ls.p1y;
-    cc.p1th = ls.p1th;
-    cc.ax2 = lc.ax2;
-    cc.ay2 = lc.ay2;
-    cc.th0 = lc.th0;
-    cc.gth2 = 0.f;   // staged in shared memory (post[0]) until the terminal cost needs it
-    if (tid == 0) {
-      post[0] = (float)(2.0 * gs[2]);
-      post[1] = neg_inv_lam_ld;
-    }
-    cc.g_inv_res = ls.g_inv_res;
-    cc.g_ox = (float)((xs[0] - sp.g_x0) * (double)ls.sq);
-    cc.g_oy = (float)((xs[1] - sp.g_y0) * (double)ls.sq);
-    cc.w_obs_100 = ls.w_obs_100;
-    cc.gW = sp.gW;
-    cc.gH = sp.gH;
-  }
+  lean_make_consts(a, xs, gs, std0_f, std1_f, neg_inv_lam_ld, post, lc, cc);
   const R margin = (float)screen_window(sp, xs, gs);   // SCREEN window of this step (common.cuh)
   const signed char* cells = grid_smem ? gcells : a.grid;
   const bool cost_to_go = sp.weighting == MPPI_WEIGHT_COST_TO_GO;
@@ -252,47 +314,11 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
     const bool valid = k_local < sp.K;
     const unsigned long long kglobal = (unsigned long long)(sp.k_offset + k_local);
     const float qscale = valid ? kLeanFixScale : 0.f;     // invalid rollouts add exactly 0 to the floor sums
-    R dx = 0.f, dy = 0.f, th = lc.th0, acc = 0.f, cth = cth0, sth = sth0;
+    LeanState st = {0.f, 0.f, lc.th0, 0.f, cth0, sth0};
     R* prow = P + PS + tid;                               // row 1 + t of this rollout's column
-
-    // one model step + running cost + prefix store (control/src/mppi:147-161); z0, z1 = the step's standard normals
+    // one model step + running cost + prefix store (control/src/mppi:147-161): lean_one_step, shared with the SM-wide kernel
     auto one_step = [&](const float4 n, float z0, float z1, int& q0, int& q1, int row) {
-      // floor-term sums: exact fixed point (2^-18), one warp integer add (REDUX, warp-uniform result) per channel
-#ifdef MPPI_EXP_NOREDUX   // measurement only (profiles/variants.py): what the floor-term sums cost -- NOT a product path
-      q0 = q1 = 0;
-#else
-      q0 = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(z0, qscale, kLeanMagic)));
-      q1 = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(z1, qscale, kLeanMagic)));
-#endif
-      // u_samp = clip(U[:,t] + eps), eps = std * z, in clip units: one FFMA.SAT each (:147-152; eps itself stays unclipped)
-      const float s0 = __saturatef(fmaf(lc.k0, z0, n.x));
-      const float s1 = __saturatef(fmaf(lc.k1, z1, n.y));
-      float ah, g;
-      lean_controls<MODEL>(lc, s0, s1, ah, g, th);
-      float sa, ca;
-      sincos_tiny(ah, sa, ca);
-      if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {           // euler, :57-58: position with the OLD heading
-        dx = fmaf(g, cth, dx);
-        dy = fmaf(g, sth, dy);
-        const float cn = fmaf(cth, ca, -(sth * sa));
-        sth = fmaf(sth, ca, cth * sa);
-        cth = cn;
-      } else {                                            // rk4, :39-54 (Simpson in x, y; see header)
-        const float c2 = fmaf(cth, ca, -(sth * sa)), s2 = fmaf(sth, ca, cth * sa);
-        const float h = g * fmaf(2.0f, ca, 4.0f);
-        dx = fmaf(h, c2, dx);
-        dy = fmaf(h, s2, dy);
-        cth = fmaf(c2, ca, -(s2 * sa));
-        sth = fmaf(s2, ca, c2 * sa);
-      }
-      // get_cost in delta form and cost units (:180-184; common.cuh running_cost), increments summed before they meet acc
-      float c = n.w * z1;
-      c = fmaf(n.z, z0, c);
-      c = fmaf(dx, dx + lc.ax2, c);
-      c = fmaf(dy, dy + lc.ay2, c);
-      if (HAS_GRID) c += lean_grid_cost(cc, cells, dx, dy);
-      acc += c;
-      prow[row * PS] = acc;
+      prow[row * PS] = lean_one_step<MODEL, HAS_GRID>(lc, cc, cells, qscale, n, z0, z1, q0, q1, st);
     };
     Normal6 za = lean_normal6(a.lean, kglobal, 0u, step);
     Normal6 zb = lean_normal6(a.lean, kglobal, 1u, step);
@@ -318,10 +344,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
         ez4[2] = qc;
       }
       prow += 6 * PS;
-      // keep (cos, sin) on the unit circle
-      const float f = fmaf(fmaf(cth, cth, sth * sth), -0.5f, 1.5f);
-      cth *= f;
-      sth *= f;
+      lean_renormalise(st);
     }
     // the last T mod 6 steps: za / zb already hold their normals
 #pragma unroll
@@ -336,9 +359,10 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) rollout_lean_kernel(const 
     }
     RTS(3);
     // rk4 wraps theta into (-pi, pi] after every step (:52-53): theta_T is the angle of the carried pair
-    if (MODEL != MPPI_MODEL_UNICYCLE_EULER) th = atan2f(sth, cth);
+    R th = st.th, acc = st.acc;
+    if (MODEL != MPPI_MODEL_UNICYCLE_EULER) th = atan2f(st.sth, st.cth);
     cc.gth2 = post[0];
-    acc += terminal_cost<R>(cc, dx, dy, th);                                 // :165-171
+    acc += terminal_cost<R>(cc, st.dx, st.dy, th);                           // :165-171
     if (!valid) acc = Math<R>::inf();
     // PDL: the reduce kernel may start getting resident now (it still waits for this grid to complete)
     if (tile + nCTA >= a.ntiles) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -486,47 +510,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) rollout_lean_sm_kernel(const __
   load_step_input(a.in, ds, xs, gs);
   LeanConsts lc;
   CostConsts<R> cc;
-  {
-    const LeanStatic& ls = a.lean;
-    lc.A0 = ls.A0;
-    lc.A1 = ls.A1;
-    lc.Ac = ls.Ac;
-    lc.G0 = ls.G0;
-    lc.G1 = ls.G1;
-    lc.Gc = ls.Gc;
-    lc.um0 = ls.um0;
-    lc.um0x2 = 2.0f * ls.um0;
-    lc.um1 = ls.um1;
-    lc.um1x2 = 2.0f * ls.um1;
-    lc.bk = ls.bk;
-    lc.k0 = std0_f * ls.inv2um0;
-    lc.k1 = std1_f * ls.inv2um1;
-    lc.std0 = std0_f;
-    lc.std1 = std1_f;
-    lc.ax2 = (float)(2.0 * (xs[0] - gs[0]) * (double)ls.sq);
-    lc.ay2 = (float)(2.0 * (xs[1] - gs[1]) * (double)ls.sq);
-    lc.th0 = (float)xs[2];
-    cc.hqx = 1.f;
-    cc.hqy = 1.f;
-    cc.hqth = 0.f;
-    cc.p1x = ls.p1x;
-    cc.p1y = ls.p1y;
-    cc.p1th = ls.p1th;
-    cc.ax2 = lc.ax2;
-    cc.ay2 = lc.ay2;
-    cc.th0 = lc.th0;
-    cc.gth2 = 0.f;
-    if (tid == 0) {
-      post[0] = (float)(2.0 * gs[2]);
-      post[1] = neg_inv_lam_ld;
-    }
-    cc.g_inv_res = ls.g_inv_res;
-    cc.g_ox = (float)((xs[0] - sp.g_x0) * (double)ls.sq);
-    cc.g_oy = (float)((xs[1] - sp.g_y0) * (double)ls.sq);
-    cc.w_obs_100 = ls.w_obs_100;
-    cc.gW = sp.gW;
-    cc.gH = sp.gH;
-  }
+  lean_make_consts(a, xs, gs, std0_f, std1_f, neg_inv_lam_ld, post, lc, cc);
   const R margin = (float)screen_window(sp, xs, gs);   // SCREEN window of this step (common.cuh)
   const signed char* cells = grid_smem ? gcells : a.grid;
   const bool cost_to_go = sp.weighting == MPPI_WEIGHT_COST_TO_GO;
@@ -542,8 +526,8 @@ __global__ void __launch_bounds__(kSmThreads, 1) rollout_lean_sm_kernel(const __
   unsigned int call = (unsigned)t_begin / 3u;
   Normal6 za = lean_normal6(a.lean, kglobal, call, step);
   Normal6 zb = lean_normal6(a.lean, kglobal, call + 1u, step);
-  R dx = 0.f, dy = 0.f, th = lc.th0, acc = 0.f, cth, sth;
-  Math<R>::sincos_(lc.th0, sth, cth);
+  LeanState st = {0.f, 0.f, lc.th0, 0.f, 0.f, 0.f};
+  Math<R>::sincos_(lc.th0, st.sth, st.cth);
   int* ezrow = ezw + (size_t)wslot * T * 2;
   RTS2(1);
   mbar_wait(bar, 0);
@@ -555,45 +539,17 @@ __global__ void __launch_bounds__(kSmThreads, 1) rollout_lean_sm_kernel(const __
   }
   if (role == 2) {   // take over the rollouts warps 12, 13 have advanced to `split`
     named_bar_sync(1, 128);
-    dx = hand[0 * BLOCK + col];
-    dy = hand[1 * BLOCK + col];
-    cth = hand[2 * BLOCK + col];
-    sth = hand[3 * BLOCK + col];
-    acc = hand[4 * BLOCK + col];
-    th = hand[5 * BLOCK + col];
+    st.dx = hand[0 * BLOCK + col];
+    st.dy = hand[1 * BLOCK + col];
+    st.cth = hand[2 * BLOCK + col];
+    st.sth = hand[3 * BLOCK + col];
+    st.acc = hand[4 * BLOCK + col];
+    st.th = hand[5 * BLOCK + col];
   }
   R* prow = P + (size_t)(1 + t_begin) * PS + col;          // row 1 + t of this rollout's column
 
-  auto one_step = [&](const float4 n, float z0, float z1, int& q0, int& q1, int row) {
-    q0 = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(z0, qscale, kLeanMagic)));
-    q1 = __reduce_add_sync(0xffffffffu, __float_as_int(fmaf(z1, qscale, kLeanMagic)));
-    const float s0 = __saturatef(fmaf(lc.k0, z0, n.x));
-    const float s1 = __saturatef(fmaf(lc.k1, z1, n.y));
-    float ah, g;
-    lean_controls<MODEL>(lc, s0, s1, ah, g, th);
-    float sa, ca;
-    sincos_tiny(ah, sa, ca);
-    if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {
-      dx = fmaf(g, cth, dx);
-      dy = fmaf(g, sth, dy);
-      const float cn = fmaf(cth, ca, -(sth * sa));
-      sth = fmaf(sth, ca, cth * sa);
-      cth = cn;
-    } else {
-      const float c2 = fmaf(cth, ca, -(sth * sa)), s2 = fmaf(sth, ca, cth * sa);
-      const float h = g * fmaf(2.0f, ca, 4.0f);
-      dx = fmaf(h, c2, dx);
-      dy = fmaf(h, s2, dy);
-      cth = fmaf(c2, ca, -(s2 * sa));
-      sth = fmaf(s2, ca, c2 * sa);
-    }
-    float c = n.w * z1;
-    c = fmaf(n.z, z0, c);
-    c = fmaf(dx, dx + lc.ax2, c);
-    c = fmaf(dy, dy + lc.ay2, c);
-    if (HAS_GRID) c += lean_grid_cost(cc, cells, dx, dy);
-    acc += c;
-    prow[row * PS] = acc;
+  auto one_step = [&](const float4 n, float z0, float z1, int& q0, int& q1, int row) {   // the same step as the per-tile kernel
+    prow[row * PS] = lean_one_step<MODEL, HAS_GRID>(lc, cc, cells, qscale, n, z0, z1, q0, q1, st);
   };
   int t6 = t_begin;
   for (; t6 + 6 <= t_end; t6 += 6) {
@@ -616,17 +572,15 @@ __global__ void __launch_bounds__(kSmThreads, 1) rollout_lean_sm_kernel(const __
       ez4[2] = qc;
     }
     prow += 6 * PS;
-    const float f = fmaf(fmaf(cth, cth, sth * sth), -0.5f, 1.5f);
-    cth *= f;
-    sth *= f;
+    lean_renormalise(st);
   }
   if (role == 1) {   // hand the state to warps 14, 15 and leave
-    hand[0 * BLOCK + col] = dx;
-    hand[1 * BLOCK + col] = dy;
-    hand[2 * BLOCK + col] = cth;
-    hand[3 * BLOCK + col] = sth;
-    hand[4 * BLOCK + col] = acc;
-    hand[5 * BLOCK + col] = th;
+    hand[0 * BLOCK + col] = st.dx;
+    hand[1 * BLOCK + col] = st.dy;
+    hand[2 * BLOCK + col] = st.cth;
+    hand[3 * BLOCK + col] = st.sth;
+    hand[4 * BLOCK + col] = st.acc;
+    hand[5 * BLOCK + col] = st.th;
     __threadfence_block();
     named_bar_arrive(1, 128);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -644,9 +598,10 @@ __global__ void __launch_bounds__(kSmThreads, 1) rollout_lean_sm_kernel(const __
     }
   }
   RTS2(3);
-  if (MODEL != MPPI_MODEL_UNICYCLE_EULER) th = atan2f(sth, cth);
+  R th = st.th, acc = st.acc;
+  if (MODEL != MPPI_MODEL_UNICYCLE_EULER) th = atan2f(st.sth, st.cth);
   cc.gth2 = post[0];
-  acc += terminal_cost<R>(cc, dx, dy, th);
+  acc += terminal_cost<R>(cc, st.dx, st.dy, th);
   if (!valid) acc = Math<R>::inf();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   RTS2(4);

@@ -384,7 +384,14 @@ def test_full_size_c2_mixed_equals_f64_and_shards_merge():
         sb = b.get_path(sb, PARK)
         sc = c.get_path(sc, PARK)
         assert rel_err(b.latest_uvec, a.latest_uvec) < 1e-9
-        print("C2 step %d: f32 vs f64 rel err %.3g; mixed stats %s" % (it, rel_err(c.latest_uvec, a.latest_uvec), b.stats()))
+        st = b.stats()
+        assert st["refine_overflow"] == 0 and st["refine_max_dev"] < st["refine_head_room"] / 4, st
+        err32 = rel_err(c.latest_uvec, a.latest_uvec)
+        # north_star's literal fp32 pipeline, ASSERTED: 1e-5 where the soft-min is well conditioned (every t has a gap between
+        # best and second-best cost-to-go > 50 lam), a loose bound where it is not
+        gap = float(orc.softmin_gaps(a.get_value_fcn()).min())
+        print("C2 step %d: f32 vs f64 rel err %.3g (min gap %.3g); mixed stats %s" % (it, err32, gap, st))
+        assert err32 < (1e-5 if gap > 0.05 else 5e-2)
         if it == 0:
             eps = a.get_noise()
             V = orc.get_cost2go(orc.Params(K=K, T=T), s0, np.zeros((2, T)), PARK, eps)
