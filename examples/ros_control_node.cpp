@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <memory>
 #include <vector>
 
 #include "mppi.hpp"
@@ -18,7 +20,24 @@ int main(int argc, char** argv) {
   // waypoints: control/config/waypoints.yaml:1 (pentagon); an empty list = parallel park (parallel.yaml:1)
   const mppi::Controller<>::Waypoints waypoints = {{1, 0}, {2, 1}, {1, 2}, {0, 2}, {0, 0}};
   mppi::DiffDrive robot;                                    // control/src/mppi:18-20
-  mppi::MPPI engine(robot, mppi::QuadraticCost(), K, T);
+  // 4th argument "user": the same robot as a caller-supplied ODE functor -- the reference's registerODE / model= hook
+  // (control/include/control/rk4.hpp:32,58; control/src/mppi:62,66) -- compiled at run time for this GPU
+  const bool user = argc > 4 && !std::strcmp(argv[4], "user");
+  std::unique_ptr<mppi::MPPI> engine_ptr;
+  if (user) {
+    mppi::UserDynamics dyn(
+        "template <typename R> __device__ void mppi_user_ode(const R x[3], const R u[2], R xdot[3]) {\n"
+        "  const R r = R(0.033), L = R(0.16);\n"
+        "  xdot[0] = (r / R(2.0)) * cos(x[2]) * (u[0] + u[1]);\n"
+        "  xdot[1] = (r / R(2.0)) * sin(x[2]) * (u[0] + u[1]);\n"
+        "  xdot[2] = (r / L) * (u[1] - u[0]);\n"
+        "}\n");
+    engine_ptr.reset(new mppi::MPPI(dyn, mppi::QuadraticCost(), K, T));
+    std::printf("dynamics: user-supplied ODE functor (NVRTC)\n");
+  } else {
+    engine_ptr.reset(new mppi::MPPI(robot, mppi::QuadraticCost(), K, T));
+  }
+  mppi::MPPI& engine = *engine_ptr;
   mppi::Controller<> node(engine, waypoints, /*thresh=*/0.05, robot.wheel_radius, robot.wheel_base);
   mppi::State x{{0.0, 0.0, 0.0}};
   int reached = 0;

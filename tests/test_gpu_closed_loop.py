@@ -78,6 +78,10 @@ def test_cpp_facade_closed_loop():
     r = subprocess.run([exe, "2048", "32", "1500"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "WAYPOINT REACHED" in r.stdout
+    # the same node with the robot handed over as a user ODE functor (mppi::UserDynamics -> mppi_create_user, NVRTC)
+    r = subprocess.run([exe, "2048", "32", "600", "user"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "user-supplied ODE functor" in r.stdout and "WAYPOINT REACHED" in r.stdout
 
 
 def test_mixed_overflow_backs_off_to_fp64_and_stays_exact():
