@@ -112,7 +112,7 @@ def test_sharded_external_exchange_survives_the_overflow_regime():
     'host' transports of ShardedMPPI) must not die when the fp32 screen's candidate lists overflow (systematic within
     centimetres of the goal for large K): the split-phase API answers MPPI_ERR_RETRY on EVERY rank, nothing is applied, and the
     repeated round trip runs in fp64 on the same noise, followed by the same hold-off schedule as mppi_step.  The overflow is
-    provoked deterministically here by a screening window of 5 cost units (thousands of rollouts inside it); two shards on one
+    provoked deterministically here by a screening window of 50 cost units (thousands of rollouts inside it); two shards on one
     device, host-staged exchange; a single fp64 engine is the reference trajectory."""
     import motion_planning_b200 as mp
     from motion_planning_b200 import _capi
@@ -124,7 +124,7 @@ def test_sharded_external_exchange_survives_the_overflow_regime():
     for r in range(G):
         kl, ko = shard_plan(K, G, r)
         eng.append(mp.MPPI(horizon=T, samples=kl, precision="mixed", seed=0, k_offset=ko, k_total=K, world_size=G, rank=r,
-                           refine_margin=5.0))
+                           refine_margin=50.0))
     s, retries, worst, attempts_log = np.zeros(3), 0, 0.0, []
     for it in range(24):
         s1 = one.get_path(s, goal)
