@@ -307,7 +307,9 @@ def run_single(args):
                 "l2": "flushed before every timed call (outside the timed interval)", "warm_l2_ms_per_step": r["e2e_warm_ms"],
                 "python_shim_ms_per_step": r["e2e_shim_ms"], "python_shim_value": K / (r["e2e_shim_ms"] * 1e-3)},
         "gpu_launches": r["launches"],
-        "kernels_ms": {"rollout": r["rollout_ms"], "reduce": r["reduce_ms"], "finalize": r["finalize_ms"]},
+        # two launches per step; the finalize phase runs in the reduce kernel's finalizer block (eager launches with events in
+        # between, so the PDL overlap of the two kernels is NOT in these two figures: their sum exceeds ms_per_step)
+        "kernels_ms": {"rollout": r["rollout_ms"], "reduce_incl_finalize": r["reduce_ms"]},
         "roofline": {"bound": "fp32_alu", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
                      "frac": achieved / tf.value if tf.value else None, "traffic": traffic,
                      "traffic_source": "from profile, NOT measured in this run: %s (dram__bytes_read.sum + dram__bytes_write.sum of one "
@@ -405,7 +407,7 @@ def run_multi(args):
     m = ShardedMPPI(T, K_total, precision=args.precision, seed=0, device=local, exchange=args.exchange)
     lib, h = m.mppi._lib, m.mppi._h
     parity = _sharded_parity(mp, dist, torch, m, rank, local, K_total, T, args.precision)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local)         # every rank samples ITS GPU (rank 0's goes into `clocks`, all medians into the line)
     dev_ms, launches, timing, _ = _bench_sharded(args, dist, torch, m, args.steps)
     # e2e: host x0 in, (u, x_next) out every step through the C ABI, closed loop on the host; every timed call starts from a
     # flushed L2 on every rank (as at N=1), the flush outside the timed intervals
@@ -454,6 +456,16 @@ def run_multi(args):
         ms5 = float(t5[0])
         info5 = m5.mppi.launch_info()
         m5.mppi.close()
+        # every rank's shard timed ALONE (no exchange, world_size 1, same K per GPU): separates what the GPUs differ by from what
+        # the coupling costs -- the coupled step cannot be faster than the slowest shard
+        alone = mp.MPPI(horizon=T5, samples=K5_TOTAL // world, precision=args.precision, seed=0, device=local)
+        alone.goal = GOAL
+        alone_ms = alone.bench(X0, steps=max(3, min(steps5, 10)), warmup=3, flush_l2=True, per_kernel=False)["step_ms"]
+        alone.close()
+        ta = torch.zeros(world, dtype=torch.float64, device="cuda")
+        ta[rank] = alone_ms
+        dist.all_reduce(ta, op=dist.ReduceOp.SUM)
+        alone_all = [float(v) for v in ta.cpu()]
         n1_ms = None
         if rank == 0:     # the same workload on ONE GPU, timed in this run: the base of the strong-scaling curve
             one5 = mp.MPPI(horizon=T5, samples=K5_TOTAL, precision=args.precision, seed=0, device=local)
@@ -465,8 +477,12 @@ def run_multi(args):
                           "per GPU, one %d-byte record exchanged per step" % (K5_TOTAL, T5, world, K5_TOTAL // world, T5 * 48),
               "n_gpus": world, "scaling": "strong", "ms_per_step": ms5, "value": K5_TOTAL / (ms5 * 1e-3), "unit": "rollouts/s",
               "state_steps_per_s": K5_TOTAL * T5 / (ms5 * 1e-3), "steps": steps5, "gpu_launches": launches5,
-              "one_gpu_same_run_ms_per_step": n1_ms, "launch": info5, "parity": parity5}
-    clocks = sampler.stop() if sampler else {}
+              "one_gpu_same_run_ms_per_step": n1_ms, "shard_alone_ms_per_rank": alone_all, "launch": info5, "parity": parity5}
+    clocks = sampler.stop()
+    tc = torch.zeros(world, dtype=torch.float64, device="cuda")
+    tc[rank] = float(clocks.get("sm_mhz") or 0.0)
+    dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+    clocks["sm_mhz_per_rank"] = [float(v) for v in tc.cpu()]
     if rank == 0:
         xbytes = T * 48
         line = {

@@ -235,8 +235,8 @@ MPPI_API mppi_status mppi_p2p_connect(mppi_handle h, const void* all_handles);
 typedef struct {
   float step_ms;        /* mean device time of one whole step (all kernels), CUDA events on the launch stream */
   float rollout_ms;     /* mean device time of the fused rollout+cost kernel alone */
-  float reduce_ms;      /* mean device time of the softmin/refine reduction kernel */
-  float finalize_ms;    /* mean device time of the update/filter/shift kernel */
+  float reduce_ms;      /* mean device time of the softmin/refine reduction kernel INCLUDING the finalize phase (its finalizer block) */
+  float finalize_ms;    /* ~0: the update/filter/shift phase is fused into the reduce kernel (kept for ABI stability) */
   int32_t launches;     /* kernels launched inside the timed region */
   int32_t steps;
   int32_t refine_candidates;  /* MIXED: fp64 re-evaluations in the last step */

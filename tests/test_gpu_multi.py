@@ -33,9 +33,10 @@ def test_sharded_equals_single_gpu(precision, exchange):
 
 
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
-def test_sharded_closed_loop_into_the_goal(exchange):
-    """the default multi-GPU controller (precision 'mixed') must survive the overflow regime near the goal on every
-    transport -- p2p redoes the step inside mppi_step, nccl / host through the MPPI_ERR_RETRY round trip."""
+def test_sharded_controller_survives_screen_overflows(exchange):
+    """the default multi-GPU controller (precision 'mixed') must survive the overflow regime of the fp32 screen
+    (systematic near a goal at large K; forced here by an absurd window) on every transport -- p2p redoes the step inside
+    mppi_step, nccl / host through the MPPI_ERR_RETRY round trip -- and stay equal to a single fp64 engine."""
     n = _ngpu()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -45,6 +46,6 @@ def test_sharded_closed_loop_into_the_goal(exchange):
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
-           "4096", "32", "mixed", exchange, "togoal"]
+           "8192", "32", "mixed", exchange, "overflow"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "DIST OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
