@@ -690,6 +690,10 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
   if (a.ll_local) {
     double* rows = Us + 4 * T;                       // [world][T][kRowDoubles]
     const unsigned int flag = a.dyn->xchg + 1u;      // (only this block ever advances xchg, at the very end)
+    // PDL: this block may have become resident while the rollout kernel's CTAs are still on their last tiles; it must not
+    // poll next to them (issue slots, LSU traffic), so the wait for rows starts when that grid has completed -- which no
+    // row can precede anyway
+    griddep_wait();
     for (int i = tid; i < sp.world * T; i += blockDim.x) {
       const int g = i / T, t = i - g * T;
       double r[kRowDoubles];
