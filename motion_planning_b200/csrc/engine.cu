@@ -328,16 +328,37 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
         cudaGetLastError();
         continue;
       }
+      // The T-step loop is throughput (issue) bound -- measured 123 cycles per warp-step and scheduler at 2 warps per
+      // scheduler, 136 at 3.5 -- so an SM's time is (its tiles) x (warps per tile) / 4 schedulers, TIMES two penalties that
+      // depend on how many CTAs are made resident per SM (a choice, <= what fits; tiles are assigned statically):
+      //   imbalance: r CTAs of w warps put ceil(r w / 4) warps on the busiest scheduler and every tile runs at its pace
+      //              (5 CTAs of 2 warps = 3,3,2,2: K = 1048576, T = 128 measured 510 us that way, 448 us expected balanced);
+      //   latency:   below ~1.6 warps per scheduler the issue slots cannot be kept busy.
+      // The SM-wide kernel cuts its seventh tile in time and carries 3.5 on every scheduler.
+      const int wpb = block / 32;
+      const int tiles_per_sm = (c.ntiles + e->num_sms - 1) / e->num_sms;
+      int best_r = c.ctas_per_sm;
+      double cost = 1e300;
+      if (sm_wide) {
+        best_r = 1;
+        cost = 3.5;
+      } else {
+        for (int r = 1; r <= c.ctas_per_sm; ++r) {
+          const double W = 0.25 * r * wpb;
+          const double imb = std::ceil(W) / W, lat = W < 1.6 ? 1.6 / W : 1.0;
+          const double cr = tiles_per_sm * 0.25 * wpb * imb * lat;
+          if (cr <= cost) {   // ties: more resident warps
+            cost = cr;
+            best_r = r;
+          }
+        }
+      }
+      c.ctas_per_sm = best_r;
       const long long resident = (long long)e->num_sms * c.ctas_per_sm;
       c.grid = (int)((c.ntiles < resident) ? c.ntiles : resident);
       c.nparts = sm_wide ? (sp.K + 63) / 64 : c.grid;
-      // the kernel is issue bound and ends with its busiest scheduler: cost = warps' worth of T-step loops on the busiest
-      // scheduler of the busiest SM (tiles are dealt round-robin over the SMs, a CTA's warps over the four schedulers);
-      // the SM-wide kernel cuts its seventh tile in time and carries 3.5 on every scheduler
-      const int tiles_per_sm = (c.ntiles + e->num_sms - 1) / e->num_sms;
-      const double sched = sm_wide ? 3.5 : (double)((tiles_per_sm * (block / 32) + 3) / 4);
-      // ties: less thread-work on the busiest SM, then the larger tile
-      const double cost = sched * 1e6 + (double)tiles_per_sm * rollouts;
+      // ties between shapes: less thread-work on the busiest SM, then the larger tile
+      cost = cost * 1e6 + (double)tiles_per_sm * rollouts;
       c.ready = true;
       if (cost < best_cost || (cost == best_cost && block > best.block)) {
         best = c;
