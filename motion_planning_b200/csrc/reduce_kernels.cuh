@@ -108,12 +108,19 @@ __device__ __forceinline__ void publish_result(const FinalizeArgs& a, int status
 // Block T of the grid (the FINALIZER) does no row work: it loads everything the finalize phase needs while the rows are
 // still being computed, then polls the rows of all ranks and finishes the step -- no ticket, no last-block election, no
 // system-scope fence on the serial tail; the exchange costs one NVLink store latency after a rank's last row.
-__device__ __forceinline__ void st_ll(uint2* p, unsigned int w, unsigned int flag) {
-  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(w), "r"(flag) : "memory");
+// (system scope only where a peer GPU is on the other end: on one GPU the rows never leave its L2)
+__device__ __forceinline__ void st_ll(uint2* p, unsigned int w, unsigned int flag, bool sys) {
+  if (sys)
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(w), "r"(flag) : "memory");
+  else
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(w), "r"(flag) : "memory");
 }
-__device__ __forceinline__ uint4 ld_ll2(const uint2* p) {   // two consecutive words (16 bytes; each half is atomic by itself)
+__device__ __forceinline__ uint4 ld_ll2(const uint2* p, bool sys) {   // two consecutive words (16 bytes; each half is atomic by itself)
   uint4 v;
-  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  if (sys)
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  else
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 // called by ALL lanes of warp 0 of a row block; `row` = kRowDoubles doubles in shared memory, complete and visible to the warp
@@ -123,7 +130,7 @@ __device__ __forceinline__ void ll_push_row(const ReduceArgs& a, int t, const do
   const unsigned int* w32 = reinterpret_cast<const unsigned int*>(row);
   for (int idx = lane; idx < world * kRowWords; idx += 32) {
     const int g = idx / kRowWords, j = idx - g * kRowWords;
-    st_ll(a.ll_peers[g] + slot * kRowWords + j, w32[j], flag);
+    st_ll(a.ll_peers[g] + slot * kRowWords + j, w32[j], flag, world > 1);
   }
 }
 // poll row (g, t) until all its words carry `flag`; false on time-out (a peer died)
@@ -134,7 +141,7 @@ __device__ __forceinline__ bool ll_read_row(const uint2* ll, int world, int T, u
   for (;;) {   // all loads of the row in flight together: one round trip per attempt
     bool ok = true;
 #pragma unroll
-    for (int d = 0; d < kRowDoubles; ++d) v[d] = ld_ll2(src + 2 * d);
+    for (int d = 0; d < kRowDoubles; ++d) v[d] = ld_ll2(src + 2 * d, world > 1);
 #pragma unroll
     for (int d = 0; d < kRowDoubles; ++d) ok &= (v[d].y == flag) & (v[d].w == flag);
     if (ok) break;
