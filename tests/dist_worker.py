@@ -19,8 +19,18 @@ def main():
     overflow = len(sys.argv) > 5 and sys.argv[5] == "overflow"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # MPPI_TEST_ONE_GPU=1: all ranks share cuda:0 (a 1-GPU lease) -- rendezvous over gloo (NCCL refuses two ranks on one device);
+    # the engines, the CUDA-IPC row exchange and the split-phase API are the same code as on N GPUs, the processes' kernels are
+    # time-sliced by the driver instead of running side by side
+    one_gpu = os.environ.get("MPPI_TEST_ONE_GPU") == "1"
+    if one_gpu:
+        local = 0
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = "cpu" if one_gpu else "cuda"
     goal = np.array([0.0, -1.0, 0.0])
     # overflow mode: an absurd screening window (50 cost units) makes the candidate lists of the fp32 screen overflow on the
     # very first step and again whenever the hold-off has run out -- what happens systematically within centimetres of a goal
@@ -40,12 +50,12 @@ def main():
         if overflow:
             # every step is compared from identical inputs (free-running loops drift apart chaotically: the soft-min amplifies
             # 1e-12 differences of the nominal by up to 1/lam per step): all ranks take rank 0's single-engine nominal
-            U = torch.from_numpy(one.latest_uvec if one is not None else np.zeros((2, T))).cuda()
+            U = torch.from_numpy(one.latest_uvec if one is not None else np.zeros((2, T))).to(dev)
             dist.broadcast(U, src=0)
             sh.mppi.latest_uvec = U.cpu().numpy()
         s = s1
     # every rank must hold the identical nominal sequence (no broadcast is ever done)
-    U = torch.from_numpy(sh.latest_uvec).cuda()
+    U = torch.from_numpy(sh.latest_uvec).to(dev)
     lo, hi = U.clone(), U.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)

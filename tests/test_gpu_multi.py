@@ -49,3 +49,24 @@ def test_sharded_controller_survives_screen_overflows(exchange):
            "8192", "32", "mixed", exchange, "overflow"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "DIST OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("precision,exchange,mode", [("mixed", "p2p", ""), ("mixed", "host", ""), ("f32", "p2p", ""),
+                                                     ("mixed", "p2p", "overflow"), ("mixed", "host", "overflow")])
+def test_two_ranks_sharing_one_gpu(precision, exchange, mode):
+    """The sharded controller on a ONE-GPU lease: two processes (gloo rendezvous), both on cuda:0.  Same engines, same CUDA-IPC
+    row exchange between the two processes' reduce kernels ('p2p': each finalizer block polls while the driver time-slices the
+    two contexts), same split-phase API with a host-staged exchange ('host'), incl. the MPPI_ERR_RETRY round trip ('overflow');
+    the result must equal the single-engine controller -- so sharded == single is checked wherever the GPU suite runs."""
+    if _ngpu() < 1:
+        pytest.skip("needs a GPU")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"),
+           "8192", "32", precision, exchange] + ([mode] if mode else [])
+    env = dict(os.environ, MPPI_TEST_ONE_GPU="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert "DIST OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
