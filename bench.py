@@ -278,7 +278,7 @@ def run_single(args):
         cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_ncu_summary.json"))
         traffic_file = "profiles/" + cands[-1]
         ncu = json.load(open(os.path.join(ROOT, traffic_file)))
-        key = [k for k in ncu if k.startswith("rollout") and ("precision %s" % args.precision) in k]
+        key = [k for k in ncu if k.startswith("rollout") and ("precision %s" % args.precision) in k and ("K %d T %d" % (K, T)) in k]
         if key:
             m_ = ncu[key[0]]
             mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
