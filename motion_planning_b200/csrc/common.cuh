@@ -23,6 +23,9 @@ constexpr int kRecordStride = 6;    // doubles per t in an exchange record: m, S
 constexpr int kRowDoubles = 8;      // fused step: a row = the record + (max |V32 - V64|, candidates) of that row
 constexpr int kMaxFusedWorld = 16;  // ranks of a fused (peer-to-peer) exchange; larger groups use the split-phase step
 constexpr int kRowWords = 2 * kRowDoubles;   // 32-bit payload words per row, each travelling with its own flag (8-byte stores)
+constexpr int kRow2Doubles = 6;     // fused step, merged row of one t: clip(U0 + dU0), clip(U1 + dU1), flag bits, candidates, max dev, -
+constexpr int kRow2Words = 2 * kRow2Doubles;
+constexpr int kRow2Overflow = 1, kRow2Bad = 2, kRow2Timeout = 4;   // flag bits of a merged row
 constexpr double kZFixScale = 1048576.0;   // 2^20: fixed-point scale of the floor-term noise sums
 constexpr double kLeanMaxYawInc = 0.125;   // LEAN rollout kernel: admission bound on |dt * yaw rate| (half of it for Euler)
 

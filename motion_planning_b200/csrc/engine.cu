@@ -83,6 +83,7 @@ struct mppi_engine {
   // row exchange of the fused step (reduce_kernels.cuh): this rank's flag-in-data buffer (exported through CUDA IPC when
   // world > 1) and the device array of all ranks' buffer pointers (own buffer + IPC mappings of the peers')
   uint2* d_ll = nullptr;
+  uint2* d_ll2 = nullptr;          // merged rows of this rank: [2 parity][T][kRow2Words]
   size_t ll_bytes = 0, ll_rows_uint2 = 0;
   unsigned int rdv_epoch = 0;
   uint2* ll_peers[kMaxFusedWorld] = {};   // host copy of the ranks' buffer pointers: they travel in the kernel arguments
@@ -592,6 +593,8 @@ static mppi_status create_impl(const mppi_params* pin, const mppi_user_model* um
   CKF(cudaMalloc(&e->d_ll, e->ll_bytes));
   CKF(cudaMemset(e->d_ll, 0, e->ll_bytes));       // flag 0 never matches an epoch + 1
   if (p.world_size == 1) e->ll_peers[0] = e->d_ll;
+  CKF(cudaMalloc(&e->d_ll2, (size_t)2 * T * kRow2Words * sizeof(uint2)));
+  CKF(cudaMemset(e->d_ll2, 0, (size_t)2 * T * kRow2Words * sizeof(uint2)));
   CKF(cudaMallocHost(&e->h_in, 6 * sizeof(double)));
   CKF(cudaMallocHost(&e->h_out, sizeof(DynState)));
   CKF(cudaHostAlloc(&e->h_res, sizeof(HostWire), cudaHostAllocMapped));
@@ -657,6 +660,7 @@ extern "C" mppi_status mppi_destroy(mppi_handle e) {
   cudaFree(e->d_debug_rts);
   for (void* q : e->p2p_opened) cudaIpcCloseMemHandle(q);
   cudaFree(e->d_ll);
+  cudaFree(e->d_ll2);
   cudaFree(e->d_grid);
   if (e->h_grid_stage) cudaFreeHost(e->h_grid_stage);
   if (e->grid_stage_ev) cudaEventDestroy(e->grid_stage_ev);
@@ -897,7 +901,7 @@ static FinalizeArgs make_fin(mppi_engine* e, bool closed_loop) {
   fa.sp = e->sp;
   fa.dyn = e->d_dyn;
   fa.gather = (e->sp.world > 1) ? e->d_gather : e->d_record;
-  fa.ll_local = nullptr;
+  fa.ll2_local = nullptr;
   fa.Umaster = e->d_Umaster;
   fa.Ulast = e->d_Ulast;
   fa.nomF = e->d_nomF;
@@ -1000,11 +1004,12 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   }
   rd.fused = fuse != FUSE_NONE ? 1 : 0;   // (callers have checked: world == 1, or the peers' row buffers are mapped)
   if (rd.fused) {
-    rd.fin.ll_local = e->d_ll;
+    rd.fin.ll2_local = e->d_ll2;
     rd.fin.gather = nullptr;
     rd.fin.debug_ts = e->d_debug_ts ? e->d_debug_ts + (size_t)e->sp.T * 8 : nullptr;
   }
   rd.rank = e->p.rank;
+  rd.ll2_local = e->d_ll2;
   for (int g = 0; g < kMaxFusedWorld; ++g) rd.ll_peers[g] = e->ll_peers[g];
   rd.debug_ts = e->d_debug_ts;
   rd.part = e->d_part;

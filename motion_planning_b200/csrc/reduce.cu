@@ -72,10 +72,8 @@ size_t rollout_smem(int kind, int T, int block, int variant, int grid_bytes_in_s
                                      : rollout_smem_bytes<float>(T, block, grid_bytes_in_smem);
 }
 
-// shared memory of the finalize phase: the 4*T doubles of the update + (fused step) the rows of all ranks
-static size_t finalize_smem(const StaticParams& sp, bool fused) {
-  return ((size_t)4 * sp.T + (fused ? (size_t)sp.world * sp.T * kRowDoubles : 0)) * sizeof(double);
-}
+// shared memory of the finalize phase: the 4*T doubles of the update
+static size_t finalize_smem(const StaticParams& sp, bool) { return (size_t)4 * sp.T * sizeof(double); }
 
 template <typename Fn>
 static cudaError_t opt_in_smem(Fn f, size_t smem) {

@@ -100,14 +100,20 @@ __device__ __forceinline__ void publish_result(const FinalizeArgs& a, int status
 
 // ---- row exchange of the fused step: flag-in-data rows (any world size; over NVLink for world > 1) -------------------
 // Every reduce block owns one time step t and ends with one ROW: the record (m, S, N0, N1, E0, E1) plus the block's
-// statistics (max |V32 - V64|, candidates).  The row leaves as kRowWords 8-byte stores, each carrying 4 bytes of payload and
-// the 4-byte flag `epoch + 1` -- an aligned 8-byte store is single-copy atomic, so a word whose flag matches IS valid and
-// neither a fence nor a separate arrival flag is needed (the scheme of NCCL's low-latency protocol).  The block stores its row
-// into the buffer of EVERY rank, its own included (plain stores into CUDA-IPC mappings for the peers): buffer layout
-// uint2 [2 parity][world][T][kRowWords], parity = epoch & 1 (a rank can be at most one step ahead of its slowest peer).
-// Block T of the grid (the FINALIZER) does no row work: it loads everything the finalize phase needs while the rows are
-// still being computed, then polls the rows of all ranks and finishes the step -- no ticket, no last-block election, no
-// system-scope fence on the serial tail; the exchange costs one NVLink store latency after a rank's last row.
+// statistics (max |V32 - V64|, candidates).  A row travels as 8-byte stores, each carrying 4 bytes of payload and the 4-byte
+// flag `epoch + 1` -- an aligned 8-byte store is single-copy atomic, so a word whose flag matches IS valid and neither a
+// fence nor a separate arrival flag is needed (the scheme of NCCL's low-latency protocol).  Two stages, both inside the
+// reduce kernel:
+//   1. the block stores its row into the stage-1 buffer of every PEER (plain stores into CUDA-IPC mappings, over NVLink;
+//      layout uint2 [2 parity][world][T][kRowWords], parity = epoch & 1: a rank can be at most one step ahead of its slowest
+//      peer), then waits for the peers' rows OF ITS OWN t -- one lane per peer, all loads of a row in flight -- and merges
+//      them: lane g holds rank g's row, the soft-min merge (control/src/mppi:189-196) is a handful of warp reductions with
+//      ONE exp per lane.  The cross-rank wait and merge are thus spread over the T row blocks; every rank forms the
+//      bit-identical update (same rows, same lane order);
+//   2. the block stores the MERGED row -- clip(U[:,t] + dU[:,t]), flag bits, statistics -- into this rank's stage-2 buffer
+//      (uint2 [2 parity][T][kRow2Words]).  Block T of the grid (the FINALIZER) does no row work: it loads what the finalize
+//      phase needs while the rows are still being computed, then polls the T merged rows (one per thread, independent of the
+//      world size) and finishes the step -- no ticket, no last-block election, no system-scope fence on the serial tail.
 // (system scope only where a peer GPU is on the other end: on one GPU the rows never leave its L2)
 __device__ __forceinline__ void st_ll(uint2* p, unsigned int w, unsigned int flag, bool sys) {
   if (sys)
@@ -123,33 +129,78 @@ __device__ __forceinline__ uint4 ld_ll2(const uint2* p, bool sys) {   // two con
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-// called by ALL lanes of warp 0 of a row block; `row` = kRowDoubles doubles in shared memory, complete and visible to the warp
-__device__ __forceinline__ void ll_push_row(const ReduceArgs& a, int t, const double* row, unsigned int flag) {
-  const int lane = threadIdx.x & 31, world = a.sp.world, T = a.sp.T;
-  const size_t slot = ((size_t)((flag - 1u) & 1u) * world + a.rank) * T + t;
-  const unsigned int* w32 = reinterpret_cast<const unsigned int*>(row);
-  for (int idx = lane; idx < world * kRowWords; idx += 32) {
-    const int g = idx / kRowWords, j = idx - g * kRowWords;
-    st_ll(a.ll_peers[g] + slot * kRowWords + j, w32[j], flag, world > 1);
-  }
-}
-// poll row (g, t) until all its words carry `flag`; false on time-out (a peer died)
-__device__ __forceinline__ bool ll_read_row(const uint2* ll, int world, int T, unsigned int flag, int g, int t, double out[kRowDoubles]) {
-  const uint2* src = ll + (((size_t)((flag - 1u) & 1u) * world + g) * T + t) * kRowWords;
+// poll ND doubles of flag-in-data words at `src` until all carry `flag`; false on time-out (a peer died)
+template <int ND>
+__device__ __forceinline__ bool ll_read(const uint2* src, unsigned int flag, bool sys, double out[ND]) {
   const long long t0 = clock64();
-  uint4 v[kRowDoubles];
-  for (;;) {   // all loads of the row in flight together: one round trip per attempt
+  uint4 v[ND];
+  for (;;) {   // all loads in flight together: one round trip per attempt
     bool ok = true;
 #pragma unroll
-    for (int d = 0; d < kRowDoubles; ++d) v[d] = ld_ll2(src + 2 * d, world > 1);
+    for (int d = 0; d < ND; ++d) v[d] = ld_ll2(src + 2 * d, sys);
 #pragma unroll
-    for (int d = 0; d < kRowDoubles; ++d) ok &= (v[d].y == flag) & (v[d].w == flag);
+    for (int d = 0; d < ND; ++d) ok &= (v[d].y == flag) & (v[d].w == flag);
     if (ok) break;
     if (clock64() - t0 > (1LL << 33)) return false;   // ~4 s
   }
 #pragma unroll
-  for (int d = 0; d < kRowDoubles; ++d) out[d] = __hiloint2double((int)v[d].z, (int)v[d].x);
+  for (int d = 0; d < ND; ++d) out[d] = __hiloint2double((int)v[d].z, (int)v[d].x);
   return true;
+}
+// Stage 1 + 2 for row t, called by ALL lanes of warp 0 of its row block.  `row` = kRowDoubles doubles in shared memory,
+// complete and visible to the warp; u_nom0 / u_nom1 = U[0][t], U[1][t] (loaded at the start of the block).
+__device__ __forceinline__ void ll_exchange_row(const ReduceArgs& a, int t, const double* row, unsigned int flag, double u_nom0, double u_nom1,
+                                                double neg_inv_lam) {
+  const StaticParams& sp = a.sp;
+  const int lane = threadIdx.x & 31, world = sp.world, T = sp.T;
+  const int par = (int)((flag - 1u) & 1u);
+  const bool sys = world > 1;
+  // stage 1: my row into every peer's buffer
+  if (sys) {
+    const size_t slot = ((size_t)par * world + a.rank) * T + t;
+    const unsigned int* w32 = reinterpret_cast<const unsigned int*>(row);
+    for (int idx = lane; idx < world * kRowWords; idx += 32) {
+      const int g = idx / kRowWords, j = idx - g * kRowWords;
+      if (g != a.rank) st_ll(a.ll_peers[g] + slot * kRowWords + j, w32[j], flag, true);
+    }
+  }
+  // lane g takes rank g's row of this t (its own from shared memory, a peer's from the stage-1 buffer when it has landed)
+  double r[kRowDoubles];
+  bool have = lane < world, ok = true;
+#pragma unroll
+  for (int d = 0; d < kRowDoubles; ++d) r[d] = 0.0;
+  if (lane == a.rank) {
+#pragma unroll
+    for (int d = 0; d < kRowDoubles; ++d) r[d] = row[d];
+  } else if (have) {
+    ok = ll_read<kRowDoubles>(a.ll_peers[a.rank] + (((size_t)par * world + lane) * T + t) * kRowWords, flag, true, r);
+  }
+  const bool timeout = __any_sync(0xffffffffu, !ok);
+  // merge (control/src/mppi:189-196 over the rows of all ranks): weights relative to the global minimum
+  const double m = warp_min<double>(have ? r[0] : Math<double>::inf());
+  const double sc = (have && r[0] != m) ? exp((r[0] - m) * neg_inv_lam) : (have ? 1.0 : 0.0);
+  const bool ovf = __any_sync(0xffffffffu, have && r[1] < 0.0);      // S < 0: that rank's fp32 screen overflowed a list
+  const double S = warp_sum<double>(r[1] * sc), N0 = warp_sum<double>(r[2] * sc), N1 = warp_sum<double>(r[3] * sc);
+  const double E0 = warp_sum<double>(r[4]), E1 = warp_sum<double>(r[5]);
+  const double dev = -warp_min<double>(-r[6]), cand = warp_sum<double>(r[7]);
+  const double den = S + sp.eps_floor * (double)sp.k_total;
+  const double u0 = u_nom0 + (N0 + sp.eps_floor * E0) / den, u1 = u_nom1 + (N1 + sp.eps_floor * E1) / den;
+  // the reference lets NaN propagate silently; here a non-finite input or an empty softmin support (S == 0 can
+  // only come from NaN costs) is reported as MPPI_ERR_NONFINITE
+  const bool bad = !isfinite(u0) || !isfinite(u1) || !(S > 0.0);
+  // stage 2: the merged row for this rank's finalizer block
+  double out[kRow2Doubles];
+  out[0] = clamp_<double>(u0, sp.u_max[0]);                                  // :198-199
+  out[1] = clamp_<double>(u1, sp.u_max[1]);
+  out[2] = (double)((ovf ? kRow2Overflow : 0) | ((bad && !ovf) ? kRow2Bad : 0) | (timeout ? kRow2Timeout : 0));
+  out[3] = cand;
+  out[4] = dev;
+  out[5] = 0.0;
+  if (lane < kRow2Words) {
+    const double v = out[lane >> 1];
+    const unsigned int w = (lane & 1) ? (unsigned int)__double2hiint(v) : (unsigned int)__double2loint(v);
+    st_ll(a.ll2_local + ((size_t)par * T + t) * kRow2Words + lane, w, flag, false);
+  }
 }
 
 // ---- kernel 2a: SOFTMIN merge.  grid = T blocks of 256 threads --------------------------------------
@@ -167,6 +218,7 @@ __global__ void __launch_bounds__(256) reduce_softmin_kernel(const __grid_consta
     return;
   }
   const unsigned int row_flag = a.fin.dyn->xchg + 1u;   // exchange epoch of this step
+  const double u_nom0 = a.fused ? a.fin.Umaster[blockIdx.x] : 0.0, u_nom1 = a.fused ? a.fin.Umaster[a.sp.T + blockIdx.x] : 0.0;
   griddep_wait();   // PDL: everything above overlapped the rollout kernel's tail
   const int t = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const Vec4* part = reinterpret_cast<const Vec4*>(a.part) + (size_t)t * a.nCTA;
@@ -233,7 +285,7 @@ __global__ void __launch_bounds__(256) reduce_softmin_kernel(const __grid_consta
   }
   if (a.fused && tid < 32) {
     __syncwarp();
-    ll_push_row(a, t, rowbuf, row_flag);
+    ll_exchange_row(a, t, rowbuf, row_flag, u_nom0, u_nom1, neg_inv_lam);
   }
 }
 
@@ -427,6 +479,7 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
   const float std0 = (float)a.fin.dyn->noise_std[0], std1 = (float)a.fin.dyn->noise_std[1];
   const unsigned int philox_step = a.fin.dyn->step;
   const unsigned int row_flag = a.fin.dyn->xchg + 1u;   // exchange epoch of this step
+  const double u_nom0 = a.fused ? a.fin.Umaster[blockIdx.x] : 0.0, u_nom1 = a.fused ? a.fin.Umaster[T + blockIdx.x] : 0.0;
   double xs_[3], gs_[3], head;
   load_step_input(a.fin.in, a.fin.dyn, xs_, gs_);
   const float window = (float)screen_window(sp, xs_, gs_, &head);   // the same value the rollout kernel listed against
@@ -572,7 +625,7 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     }
     if (a.fused) {
       __syncwarp();
-      ll_push_row(a, t, rowbuf, row_flag);
+      ll_exchange_row(a, t, rowbuf, row_flag, u_nom0, u_nom1, neg_inv_lam);
     }
   }
   TS(4);
@@ -675,43 +728,36 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       }
     }
   }
-  // -- the records of all ranks.  Fused step: poll the flag-in-data rows (this rank's own blocks and, over NVLink, the peers'),
-  //    one row per thread with its eight 16-byte loads in flight together, into shared memory; otherwise the gathered records
-  //    of a previous kernel / copy
+  // -- the update of all ranks.  Fused step: the row blocks have already merged the ranks' rows of their t and clipped the
+  //    update (ll_exchange_row); poll those T merged rows, one per thread.  Otherwise (split-phase step with an external
+  //    exchange, mppi_update_action): merge the gathered records of a previous kernel / copy here.
   __shared__ int timed_out, s_cand;
   __shared__ unsigned long long s_dev;
-  const double* recs = a.gather;
-  int stride = kRecordStride;
   if (tid == 0) {
     timed_out = 0;
     s_cand = 0;
     s_dev = 0ull;
   }
-  // nominal controls of this thread's (c, t): loaded before the wait
-  double u_nom[2] = {0.0, 0.0};
-  {
-    int q = 0;
-    for (int idx = tid; idx < 2 * T && q < 2; idx += blockDim.x, ++q) u_nom[q] = a.Umaster[idx];
-  }
   __syncthreads();
-  if (a.ll_local) {
-    double* rows = Us + 4 * T;                       // [world][T][kRowDoubles]
+  if (a.ll2_local) {
     const unsigned int flag = a.dyn->xchg + 1u;      // (only this block ever advances xchg, at the very end)
     // PDL: this block may have become resident while the rollout kernel's CTAs are still on their last tiles; it must not
     // poll next to them (issue slots, LSU traffic), so the wait for rows starts when that grid has completed -- which no
     // row can precede anyway
     griddep_wait();
-    for (int i = tid; i < sp.world * T; i += blockDim.x) {
-      const int g = i / T, t = i - g * T;
-      double r[kRowDoubles];
-      if (!ll_read_row(a.ll_local, sp.world, T, flag, g, t, r)) timed_out = 1;
-#pragma unroll
-      for (int d = 0; d < kRowDoubles; ++d) rows[(size_t)i * kRowDoubles + d] = r[d];
-      if (r[7] != 0.0) atomicAdd(&s_cand, (int)r[7]);
-      if (r[6] > 0.0) atomicMax(&s_dev, (unsigned long long)__double_as_longlong(r[6]));   // non-negative doubles order like their bits
+    const uint2* base = a.ll2_local + (size_t)((flag - 1u) & 1u) * T * kRow2Words;
+    for (int t = tid; t < T; t += blockDim.x) {
+      double r[kRow2Doubles];
+      if (!ll_read<kRow2Doubles>(base + (size_t)t * kRow2Words, flag, false, r)) timed_out = 1;
+      Us[t] = r[0];
+      Us[T + t] = r[1];
+      const int bits = (int)r[2];
+      if (bits & kRow2Overflow) any_ovf = 1;
+      if (bits & kRow2Bad) bad = 1;
+      if (bits & kRow2Timeout) timed_out = 1;
+      if (r[3] != 0.0) atomicAdd(&s_cand, (int)r[3]);
+      if (r[4] > 0.0) atomicMax(&s_dev, (unsigned long long)__double_as_longlong(r[4]));   // non-negative doubles order like their bits
     }
-    recs = rows;
-    stride = kRowDoubles;
     __syncthreads();
     if (timed_out) {   // a peer never delivered (it died): report, leave the controller state untouched
       if (owner && a.mode == 0) {
@@ -725,12 +771,12 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       dev_r = __longlong_as_double((long long)s_dev);
       if (a.debug_ts) a.debug_ts[1] = gtime();
     }
-  }
+  } else {
   // -- merge the records of all ranks and apply the weighted noise (control/src/mppi:189-199) ----
-  const double neg_inv_lam = -1.0 / lam;
-  {
-    int q = 0;
-    for (int idx = tid; idx < 2 * T; idx += blockDim.x, ++q) {
+    const double* recs = a.gather;
+    const int stride = kRecordStride;
+    const double neg_inv_lam = -1.0 / lam;
+    for (int idx = tid; idx < 2 * T; idx += blockDim.x) {
       const int c = idx / T, t = idx - c * T;
       double m = Math<double>::inf();
       for (int g = 0; g < sp.world; ++g) m = fmin(m, recs[((size_t)g * T + t) * stride]);
@@ -748,7 +794,7 @@ __device__ void finalize_body(const FinalizeArgs& a, double* Us) {
       // MIXED: a record with S < 0 means some rank's fp32 screen overflowed a candidate list (see below)
       if (ovf) any_ovf = 1;
       const double dU = (N + sp.eps_floor * E) / (S + sp.eps_floor * (double)sp.k_total);
-      const double u = (q < 2 ? u_nom[q] : a.Umaster[idx]) + dU;
+      const double u = a.Umaster[idx] + dU;
       // the reference lets NaN propagate silently; here a non-finite input or an empty
       // softmin support (S == 0 can only come from NaN costs) is reported as MPPI_ERR_NONFINITE
       if (!isfinite(u) || !(S > 0.0)) atomicOr(&bad, 1);

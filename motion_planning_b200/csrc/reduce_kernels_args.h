@@ -46,10 +46,11 @@ struct FinalizeArgs {
   double sg_inv_norm[4];     // 1 / sum_j p_i(z_j)^2
   int mode;                  // 0: full step, 1: update only (mppi_update_action)
   int closed_loop;           // 1: dyn->x0 <- x_next (device-resident loop of mppi_bench)
-  // row exchange of the fused step (any world size): the finalizer block reads the rows of ALL ranks (its own included)
-  // from this rank's flag-in-data buffer, uint2 [2 parity][world][T][kRowWords] (see reduce_kernels.cuh); nullptr: the
-  // records are taken from `gather` (split-phase step with an external exchange, mppi_update_action)
-  const uint2* ll_local;
+  // fused step (any world size): the finalizer block reads the MERGED row of every t -- the clipped update of all ranks,
+  // formed by the row blocks themselves -- from this rank's flag-in-data buffer uint2 [2 parity][T][kRow2Words] (see
+  // reduce_kernels.cuh); nullptr: the records are taken from `gather` and merged here (split-phase step with an external
+  // exchange, mppi_update_action)
+  const uint2* ll2_local;
   unsigned long long* debug_ts;   // optional 8 globaltimer stamps of the finalize phase (profiling aid): [1] all rows seen,
                                   // [3] filter coefficients done, [4] result published
   StepInput in;              // x0 / goal of this step (also used by the reduce kernel's fp64 re-evaluation)
@@ -70,6 +71,7 @@ struct ReduceArgs {
   int fused;                 // 1: rows leave through the flag-in-data buffers and block T of the grid (the finalizer) runs the
                              //    finalize phase as soon as the rows of all ranks have arrived; 0: rows go to `record` only
   int rank;
+  uint2* ll2_local;          // this rank's buffer of merged rows (written by its row blocks, read by its finalizer block)
   uint2* ll_peers[kMaxFusedWorld];   // row-buffer base pointers of all ranks, IN the argument block (no dependent load on the
                              // serial tail): this rank's own buffer and, for world > 1, the CUDA IPC mappings of the peers'
                              // buffers (stores travel over NVLink)

@@ -32,15 +32,18 @@ for rep in range(3):
     ts = ts.astype(np.int64)
     rows, fin = ts[:T], ts[T]
     t0 = rows[:, 0].min()
-    res.append([r["step_ms"] * 1e3, (rows[:, 4].max() - t0) / 1e3, (fin[1] - t0) / 1e3, (fin[3] - t0) / 1e3, (fin[2] - t0) / 1e3,
-                (rows[:, 3] - rows[:, 2]).mean() / 1e3, (rows[:, 4] - rows[:, 3]).mean() / 1e3])
+    ph = [(rows[:, j] - rows[:, j - 1]) / 1e3 for j in range(1, 5)]          # A, B, C, D (D = soft-min + exchange + merge)
+    res.append([r["step_ms"] * 1e3, (rows[:, 0].max() - t0) / 1e3, (rows[:, 4].max() - t0) / 1e3, (fin[1] - t0) / 1e3, (fin[3] - t0) / 1e3,
+                (fin[2] - t0) / 1e3] + [f(x) for x in ph for f in (np.mean, np.max)] + [float(r["refine_candidates"])])
 out = torch.tensor(res[-1], dtype=torch.float64, device="cuda")
 allr = [torch.empty_like(out) for _ in range(world)]
 dist.all_gather(allr, out)
 if rank == 0:
-    print("world %d K_total %d T %d (us; per rank): step | own last row pushed | all rows of all ranks seen | filter coefficients | "
-          "finalizer end | phase C mean | phase D mean" % (world, K, T))
+    print("world %d K_total %d T %d (us; per rank): step | row blocks start spread | own last row done | merged rows seen by the finalizer | "
+          "filter coefficients | finalizer end | phases A B C D as mean,max | candidates" % (world, K, T))
     for g, v in enumerate(allr):
-        print("  rank %d: " % g + "  ".join("%7.2f" % x for x in v.tolist()))
+        v = v.tolist()
+        print("  rank %d: " % g + "  ".join("%6.2f" % x for x in v[:6]) + "  |  " + "  ".join("%5.2f,%5.2f" % (v[6 + 2 * i], v[7 + 2 * i]) for i in range(4))
+              + "  | %d" % v[14])
 dist.barrier()
 dist.destroy_process_group()
