@@ -164,25 +164,56 @@ __device__ __forceinline__ void ll_exchange_row(const ReduceArgs& a, int t, cons
       if (g != a.rank) st_ll(a.ll_peers[g] + slot * kRowWords + j, w32[j], flag, true);
     }
   }
-  // lane g takes rank g's row of this t (its own from shared memory, a peer's from the stage-1 buffer when it has landed)
-  double r[kRowDoubles];
-  bool have = lane < world, ok = true;
+  double m, S, N0, N1, E0, E1, dev, cand;
+  bool ovf, timeout = false;
+  if (!sys) {   // one rank: the row IS the merged record (every lane computes the same update; no shuffles on the serial tail)
+    m = row[0];
+    S = row[1];
+    N0 = row[2];
+    N1 = row[3];
+    E0 = row[4];
+    E1 = row[5];
+    dev = row[6];
+    cand = row[7];
+    ovf = S < 0.0;               // S < 0: the fp32 screen overflowed a candidate list
+  } else {
+    // lane g takes rank g's row of this t (its own from shared memory, a peer's from the stage-1 buffer when it has landed)
+    double r[kRowDoubles];
+    const bool have = lane < world;
+    bool ok = true;
 #pragma unroll
-  for (int d = 0; d < kRowDoubles; ++d) r[d] = 0.0;
-  if (lane == a.rank) {
+    for (int d = 0; d < kRowDoubles; ++d) r[d] = 0.0;
+    if (lane == a.rank) {
 #pragma unroll
-    for (int d = 0; d < kRowDoubles; ++d) r[d] = row[d];
-  } else if (have) {
-    ok = ll_read<kRowDoubles>(a.ll_peers[a.rank] + (((size_t)par * world + lane) * T + t) * kRowWords, flag, true, r);
+      for (int d = 0; d < kRowDoubles; ++d) r[d] = row[d];
+    } else if (have) {
+      ok = ll_read<kRowDoubles>(a.ll_peers[a.rank] + (((size_t)par * world + lane) * T + t) * kRowWords, flag, true, r);
+    }
+    timeout = __any_sync(0xffffffffu, !ok);
+    // merge (control/src/mppi:189-196 over the rows of all ranks): weights relative to the global minimum.  Butterfly
+    // reductions over the lanes that hold a row (log2 of the next power of two of `world` steps); the eight reductions are
+    // independent chains and overlap
+    int top = 1;
+    while (top < world) top <<= 1;
+    auto red_sum = [&](double v) {
+      for (int o = top >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      return v;
+    };
+    auto red_min = [&](double v) {
+      for (int o = top >> 1; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+      return v;
+    };
+    m = red_min(have ? r[0] : Math<double>::inf());
+    const double sc = (have && r[0] != m) ? exp((r[0] - m) * neg_inv_lam) : (have ? 1.0 : 0.0);
+    ovf = __any_sync(0xffffffffu, have && r[1] < 0.0);      // S < 0: that rank's fp32 screen overflowed a list
+    S = red_sum(r[1] * sc);
+    N0 = red_sum(r[2] * sc);
+    N1 = red_sum(r[3] * sc);
+    E0 = red_sum(r[4]);
+    E1 = red_sum(r[5]);
+    dev = -red_min(-r[6]);
+    cand = red_sum(r[7]);
   }
-  const bool timeout = __any_sync(0xffffffffu, !ok);
-  // merge (control/src/mppi:189-196 over the rows of all ranks): weights relative to the global minimum
-  const double m = warp_min<double>(have ? r[0] : Math<double>::inf());
-  const double sc = (have && r[0] != m) ? exp((r[0] - m) * neg_inv_lam) : (have ? 1.0 : 0.0);
-  const bool ovf = __any_sync(0xffffffffu, have && r[1] < 0.0);      // S < 0: that rank's fp32 screen overflowed a list
-  const double S = warp_sum<double>(r[1] * sc), N0 = warp_sum<double>(r[2] * sc), N1 = warp_sum<double>(r[3] * sc);
-  const double E0 = warp_sum<double>(r[4]), E1 = warp_sum<double>(r[5]);
-  const double dev = -warp_min<double>(-r[6]), cand = warp_sum<double>(r[7]);
   const double den = S + sp.eps_floor * (double)sp.k_total;
   const double u0 = u_nom0 + (N0 + sp.eps_floor * E0) / den, u1 = u_nom1 + (N1 + sp.eps_floor * E1) / den;
   // the reference lets NaN propagate silently; here a non-finite input or an empty softmin support (S == 0 can
@@ -267,13 +298,15 @@ __global__ void __launch_bounds__(256) reduce_softmin_kernel(const __grid_consta
   if (tid == 0) {
     double s0, s1;
     floor_scale(a.sp, a.fin.dyn, s0, s1);
-    double* r = a.record + (size_t)t * kRecordStride;
-    r[0] = m;
-    r[1] = v5[0];
-    r[2] = v5[1];
-    r[3] = v5[2];
-    r[4] = v5[3] * s0;
-    r[5] = v5[4] * s1;
+    if (!a.fused) {   // split-phase step: the record is exchanged by the host's transport
+      double* r = a.record + (size_t)t * kRecordStride;
+      r[0] = m;
+      r[1] = v5[0];
+      r[2] = v5[1];
+      r[3] = v5[2];
+      r[4] = v5[3] * s0;
+      r[5] = v5[4] * s1;
+    }
     rowbuf[0] = m;
     rowbuf[1] = v5[0];
     rowbuf[2] = v5[1];
@@ -604,19 +637,17 @@ __global__ void __launch_bounds__(256) reduce_screen_kernel(const __grid_constan
     if (lane == 0) {
       const double s0 = sp.noise_external ? 1.0 : (double)std0 / kZFixScale;   // integer floor sums of z -> sums of eps
       const double s1 = sp.noise_external ? 1.0 : (double)std1 / kZFixScale;
-      double* r = a.record + (size_t)t * kRecordStride;
-      r[0] = m64;
-      r[1] = overflow ? -1.0 : S;   // S < 0 marks a candidate-list overflow for every rank that merges this record
-      r[2] = N0;
-      r[3] = N1;
-      r[4] = E0 * s0;
-      r[5] = E1 * s1;
-      if (a.fused) {   // statistics travel with the row
+      // S < 0 marks a candidate-list overflow for every rank that merges this record
+      const double rec[6] = {m64, overflow ? -1.0 : S, N0, N1, E0 * s0, E1 * s1};
+      if (a.fused) {   // the row (record + statistics) goes through the exchange
 #pragma unroll
-        for (int i = 0; i < 6; ++i) rowbuf[i] = r[i];
+        for (int i = 0; i < 6; ++i) rowbuf[i] = rec[i];
         rowbuf[6] = dev;
         rowbuf[7] = (double)n;
-      } else {
+      } else {        // split-phase step: the record is exchanged by the host's transport
+        double* r = a.record + (size_t)t * kRecordStride;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) r[i] = rec[i];
         atomicAdd(&a.fin.dyn->refine_candidates, n);
         if (overflow) atomicOr(&a.fin.dyn->refine_overflow, 1);
         // max of non-negative doubles == max of their bit patterns
