@@ -1574,7 +1574,16 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
     e->flush_bytes = (size_t)256 << 20;   // > 126 MB L2
     CK(cudaMalloc(&e->d_flush, e->flush_bytes));
   }
-  for (int i = 0; i < warmup; ++i) CK(cudaGraphLaunch(e->g_loop, e->stream));
+  // MPPI_B200_BENCH=eager: the two kernels of a step are launched directly instead of through the captured graph (the host
+  // runs far ahead of the device in this loop either way; experiment on the device-side start latency / jitter of the two)
+  const char* bm = getenv("MPPI_B200_BENCH");
+  const bool eager = bm && !strcmp(bm, "eager");
+  auto launch_step = [&]() -> mppi_status {
+    if (eager) return launch_local(e, e->stream, e->p.precision, FUSE_LOOP, nullptr);
+    CK(cudaGraphLaunch(e->g_loop, e->stream));
+    return MPPI_OK;
+  };
+  for (int i = 0; i < warmup; ++i) CKS(launch_step());
   CK(cudaStreamSynchronize(e->stream));
   std::vector<cudaEvent_t> ev((size_t)2 * steps);
   for (auto& v : ev) CK(cudaEventCreate(&v));
@@ -1582,7 +1591,7 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
     if (flush_l2) CK(flush_l2_launch(e->stream, e->d_flush, e->flush_bytes, (unsigned)(i & 0xff)));
     CKS(rendezvous(e));
     CK(cudaEventRecord(ev[2 * i], e->stream));
-    CK(cudaGraphLaunch(e->g_loop, e->stream));
+    CKS(launch_step());
     CK(cudaEventRecord(ev[2 * i + 1], e->stream));
   }
   CK(cudaStreamSynchronize(e->stream));
