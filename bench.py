@@ -297,7 +297,7 @@ def run_single(args):
         "data": "synthetic",
         "config": {"workload": "diff-drive parallel-park K=%d T=%d (BASELINE.json configs[1])" % (K, T), "K": K, "T": T,
                    "precision": args.precision, "weighting": "cost_to_go (reference)", "noise": "Philox4x32-10 in registers, 6 normals (3 steps x 2 channels) per call",
-                   "l2": "flushed between timed steps (256 MiB overwritten by a store kernel outside the timed intervals)",
+                   "l2": "flushed between timed steps, outside the timed intervals: 256 MiB overwritten, then 256 MiB of clean lines read (the step starts cold but is not charged the write-back of the flush's own dirty lines)",
                    "loop": "closed loop on the model, state resident in HBM", "launch": r["launch"]},
         "state_steps_per_s": value * T,
         "e2e": {"value": K / (r["e2e_ms"] * 1e-3), "unit": "rollouts/s", "h2d_bytes_per_step": r["io"][0],

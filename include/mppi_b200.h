@@ -259,7 +259,8 @@ MPPI_API mppi_status mppi_measure_fp32_peak(int32_t device, double* tflops, doub
 
 /* bytes mppi_step moves per call: host->device (x0, goal) and device->host (result block). */
 MPPI_API mppi_status mppi_io_bytes(mppi_handle h, size_t* h2d, size_t* d2h);
-/* measurement aid: overwrite a 256 MiB device buffer (> L2) and synchronise, so the next step starts cache-cold. */
+/* measurement aid: overwrite 256 MiB (> L2), then read 256 MiB of clean lines, and synchronise: the next step starts
+ * cache-cold without inheriting the write-back of the flush's own dirty lines. */
 MPPI_API mppi_status mppi_debug_flush_l2(mppi_handle h);
 /* launch configuration of the rollout kernel (diagnostics): block, grid, tiles, dynamic smem, CTAs/SM, regs,
  * code path (0 general, 1 fast, 2 lean), reserved */

@@ -1571,8 +1571,9 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
   int ovf_before = 0;
   CK(memcpy_on(e, &ovf_before, &e->d_dyn->overflow_total, sizeof(int), cudaMemcpyDeviceToHost));
   if (flush_l2 && !e->d_flush) {
-    e->flush_bytes = (size_t)256 << 20;   // > 126 MB L2
+    e->flush_bytes = (size_t)512 << 20;   // 256 MiB overwritten + 256 MiB read, each > 126 MB L2 (reduce.cu: flush_l2_kernel)
     CK(cudaMalloc(&e->d_flush, e->flush_bytes));
+    CK(cudaMemset(e->d_flush, 0, e->flush_bytes));
   }
   // MPPI_B200_BENCH=eager: the two kernels of a step are launched directly instead of through the captured graph (the host
   // runs far ahead of the device in this loop either way; experiment on the device-side start latency / jitter of the two)
@@ -1689,8 +1690,9 @@ extern "C" mppi_status mppi_io_bytes(mppi_handle e, size_t* h2d, size_t* d2h) {
 extern "C" mppi_status mppi_debug_flush_l2(mppi_handle e) {
   ENTER(e);
   if (!e->d_flush) {
-    e->flush_bytes = (size_t)256 << 20;   // > 126 MB L2
+    e->flush_bytes = (size_t)512 << 20;   // 256 MiB overwritten + 256 MiB read, each > 126 MB L2 (reduce.cu: flush_l2_kernel)
     CK(cudaMalloc(&e->d_flush, e->flush_bytes));
+    CK(cudaMemset(e->d_flush, 0, e->flush_bytes));
   }
   CK(flush_l2_launch(e->stream, e->d_flush, e->flush_bytes, (unsigned)(e->seq & 0xff)));
   CKS(rendezvous(e));
