@@ -227,6 +227,10 @@ __device__ __forceinline__ void ll_exchange_row(const ReduceArgs& a, int t, cons
   out[3] = cand;
   out[4] = dev;
   out[5] = 0.0;
+  if (sys) {   // the butterflies over `world` lanes leave the full result in the lanes below the next power of two only
+#pragma unroll
+    for (int k = 0; k < kRow2Doubles; ++k) out[k] = __shfl_sync(0xffffffffu, out[k], 0);
+  }
   if (lane < kRow2Words) {
     const double v = out[lane >> 1];
     const unsigned int w = (lane & 1) ? (unsigned int)__double2hiint(v) : (unsigned int)__double2loint(v);
