@@ -499,8 +499,9 @@ def run_multi(args):
             "config": {"workload": "diff-drive parallel-park K=%d per GPU (K_total=%d) T=%d, rollouts sharded over ranks, "
                                    "one %d-byte record exchanged all-to-all per step" % (K_PER_GPU, K_total, T, xbytes),
                        "K_total": K_total, "T": T, "precision": args.precision,
-                       "exchange": {"p2p": "fused: every reduce block stores its row of the record into every peer's memory over NVLink "
-                                           "(CUDA IPC) and raises a per-row flag; the finalize phase waits on the rows; one CUDA graph per rank",
+                       "exchange": {"p2p": "fused: every reduce block stores its row of the record into every peer's memory over NVLink (CUDA IPC) "
+                                           "as flag-in-data words, merges the peers' rows of its own t, and the finalizer block reads T "
+                                           "merged rows; two kernels per rank, no collective call",
                                     "nccl": "ncclAllGather of the device-resident records (torch.distributed)",
                                     "host": "host-staged all-gather"}[exchange],
                        "l2": "flushed between timed steps", "timing": timing, "launch": launch_info},
