@@ -368,13 +368,13 @@ def _sharded_parity(mp, dist, torch, m, rank, local, K_total, T, precision, step
 def _bench_sharded(args, dist, torch, m, steps):
     """device-timed closed loop of a sharded engine (max over ranks is taken by the caller)"""
     if m.exchange == "p2p":
-        # the exchange lives inside the per-rank CUDA graph: time the device-resident closed loop with CUDA
-        # events on the engine's launch stream (ranks run in lockstep through the arrival flags)
+        # the exchange lives inside the reduce kernel: time the device-resident closed loop with CUDA events on the
+        # engine's launch stream (ranks run in lockstep through the rows' flags)
         m.mppi.goal = GOAL
         dist.barrier()
         torch.cuda.synchronize()
         r = m.mppi.bench(X0, steps=steps, warmup=args.warmup, flush_l2=True, per_kernel=False)
-        return r["step_ms"], r["launches"], "CUDA events on the engine's launch stream around each graph launch, max over ranks", r
+        return r["step_ms"], r["launches"], "CUDA events on the engine's launch stream around the two launches of each step, max over ranks", r
     s = X0.copy()
     for _ in range(args.warmup):
         s = m.get_path(s, GOAL)

@@ -247,7 +247,8 @@ typedef struct {
 } mppi_timing;
 
 /* Device-resident closed loop on the model (x0 <- x_next on the device, as solve_path does,
- * control/src/mppi:117-119): `warmup` untimed + `steps` timed steps; inputs never leave HBM.
+ * control/src/mppi:117-119): `warmup` untimed + `steps` timed steps; inputs never leave HBM.  The two kernels of a step are
+ * launched back to back by a host that runs ahead of the device (MPPI_B200_BENCH=graph replays a captured CUDA graph instead).
  * flush_l2 != 0 writes a > L2-sized buffer between timed steps (outside the timed intervals).
  * per_kernel != 0 additionally brackets every kernel with events (eager launches). */
 MPPI_API mppi_status mppi_bench(mppi_handle h, const double x0[3], int32_t steps, int32_t warmup,

@@ -3,8 +3,8 @@
 // One engine = one CUDA device.  A step (= MPPI.get_path, control/src/mppi:85-102) is TWO kernel launches and no copy:
 //   rollout_{lean,lean_sm,}_kernel --PDL--> reduce_{softmin,screen}_kernel (+ exchange and finalize in its last block)
 // x0 / goal ride in the kernels' argument buffers, the result block is stored by the finalize phase into mapped pinned
-// host memory; all controller state (nominal U, noise step counter) stays resident in HBM.  mppi_bench replays the same
-// two launches from a CUDA graph with x0 resident on the device (closed loop on the model).
+// host memory; all controller state (nominal U, noise step counter) stays resident in HBM.  mppi_bench issues the same two
+// launches with x0 resident on the device (closed loop on the model; optionally from a captured CUDA graph).
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -1566,7 +1566,10 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
     return MPPI_ERR_STATE;
   }
   CKS(pre_step(e, x0));
-  CKS(build_graphs(e));
+  {
+    const char* bm0 = getenv("MPPI_B200_BENCH");
+    if (bm0 && !strcmp(bm0, "graph")) CKS(build_graphs(e));
+  }
   CK(memcpy_on(e, e->d_dyn, e->h_in, 6 * sizeof(double), cudaMemcpyHostToDevice));
   int ovf_before = 0;
   CK(memcpy_on(e, &ovf_before, &e->d_dyn->overflow_total, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1575,10 +1578,12 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
     CK(cudaMalloc(&e->d_flush, e->flush_bytes));
     CK(cudaMemset(e->d_flush, 0, e->flush_bytes));
   }
-  // MPPI_B200_BENCH=eager: the two kernels of a step are launched directly instead of through the captured graph (the host
-  // runs far ahead of the device in this loop either way; experiment on the device-side start latency / jitter of the two)
+  // The two kernels of a step are launched directly; MPPI_B200_BENCH=graph replays them from the captured CUDA graph instead.
+  // The host runs far ahead of the device in this loop either way, and measured on this part the graph's device-side start
+  // latency is the longer one: 39.2 us per step through the graph against 38.8 us eager at N = 1, 54.0 against 52.9 us at
+  // N = 8 (profiles/README.md) -- a graph saves HOST launch time, which is not on this loop's critical path.
   const char* bm = getenv("MPPI_B200_BENCH");
-  const bool eager = bm && !strcmp(bm, "eager");
+  const bool eager = !(bm && !strcmp(bm, "graph"));
   auto launch_step = [&]() -> mppi_status {
     if (eager) return launch_local(e, e->stream, e->p.precision, FUSE_LOOP, nullptr);
     CK(cudaGraphLaunch(e->g_loop, e->stream));
