@@ -30,7 +30,8 @@ for prec in ("mixed", "f32"):
         x[:] = xn
     wall = (time.perf_counter() - t0) / steps * 1e6
     lib.mppi_debug_host_timing(h, _capi.dptr(out))
-    m.initialize()          # the device-resident loop restarts from x0 = 0 with a zero nominal
+    m.initialize()          # the device-resident loop restarts from x0 = 0 with a zero nominal ...
+    m.goal = goal           # ... towards the same goal (bench() sends the attribute, the loop above set it through the C ABI)
     dev = m.bench(np.zeros(3), steps=50, warmup=5, flush_l2=False, per_kernel=False)["step_ms"] * 1e3
     print("%s K=%d T=%d: wall %.2f us per mppi_step (warm L2, python loop); inside the call: to rollout launched %.2f, "
           "to reduce launched %.2f, to result seen %.2f, to return %.2f (sum %.2f); device-resident step %.2f us"
