@@ -222,9 +222,10 @@ MPPI_API mppi_status mppi_step_finish(mppi_handle h, double u_out[2], double x_n
 
 /* ---- fused peer-to-peer exchange over NVLink (ranks of one node) --------------------------------------
  * Instead of a collective call between mppi_step_local and mppi_step_finish, the ranks map each other's
- * exchange buffers (CUDA IPC): the reduce kernel of rank r stores its record straight into every peer's
- * buffer and raises an arrival flag, the finalize kernel spins on its own flags.  After connecting,
- * mppi_step / mppi_bench work for world_size > 1 and the whole sharded step is ONE CUDA graph per rank.
+ * row buffers (CUDA IPC): every block of rank r's reduce kernel stores the row of its time step straight into every peer's
+ * buffer as flag-in-data words (8-byte stores carrying 4 bytes of payload and the step's flag: no fence, no arrival flag),
+ * merges the peers' rows of the same time step, and the finalizer block of the same kernel finishes the update.  After
+ * connecting, mppi_step / mppi_bench work for world_size > 1 and the whole sharded step is TWO kernel launches per rank.
  *   1. every rank: mppi_p2p_export(h, handle)      -- 64-byte cudaIpcMemHandle_t of its buffer
  *   2. all-gather the handles by any means (rank-major, world_size x 64 bytes)
  *   3. every rank: mppi_p2p_connect(h, all_handles)                                                  */

@@ -98,7 +98,7 @@ struct DynState {
   double last_max_dev;
   double last_head;      // head-room of the screening window of the last finished step
   int overflow_total;    // steps that hit a candidate-list overflow since creation
-  unsigned int xchg;     // p2p exchange epoch: +1 per step, never rewound (arrival flags carry xchg+1)
+  unsigned int xchg;     // row-exchange epoch: +1 per step, never rewound (the rows' flag-in-data words carry xchg + 1)
   // fp32 mirrors of lam / noise_std kept by the host (LEAN rollout prologue: no fp64 division, no conversions)
   float neg_inv_lam_f;
   float noise_std_f[2];

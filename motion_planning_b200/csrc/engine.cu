@@ -1,7 +1,7 @@
 // engine.cu -- host side of libmppi_b200.so: the C ABI declared in include/mppi_b200.h.
 //
 // One engine = one CUDA device.  A step (= MPPI.get_path, control/src/mppi:85-102) is TWO kernel launches and no copy:
-//   rollout_{lean,lean_sm,}_kernel --PDL--> reduce_{softmin,screen}_kernel (+ exchange and finalize in its last block)
+//   rollout_{lean,lean_sm,}_kernel --PDL--> reduce_{softmin,screen}_kernel (T row blocks with the row exchange + 1 finalizer block)
 // x0 / goal ride in the kernels' argument buffers, the result block is stored by the finalize phase into mapped pinned
 // host memory; all controller state (nominal U, noise step counter) stays resident in HBM.  mppi_bench issues the same two
 // launches with x0 resident on the device (closed loop on the model; optionally from a captured CUDA graph).
@@ -916,7 +916,7 @@ static FinalizeArgs make_fin(mppi_engine* e, bool closed_loop) {
 
 enum FuseMode { FUSE_NONE = 0, FUSE_STEP = 1, FUSE_LOOP = 2 };
 
-// rollout + reduce (+ finalize fused into the reduce kernel's last block when fuse != FUSE_NONE)
+// rollout + reduce (+ row exchange and the finalizer block inside the reduce kernel when fuse != FUSE_NONE)
 // `in` != nullptr: x0 / goal travel as kernel arguments and the result is published to e->h_res under e->seq
 static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, int fuse, KernelEvents* kev,
                                 const StepInput* in = nullptr) {
@@ -1611,7 +1611,7 @@ extern "C" mppi_status mppi_bench(mppi_handle e, const double x0[3], int32_t ste
   mppi_timing t{};
   t.step_ms = (float)(total / steps);
   t.steps = steps;
-  t.launches = 2 * steps;   // rollout + reduce (exchange and finalize run in the reduce kernel's last block)
+  t.launches = 2 * steps;   // rollout + reduce (row exchange and finalize run inside the reduce kernel)
   if (per_kernel) {
     KernelEvents kev;
     kev.on = true;

@@ -46,10 +46,10 @@ class _DevBuf(object):
 class ShardedMPPI(object):
     """`MPPI` whose `samples` are sharded over the ranks of a torch.distributed process group.
 
-    exchange='p2p'  (default with the nccl backend): the ranks map each other's exchange buffers through
-                    CUDA IPC once; afterwards the reduce kernel stores the record straight into every
-                    peer's memory over NVLink and the finalize kernel spins on arrival flags -- the whole
-                    sharded step is one CUDA graph per rank and no collective is called per step.
+    exchange='p2p'  (default with the nccl backend): the ranks map each other's row buffers through CUDA IPC once;
+                    afterwards every reduce block stores the row of its time step straight into every peer's memory over
+                    NVLink as flag-in-data words, merges the peers' rows of the same step, and the finalizer block of each
+                    rank's reduce kernel finishes the update -- two kernels per rank and no collective call per step.
     exchange='nccl' all-gathers the device-resident records in place with NCCL (engine kernels and the
                     collective share one stream, no host sync in between).
     exchange='host' stages the 3 KB record through host memory (works with any backend, e.g. gloo).
