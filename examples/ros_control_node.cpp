@@ -22,9 +22,22 @@ int main(int argc, char** argv) {
   mppi::DiffDrive robot;                                    // control/src/mppi:18-20
   // 4th argument "user": the same robot as a caller-supplied ODE functor -- the reference's registerODE / model= hook
   // (control/include/control/rk4.hpp:32,58; control/src/mppi:62,66) -- compiled at run time for this GPU
+  //               "kinematic": the robot as a kinematic functor (speed and yaw rate from the wheel speeds), which runs the
+  //               headline mixed-precision pipeline
   const bool user = argc > 4 && !std::strcmp(argv[4], "user");
+  const bool kinematic = argc > 4 && !std::strcmp(argv[4], "kinematic");
   std::unique_ptr<mppi::MPPI> engine_ptr;
-  if (user) {
+  if (kinematic) {
+    const double r = robot.wheel_radius, L = robot.wheel_base, wmax = 6.35492;
+    mppi::UserKinematics dyn(
+        "template <typename R> __device__ void mppi_user_speed_yaw(const R u[2], R* speed, R* yaw_rate) {\n"
+        "  *speed = R(0.5 * 0.033) * (u[0] + u[1]);\n"
+        "  *yaw_rate = R(0.033 / 0.16) * (u[1] - u[0]);\n"
+        "}\n",
+        /*speed bound=*/r * wmax, /*yaw-rate bound=*/r / L * 2 * wmax);
+    engine_ptr.reset(new mppi::MPPI(dyn, mppi::QuadraticCost(), K, T));   // Options().precision = MIXED
+    std::printf("dynamics: user-supplied kinematic functor (NVRTC), precision mixed\n");
+  } else if (user) {
     mppi::UserDynamics dyn(
         "template <typename R> __device__ void mppi_user_ode(const R x[3], const R u[2], R xdot[3]) {\n"
         "  const R r = R(0.033), L = R(0.16);\n"

@@ -84,6 +84,8 @@ struct UserDynamics {
   bool wrap_theta = true;      // control/src/mppi:52-53
   double u_max0 = 6.35492, u_max1 = 6.35492;
   double noise_std0 = 0.9, noise_std1 = 0.9;
+  int kind = 0;                // mppi_user_model.kind: 0 ODE functor, 1 kinematic functor (UserKinematics below)
+  double speed_max = 0.0, yaw_rate_max = 0.0;
   UserDynamics() = default;
   explicit UserDynamics(std::string src) : ode_source(std::move(src)) {}
   void apply(mppi_params& p) const {
@@ -92,6 +94,22 @@ struct UserDynamics {
     p.u_max[1] = u_max1;
     p.noise_std[0] = noise_std0;
     p.noise_std[1] = noise_std1;
+  }
+};
+
+// A caller-supplied KINEMATIC model: forward speed and yaw rate as functions of the controls,
+//   template <typename R> __device__ void mppi_user_speed_yaw(const R u[2], R* speed, R* yaw_rate) { ... }
+// for xdot = speed cos(theta), ydot = speed sin(theta), thetadot = yaw_rate -- the family dd_dynamics / unicycle_dynamics
+// (control/src/mppi:23-36) belong to.  The functor is dropped into the built-in kernels: every precision works, MIXED included
+// (give speed_max / yaw_rate_max, bounds of |speed| and |yaw_rate| over the clipped controls).  integrator 0 = rk4 with the theta
+// wrap (:39-54), 1 = Euler without (:57-58).
+struct UserKinematics : UserDynamics {
+  UserKinematics(std::string src, double speed_bound, double yaw_rate_bound, int integrator_ = 0) : UserDynamics(std::move(src)) {
+    kind = 1;
+    integrator = integrator_;
+    wrap_theta = integrator_ == 0;
+    speed_max = speed_bound;
+    yaw_rate_max = yaw_rate_bound;
   }
 };
 
@@ -156,17 +174,21 @@ class MPPI {
     p.device = opt.device;
     dyn.apply(p);
     cost.apply(p);
-    constexpr bool user_dyn = std::is_same<Dynamics, UserDynamics>::value, user_cost = std::is_same<Cost, UserCost>::value;
+    constexpr bool user_dyn = std::is_base_of<UserDynamics, Dynamics>::value, user_cost = std::is_same<Cost, UserCost>::value;
     static_assert(user_dyn || !user_cost, "a UserCost functor needs UserDynamics (the kernels are instantiated for the pair)");
     if constexpr (user_dyn) {
       std::string text = dyn.ode_source;
       if constexpr (user_cost) text += "\n" + cost.source;
-      mppi_user_model um;
+      mppi_user_model um = {};
       um.source = text.c_str();
       um.integrator = dyn.integrator;
       um.wrap_theta = dyn.wrap_theta ? 1 : 0;
       um.has_cost = user_cost ? 1 : 0;
-      if (p.precision == MPPI_PRECISION_MIXED) p.precision = MPPI_PRECISION_F64;   // user models: F64 (default) or F32
+      um.kind = dyn.kind;
+      um.speed_max = dyn.speed_max;
+      um.yaw_rate_max = dyn.yaw_rate_max;
+      // MIXED needs a kinematic functor with stated bounds and the built-in cost; otherwise F64 (the default of user models)
+      if (p.precision == MPPI_PRECISION_MIXED && !(dyn.kind == 1 && !user_cost && dyn.speed_max > 0)) p.precision = MPPI_PRECISION_F64;
       check(mppi_create_user(&p, &um, &h_), "mppi_create_user");
     } else {
       check(mppi_create(&p, &h_), "mppi_create");

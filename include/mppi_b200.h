@@ -122,8 +122,14 @@ MPPI_API mppi_status mppi_destroy(mppi_handle h);
  * (control/include/control/rk4.hpp:32,58).  Here the functor is CUDA source text, compiled for sm_100a at run time (NVRTC)
  * into its own instantiation of the rollout / reduce / finalize kernels:
  *
- *   required   template <typename R> __device__ void mppi_user_ode(const R x[3], const R u[2], R xdot[3]);
- *   optional   (has_cost != 0)
+ *   kind 0     template <typename R> __device__ void mppi_user_ode(const R x[3], const R u[2], R xdot[3]);
+ *              an arbitrary ODE of (x, y, theta), integrated by the generic integrator below; precision F64 or F32
+ *   kind 1     template <typename R> __device__ void mppi_user_speed_yaw(const R u[2], R* speed, R* yaw_rate);
+ *              a KINEMATIC functor: xdot = speed(u) cos(theta), ydot = speed(u) sin(theta), thetadot = yaw_rate(u) -- the family
+ *              every built-in model belongs to (dd_dynamics, unicycle_dynamics: control/src/mppi:23-36).  It is dropped into the
+ *              built-in kernels, so all three precisions work (the fp32 screen of MIXED needs speed_max / yaw_rate_max, bounds
+ *              of |speed| and |yaw_rate| over the clipped controls) and a functor that restates a built-in model reproduces it
+ *   optional   (has_cost != 0; precision F64 or F32)
  *              template <typename R> __device__ R mppi_user_running_cost(const R x[3], const R goal[3], const R u_nom[2],
  *                                                                       const R eps[2], int t);
  *              template <typename R> __device__ R mppi_user_terminal_cost(const R x[3], const R goal[3]);
@@ -132,13 +138,16 @@ MPPI_API mppi_status mppi_destroy(mppi_handle h);
  * eps = the sample's noise.  R is float or double (both are instantiated).  Without a cost functor the reference's quadratic
  * cost (Q, R, P1 of mppi_params, control/src/mppi:165-171,180-184) applies.  integrator: 0 = classic RK4 with the control
  * held over the step (control/src/mppi:39-50), 1 = explicit Euler (:57-58); wrap_theta != 0 wraps theta into (-pi, pi] after
- * every step (:52-53).  Precision F64 or F32 (the fp32 screen of MIXED relies on properties of the built-in models).
- * params->model is ignored (set to MPPI_MODEL_USER).  Compilation errors: MPPI_ERR_INVALID, text in mppi_last_error(). */
+ * every step (:52-53); a kind-1 functor is integrated like the built-in models: integrator 0 = rk4 WITH the wrap, 1 = Euler
+ * WITHOUT it (wrap_theta must say the same).  params->model is ignored (set to MPPI_MODEL_USER).  Compilation errors: MPPI_ERR_INVALID, text in mppi_last_error(). */
 typedef struct {
   const char* source;        /* CUDA C++ text defining the functions above */
   int32_t integrator;        /* 0 RK4, 1 explicit Euler */
   int32_t wrap_theta;
   int32_t has_cost;
+  int32_t kind;              /* 0 ODE functor, 1 kinematic functor */
+  double speed_max;          /* kind 1 with precision MIXED: max |speed| over the clipped controls */
+  double yaw_rate_max;       /* kind 1 with precision MIXED: max |yaw_rate| over the clipped controls */
 } mppi_user_model;
 MPPI_API mppi_status mppi_create_user(const mppi_params* p, const mppi_user_model* um, mppi_handle* out);
 /* Compile a functor text without creating an engine (needs no GPU): MPPI_OK, or MPPI_ERR_INVALID with the compiler's log in

@@ -39,7 +39,8 @@ class MppiParams(C.Structure):
 
 class MppiUserModel(C.Structure):
     """mirror of `mppi_user_model`."""
-    _fields_ = [("source", C.c_char_p), ("integrator", C.c_int32), ("wrap_theta", C.c_int32), ("has_cost", C.c_int32)]
+    _fields_ = [("source", C.c_char_p), ("integrator", C.c_int32), ("wrap_theta", C.c_int32), ("has_cost", C.c_int32),
+                ("kind", C.c_int32), ("speed_max", C.c_double), ("yaw_rate_max", C.c_double)]
 
 
 class MppiTiming(C.Structure):

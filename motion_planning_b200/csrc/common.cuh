@@ -360,7 +360,7 @@ struct ModelConsts {
   R x0, y0;     // start position of the step: a user ODE (MPPI_MODEL_USER) sees absolute coordinates
 };
 
-#ifdef MPPI_USER_MODEL
+#if defined(MPPI_USER_MODEL) && !defined(MPPI_USER_KINEMATIC)
 // ---- caller-supplied functors (mppi_create_user; the text is compiled together with these headers by NVRTC) ----------
 //   template <typename R> __device__ void mppi_user_ode(const R x[3], const R u[2], R xdot[3]);
 //   (MPPI_USER_COST)  mppi_user_running_cost<R>(x, goal, u_nom, eps, t),  mppi_user_terminal_cost<R>(x, goal)
@@ -395,8 +395,29 @@ __device__ __forceinline__ void user_integrate(R dt, const R x[3], const R u[2],
 }
 #endif
 
+// true for the models integrated by explicit Euler without a theta wrap (control/src/mppi:57-58): the reference's unicycle, and a
+// caller's kinematic functor that asks for it
+template <int MODEL>
+struct EulerLike {
+#if defined(MPPI_USER_KINEMATIC) && MPPI_USER_INTEGRATOR == 1
+  static constexpr bool value = MODEL == MPPI_MODEL_UNICYCLE_EULER || MODEL == MPPI_MODEL_USER;
+#else
+  static constexpr bool value = MODEL == MPPI_MODEL_UNICYCLE_EULER;
+#endif
+};
+
 template <typename R, int MODEL>
 __device__ __forceinline__ void speed_yaw(const ModelConsts<R>& mc, R u0, R u1, R& s, R& w) {
+#ifdef MPPI_USER_KINEMATIC
+  // a caller's KINEMATIC functor (mppi_create_user, kind 1): forward speed and yaw rate as functions of the controls --
+  //   xdot = s(u) cos(theta), ydot = s(u) sin(theta), thetadot = w(u)
+  // the family all built-in models belong to; everything else (integrator, screen, fp64 re-evaluation) is the built-in code
+  if (MODEL == MPPI_MODEL_USER) {
+    const R u[2] = {u0, u1};
+    mppi_user_speed_yaw<R>(u, &s, &w);
+    return;
+  }
+#endif
   if (MODEL == MPPI_MODEL_DIFF_DRIVE) {          // dd_dynamics, control/src/mppi:23-30
     s = mc.half_r * (u0 + u1);
     w = mc.r_over_L * (u1 - u0);
@@ -421,7 +442,7 @@ __device__ __forceinline__ void speed_yaw(const ModelConsts<R>& mc, R u0, R u1, 
 // the increment's sin/cos are plain polynomials and one wrap turn suffices: no branch in the step.
 template <typename R, int MODEL, bool FAST = false>
 __device__ __forceinline__ void model_step(const ModelConsts<R>& mc, R u0, R u1, R& dx, R& dy, R& th, R& c, R& s) {
-#ifdef MPPI_USER_MODEL
+#if defined(MPPI_USER_MODEL) && !defined(MPPI_USER_KINEMATIC)
   if (MODEL == MPPI_MODEL_USER) {   // the caller's ODE through the generic integrator; (c, s) are not carried
     const R x[3] = {mc.x0 + dx, mc.y0 + dy, th}, u[2] = {u0, u1};
     R xn[3];
@@ -435,7 +456,7 @@ __device__ __forceinline__ void model_step(const ModelConsts<R>& mc, R u0, R u1,
   R spd, w;
   speed_yaw<R, MODEL>(mc, u0, u1, spd, w);
   const R kth = mc.dt * w;
-  if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {       // euler, control/src/mppi:57-58 (no wrap)
+  if (EulerLike<MODEL>::value) {                  // euler, control/src/mppi:57-58 (no wrap)
     dx = Math<R>::fma_(mc.dt * spd, c, dx);
     dy = Math<R>::fma_(mc.dt * spd, s, dy);
     th = th + kth;

@@ -115,6 +115,8 @@ struct mppi_engine {
   size_t flush_bytes = 0;
   KindCfg cfg[3];
   bool user_has_cost = false;
+  int user_kind = 0;                        // 0 ODE functor, 1 kinematic functor (mppi_user_model.kind)
+  double user_speed_max = 0, user_yaw_max = 0;   // kind 1: bounds of |speed|, |yaw rate| (the screening window of MIXED)
   UserKernels* user = nullptr;   // MPPI_MODEL_USER: the step's kernels instantiated at run time for the caller's functors
   // pinned host staging
   double* h_in = nullptr;      // x0[3], goal[3]
@@ -215,8 +217,9 @@ static void set_window(mppi_engine* e, double lam) {
   } else if (sp.model == MPPI_MODEL_BICYCLE) {
     v = sp.u_max[0];
     w = sp.u_max[0] * std::tan(std::fmin(sp.u_max[1], 1.55)) / sp.wheel_L;
-  } else {
-    v = w = 0.0;   // MPPI_MODEL_USER: no fp32 screen (precision MIXED is refused), the window is not used
+  } else {   // MPPI_MODEL_USER: a kinematic functor states its bounds (an ODE functor has no fp32 screen; the window is not used)
+    v = e->user_speed_max;
+    w = e->user_yaw_max;
   }
   const double D = v * horizon, Th = w * horizon;
   const double cA = sp.T * 0.5 * std::fmax(sp.q[0], sp.q[1]) + std::fmax(sp.p1[0], sp.p1[1]);
@@ -279,15 +282,15 @@ static bool try_configure(mppi_engine* e, int gin, size_t* max_ctas) {
   for (int kind = 0; kind < 3; ++kind) {
     KindCfg best;
     double best_cost = 1e300;
-    if (e->user) {   // run-time instantiation: general code path, tiles of 64, soft-min families only
-      if (kind != ROLLOUT_F32_SCREEN) {
+    if (e->user) {   // run-time instantiation: general code path, tiles of 64; the screen family for kinematic functors only
+      if (kind != ROLLOUT_F32_SCREEN || e->user_kind == 1) {
         KindCfg c;
         c.variant = ROLLOUT_GENERAL;
         c.block = 64;
         c.ntiles = (sp.K + 63) / 64;
         c.smem = rollout_smem(kind, sp.T, 64, ROLLOUT_GENERAL, gin);
         if (c.smem <= 227 * 1024 &&
-            user_rollout_prepare(e->user, kind == ROLLOUT_F64_SOFTMIN, has_grid, c.smem, &c.ctas_per_sm, &c.regs) == cudaSuccess &&
+            user_rollout_prepare(e->user, kind, has_grid, c.smem, &c.ctas_per_sm, &c.regs) == cudaSuccess &&
             c.ctas_per_sm >= 1) {
           const long long resident = (long long)e->num_sms * c.ctas_per_sm;
           c.grid = (int)((c.ntiles < resident) ? c.ntiles : resident);
@@ -495,9 +498,16 @@ static mppi_status create_impl(const mppi_params* pin, const mppi_user_model* um
     return MPPI_ERR_INVALID;
   }
   if (um && p.precision == MPPI_PRECISION_MIXED) {
-    set_err("a user-defined model runs with precision F64 or F32: the fp32 screen of MIXED (delta-form cost, time-parallel fp64 "
-            "re-evaluation) relies on properties of the built-in models");
-    return MPPI_ERR_UNSUPPORTED;
+    if (um->kind != 1 || um->has_cost) {
+      set_err("precision MIXED needs a KINEMATIC functor (mppi_user_model.kind 1) and the built-in cost: its fp32 screen (delta-form "
+              "cost, time-parallel fp64 re-evaluation) relies on xdot = s(u) cos(theta), ydot = s(u) sin(theta), thetadot = w(u); "
+              "use precision F64 or F32");
+      return MPPI_ERR_UNSUPPORTED;
+    }
+    if (!(um->speed_max > 0) || !(um->yaw_rate_max >= 0) || !std::isfinite(um->speed_max) || !std::isfinite(um->yaw_rate_max)) {
+      set_err("precision MIXED with a kinematic functor needs speed_max > 0 and yaw_rate_max >= 0 (bounds over the clipped controls)");
+      return MPPI_ERR_INVALID;
+    }
   }
   if (p.precision == MPPI_PRECISION_MIXED && p.T > 400) {
     set_err("precision MIXED supports T <= 400 (fp64 refinement scratch is 56*T bytes per warp); use F64 or F32");
@@ -564,6 +574,11 @@ static mppi_status create_impl(const mppi_params* pin, const mppi_user_model* um
   sp.eps_floor = p.eps_floor;
   sp.seed = p.seed;
   sp.g_inv_res = 1.0;
+  if (um) {
+    e->user_kind = um->kind;
+    e->user_speed_max = um->speed_max;
+    e->user_yaw_max = um->yaw_rate_max;
+  }
   set_window(e, p.lambda);
 
   const int T = p.T;
@@ -986,7 +1001,7 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   }
   if (kev && kev->on) CK(cudaEventRecord(kev->ev[0], st));
   if (e->user)
-    CK(user_rollout_launch(e->user, kind == ROLLOUT_F64_SOFTMIN, e->sp.has_grid != 0, c.grid, c.smem, st, ra));
+    CK(user_rollout_launch(e->user, kind, e->sp.has_grid != 0, c.grid, c.smem, st, ra));
   else
     CK(rollout_launch(kind, e->sp.model, e->sp.has_grid != 0, c.block, c.variant, c.grid, c.smem, st, ra));
   e->tp_launch1 = std::chrono::steady_clock::now();
@@ -1021,7 +1036,9 @@ static mppi_status launch_local(mppi_engine* e, cudaStream_t st, int precision, 
   rd.eps_ext = e->d_eps_ext;
   rd.record = e->d_record;
   rd.nCTA = c.nparts;
-  if (e->user)
+  if (e->user && kind == ROLLOUT_F32_SCREEN)
+    CK(user_reduce_screen_launch(e->user, e->sp.has_grid != 0, e->sp.T, st, rd));
+  else if (e->user)
     CK(user_reduce_softmin_launch(e->user, kind == ROLLOUT_F64_SOFTMIN, e->sp.T, st, rd));
   else if (kind == ROLLOUT_F32_SCREEN)
     CK(reduce_screen_launch(e->sp.model, e->sp.has_grid != 0, e->sp.T, st, rd));

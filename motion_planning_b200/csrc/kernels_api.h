@@ -39,8 +39,9 @@ struct UserKernels;
 mppi_status user_kernels_build(const mppi_user_model* um, UserKernels** out, std::string* err);
 void user_kernels_free(UserKernels* uk);
 mppi_status user_model_check(const mppi_user_model* um, std::string* err, size_t* cubin_bytes);
-cudaError_t user_rollout_prepare(const UserKernels* uk, bool f64, bool has_grid, size_t smem, int* ctas_per_sm, int* regs);
-cudaError_t user_rollout_launch(const UserKernels* uk, bool f64, bool has_grid, int grid, size_t smem, cudaStream_t st, const RolloutArgs& a);
+cudaError_t user_rollout_prepare(const UserKernels* uk, int kind, bool has_grid, size_t smem, int* ctas_per_sm, int* regs);
+cudaError_t user_rollout_launch(const UserKernels* uk, int kind, bool has_grid, int grid, size_t smem, cudaStream_t st, const RolloutArgs& a);
+cudaError_t user_reduce_screen_launch(const UserKernels* uk, bool has_grid, int T, cudaStream_t st, const ReduceArgs& a);
 cudaError_t user_reduce_softmin_launch(const UserKernels* uk, bool f64, int T, cudaStream_t st, const ReduceArgs& a);
 cudaError_t user_finalize_launch(const UserKernels* uk, cudaStream_t st, const FinalizeArgs& a);
 cudaError_t user_model_step_launch(const UserKernels* uk, cudaStream_t st, const StaticParams& sp, const double* x, const double* u, int n,

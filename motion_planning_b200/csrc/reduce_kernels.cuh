@@ -405,7 +405,7 @@ __device__ double resim_cost_to_go_f64(const StaticParams& sp, const DynState* d
       const double th_pre = carry + (s_thn[t] - v);
       const double spd = s_spd[t];
       double thn;
-      if (MODEL == MPPI_MODEL_UNICYCLE_EULER) {
+      if (EulerLike<MODEL>::value) {
         double sn, cs;
         Math<double>::sincos_(th_pre, sn, cs);
         ix = mc.dt * spd * cs;
@@ -712,9 +712,13 @@ __device__ void model_step_abs_f64(const StaticParams& sp, const double x[3], do
 
 __device__ inline void model_step_dispatch_f64(const StaticParams& sp, const double x[3], double u0, double u1, double out[3]) {
 #ifdef MPPI_USER_MODEL
-  if (sp.model == MPPI_MODEL_USER) {   // perform_action / the `model` functor with the caller's ODE
+  if (sp.model == MPPI_MODEL_USER) {   // perform_action / the `model` functor with the caller's functor
+#ifdef MPPI_USER_KINEMATIC
+    model_step_abs_f64<MPPI_MODEL_USER>(sp, x, u0, u1, out);
+#else
     const double u[2] = {u0, u1};
     user_integrate<double>(sp.dt, x, u, out);
+#endif
     return;
   }
 #endif

@@ -77,7 +77,12 @@ class UserModel(_Model):
         cost_source   optional: mppi_user_running_cost<R>(x, goal, u_nom, eps, t) and mppi_user_terminal_cost<R>(x, goal)
                       replacing get_cost (:180-184) and the terminal cost (:165-171)
 
-    Engines with a user model run with precision 'f64' (default) or 'f32'."""
+    Engines with a user model run with precision 'f64' (default) or 'f32'.  See KinematicModel for functors that also run
+    the headline precision 'mixed'."""
+
+    kind = 0
+    speed_max = 0.0
+    yaw_rate_max = 0.0
 
     def __init__(self, ode_source, name="user_model", integrator="rk4", wrap_theta=True, cost_source=None):
         _Model.__init__(self, name, _capi.MODEL_USER)
@@ -88,7 +93,12 @@ class UserModel(_Model):
 
     def _spec(self):
         self._src_bytes = self.source.encode("utf-8")       # kept alive for the duration of the call
-        return _capi.MppiUserModel(self._src_bytes, self.integrator, int(self.wrap_theta), int(self.has_cost))
+        return _capi.MppiUserModel(self._src_bytes, self.integrator, int(self.wrap_theta), int(self.has_cost), self.kind,
+                                   float(self.speed_max), float(self.yaw_rate_max))
+
+    def _screenable(self):
+        """can the engine run precision 'mixed' for this model?"""
+        return self.kind == 1 and not self.has_cost and self.speed_max > 0
 
     def check(self):
         """compile only (no GPU needed); raises MppiError with the compiler's log"""
@@ -98,6 +108,25 @@ class UserModel(_Model):
     def _create_engine(self, lib, p, h):
         um = self._spec()
         _capi.check(lib.mppi_create_user(C.byref(p), C.byref(um), C.byref(h)), "mppi_create_user")
+
+
+class KinematicModel(UserModel):
+    """A caller-supplied KINEMATIC model (mppi_user_model.kind 1): forward speed and yaw rate as functions of the controls,
+
+        source        template <typename R> __device__ void mppi_user_speed_yaw(const R u[2], R* speed, R* yaw_rate) {...}
+
+    for xdot = speed cos(theta), ydot = speed sin(theta), thetadot = yaw_rate -- the family dd_dynamics and unicycle_dynamics
+    (control/src/mppi:23-36) belong to.  The functor is dropped into the built-in kernels, so every precision works, 'mixed'
+    (the default, as for the built-in models) included; 'mixed' needs speed_max / yaw_rate_max, bounds of |speed| and
+    |yaw_rate| over the clipped controls (they size the fp32 screening window; a bound that is too small costs fp64 re-runs,
+    not correctness).  integrator "rk4" wraps theta after the step (:39-54), "euler" does not (:57-58)."""
+
+    kind = 1
+
+    def __init__(self, source, name="kinematic_model", integrator="rk4", speed_max=0.0, yaw_rate_max=0.0, cost_source=None):
+        UserModel.__init__(self, source, name=name, integrator=integrator, wrap_theta=(integrator == "rk4"), cost_source=cost_source)
+        self.speed_max = speed_max
+        self.yaw_rate_max = yaw_rate_max
 
 
 rk4 = _Model("rk4", _capi.MODEL_DIFF_DRIVE)                 # control/src/mppi:39-54 (+ dd_dynamics :23-30)
@@ -190,7 +219,7 @@ class MPPI(object):
         p.K, p.T = self.samples, self.horizon
         p.model = self.model.model_id
         p.dt = self.dt
-        p.precision = _PRECISIONS[o.pop("precision", "f64" if isinstance(self.model, UserModel) else "mixed")]
+        p.precision = _PRECISIONS[o.pop("precision", "f64" if (isinstance(self.model, UserModel) and not self.model._screenable()) else "mixed")]
         p.weighting = _WEIGHTINGS[o.pop("weighting", "cost_to_go")]
         p.seed = int(o.pop("seed", 0))
         p.device = int(o.pop("device", 0))

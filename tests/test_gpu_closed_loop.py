@@ -82,6 +82,10 @@ def test_cpp_facade_closed_loop():
     r = subprocess.run([exe, "2048", "32", "600", "user"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "user-supplied ODE functor" in r.stdout and "WAYPOINT REACHED" in r.stdout
+    # ... and as a kinematic functor (mppi::UserKinematics, precision MIXED)
+    r = subprocess.run([exe, "2048", "32", "600", "kinematic"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "kinematic functor" in r.stdout and "WAYPOINT REACHED" in r.stdout
 
 
 def test_mixed_overflow_backs_off_to_fp64_and_stays_exact():

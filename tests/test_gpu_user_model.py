@@ -131,3 +131,132 @@ def test_user_model_fp32_and_grid_and_errors():
     assert ei.value.status == 1 and "nope" in str(ei.value)
     a.close()
     b.close()
+
+
+def test_kinematic_functor_restating_the_builtin_diff_drive_reproduces_it(monkeypatch):
+    """mppi_user_model.kind 1: the functor replaces speed_yaw() inside the BUILT-IN kernels.  dd_dynamics (control/src/mppi:23-30)
+    as a kinematic functor, against the built-in diff-drive pinned to the same (general) code path: same instructions around
+    the functor, so precision 'mixed' must agree to rounding of the functor's own constants -- far inside 1e-9 -- and both
+    self-checks of the screen must hold."""
+    M = mp()
+    K, T = 8192, 32
+    kin = M.KinematicModel(um.DD_KIN_CUDA, name="dd_kin", **um.DD_KIN_BOUNDS)
+    user = M.MPPI(model=kin, horizon=T, samples=K, seed=4)         # precision defaults to 'mixed' for a screenable functor
+    user64 = M.MPPI(model=kin, horizon=T, samples=K, precision="f64", seed=4)
+    monkeypatch.setenv("MPPI_B200_VARIANT", "general")
+    built = M.MPPI(horizon=T, samples=K, precision="mixed", seed=4)
+    monkeypatch.delenv("MPPI_B200_VARIANT")
+    user64.set_capture(True)
+    p = orc.Params(K=K, T=T)
+    s, U = np.array([0.1, 0.0, 0.4]), np.zeros((2, T))
+    for it in range(4):
+        s_in = s.copy()
+        su = user.get_path(s_in, PARK)
+        s64 = user64.get_path(s_in, PARK)
+        s = built.get_path(s_in, PARK)
+        assert rel_err(user.latest_uvec, built.latest_uvec) < 1e-9
+        assert rel_err(user.latest_uvec, user64.latest_uvec) < 1e-9
+        np.testing.assert_allclose(su, s, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(s64, s, rtol=0, atol=1e-12)
+        st, sb = user.stats(), built.stats()
+        assert st["refine_overflow"] == 0 and st["refine_candidates"] >= T
+        assert st["refine_candidates"] == sb["refine_candidates"]             # the same screen on the same noise
+        assert 0 < st["refine_head_room"] < 0.1 and st["refine_max_dev"] < st["refine_head_room"] / 4, st
+        assert abs(st["refine_head_room"] - sb["refine_head_room"]) < 1e-9 * sb["refine_head_room"]   # the stated bounds == the built-in's
+        out = orc.step(p, s_in, PARK, U, user64.get_noise())
+        np.testing.assert_allclose(user.latest_uvec, out["U_shift"], rtol=1e-8, atol=1e-9)
+        U = out["U_shift"]
+        for m in (user, user64):
+            m.latest_uvec = built.latest_uvec
+    for m in (user, user64, built):
+        m.close()
+
+
+@pytest.mark.parametrize("integrator", ["rk4", "euler"])
+def test_kinematic_functor_of_a_new_vehicle_all_precisions(integrator):
+    """a vehicle no built-in model is (slipping tracks), at a rollout count where the screen matters: f64 against the oracle's
+    generic integrator (the model as an ODE) and against the reference class where it travelled; mixed == f64 at 1e-9 with the
+    screen's self-checks; f32 within the conditioning bound; a grid in play."""
+    M = mp()
+    K, T = 16384, 32
+    kin = M.KinematicModel(um.SLIP_KIN_CUDA, name="slip", integrator=integrator, **um.SLIP_KIN_BOUNDS)
+    wrap = integrator == "rk4"
+    g = np.zeros((40, 40), dtype=np.int8)
+    g[18:24, 24:30] = 100
+    grid = dict(grid=g, grid_res=0.05, grid_origin=np.array([-1.0, -1.0]), w_obs=50.0)
+    eng = {}
+    for prec in ("f64", "mixed", "f32"):
+        eng[prec] = M.MPPI(model=kin, horizon=T, samples=K, precision=prec, seed=6)
+        eng[prec].set_grid(g, 0.05, np.array([-1.0, -1.0]), 50.0)
+    eng["f64"].set_capture(True)
+    p = orc.Params(K=K, T=T, model=orc.MODEL_USER, user_ode=um.slip_numpy, user_integrator=integrator, user_wrap=wrap, **grid)
+    s, goal = np.array([0.0, 0.0, 0.2]), np.array([0.8, 0.1, 0.0])
+    U = np.full((2, T), 5.0)
+    for m in eng.values():
+        m.latest_uvec = U
+    for it in range(3):
+        s_in = s.copy()
+        s = eng["f64"].get_path(s_in, goal)
+        sm = eng["mixed"].get_path(s_in, goal)
+        eng["f32"].get_path(s_in, goal)
+        out = orc.step(p, s_in, goal, U, eng["f64"].get_noise())
+        np.testing.assert_allclose(eng["f64"].get_value_fcn(), out["V"], rtol=1e-10)
+        np.testing.assert_allclose(eng["f64"].latest_uvec, out["U_shift"], rtol=1e-8, atol=1e-9)
+        np.testing.assert_allclose(s, out["x_next"], rtol=1e-9, atol=1e-12)
+        assert rel_err(eng["mixed"].latest_uvec, eng["f64"].latest_uvec) < 1e-9
+        np.testing.assert_allclose(sm, s, rtol=0, atol=1e-12)
+        st = eng["mixed"].stats()
+        assert st["refine_overflow"] == 0 and st["refine_candidates"] >= T
+        assert 0 < st["refine_head_room"] < 0.1 and st["refine_max_dev"] < st["refine_head_room"] / 4, st
+        assert rel_err(eng["f32"].latest_uvec, eng["f64"].latest_uvec) < 5e-2
+        U = out["U_shift"]
+        eng["f32"].latest_uvec = eng["f64"].latest_uvec
+        eng["mixed"].latest_uvec = eng["f64"].latest_uvec
+    if ref_loader.available() and integrator == "rk4":
+        R = ref_loader.load_reference()
+        ref = R.MPPI(model=orc.user_model_step(um.slip_numpy, integrator, wrap), horizon=T, samples=512)
+        small = M.MPPI(model=kin, horizon=T, samples=512, seed=1)              # mixed
+        small.set_capture(True)
+        s0, g0 = np.array([0.2, -0.1, 0.7]), np.array([0.6, -0.5, -0.3])
+        xg = small.get_path(s0, g0)
+        feed, orig = iter(small.get_noise()), np.random.normal
+        np.random.normal = lambda *a, **k: next(feed).copy()
+        try:
+            xr = ref.get_path(s0, g0)
+        finally:
+            np.random.normal = orig
+        np.testing.assert_allclose(xg, xr, rtol=1e-8, atol=1e-11)
+        np.testing.assert_allclose(small.latest_uvec, ref.latest_uvec, rtol=1e-8, atol=1e-8)
+        small.close()
+    # perform_action / the model functor with the kinematic functor
+    rng = np.random.RandomState(0)
+    xs, us = rng.normal(size=(3, 40)) * 2, rng.normal(size=(2, 40)) * 3
+    np.testing.assert_allclose(kin(xs, us, 1.0 / T), orc.user_model_step(um.slip_numpy, integrator, wrap)(xs, us, 1.0 / T), rtol=1e-11, atol=1e-13)
+    for m in eng.values():
+        m.close()
+
+
+def test_kinematic_functor_errors_and_understated_bounds():
+    M = mp()
+    K, T = 4096, 32
+    with pytest.raises(M.MppiError) as ei:       # mixed without bounds
+        M.MPPI(model=M.KinematicModel(um.SLIP_KIN_CUDA), horizon=T, samples=K, precision="mixed")
+    assert ei.value.status == 1
+    with pytest.raises(M.MppiError) as ei:       # mixed with a cost functor: the screen's delta-form cost is the built-in one
+        M.MPPI(model=M.KinematicModel(um.SLIP_KIN_CUDA, cost_source=um.COST_CUDA, **um.SLIP_KIN_BOUNDS), horizon=T, samples=K, precision="mixed")
+    assert ei.value.status == 4
+    # bounds understated 100x: the window's head-room shrinks; whatever the screen then does, the safety net (a step whose
+    # measured fp32 error exceeds half the head-room is redone in fp64) keeps the result equal to f64
+    lying = M.KinematicModel(um.SLIP_KIN_CUDA, speed_max=um.SLIP_KIN_BOUNDS["speed_max"] / 100, yaw_rate_max=um.SLIP_KIN_BOUNDS["yaw_rate_max"] / 100)
+    a = M.MPPI(model=lying, horizon=T, samples=K, precision="f64", seed=3)
+    b = M.MPPI(model=lying, horizon=T, samples=K, precision="mixed", seed=3)
+    s = np.zeros(3)
+    for it in range(3):
+        sa = a.get_path(s, PARK)
+        sb = b.get_path(s, PARK)
+        assert rel_err(b.latest_uvec, a.latest_uvec) < 1e-9
+        np.testing.assert_allclose(sb, sa, rtol=0, atol=1e-12)
+        b.latest_uvec = a.latest_uvec
+        s = sa
+    a.close()
+    b.close()

@@ -72,3 +72,14 @@ def test_user_model_text_is_compiled_without_a_gpu():
     with pytest.raises(mp.MppiError) as ei:
         mp.UserModel("template <typename R> __device__ void mppi_user_ode(const R x[3], const R u[2], R xdot[3]) { xdot[0] = nope; }").check()
     assert ei.value.status == 1 and "nope" in str(ei.value)
+    # kinematic functors (kind 1) instantiate the screen family and its fp64 re-evaluation as well
+    for integ in ("rk4", "euler"):
+        mp.KinematicModel(um.SLIP_KIN_CUDA, integrator=integ, **um.SLIP_KIN_BOUNDS).check()
+    k = mp.KinematicModel(um.DD_KIN_CUDA, **um.DD_KIN_BOUNDS)
+    assert k._screenable() and k.wrap_theta and not mp.KinematicModel(um.DD_KIN_CUDA)._screenable()
+    k.wrap_theta = False                          # a kinematic functor is integrated like the built-in models: rk4 wraps
+    with pytest.raises(mp.MppiError) as ei:
+        k.check()
+    assert ei.value.status == 1
+    with pytest.raises(mp.MppiError):             # an ODE functor's text is not a kinematic functor
+        mp.KinematicModel(um.DD_CUDA).check()

@@ -65,3 +65,34 @@ def running_cost_numpy(st, goal, u, eps_t, t):
 def terminal_cost_numpy(st, goal):
     d = st - np.asarray(goal)[:, None]
     return 1000.0 * (d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+
+
+# (4) KINEMATIC functors (mppi_user_model.kind 1): speed and yaw rate from the controls.  The reference's diff-drive (:23-30) ...
+DD_KIN_CUDA = """
+template <typename R> __device__ void mppi_user_speed_yaw(const R u[2], R* speed, R* yaw_rate) {
+  *speed = R(0.5 * 0.033) * (u[0] + u[1]);
+  *yaw_rate = R(0.033 / 0.16) * (u[1] - u[0]);
+}
+"""
+DD_KIN_BOUNDS = dict(speed_max=0.033 * 6.35492, yaw_rate_max=0.033 / 0.16 * 2 * 6.35492)
+
+# ... and a vehicle none of the built-in models is: a tracked base whose tracks slip more the harder they are driven apart
+SLIP_KIN_CUDA = """
+template <typename R> __device__ void mppi_user_speed_yaw(const R u[2], R* speed, R* yaw_rate) {
+  const R r = R(0.033), L = R(0.16);
+  const R d = u[1] - u[0];
+  const R slip = R(1.0) / (R(1.0) + R(0.02) * d * d);
+  *speed = R(0.5) * r * (u[0] + u[1]) * (R(0.6) + R(0.4) * slip);
+  *yaw_rate = r / L * d * slip;
+}
+"""
+# |speed| <= r * u_max; |yaw| = (r / L) |d| / (1 + 0.02 d^2) is largest at |d| = 1 / sqrt(0.02)
+SLIP_KIN_BOUNDS = dict(speed_max=0.033 * 6.35492, yaw_rate_max=0.033 / 0.16 * 0.5 / np.sqrt(0.02))
+
+
+def slip_numpy(x, u):
+    r, L = 0.033, 0.16
+    d = u[1, :] - u[0, :]
+    slip = 1.0 / (1.0 + 0.02 * d * d)
+    s = 0.5 * r * (u[0, :] + u[1, :]) * (0.6 + 0.4 * slip)
+    return np.array([s * np.cos(x[2, :]), s * np.sin(x[2, :]), r / L * d * slip])
