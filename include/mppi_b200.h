@@ -139,7 +139,9 @@ MPPI_API mppi_status mppi_destroy(mppi_handle h);
  * cost (Q, R, P1 of mppi_params, control/src/mppi:165-171,180-184) applies.  integrator: 0 = classic RK4 with the control
  * held over the step (control/src/mppi:39-50), 1 = explicit Euler (:57-58); wrap_theta != 0 wraps theta into (-pi, pi] after
  * every step (:52-53); a kind-1 functor is integrated like the built-in models: integrator 0 = rk4 WITH the wrap, 1 = Euler
- * WITHOUT it (wrap_theta must say the same).  params->model is ignored (set to MPPI_MODEL_USER).  Compilation errors: MPPI_ERR_INVALID, text in mppi_last_error(). */
+ * WITHOUT it (wrap_theta must say the same).  params->model is ignored (set to MPPI_MODEL_USER).  Compilation errors:
+ * MPPI_ERR_INVALID, text in mppi_last_error().  Zero-initialise the struct (`mppi_user_model um = {0};`): every field's zero is
+ * its default. */
 typedef struct {
   const char* source;        /* CUDA C++ text defining the functions above */
   int32_t integrator;        /* 0 RK4, 1 explicit Euler */

@@ -73,3 +73,30 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
                 assert "mppi_oracle" not in txt and "ref_loader" not in txt, f
+
+
+def test_every_struct_layout_matches_its_ctypes_mirror(tmp_path):
+    """include/mppi_b200.h compiled as plain C (the header is the contract a cgo / JNI / ctypes binding reads): sizeof and every
+    field offset of mppi_params, mppi_user_model and mppi_timing against the ctypes mirrors the Python host side uses."""
+    structs = {"mppi_params": _capi.MppiParams, "mppi_user_model": _capi.MppiUserModel, "mppi_timing": _capi.MppiTiming}
+    lines = ["#include <stddef.h>", "#include <stdio.h>", '#include "mppi_b200.h"', "int main(void) {"]
+    for cname, mirror in structs.items():
+        lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in mirror._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname.rstrip("_")))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = str(tmp_path / "layout")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, fname, value = line.split()
+        mirror = structs[cname]
+        want = ctypes.sizeof(mirror) if fname == "sizeof" else getattr(mirror, fname).offset
+        assert int(value) == want, line
+        seen += 1
+    assert seen == sum(len(m._fields_) + 1 for m in structs.values())
