@@ -10,8 +10,11 @@
 //                                           (control/include/control/TrajMPC.hpp:72,110-122)
 //   - no Eigen dependency (std::array), so it builds in a plain catkin C++17 package
 //     (control/CMakeLists.txt:5-9).
-// On the device the dynamics and cost "functors" are compile-time kernel template arguments selected
-// by the tag types below; arbitrary std::function models cannot run inside the rollout kernel.
+// On the device the dynamics and cost "functors" are compile-time kernel template arguments: the tag types
+// below select the built-in instantiations, UserDynamics / UserKinematics / UserCost hand a caller's functor
+// over as CUDA text that is compiled at run time.  A host std::function cannot run inside the rollout kernel;
+// mppi::RK4 at the end of this file is the reference's host-side integrator interface (registerODE / solve)
+// for code that simulates a plant beside the controller.
 #ifndef MPPI_HPP_
 #define MPPI_HPP_
 
@@ -19,6 +22,7 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -426,6 +430,62 @@ class Controller {
   State start_{{0, 0, 0}}, goal_{{0, 0, 0}};
   Control last_u_{{0, 0}};
 };
+
+// ---- host-side integrator (NOT on the engine's path) ------------------------------------------------
+// The interface of the reference's control::RK4 (control/include/control/rk4.hpp:19-62) without Eigen: a fixed-step classic
+// Runge-Kutta over a registered ODE `ode(x, u, xdot_out)`, the control held over each step.  For host code around the
+// controller -- a simulated plant that feeds odometry back, a planner that previews a control sequence; the rollouts of MPPI
+// itself never come through here (they run in the kernels, from the same ODE handed over as text: UserDynamics).
+//   solve(x0, U, horizon): floor(horizon / dt) steps, step i uses column i of U; returns the states AFTER each step
+//   (control/src/control/rk4.cpp:56-84); the stage order is that of rk4.cpp:115-138
+template <size_t NX, size_t NU>
+class RK4 {
+ public:
+  using X = std::array<double, NX>;
+  using U = std::array<double, NU>;
+  using Ode = std::function<void(const X&, const U&, X&)>;
+  explicit RK4(double dt) : dt_(dt) {}
+  void registerODE(Ode ode) { ode_ = std::move(ode); }
+  void integrate(X& x, const U& u) const {   // one step, in place
+    if (!ode_) throw std::logic_error("mppi::RK4: no ODE registered");
+    X k1{}, k2{}, k3{}, k4{}, tmp{};
+    ode_(x, u, k1);
+    for (size_t i = 0; i < NX; ++i) tmp[i] = x[i] + dt_ * (0.5 * k1[i]);
+    ode_(tmp, u, k2);
+    for (size_t i = 0; i < NX; ++i) tmp[i] = x[i] + dt_ * (0.5 * k2[i]);
+    ode_(tmp, u, k3);
+    for (size_t i = 0; i < NX; ++i) tmp[i] = x[i] + dt_ * k3[i];
+    ode_(tmp, u, k4);
+    for (size_t i = 0; i < NX; ++i) x[i] += (dt_ / 6.0) * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
+  }
+  std::vector<X> solve(const X& x0, const std::vector<U>& u, double horizon) const {
+    const size_t n = static_cast<size_t>(horizon / dt_);
+    if (u.size() < n) throw std::invalid_argument("mppi::RK4::solve: the control signal is shorter than horizon / dt");
+    std::vector<X> traj;
+    traj.reserve(n);
+    X x = x0;
+    for (size_t i = 0; i < n; ++i) {
+      integrate(x, u[i]);
+      traj.push_back(x);
+    }
+    return traj;
+  }
+  double dt() const { return dt_; }
+
+ private:
+  double dt_;
+  Ode ode_;
+};
+
+// the reference's diff-drive ODE (dd_dynamics, control/src/mppi:23-30) for mppi::RK4<3, 2>::registerODE
+inline RK4<3, 2>::Ode diffDriveOde(const DiffDrive& robot) {
+  const double half_r = 0.5 * robot.wheel_radius, r_over_L = robot.wheel_radius / robot.wheel_base;
+  return [half_r, r_over_L](const State& x, const Control& u, State& xdot) {
+    xdot[0] = half_r * std::cos(x[2]) * (u[0] + u[1]);
+    xdot[1] = half_r * std::sin(x[2]) * (u[0] + u[1]);
+    xdot[2] = r_over_L * (u[1] - u[0]);
+  };
+}
 
 }  // namespace mppi
 #endif  // MPPI_HPP_

@@ -118,3 +118,30 @@ def test_cpp_path_tracking_matches_python_mirror(exe):
         np.testing.assert_allclose([float(v) for v in gline[3:8]], e[2:7], rtol=0, atol=1e-12)
         assert (int(gline[8]), int(gline[9])) == e[7:]
     assert expect[-1][1] == 1 and stub.steps > 10 and stub.resets == 1      # reached the end, one initialise only
+
+
+def test_cpp_host_rk4_matches_the_reference_integrator(tmp_path):
+    """mppi::RK4 (the interface of control::RK4, control/include/control/rk4.hpp:19-62) over dd_dynamics against the oracle's
+    rk4 WITHOUT the theta wrap (the C++ integrator has none, control/src/control/rk4.cpp:115-138): same stage order, so the
+    trajectories agree to rounding; solve() returns floor(horizon / dt) states."""
+    from oracle import mppi_oracle as orc
+    out = str(tmp_path / "rk4_check")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "rk4_check.cpp"),
+           "-L" + LIBDIR, "-lmppi_b200", "-Wl,-rpath," + LIBDIR, "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rng = np.random.RandomState(3)
+    n, dt = 80, 1.0 / 64
+    U = rng.uniform(-6.0, 6.0, size=(n, 2)) + np.array([-3.0, 3.0])   # turning left on average
+    x0 = np.array([0.3, -0.2, 2.9])                       # close to pi: the trajectory crosses it, unwrapped
+    text = "%r %r %d\n%r %r %r\n" % (dt, 1.0, n, *x0.tolist()) + "".join("%r %r\n" % (a, b) for a, b in U.tolist())
+    r = subprocess.run([out], input=text, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    traj = np.array([[float(v) for v in line.split()] for line in r.stdout.splitlines()])
+    assert traj.shape == (64, 3)                          # floor(1.0 / dt) steps although 80 controls were given
+    x = x0.copy()
+    step = orc.user_model_step(orc.dd_dynamics, "rk4", False)
+    for i in range(64):
+        x = step(x.reshape(3, 1), U[i].reshape(2, 1), dt)[:, 0]
+        np.testing.assert_allclose(traj[i], x, rtol=1e-13, atol=1e-15)
+    assert np.max(np.abs(traj[:, 2])) > np.pi             # no wrap in the C++ integrator
