@@ -161,15 +161,18 @@ def test_oracle_euler_model_matches_live_reference(seed):
 
 @pytest.mark.skipif(ref_loader.available() is None, reason="reference not loadable here")
 @pytest.mark.parametrize("integrator,wrap", [("rk4", True), ("euler", False)])
-def test_oracle_user_model_matches_live_reference_through_its_model_hook(integrator, wrap):
+@pytest.mark.parametrize("ode_name", ["skid_numpy", "slip_numpy"])
+def test_oracle_user_model_matches_live_reference_through_its_model_hook(integrator, wrap, ode_name):
     """an arbitrary ODE plugged into the UNMODIFIED reference class through its own `model=` constructor
     argument (control/src/mppi:62,66,154,213) -- here one whose speed and yaw rate depend on the state -- and, for the cost
-    functor, a subclass overriding get_cost (:180-184).  Pins the oracle's MODEL_USER path and its cost hooks."""
+    functor, a subclass overriding get_cost (:180-184).  Pins the oracle's MODEL_USER path and its cost hooks.  slip_numpy is
+    the NumPy twin of the KINEMATIC functor the GPU tests run (speed and yaw rate from the controls only)."""
     import user_models as um
     ref = ref_loader.load_reference()
     rng = np.random.RandomState(77)
     K, T = 24, 12
-    model = orc.user_model_step(um.skid_numpy, integrator, wrap)
+    ode = getattr(um, ode_name)
+    model = orc.user_model_step(ode, integrator, wrap)
 
     class CostMPPI(ref.MPPI):
         def get_cost(self, state, goal, u, lam, sig, eps):
@@ -178,7 +181,7 @@ def test_oracle_user_model_matches_live_reference_through_its_model_hook(integra
     for cls, cost in ((ref.MPPI, False), (CostMPPI, True)):
         m = cls(model=model, horizon=T, samples=K)
         m.latest_uvec = rng.normal(size=(2, T)) * 2
-        p = orc.Params(K=K, T=T, model=orc.MODEL_USER, user_ode=um.skid_numpy, user_integrator=integrator, user_wrap=wrap)
+        p = orc.Params(K=K, T=T, model=orc.MODEL_USER, user_ode=ode, user_integrator=integrator, user_wrap=wrap)
         if cost:
             p.user_running_cost, p.user_terminal_cost = um.running_cost_numpy, um.terminal_cost_numpy
         x0, goal = np.array([0.2, -0.1, 0.7]), np.array([0.6, -0.5, -0.3])
